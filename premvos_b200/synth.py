@@ -1,0 +1,123 @@
+"""Seeded synthetic weights and DAVIS/Sintel-shaped frames (there is no network for real
+checkpoints or datasets).  Everything is generated with numpy's PCG64 so the
+same seed gives the same bytes in the build container and on the GPU box."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+
+
+def pwc_param_shapes() -> "OrderedDict[str, tuple]":
+    """Reference state_dict keys/shapes (code/optical_flow_net-PWC-Net/models/PWCNet.py:50-131),
+    in registration order: 128 tensors, 9 374 340 parameters."""
+    t = OrderedDict()
+
+    def conv(name, cin, cout, seq=True):
+        key = name + (".0" if seq else "")
+        t[key + ".weight"] = (cout, cin, 3, 3)
+        t[key + ".bias"] = (cout,)
+
+    def deconv(name, cin, cout):
+        t[name + ".weight"] = (cin, cout, 4, 4)
+        t[name + ".bias"] = (cout,)
+
+    chans = [3, 16, 32, 64, 96, 128, 196]
+    for lvl in range(1, 7):
+        ci, co = chans[lvl - 1], chans[lvl]
+        names = ("conv%da" % lvl, "conv%daa" % lvl, "conv%db" % lvl)
+        if lvl == 6:  # the reference applies conv6aa (stride 2) first, PWCNet.py:65-67,193
+            names = ("conv6aa", "conv6a", "conv6b")
+        conv(names[0], ci, co)
+        conv(names[1], co, co)
+        conv(names[2], co, co)
+    dd = [128, 256, 352, 416, 448]
+    for lvl, extra in ((6, 0), (5, 132), (4, 100), (3, 68), (2, 36)):
+        od = 81 + extra
+        for i, (cin, cout) in enumerate(((od, 128), (od + dd[0], 128), (od + dd[1], 96),
+                                         (od + dd[2], 64), (od + dd[3], 32))):
+            conv("conv%d_%d" % (lvl, i), cin, cout)
+        conv("predict_flow%d" % lvl, od + dd[4], 2, seq=False)
+        deconv("deconv%d" % lvl, 2, 2)
+        if lvl != 2:
+            deconv("upfeat%d" % lvl, od + dd[4], 2)
+    for name, cin, cout in (("dc_conv1", 565, 128), ("dc_conv2", 128, 128), ("dc_conv3", 128, 128),
+                            ("dc_conv4", 128, 96), ("dc_conv5", 96, 64), ("dc_conv6", 64, 32)):
+        conv(name, cin, cout)
+    conv("dc_conv7", 32, 2, seq=False)
+    return t
+
+
+def pwc_synthetic_state_dict(seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """He-normal (fan_in) weights like the reference's own init (PWCNet.py:133-137) plus small
+    non-zero biases so the bias path is exercised.  Flow heads are scaled x2 (up-features x0.5) so the
+    synthetic flows move the warping layer by a few pixels per level."""
+    rng = np.random.default_rng(seed)
+    sd = OrderedDict()
+    for name, shape in pwc_param_shapes().items():
+        if name.endswith(".weight"):
+            if "deconv" in name or "upfeat" in name:
+                fan_in = shape[1] * shape[2] * shape[3]  # torch fan_in of a ConvTranspose2d weight
+            else:
+                fan_in = shape[1] * shape[2] * shape[3]
+            std = np.sqrt(2.0 / fan_in)
+            if name.startswith("predict_flow"):
+                std *= 2.0
+            elif name.startswith("dc_conv7") or name.startswith("upfeat"):
+                std *= 0.5
+            sd[name] = (rng.standard_normal(shape) * std).astype(np.float32)
+        else:
+            sd[name] = (rng.standard_normal(shape) * 0.02).astype(np.float32)
+    return sd
+
+
+def _smooth_texture(rng, h, w, c=3, octaves=(2, 4, 8, 16, 32, 64)):
+    """Band-limited random texture in [0,255]: sum of bilinearly up-sampled noise octaves."""
+    img = np.zeros((h, w, c), dtype=np.float64)
+    for o in octaves:
+        gh, gw = h // o + 3, w // o + 3
+        g = rng.random((gh, gw, c))
+        ys = np.arange(h) / o
+        xs = np.arange(w) / o
+        y0 = ys.astype(np.int64)
+        x0 = xs.astype(np.int64)
+        fy = (ys - y0)[:, None, None]
+        fx = (xs - x0)[None, :, None]
+        a = g[y0][:, x0]
+        b = g[y0][:, x0 + 1]
+        cc = g[y0 + 1][:, x0]
+        d = g[y0 + 1][:, x0 + 1]
+        img += (a * (1 - fy) * (1 - fx) + b * (1 - fy) * fx + cc * fy * (1 - fx) + d * fy * fx) * o
+    img -= img.min()
+    img /= img.max()
+    return img * 255.0
+
+
+def synthetic_frame_pair(h: int = 436, w: int = 1024, seed: int = 1, shift=(3.7, -2.2), noise_sigma=2.0):
+    """Two uint8 RGB frames [h,w,3]; frame 2 = frame 1 translated by ``shift`` (x,y) px + noise."""
+    rng = np.random.default_rng(seed)
+    m = 16
+    big = _smooth_texture(rng, h + 2 * m, w + 2 * m)
+    f1 = big[m:m + h, m:m + w]
+    dx, dy = shift
+    ys = np.arange(h) + m - dy
+    xs = np.arange(w) + m - dx
+    y0 = np.floor(ys).astype(np.int64)
+    x0 = np.floor(xs).astype(np.int64)
+    fy = (ys - y0)[:, None, None]
+    fx = (xs - x0)[None, :, None]
+    f2 = (big[y0][:, x0] * (1 - fy) * (1 - fx) + big[y0][:, x0 + 1] * (1 - fy) * fx
+          + big[y0 + 1][:, x0] * fy * (1 - fx) + big[y0 + 1][:, x0 + 1] * fy * fx)
+    f2 = f2 + rng.standard_normal(f2.shape) * noise_sigma
+    to_u8 = lambda a: np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    return to_u8(f1), to_u8(f2)
+
+
+def synthetic_pwc_input(batch: int, h_: int, w_: int, seed: int = 1) -> np.ndarray:
+    """float32 [batch,6,h_,w_] network input (BGR/255), h_/w_ already multiples of 64."""
+    out = np.empty((batch, 6, h_, w_), dtype=np.float32)
+    for b in range(batch):
+        f1, f2 = synthetic_frame_pair(h_, w_, seed=seed + b, shift=(3.7 - 0.9 * b, -2.2 + 0.7 * b))
+        for k, f in enumerate((f1, f2)):
+            out[b, 3 * k:3 * k + 3] = np.transpose(f[:, :, ::-1].astype(np.float32) / np.float32(255.0), (2, 0, 1))
+    return out
