@@ -1,0 +1,117 @@
+/* premvos_b200 -- C ABI of the B200-native PReMVOS hot path.
+ *
+ * Plain pointers and sizes only (no torch / THC types).  Every entry point returns 0 on success,
+ * a positive cudaError_t value when CUDA failed, or a negative PREMVOS_ERR_* code for argument
+ * errors; premvos_last_error() returns a human-readable description for the calling thread.
+ * Nothing here allocates behind the caller's back inside a forward call: all device memory of a
+ * network handle is allocated by *_create / *_finalize.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo, code/optical_flow_net-PWC-Net):
+ *   premvos_corr_forward   <- int corr_cuda_forward(THCudaTensor* input1, input2, rbot1, rbot2, output,
+ *                                 int pad_size, kernel_size, max_displacement, stride1, stride2,
+ *                                 corr_type_multiply)
+ *                             external_packages/correlation-pytorch-master/correlation-pytorch/
+ *                             correlation_package/src/corr_cuda.h:1-11, corr_cuda.c:7-82
+ *                             (bound by cffi in correlation_package/_ext/corr/__init__.py:1-12 and
+ *                             called from functions/corr.py:24-32)
+ *   premvos_pwc_*          <- models.pwc_dc_net(path) / PWCDCNet.forward, models/PWCNet.py:179-272,
+ *                             496-505, driven by script_pwc_multi.py:33-70 (one device round trip
+ *                             per frame pair)
+ */
+#ifndef PREMVOS_B200_H
+#define PREMVOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PREMVOS_OK 0
+#define PREMVOS_ERR_INVALID_ARG (-1)   /* null pointer, non-positive size, size not a multiple of 64 ... */
+#define PREMVOS_ERR_UNSUPPORTED (-2)   /* a configuration the hot path never uses (see each function)  */
+#define PREMVOS_ERR_UNKNOWN_PARAM (-3) /* premvos_pwc_set_param: name is not a PWC-DC-Net state_dict key */
+#define PREMVOS_ERR_BAD_SHAPE (-4)     /* premvos_pwc_set_param: numel does not match the parameter    */
+#define PREMVOS_ERR_NOT_READY (-5)     /* forward before finalize, or parameters missing at finalize   */
+#define PREMVOS_ERR_NO_DEVICE (-6)     /* no sm_100 device visible                                      */
+
+/* Library / build identification, e.g. "premvos_b200 0.1 sm_100a". */
+const char* premvos_version(void);
+/* Description of the last error on this thread ("" if none). */
+const char* premvos_last_error(void);
+/* Total number of CUDA kernels launched (or captured into graphs) by this library so far in this
+ * process; bench.py reads it around the timed region to report `gpu_launches`. */
+int64_t premvos_kernel_launch_count(void);
+/* Per-launch profiling for bench.py's roofline leg.  Between begin and end every kernel launched by
+ * this library is bracketed by CUDA events on its launching stream (CUDA graphs are bypassed while
+ * profiling).  premvos_profile_end synchronises and writes one text line per kernel name into buf:
+ * "name launches total_ms algorithmic_flops algorithmic_bytes\n". */
+int premvos_profile_begin(void);
+int premvos_profile_end(char* buf, int buflen);
+
+/* ---------------------------------------------------------------------------------------------
+ * Correlation (cost volume), forward only, "multiply" variant.
+ *
+ * input1, input2 : device, contiguous fp32 NCHW [batch, channels, height, width]
+ * output         : device, contiguous fp32 NCHW [batch, (2*(max_displacement/stride2)+1)^2, OH, OW]
+ *                  with OH = ceil((height + 2*pad_size - 2*(max_displacement + (kernel_size-1)/2)) / stride1)
+ *                  (corr_cuda.c:23-45); caller-owned -- unlike the reference the callee never resizes,
+ *                  zero-fills scratch tensors or frees anything (corr_cuda.c:52-60,77-78).
+ * out[b, (dy/stride2+r)*(2r+1) + (dx/stride2+r), y, x] =
+ *        (1/(k*k*C)) * sum_{j,i<k} sum_c in1pad[b,c,y1+j,x1+i] * in2pad[b,c,y1+dy+j,x1+dx+i]
+ * with x1 = x*stride1 + max_displacement (corr_cuda_kernel.cu:59-127), zero outside the images.
+ * corr_type_multiply must be 1 (PWCNet.py:69); 0 (the L1 "subtract" variant) returns
+ * PREMVOS_ERR_UNSUPPORTED.  stream is a cudaStream_t (NULL = default stream).
+ * The reference returns 1 always and exit(-1)s on a launch error; this returns an error code.
+ * --------------------------------------------------------------------------------------------- */
+int premvos_corr_output_shape(int height, int width, int pad_size, int kernel_size,
+                              int max_displacement, int stride1, int stride2, int* out_channels,
+                              int* out_height, int* out_width);
+int premvos_corr_forward(const float* input1, const float* input2, float* output, int batch,
+                         int channels, int height, int width, int pad_size, int kernel_size,
+                         int max_displacement, int stride1, int stride2, int corr_type_multiply,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PWC-DC-Net forward (optical flow).
+ *
+ * Life cycle: create(batch,H,W) -> set_param(name, host fp32 data) for each of the 128 state_dict
+ * tensors (names exactly as in the reference checkpoint: "conv1a.0.weight", "predict_flow6.bias",
+ * "upfeat5.weight", "dc_conv7.weight" ...; layouts as torch stores them: Conv2d [Cout,Cin,3,3],
+ * ConvTranspose2d [Cin,Cout,4,4]) -> finalize() (packs + uploads weights, allocates all activation
+ * buffers, captures the CUDA graph) -> forward()* -> destroy().
+ *
+ * x    : fp32 NCHW [batch, 6, height, width], channels = BGR/255 of frame 1 then frame 2
+ *        (script_pwc_multi.py:47-56); height and width must be multiples of 64.
+ * flow : fp32 NCHW [batch, 2, height/4, width/4] = the eval-mode output `flow2` (PWCNet.py:269-272),
+ *        in units of input pixels / 20.
+ * premvos_pwc_forward      : x and flow are DEVICE pointers; enqueues on `stream`, does not sync.
+ * premvos_pwc_forward_host : x and flow are HOST pointers (pinned or pageable); copies x to the
+ *        device, runs the network, copies flow back and synchronises -- the end-to-end call.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct premvos_pwc premvos_pwc_t;
+
+int premvos_pwc_create(premvos_pwc_t** out, int batch, int height, int width);
+int premvos_pwc_set_param(premvos_pwc_t* net, const char* name, const float* host_data, int64_t numel);
+int premvos_pwc_finalize(premvos_pwc_t* net);
+int premvos_pwc_forward(premvos_pwc_t* net, const float* x_dev, float* flow_dev, void* stream);
+int premvos_pwc_forward_host(premvos_pwc_t* net, const float* x_host, float* flow_host);
+/* Number of kernel launches one forward() performs (nodes of the captured graph). */
+int premvos_pwc_launches_per_forward(const premvos_pwc_t* net);
+/* Number of convolution layers of this handle that run on the tcgen05 tensor-core path (0 = pure
+ * fp32 SIMT); valid after finalize. */
+int premvos_pwc_tensor_core_layers(const premvos_pwc_t* net);
+/* Set before finalize: 0 = fp32 SIMT convolutions everywhere; 1 (default) = tcgen05 tensor-core
+ * implicit-GEMM convolutions (split-bf16 x3, fp32 accumulate) where the layer shape allows. */
+int premvos_pwc_set_option(premvos_pwc_t* net, const char* key, int value);
+/* Test hook: copy an intermediate of the LAST forward to a host fp32 NCHW buffer.  Names follow the
+ * reference's variable names in PWCDCNet.forward: "c11".."c16", "c21".."c26", "corr6".."corr2",
+ * "warp5".."warp2", "flow6".."flow2" (flow2 = before the context net), "up_flow6".."up_flow3",
+ * "up_feat6".."up_feat3", "dc6".  *numel receives the element count; pass host_out = NULL to query. */
+int premvos_pwc_get_tensor(premvos_pwc_t* net, const char* name, float* host_out, int64_t* numel);
+void premvos_pwc_destroy(premvos_pwc_t* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PREMVOS_B200_H */

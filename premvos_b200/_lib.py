@@ -1,0 +1,83 @@
+"""ctypes binding of include/premvos_b200.h.  Fails loudly: there is no CPU or PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpremvos_b200.so")
+
+# every symbol include/premvos_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "premvos_version", "premvos_last_error", "premvos_kernel_launch_count", "premvos_profile_begin",
+    "premvos_profile_end",
+    "premvos_corr_output_shape", "premvos_corr_forward",
+    "premvos_pwc_create", "premvos_pwc_set_param", "premvos_pwc_finalize", "premvos_pwc_forward",
+    "premvos_pwc_forward_host", "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
+    "premvos_pwc_get_tensor", "premvos_pwc_destroy", "premvos_pwc_tensor_core_layers",
+]
+
+_lib = None
+
+
+class PremvosError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("premvos_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the CUDA library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "premvos_b200: %s is missing. Build it with `python -m premvos_b200.build` (needs nvcc). "
+            "There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_int, c_void_p, c_char_p, c_i64 = ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64
+    P = ctypes.POINTER
+    L.premvos_version.restype = c_char_p
+    L.premvos_last_error.restype = c_char_p
+    L.premvos_kernel_launch_count.restype = c_i64
+    L.premvos_profile_end.argtypes = [c_char_p, c_int]
+    L.premvos_corr_output_shape.argtypes = [c_int] * 7 + [P(c_int)] * 3
+    L.premvos_corr_forward.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]
+    L.premvos_pwc_create.argtypes = [P(c_void_p), c_int, c_int, c_int]
+    L.premvos_pwc_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
+    L.premvos_pwc_finalize.argtypes = [c_void_p]
+    L.premvos_pwc_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    L.premvos_pwc_forward_host.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.premvos_pwc_launches_per_forward.argtypes = [c_void_p]
+    L.premvos_pwc_tensor_core_layers.argtypes = [c_void_p]
+    L.premvos_pwc_set_option.argtypes = [c_void_p, c_char_p, c_int]
+    L.premvos_pwc_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
+    L.premvos_pwc_destroy.argtypes = [c_void_p]
+    L.premvos_pwc_destroy.restype = None
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise PremvosError(code, lib().premvos_last_error().decode("utf-8", "replace"))
+
+
+def kernel_launch_count() -> int:
+    return int(lib().premvos_kernel_launch_count())
+
+
+def profile_begin() -> None:
+    check(lib().premvos_profile_begin())
+
+
+def profile_end() -> dict:
+    """-> {kernel name: {"launches", "ms", "flops", "bytes"}} for everything launched since profile_begin()."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().premvos_profile_end(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms, fl, by = line.rsplit(" ", 4)
+        out[name] = {"launches": int(cnt), "ms": float(ms), "flops": float(fl), "bytes": float(by)}
+    return out

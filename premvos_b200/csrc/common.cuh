@@ -1,0 +1,125 @@
+// Shared declarations for the premvos_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/premvos_b200.h"
+
+namespace premvos {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_last_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define PV_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::premvos::fail((int)_e, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                             cudaGetErrorString(_e));                                      \
+  } while (0)
+
+#define PV_CHECK(cond, code, ...)                          \
+  do {                                                     \
+    if (!(cond)) return ::premvos::fail((code), __VA_ARGS__); \
+  } while (0)
+
+#define PV_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+extern std::atomic<int64_t> g_launch_count;
+// Called once per kernel launch (also while capturing: one graph node == one launch).
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+// Per-launch profiling (bench.py's roofline leg): when enabled every launcher brackets its kernel
+// with CUDA events on the launching stream and records the launch's algorithmic FLOPs / bytes.
+bool profiling_enabled();
+void prof_before(cudaStream_t st);
+void prof_after(const char* what, cudaStream_t st, double flops, double bytes);
+inline int after_launch(const char* what, cudaStream_t st = nullptr, double flops = 0.0, double bytes = 0.0) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  if (profiling_enabled()) prof_after(what, st, flops, bytes);
+  return 0;
+}
+
+// ---- tensor view: channels-last activations -----------------------------------------------------
+// Element (n,y,x,c) lives at p[((n*H + y)*W + x)*cs + coff + c].  A view can therefore name a
+// channel range inside a wider "slab" (the DenseNet concat buffers of the PWC decoder).
+struct TView {
+  float* p = nullptr;
+  int N = 0, H = 0, W = 0;
+  int cs = 0;    // pixel stride in floats
+  int coff = 0;  // first channel of this view inside the pixel
+  int C = 0;     // logical channels of this view
+  TView slice(int off, int c) const {
+    TView v = *this;
+    v.coff = coff + off;
+    v.C = c;
+    return v;
+  }
+  TView batch_range(int n0, int n) const {
+    TView v = *this;
+    v.p = p + (size_t)n0 * H * W * cs;
+    v.N = n;
+    return v;
+  }
+  size_t pixels() const { return (size_t)N * H * W; }
+};
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- convolution (fp32 SIMT implicit GEMM), conv_simt.cu ---------------------------------------
+struct ConvWeightsSimt {
+  float* w = nullptr;     // device [R*S][CinP][CoutP], zero padded
+  float* bias = nullptr;  // device [CoutP]
+  int R = 3, S = 3, Cin = 0, Cout = 0, CinP = 0, CoutP = 0;
+};
+// host_w: torch Conv2d layout [Cout][Cin][R][S]; host_b: [Cout]
+int pack_conv_weights_simt(ConvWeightsSimt* out, const float* host_w, const float* host_b, int Cout,
+                           int Cin, int R, int S);
+void free_conv_weights_simt(ConvWeightsSimt* w);
+// out = act(conv(in) + bias); act = LeakyReLU(slope) (slope 1 = identity, 0 = ReLU)
+int conv2d_simt(const TView& in, const TView& out, const ConvWeightsSimt& w, int stride, int dil,
+                float slope, cudaStream_t st);
+
+// Small-Cout (<=4) 3x3 convolution, one warp per output pixel (predict_flow / dc_conv7).
+struct SmallConvWeights {
+  float* w = nullptr;     // device [9][Cout][CinP4]
+  float* bias = nullptr;  // device [Cout]
+  int Cin = 0, CinP = 0, Cout = 0;
+};
+int pack_small_conv_weights(SmallConvWeights* out, const float* host_w, const float* host_b, int Cout, int Cin);
+void free_small_conv_weights(SmallConvWeights* w);
+// out (channels-last view) = conv3x3(in) + bias [+ addend]; if nchw_out != nullptr the result is
+// (also) written as contiguous NCHW [N,Cout,H,W] there.
+int conv3x3_small_cout(const TView& in, const TView& out, const SmallConvWeights& w, const TView* addend,
+                       float* nchw_out, cudaStream_t st);
+
+// ConvTranspose2d 4x4 stride 2 pad 1 with Cout == 2 (deconvL / upfeatL), one warp per output pixel.
+struct DeconvWeights {
+  float* w = nullptr;     // device [16][2][CinP4]   (tap = ky*4+kx)
+  float* bias = nullptr;  // device [2]
+  int Cin = 0, CinP = 0;
+};
+int pack_deconv_weights(DeconvWeights* out, const float* host_w /*[Cin][2][4][4]*/, const float* host_b, int Cin);
+void free_deconv_weights(DeconvWeights* w);
+int deconv4x4s2_cout2(const TView& in, const TView& out /*[N,2H,2W], C=2*/, const DeconvWeights& w, cudaStream_t st);
+
+// ---- correlation / warp / layout, corr.cu warp.cu ------------------------------------------------
+// 9x9 (md=4) cost volume on channels-last features; writes 81 channels (LeakyReLU(slope) fused) into
+// `out` and, if c1_copy.p != nullptr, copies f1's channels there (the decoder slab's c1 slot).
+int corr81_nhwc(const TView& f1, const TView& f2, const TView& out, const TView& c1_copy, float slope,
+                cudaStream_t st);
+// PWCDCNet.warp: out = bilinear(x2, pos + flow*flow_scale) * validity mask
+int warp_nhwc(const TView& x2, const TView& flow, float flow_scale, const TView& out, cudaStream_t st);
+// x: NCHW [B,6,H,W] -> img: channels-last [2B,H,W,4] (image 1 of every pair first, then image 2)
+int pack_pair_input(const float* x_nchw, int B, int H, int W, const TView& img, cudaStream_t st);
+
+}  // namespace premvos
