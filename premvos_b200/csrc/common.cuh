@@ -1,6 +1,8 @@
 // Shared declarations for the premvos_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <string.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -52,8 +54,12 @@ inline int after_launch(const char* what, cudaStream_t st = nullptr, double flop
 // ---- tensor view: channels-last activations -----------------------------------------------------
 // Element (n,y,x,c) lives at p[((n*H + y)*W + x)*cs + coff + c].  A view can therefore name a
 // channel range inside a wider "slab" (the DenseNet concat buffers of the PWC decoder).
+// Two storage formats share the view: fp32 (p) or SPLIT bf16 (hi, lo with x = hi + lo, the operand
+// format of the tensor-core convolutions; same bytes per element as fp32).
 struct TView {
   float* p = nullptr;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
   int N = 0, H = 0, W = 0;
   int cs = 0;    // pixel stride in floats
   int coff = 0;  // first channel of this view inside the pixel
@@ -66,14 +72,40 @@ struct TView {
   }
   TView batch_range(int n0, int n) const {
     TView v = *this;
-    v.p = p + (size_t)n0 * H * W * cs;
+    size_t off = (size_t)n0 * H * W * cs;
+    if (p) v.p = p + off;
+    if (hi) { v.hi = hi + off; v.lo = lo + off; }
     v.N = n;
     return v;
   }
+  bool split() const { return hi != nullptr; }
+  bool null() const { return p == nullptr && hi == nullptr; }
   size_t pixels() const { return (size_t)N * H * W; }
 };
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+#ifdef __CUDACC__
+// split-bf16 element access: x = hi + lo
+__device__ __forceinline__ float ld_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long i) {
+  return __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+__device__ __forceinline__ float4 ld4_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long i) {  // i % 4 == 0
+  const uint2 h = *reinterpret_cast<const uint2*>(hi + i);
+  const uint2 l = *reinterpret_cast<const uint2*>(lo + i);
+  float4 r;
+  r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ void st_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long i, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+#endif
 
 // ---- convolution (fp32 SIMT implicit GEMM), conv_simt.cu ---------------------------------------
 struct ConvWeightsSimt {
@@ -111,6 +143,37 @@ struct DeconvWeights {
 int pack_deconv_weights(DeconvWeights* out, const float* host_w /*[Cin][2][4][4]*/, const float* host_b, int Cin);
 void free_deconv_weights(DeconvWeights* w);
 int deconv4x4s2_cout2(const TView& in, const TView& out /*[N,2H,2W], C=2*/, const DeconvWeights& w, cudaStream_t st);
+
+// ---- convolution on tcgen05 tensor cores (split-bf16 x3, fp32 accumulate), conv_umma.cu ----------
+struct ConvWeightsUmma {
+  __nv_bfloat16* w_hi = nullptr;  // device [R*S][CoutP][KP], K contiguous, zero padded
+  __nv_bfloat16* w_lo = nullptr;
+  float* bias = nullptr;          // device [CoutP]
+  int R = 3, S = 3, Cin = 0, Cout = 0, KP = 0, CoutP = 0, BN = 0;
+  alignas(64) unsigned char map_hi[128];  // CUtensorMap of w_hi / w_lo
+  alignas(64) unsigned char map_lo[128];
+};
+struct ConvPlanUmma {  // everything one launch needs; built once per layer at finalize time
+  alignas(64) unsigned char map_a_hi[128];
+  alignas(64) unsigned char map_a_lo[128];
+  alignas(64) unsigned char map_w_hi[128];
+  alignas(64) unsigned char map_w_lo[128];
+  alignas(16) unsigned char args[160];
+  int grid_x = 0, grid_y = 0, smem_bytes = 0;
+  double flops = 0, bytes = 0;
+};
+bool conv_umma_supported(int Cin, int Cout, int R, int S, int stride);
+int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S);
+void free_conv_weights_umma(ConvWeightsUmma* w);
+// in: split view; out: split view (hi/lo) or fp32 view.  Stride 1, "same" padding dil*(R/2).
+int plan_conv_umma(ConvPlanUmma* plan, const TView& in, const TView& out, const ConvWeightsUmma& w, int dil, float slope);
+int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st);
+
+// ---- layout / format conversion, layout.cu ---------------------------------------------------------
+// NCHW fp32 [N,C,H,W] -> channels-last view (fp32 or split)
+int nchw_to_view(const float* src, const TView& dst, cudaStream_t st);
+// channels-last view (fp32 or split) -> NCHW fp32
+int view_to_nchw(const TView& src, float* dst, cudaStream_t st);
 
 // ---- correlation / warp / layout, corr.cu warp.cu ------------------------------------------------
 // 9x9 (md=4) cost volume on channels-last features; writes 81 channels (LeakyReLU(slope) fused) into

@@ -224,6 +224,7 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) conv_simt_kernel(ConvArgs
 
 int conv2d_simt(const TView& in, const TView& out, const ConvWeightsSimt& w, int stride, int dil,
                 float slope, cudaStream_t st) {
+  PV_CHECK(!in.split() && !out.split(), PREMVOS_ERR_INVALID_ARG, "conv2d_simt: fp32 views only");
   PV_CHECK(in.C == w.Cin && out.C == w.Cout, PREMVOS_ERR_INVALID_ARG, "conv2d_simt: channel mismatch (%d,%d) vs (%d,%d)",
            in.C, out.C, w.Cin, w.Cout);
   PV_CHECK((in.cs % 4) == 0 && (in.coff % 4) == 0 && in.coff + round_up(in.C, 4) <= in.cs, PREMVOS_ERR_INVALID_ARG,
@@ -261,7 +262,7 @@ int conv2d_simt(const TView& in, const TView& out, const ConvWeightsSimt& w, int
 // Cout <= 4, 3x3, pad 1: one warp per output pixel
 // ------------------------------------------------------------------------------------------------
 struct SmallConvArgs {
-  const float* in; int in_cs, in_coff, Cin, CinP;
+  const float* in; const __nv_bfloat16 *in_hi, *in_lo; int in_cs, in_coff, Cin, CinP;
   int N, H, W;
   const float* w; const float* bias; int Cout;
   float* out; int out_cs, out_coff;
@@ -269,7 +270,7 @@ struct SmallConvArgs {
   float* nchw;
 };
 
-template <int COUT>
+template <int COUT, bool IN_SPLIT>
 __global__ void __launch_bounds__(256) conv3x3_small_kernel(SmallConvArgs a) {
   const int lane = threadIdx.x & 31;
   const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -284,10 +285,10 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(SmallConvArgs a) {
   for (int t = 0; t < 9; t++) {
     int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
     if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) continue;  // warp-uniform
-    const float* ip = a.in + (((long)n * a.H + iy) * a.W + ix) * a.in_cs + a.in_coff;
+    const long ibase = (((long)n * a.H + iy) * a.W + ix) * a.in_cs + a.in_coff;
     const float* wp = a.w + (size_t)t * COUT * a.CinP;
     for (int c = lane * 4; c < a.CinP; c += 128) {
-      float4 v = *reinterpret_cast<const float4*>(ip + c);
+      float4 v = IN_SPLIT ? ld4_split(a.in_hi, a.in_lo, ibase + c) : *reinterpret_cast<const float4*>(a.in + ibase + c);
 #pragma unroll
       for (int co = 0; co < COUT; co++) {
         float4 wv = *reinterpret_cast<const float4*>(wp + (size_t)co * a.CinP + c);
@@ -321,9 +322,10 @@ int conv3x3_small_cout(const TView& in, const TView& out, const SmallConvWeights
   PV_CHECK((in.cs % 4) == 0 && (in.coff % 4) == 0 && in.coff + w.CinP <= in.cs, PREMVOS_ERR_INVALID_ARG,
            "conv3x3_small_cout: input view not float4-addressable");
   SmallConvArgs a;
-  a.in = in.p; a.in_cs = in.cs; a.in_coff = in.coff; a.Cin = in.C; a.CinP = w.CinP;
+  a.in = in.p; a.in_hi = in.hi; a.in_lo = in.lo; a.in_cs = in.cs; a.in_coff = in.coff; a.Cin = in.C; a.CinP = w.CinP;
   a.N = in.N; a.H = in.H; a.W = in.W;
   a.w = w.w; a.bias = w.bias; a.Cout = w.Cout;
+  PV_CHECK(!out.split() && (!addend || !addend->split()), PREMVOS_ERR_INVALID_ARG, "conv3x3_small_cout: fp32 outputs only");
   a.out = out.p; a.out_cs = out.cs; a.out_coff = out.coff;
   a.add = addend ? addend->p : nullptr;
   a.add_cs = addend ? addend->cs : 0;
@@ -331,7 +333,8 @@ int conv3x3_small_cout(const TView& in, const TView& out, const SmallConvWeights
   a.nchw = nchw_out;
   long P = (long)in.N * in.H * in.W;
   prof_before(st);
-  conv3x3_small_kernel<2><<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
+  if (in.split()) conv3x3_small_kernel<2, true><<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
+  else conv3x3_small_kernel<2, false><<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
   return after_launch("conv3x3_small_kernel", st, 2.0 * P * 9 * w.Cin * 2, 4.0 * P * (w.Cin + 2));
 }
 
@@ -339,12 +342,13 @@ int conv3x3_small_cout(const TView& in, const TView& out, const SmallConvWeights
 // ConvTranspose2d 4x4 / stride 2 / pad 1 / Cout 2: out[oy,ox] gathers in[(oy+1-ky)/2,(ox+1-kx)/2]
 // ------------------------------------------------------------------------------------------------
 struct DeconvArgs {
-  const float* in; int in_cs, in_coff, CinP;
+  const float* in; const __nv_bfloat16 *in_hi, *in_lo; int in_cs, in_coff, CinP;
   int N, H, W;  // input size; output is 2H x 2W
   const float* w; const float* bias;
-  float* out; int out_cs, out_coff;
+  float* out; __nv_bfloat16 *out_hi, *out_lo; int out_cs, out_coff;
 };
 
+template <bool IN_SPLIT, bool OUT_SPLIT>
 __global__ void __launch_bounds__(256) deconv4x4_kernel(DeconvArgs a) {
   const int lane = threadIdx.x & 31;
   const int Ho = a.H * 2, Wo = a.W * 2;
@@ -365,10 +369,10 @@ __global__ void __launch_bounds__(256) deconv4x4_kernel(DeconvArgs a) {
       int kx = ((ox + 1) & 1) + 2 * b_;
       int ix = (ox + 1 - kx) / 2;
       if (ox + 1 - kx < 0 || ix >= a.W) continue;
-      const float* ip = a.in + (((long)n * a.H + iy) * a.W + ix) * a.in_cs + a.in_coff;
+      const long ibase = (((long)n * a.H + iy) * a.W + ix) * a.in_cs + a.in_coff;
       const float* wp = a.w + (size_t)(ky * 4 + kx) * 2 * a.CinP;
       for (int c = lane * 4; c < a.CinP; c += 128) {
-        float4 v = *reinterpret_cast<const float4*>(ip + c);
+        float4 v = IN_SPLIT ? ld4_split(a.in_hi, a.in_lo, ibase + c) : *reinterpret_cast<const float4*>(a.in + ibase + c);
         float4 w0 = *reinterpret_cast<const float4*>(wp + c);
         float4 w1 = *reinterpret_cast<const float4*>(wp + a.CinP + c);
         acc0 = fmaf(v.x, w0.x, acc0); acc0 = fmaf(v.y, w0.y, acc0);
@@ -385,7 +389,8 @@ __global__ void __launch_bounds__(256) deconv4x4_kernel(DeconvArgs a) {
   }
   if (lane < 2) {
     float v = (lane == 0 ? acc0 : acc1) + a.bias[lane];
-    a.out[pix * a.out_cs + a.out_coff + lane] = v;
+    if (OUT_SPLIT) st_split(a.out_hi, a.out_lo, pix * a.out_cs + a.out_coff + lane, v);
+    else a.out[pix * a.out_cs + a.out_coff + lane] = v;
   }
 }
 
@@ -395,13 +400,17 @@ int deconv4x4s2_cout2(const TView& in, const TView& out, const DeconvWeights& w,
   PV_CHECK((in.coff % 4) == 0 && in.coff + w.CinP <= in.cs && (in.cs % 4) == 0, PREMVOS_ERR_INVALID_ARG,
            "deconv4x4s2_cout2: input view not addressable");
   DeconvArgs a;
-  a.in = in.p; a.in_cs = in.cs; a.in_coff = in.coff; a.CinP = w.CinP;
+  a.in = in.p; a.in_hi = in.hi; a.in_lo = in.lo; a.in_cs = in.cs; a.in_coff = in.coff; a.CinP = w.CinP;
   a.N = in.N; a.H = in.H; a.W = in.W;
   a.w = w.w; a.bias = w.bias;
-  a.out = out.p; a.out_cs = out.cs; a.out_coff = out.coff;
+  a.out = out.p; a.out_hi = out.hi; a.out_lo = out.lo; a.out_cs = out.cs; a.out_coff = out.coff;
   long P = (long)out.N * out.H * out.W;
   prof_before(st);
-  deconv4x4_kernel<<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
+  const unsigned nb = (unsigned)((P + 7) / 8);
+  if (in.split() && out.split()) deconv4x4_kernel<true, true><<<nb, 256, 0, st>>>(a);
+  else if (!in.split() && out.split()) deconv4x4_kernel<false, true><<<nb, 256, 0, st>>>(a);
+  else if (in.split() && !out.split()) deconv4x4_kernel<true, false><<<nb, 256, 0, st>>>(a);
+  else deconv4x4_kernel<false, false><<<nb, 256, 0, st>>>(a);
   return after_launch("deconv4x4_kernel", st, 2.0 * P * 4 * w.Cin * 2, 4.0 * ((double)in.pixels() * w.Cin + 2.0 * P));
 }
 

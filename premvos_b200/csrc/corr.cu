@@ -26,13 +26,14 @@ constexpr size_t CORR_SMEM = (size_t)(HALO_H * HALO_W + CT_H * CT_W) * PITCH * s
 
 struct CorrArgs {
   const float* f1; const float* f2; float* out; float* c1;
+  __nv_bfloat16 *out_hi, *out_lo, *c1_hi, *c1_lo;   // split-bf16 destinations (decoder slab in tensor-core mode)
   // channels-last: element (n,y,x,c) at ((n*H+y)*W+x)*cs + coff + c ; NCHW: ((n*C+c)*H+y)*W+x
   int f1_cs, f1_coff, f2_cs, f2_coff, out_cs, out_coff, c1_cs, c1_coff;
   int B, C, H, W;
   float slope;
 };
 
-template <bool NHWC>
+template <bool NHWC, bool OUT_SPLIT>
 __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(CorrArgs a) {
   extern __shared__ float smem[];
   float* s2 = smem;                              // [HALO_H*HALO_W][PITCH]
@@ -84,9 +85,13 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(CorrArgs a) {
           } else {
             for (int k = 0; k < 4; k++) if (c + k < a.C) v[k] = src[k];
           }
-          if (a.c1) {  // fused copy of f1 into the decoder slab
-            float* dst = a.c1 + (((long)n * a.H + gy) * a.W + gx) * a.c1_cs + a.c1_coff + c;
-            for (int k = 0; k < 4; k++) if (c + k < a.C) dst[k] = v[k];
+          if (OUT_SPLIT ? (a.c1_hi != nullptr) : (a.c1 != nullptr)) {  // fused copy of f1 into the decoder slab
+            long di = (((long)n * a.H + gy) * a.W + gx) * a.c1_cs + a.c1_coff + c;
+            for (int k = 0; k < 4; k++)
+              if (c + k < a.C) {
+                if (OUT_SPLIT) st_split(a.c1_hi, a.c1_lo, di + k, v[k]);
+                else a.c1[di + k] = v[k];
+              }
           }
         }
         float* d = s1 + tp * PITCH + q * 4;
@@ -144,8 +149,11 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_kernel(CorrArgs a) {
     for (int i = tid; i < CT_H * CT_W * 81; i += CORR_THREADS) {
       int tp = i / 81, k = i - tp * 81;
       int yy = y0 + (tp >> 5), xx = x0 + (tp & 31);
-      if (yy < a.H && xx < a.W)
-        a.out[(((long)n * a.H + yy) * a.W + xx) * a.out_cs + a.out_coff + k] = so[i];
+      if (yy < a.H && xx < a.W) {
+        long oi = (((long)n * a.H + yy) * a.W + xx) * a.out_cs + a.out_coff + k;
+        if (OUT_SPLIT) st_split(a.out_hi, a.out_lo, oi, so[i]);
+        else a.out[oi] = so[i];
+      }
     }
   } else {
     if (gy < a.H && gx < a.W) {
@@ -163,20 +171,25 @@ int corr81_nhwc(const TView& f1, const TView& f2, const TView& out, const TView&
                 cudaStream_t st) {
   PV_CHECK(f1.C == f2.C && f1.H == f2.H && f1.W == f2.W && f1.N == f2.N && out.C == 81 && out.H == f1.H &&
                out.W == f1.W && out.N == f1.N, PREMVOS_ERR_INVALID_ARG, "corr81_nhwc: shape mismatch");
+  PV_CHECK(!f1.split() && !f2.split() && (c1_copy.null() || c1_copy.split() == out.split()), PREMVOS_ERR_INVALID_ARG,
+           "corr81_nhwc: features must be fp32 views; c1 copy must use the output's storage format");
   static bool attr_set = false;
   if (!attr_set) {
-    PV_CUDA(cudaFuncSetAttribute(corr81_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));
+    PV_CUDA(cudaFuncSetAttribute(corr81_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));
+    PV_CUDA(cudaFuncSetAttribute(corr81_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));
     attr_set = true;
   }
   CorrArgs a;
   a.f1 = f1.p; a.f2 = f2.p; a.out = out.p; a.c1 = c1_copy.p;
+  a.out_hi = out.hi; a.out_lo = out.lo; a.c1_hi = c1_copy.hi; a.c1_lo = c1_copy.lo;
   a.f1_cs = f1.cs; a.f1_coff = f1.coff; a.f2_cs = f2.cs; a.f2_coff = f2.coff;
   a.out_cs = out.cs; a.out_coff = out.coff; a.c1_cs = c1_copy.cs; a.c1_coff = c1_copy.coff;
   a.B = f1.N; a.C = f1.C; a.H = f1.H; a.W = f1.W; a.slope = slope;
   dim3 grid((f1.W + CT_W - 1) / CT_W, (f1.H + CT_H - 1) / CT_H, f1.N);
   const double px = (double)f1.pixels();
   prof_before(st);
-  corr81_kernel<true><<<grid, CORR_THREADS, CORR_SMEM, st>>>(a);
+  if (out.split()) corr81_kernel<true, true><<<grid, CORR_THREADS, CORR_SMEM, st>>>(a);
+  else corr81_kernel<true, false><<<grid, CORR_THREADS, CORR_SMEM, st>>>(a);
   return after_launch("corr81_kernel<nhwc>", st, 2.0 * 81 * f1.C * px, 4.0 * (2.0 * f1.C + 81) * px);
 }
 
@@ -247,7 +260,7 @@ extern "C" int premvos_corr_forward(const float* input1, const float* input2, fl
   if (pad_size == MDISP && max_displacement == MDISP && kernel_size == 1 && stride1 == 1 && stride2 == 1) {
     static bool attr_set = false;
     if (!attr_set) {
-      PV_CUDA(cudaFuncSetAttribute(corr81_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));
+      PV_CUDA(cudaFuncSetAttribute(corr81_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));
       attr_set = true;
     }
     CorrArgs a = {};
@@ -256,7 +269,7 @@ extern "C" int premvos_corr_forward(const float* input1, const float* input2, fl
     dim3 grid((width + CT_W - 1) / CT_W, (height + CT_H - 1) / CT_H, batch);
     const double px = (double)batch * height * width;
     prof_before(st);
-    corr81_kernel<false><<<grid, CORR_THREADS, CORR_SMEM, st>>>(a);
+    corr81_kernel<false, false><<<grid, CORR_THREADS, CORR_SMEM, st>>>(a);
     return after_launch("corr81_kernel<nchw>", st, 2.0 * 81 * channels * px, 4.0 * (2.0 * channels + 81) * px);
   }
   CorrGenericArgs g;

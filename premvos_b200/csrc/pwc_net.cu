@@ -45,7 +45,7 @@ int level_od(int L) { return L == 6 ? 81 : 81 + LEVEL_CH[L] + 4; }
 struct premvos_pwc {
   int B = 0, H = 0, W = 0;
   bool finalized = false;
-  int opt_tensor_cores = 0;
+  int opt_tensor_cores = 1;
   int opt_cuda_graph = 1;
   std::map<std::string, std::vector<float>> params;
   std::map<std::string, std::vector<int64_t>> shapes;  // expected shapes
@@ -62,6 +62,9 @@ struct premvos_pwc {
   DeconvWeights w_deconv[7], w_upfeat[7];
   ConvWeightsSimt w_dc[6];
   SmallConvWeights w_dc7;
+  // tensor-core mode: decoder + context convolutions on tcgen05 (split-bf16 slabs)
+  ConvWeightsUmma wt_dec[7][5], wt_dc[6];
+  ConvPlanUmma plan_dec[7][5], plan_dc[6];
 
   cudaStream_t stream = nullptr;  // internal stream (forward_host, capture)
   cudaGraph_t graph = nullptr;
@@ -115,14 +118,19 @@ int64_t numel_of(const std::vector<int64_t>& s) {
   return n;
 }
 
-int alloc_view(premvos_pwc* n, TView* v, int N, int H, int W, int C, int cs) {
+int alloc_view(premvos_pwc* n, TView* v, int N, int H, int W, int C, int cs, bool split = false) {
   v->N = N; v->H = H; v->W = W; v->C = C; v->cs = cs; v->coff = 0;
-  size_t bytes = (size_t)N * H * W * cs * sizeof(float);
-  void* p = nullptr;
-  PV_CUDA(cudaMalloc(&p, bytes));
-  PV_CUDA(cudaMemset(p, 0, bytes));
-  n->allocs.push_back(p);
-  v->p = (float*)p;
+  size_t elems = (size_t)N * H * W * cs;
+  for (int k = 0; k < (split ? 2 : 1); k++) {
+    size_t bytes = elems * (split ? sizeof(__nv_bfloat16) : sizeof(float));
+    void* p = nullptr;
+    PV_CUDA(cudaMalloc(&p, bytes));
+    PV_CUDA(cudaMemset(p, 0, bytes));
+    n->allocs.push_back(p);
+    if (!split) v->p = (float*)p;
+    else if (k == 0) v->hi = (__nv_bfloat16*)p;
+    else v->lo = (__nv_bfloat16*)p;
+  }
   return 0;
 }
 
@@ -139,7 +147,10 @@ int pack_all_weights(premvos_pwc* n) {
     int cin = level_od(L);
     for (int i = 0; i < 5; i++) {
       std::string k = "conv" + std::to_string(L) + "_" + std::to_string(i) + ".0";
-      PV_TRY(pack_conv_weights_simt(&n->w_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3));
+      if (n->opt_tensor_cores)
+        PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3));
+      else
+        PV_TRY(pack_conv_weights_simt(&n->w_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3));
       cin += DEC_OUT[i];
     }
     std::string pf = "predict_flow" + std::to_string(L);
@@ -154,7 +165,10 @@ int pack_all_weights(premvos_pwc* n) {
   int cin = level_od(2) + 448;
   for (int i = 0; i < 6; i++) {
     std::string k = "dc_conv" + std::to_string(i + 1) + ".0";
-    PV_TRY(pack_conv_weights_simt(&n->w_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
+    if (n->opt_tensor_cores)
+      PV_TRY(pack_conv_weights_umma(&n->wt_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
+    else
+      PV_TRY(pack_conv_weights_simt(&n->w_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
     cin = DC_OUT[i];
   }
   PV_TRY(pack_small_conv_weights(&n->w_dc7, P(n, "dc_conv7.weight"), P(n, "dc_conv7.bias"), 2, 32));
@@ -171,12 +185,31 @@ int alloc_activations(premvos_pwc* n) {
   for (int L = 6; L >= 2; L--) {
     int h = n->H >> L, w = n->W >> L;
     int ctot = level_od(L) + 448;
-    PV_TRY(alloc_view(n, &n->slab[L], B, h, w, ctot, round_up(ctot, 8)));
+    PV_TRY(alloc_view(n, &n->slab[L], B, h, w, ctot, round_up(ctot, 8), n->opt_tensor_cores != 0));
     PV_TRY(alloc_view(n, &n->flow[L], B, h, w, 2, 4));
     if (L != 6) PV_TRY(alloc_view(n, &n->warpbuf[L], B, h, w, LEVEL_CH[L], round_up(LEVEL_CH[L], 4)));
   }
-  PV_TRY(alloc_view(n, &n->ctxA, B, n->H >> 2, n->W >> 2, 128, 128));
-  PV_TRY(alloc_view(n, &n->ctxB, B, n->H >> 2, n->W >> 2, 128, 128));
+  PV_TRY(alloc_view(n, &n->ctxA, B, n->H >> 2, n->W >> 2, 128, 128, n->opt_tensor_cores != 0));
+  PV_TRY(alloc_view(n, &n->ctxB, B, n->H >> 2, n->W >> 2, 128, 128, n->opt_tensor_cores != 0));
+  if (n->opt_tensor_cores) {  // one launch plan (tensor maps + arguments) per tensor-core layer
+    for (int L = 6; L >= 2; L--) {
+      const int ctot = level_od(L) + 448;
+      for (int i = 0; i < 5; i++) {
+        TView in = n->slab[L].slice(DEC_IN_OFF[i], ctot - DEC_IN_OFF[i]);
+        TView out = n->slab[L].slice(DEC_OUT_OFF[i], DEC_OUT[i]);
+        PV_TRY(plan_conv_umma(&n->plan_dec[L][i], in, out, n->wt_dec[L][i], 1, 0.1f));
+        n->tensor_core_layers++;
+      }
+    }
+    TView in = n->slab[2].slice(0, level_od(2) + 448);
+    TView bufs[2] = {n->ctxA, n->ctxB};
+    for (int i = 0; i < 6; i++) {
+      TView out = bufs[i & 1].slice(0, DC_OUT[i]);
+      PV_TRY(plan_conv_umma(&n->plan_dc[i], in, out, n->wt_dc[i], DC_DIL[i], 0.1f));
+      n->tensor_core_layers++;
+      in = out;
+    }
+  }
   size_t xin = (size_t)B * 6 * n->H * n->W * sizeof(float);
   size_t fout = (size_t)B * 2 * (n->H / 4) * (n->W / 4) * sizeof(float);
   PV_CUDA(cudaMalloc((void**)&n->x_in, xin));
@@ -220,7 +253,8 @@ int run_middle(premvos_pwc* n, cudaStream_t st) {
     for (int i = 0; i < 5; i++) {
       TView in = slab.slice(DEC_IN_OFF[i], ctot - DEC_IN_OFF[i]);
       TView out = slab.slice(DEC_OUT_OFF[i], DEC_OUT[i]);
-      PV_TRY(conv2d_simt(in, out, n->w_dec[L][i], 1, 1, 0.1f, st));
+      if (n->opt_tensor_cores) PV_TRY(launch_conv_umma(n->plan_dec[L][i], st));
+      else PV_TRY(conv2d_simt(in, out, n->w_dec[L][i], 1, 1, 0.1f, st));
     }
     TView all = slab.slice(0, ctot);
     TView flow = n->flow[L].slice(0, 2);
@@ -237,7 +271,8 @@ int run_middle(premvos_pwc* n, cudaStream_t st) {
   TView bufs[2] = {n->ctxA, n->ctxB};
   for (int i = 0; i < 6; i++) {
     TView out = bufs[i & 1].slice(0, DC_OUT[i]);
-    PV_TRY(conv2d_simt(in, out, n->w_dc[i], 1, DC_DIL[i], 0.1f, st));
+    if (n->opt_tensor_cores) PV_TRY(launch_conv_umma(n->plan_dc[i], st));
+    else PV_TRY(conv2d_simt(in, out, n->w_dc[i], 1, DC_DIL[i], 0.1f, st));
     in = out;
   }
   return 0;
@@ -393,15 +428,15 @@ extern "C" int premvos_pwc_get_tensor(premvos_pwc_t* n, const char* name, float*
   *numel = (int64_t)v.N * v.C * v.H * v.W;
   if (!host_out) return 0;
   PV_CUDA(cudaDeviceSynchronize());
-  std::vector<float> tmp((size_t)v.N * v.H * v.W * v.cs);
-  PV_CUDA(cudaMemcpy(tmp.data(), v.p, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
-  for (int b = 0; b < v.N; b++)
-    for (int c = 0; c < v.C; c++)
-      for (int y = 0; y < v.H; y++)
-        for (int x = 0; x < v.W; x++)
-          host_out[(((size_t)b * v.C + c) * v.H + y) * v.W + x] =
-              tmp[(((size_t)b * v.H + y) * v.W + x) * v.cs + v.coff + c];
-  return 0;
+  float* dtmp = nullptr;
+  PV_CUDA(cudaMalloc((void**)&dtmp, (size_t)(*numel) * sizeof(float)));
+  int r = view_to_nchw(v, dtmp, nullptr);
+  if (r == 0) {
+    cudaError_t e = cudaMemcpy(host_out, dtmp, (size_t)(*numel) * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) r = fail((int)e, "premvos_pwc_get_tensor: %s", cudaGetErrorString(e));
+  }
+  cudaFree(dtmp);
+  return r;
 }
 
 extern "C" void premvos_pwc_destroy(premvos_pwc_t* n) {
@@ -419,6 +454,9 @@ extern "C" void premvos_pwc_destroy(premvos_pwc_t* n) {
     free_deconv_weights(&n->w_upfeat[L]);
   }
   for (int i = 0; i < 6; i++) free_conv_weights_simt(&n->w_dc[i]);
+  for (int L = 2; L <= 6; L++)
+    for (int i = 0; i < 5; i++) free_conv_weights_umma(&n->wt_dec[L][i]);
+  for (int i = 0; i < 6; i++) free_conv_weights_umma(&n->wt_dc[i]);
   free_small_conv_weights(&n->w_dc7);
   if (n->stream) cudaStreamDestroy(n->stream);
   delete n;

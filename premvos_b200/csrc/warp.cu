@@ -14,12 +14,13 @@ namespace premvos {
 
 struct WarpArgs {
   const float* x; int x_cs, x_coff;
-  const float* flow; int f_cs, f_coff;
+  const float* flow; const __nv_bfloat16 *flow_hi, *flow_lo; int f_cs, f_coff;
   float* out; int o_cs, o_coff;
   int N, H, W, C;
   float scale;
 };
 
+template <bool FLOW_SPLIT>
 __global__ void __launch_bounds__(256) warp_kernel(WarpArgs a) {
   const int lane = threadIdx.x & 31;
   const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -28,8 +29,9 @@ __global__ void __launch_bounds__(256) warp_kernel(WarpArgs a) {
   const int n = (int)(pix / ((long)a.H * a.W));
   const int rem = (int)(pix - (long)n * a.H * a.W);
   const int y = rem / a.W, x = rem - y * a.W;
-  const float u = __fmul_rn(a.flow[pix * a.f_cs + a.f_coff + 0], a.scale);
-  const float v = __fmul_rn(a.flow[pix * a.f_cs + a.f_coff + 1], a.scale);
+  const long fi = pix * a.f_cs + a.f_coff;
+  const float u = __fmul_rn(FLOW_SPLIT ? ld_split(a.flow_hi, a.flow_lo, fi) : a.flow[fi], a.scale);
+  const float v = __fmul_rn(FLOW_SPLIT ? ld_split(a.flow_hi, a.flow_lo, fi + 1) : a.flow[fi + 1], a.scale);
   // PWCNet.py:157-162 then grid_sample's un-normalisation ((g+1)/2)*(size-1)
   const float wm1 = (float)max(a.W - 1, 1), hm1 = (float)max(a.H - 1, 1);
   float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)x, u)), wm1), 1.0f);
@@ -80,12 +82,14 @@ int warp_nhwc(const TView& x2, const TView& flow, float flow_scale, const TView&
            PREMVOS_ERR_INVALID_ARG, "warp_nhwc: views must be float4-addressable");
   WarpArgs a;
   a.x = x2.p; a.x_cs = x2.cs; a.x_coff = x2.coff;
-  a.flow = flow.p; a.f_cs = flow.cs; a.f_coff = flow.coff;
+  PV_CHECK(!x2.split() && !out.split(), PREMVOS_ERR_INVALID_ARG, "warp_nhwc: features must be fp32 views");
+  a.flow = flow.p; a.flow_hi = flow.hi; a.flow_lo = flow.lo; a.f_cs = flow.cs; a.f_coff = flow.coff;
   a.out = out.p; a.o_cs = out.cs; a.o_coff = out.coff;
   a.N = x2.N; a.H = x2.H; a.W = x2.W; a.C = x2.C; a.scale = flow_scale;
   long P = (long)x2.N * x2.H * x2.W;
   prof_before(st);
-  warp_kernel<<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
+  if (flow.split()) warp_kernel<true><<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
+  else warp_kernel<false><<<(unsigned)((P + 7) / 8), 256, 0, st>>>(a);
   return after_launch("warp_kernel", st, 8.0 * P * x2.C, 4.0 * P * (2.0 * x2.C + 2));
 }
 
