@@ -73,6 +73,24 @@ int premvos_corr_forward(const float* input1, const float* input2, float* output
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * One convolution layer on the tensor-core path (bring-up / parity hook; the networks below fuse their
+ * layers and never go through NCHW).  Replaces a torch nn.Conv2d(+LeakyReLU) forward as the reference
+ * builds it in models/PWCNet.py:24-28, or a tensorpack Conv2D(+BN folded)+ReLU in proposal_net/basemodel.py:51-60.
+ *
+ * x        : device fp32 NCHW [batch, cin, height, width]
+ * w, bias  : HOST fp32, torch layout [cout, cin, kh, kw] / [cout] (bias may be NULL)
+ * residual : device fp32 NCHW [batch, cout, OH, OW] or NULL; added before the activation
+ * out      : device fp32 NCHW [batch, cout, OH, OW], OH = (height + pad_top + pad_bottom - dilation*(kh-1) - 1)/stride + 1
+ * out = act(conv(x) + bias + residual), act = LeakyReLU(slope) (slope 1 = identity, 0 = ReLU); cross-correlation,
+ * explicit zero padding per side (so TF "SAME"/tensorpack asymmetric pads are expressible).  stride 1 or 2.
+ * Arithmetic: split-bf16 x3 tcgen05 MMAs, fp32 accumulate (~1e-5 relative).  Synchronises `stream`.
+ * --------------------------------------------------------------------------------------------- */
+int premvos_conv2d_forward(const float* x, const float* w, const float* bias, const float* residual, float* out,
+                           int batch, int cin, int height, int width, int cout, int kh, int kw, int stride,
+                           int dilation, int pad_top, int pad_left, int pad_bottom, int pad_right, float slope,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * PWC-DC-Net forward (optical flow).
  *
  * Life cycle: create(batch,H,W) -> set_param(name, host fp32 data) for each of the 128 state_dict
@@ -102,7 +120,7 @@ int premvos_pwc_launches_per_forward(const premvos_pwc_t* net);
  * fp32 SIMT); valid after finalize. */
 int premvos_pwc_tensor_core_layers(const premvos_pwc_t* net);
 /* Set before finalize: 0 = fp32 SIMT convolutions everywhere; 1 (default) = tcgen05 tensor-core
- * implicit-GEMM convolutions (split-bf16 x3, fp32 accumulate) where the layer shape allows. */
+ * implicit-GEMM convolutions (split-bf16 x3, fp32 accumulate) for every convolution of the network. */
 int premvos_pwc_set_option(premvos_pwc_t* net, const char* key, int value);
 /* Test hook: copy an intermediate of the LAST forward to a host fp32 NCHW buffer.  Names follow the
  * reference's variable names in PWCDCNet.forward: "c11".."c16", "c21".."c26", "corr6".."corr2",

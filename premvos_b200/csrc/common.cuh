@@ -144,30 +144,83 @@ int pack_deconv_weights(DeconvWeights* out, const float* host_w /*[Cin][2][4][4]
 void free_deconv_weights(DeconvWeights* w);
 int deconv4x4s2_cout2(const TView& in, const TView& out /*[N,2H,2W], C=2*/, const DeconvWeights& w, cudaStream_t st);
 
+// ---- CP8: channel-chunk-planar split-bf16 activations (tensor-core path) ----------------------------
+// Element (n, c, y, x) of a view lives at  plane[(((n*chunks + c0 + c/8) * H + y) * W + x) * 8 + c%8]
+// in both the hi and the lo plane (x = hi + lo).  A view names a range of 8-channel chunk planes of a
+// wider buffer (the DenseNet slabs of the PWC decoder); channels of the last chunk beyond C hold zeros.
+struct CView {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int N = 0, H = 0, W = 0;
+  int chunks = 0;  // chunk planes per image in the underlying buffer
+  int c0 = 0;      // first chunk plane of this view
+  int C = 0;       // logical channels (the view spans (C+7)/8 planes)
+  CView slice(int chunk_off, int c) const {
+    CView v = *this;
+    v.c0 = c0 + chunk_off;
+    v.C = c;
+    return v;
+  }
+  CView batch_range(int n0, int n) const {
+    CView v = *this;
+    size_t off = (size_t)n0 * chunks * H * W * 8;
+    v.hi = hi + off; v.lo = lo + off; v.N = n;
+    return v;
+  }
+  bool null() const { return hi == nullptr; }
+  int vchunks() const { return (C + 7) / 8; }
+  size_t pixels() const { return (size_t)N * H * W; }
+};
+
 // ---- convolution on tcgen05 tensor cores (split-bf16 x3, fp32 accumulate), conv_umma.cu ----------
 struct ConvWeightsUmma {
-  __nv_bfloat16* w_hi = nullptr;  // device [R*S][CoutP][KP], K contiguous, zero padded
+  __nv_bfloat16* w_hi = nullptr;  // device, packed shared-memory images [ntile][tap][kblock][KC][BN][8]
   __nv_bfloat16* w_lo = nullptr;
-  float* bias = nullptr;          // device [CoutP]
-  int R = 3, S = 3, Cin = 0, Cout = 0, KP = 0, CoutP = 0, BN = 0;
-  alignas(64) unsigned char map_hi[128];  // CUtensorMap of w_hi / w_lo
-  alignas(64) unsigned char map_lo[128];
+  float* bias = nullptr;          // device [ntiles*BN]
+  int R = 3, S = 3, Cin = 0, CinPhys = 0, Cout = 0, KC = 2, kblocks = 0, BN = 0, ntiles = 0;
+};
+struct ConvGeom {
+  int stride = 1, dil = 1;
+  int pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0;
+  float slope = 1.f;  // LeakyReLU slope applied after bias (+ residual): 1 = identity, 0 = ReLU
+  static ConvGeom same3x3(int dil, float slope) { ConvGeom g; g.dil = dil; g.pad_t = g.pad_l = g.pad_b = g.pad_r = dil; g.slope = slope; return g; }
+};
+struct ConvOut {
+  CView cp;    // CP8 split output (optional)
+  TView f32;   // fp32 channels-last output (optional; small heads)
+  CView res;   // optional residual added before the activation (same shape as the output)
 };
 struct ConvPlanUmma {  // everything one launch needs; built once per layer at finalize time
   alignas(64) unsigned char map_a_hi[128];
   alignas(64) unsigned char map_a_lo[128];
-  alignas(64) unsigned char map_w_hi[128];
-  alignas(64) unsigned char map_w_lo[128];
-  alignas(16) unsigned char args[160];
-  int grid_x = 0, grid_y = 0, smem_bytes = 0;
+  alignas(16) unsigned char args[256];
+  int grid_x = 0, grid_y = 0, smem_bytes = 0, halo = 0, MT = 0;
   double flops = 0, bytes = 0;
 };
-bool conv_umma_supported(int Cin, int Cout, int R, int S, int stride);
-int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S);
+// host_w: torch Conv2d layout [Cout][Cin][R][S].  cin_map (optional): physical channel (inside the input
+// view) of every reference input channel, cin_phys = physical channel count of that view.
+int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
+                           const int* cin_map = nullptr, int cin_phys = 0);
 void free_conv_weights_umma(ConvWeightsUmma* w);
-// in: split view; out: split view (hi/lo) or fp32 view.  Stride 1, "same" padding dil*(R/2).
-int plan_conv_umma(ConvPlanUmma* plan, const TView& in, const TView& out, const ConvWeightsUmma& w, int dil, float slope);
+int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g);
 int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st);
+
+// ---- CP8 companions of the tensor-core path, cp8_ops.cu -----------------------------------------------
+// x: NCHW fp32 [B,6,H,W] -> img CP8 [2B, 1 chunk, H, W] (ch 0..2 = BGR of image 1 for n < B, image 2 for n >= B)
+int pack_pair_input_cp8(const float* x_nchw, int B, int H, int W, const CView& img, cudaStream_t st);
+// PWCDCNet.warp on CP8 features; flow = channels [flow_ch, flow_ch+2) of chunk plane flow.c0
+int warp_cp8(const CView& x2, const CView& flow, int flow_ch, float flow_scale, const CView& out, cudaStream_t st);
+// 9x9 cost volume: out = 11 chunk planes (81 channels + 7 zeros), LeakyReLU fused; c1_copy (optional) receives f1's planes
+int corr81_cp8(const CView& f1, const CView& f2, const CView& out, const CView& c1_copy, float slope, cudaStream_t st);
+// head: fp32 channels-last [B,H,W,16] = {flow 2, upfeat phases 8 ((py*2+px)*2+co), ...}.  Writes chunk plane `dst`
+// of the next level's slab: [deconv(flow) 2, pixel-shuffled up_feat 2, 0 0 0 0] at [B,2H,2W].
+int level_up_cp8(const TView& head, const float* deconv_w /*device [2][2][4][4]*/, const float* deconv_b, const CView& dst,
+                 cudaStream_t st);
+// out NCHW [B,2,H,W] = a[...,0:2] + b[...,0:2]   (flow2 + dc_conv7)
+int flow_finish(const TView& a, const TView& b, float* out_nchw, cudaStream_t st);
+// NCHW fp32 <-> CP8 (ch_off = first channel inside chunk plane v.c0; writes zero to the padding channels when ch_off == 0)
+int nchw_to_cp8(const float* src, const CView& dst, cudaStream_t st);
+int cp8_to_nchw(const CView& src, int ch_off, float* dst, cudaStream_t st);
 
 // ---- layout / format conversion, layout.cu ---------------------------------------------------------
 // NCHW fp32 [N,C,H,W] -> channels-last view (fp32 or split)

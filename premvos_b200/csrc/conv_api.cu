@@ -1,0 +1,65 @@
+// Single-layer C-ABI entry point of the tensor-core convolution (bring-up / parity hook): NCHW fp32 in,
+// NCHW fp32 out, everything in between exactly as the fused networks run it (CP8 split-bf16 planes,
+// TMA + tcgen05 implicit GEMM).  Allocates its scratch per call -- not a hot-path function.
+#include <vector>
+
+#include "common.cuh"
+
+using namespace premvos;
+
+namespace {
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  int cview(CView* v, int N, int C, int H, int W) {
+    v->N = N; v->H = H; v->W = W; v->chunks = (C + 7) / 8; v->c0 = 0; v->C = C;
+    const size_t bytes = (size_t)N * v->chunks * H * W * 8 * sizeof(__nv_bfloat16);
+    for (int k = 0; k < 2; k++) {
+      void* p = nullptr;
+      PV_CUDA(cudaMalloc(&p, bytes));
+      ptrs.push_back(p);
+      (k == 0 ? v->hi : v->lo) = (__nv_bfloat16*)p;
+    }
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" int premvos_conv2d_forward(const float* x_dev, const float* w_host, const float* bias_host, const float* residual_dev,
+                                      float* out_dev, int batch, int cin, int height, int width, int cout, int kh, int kw,
+                                      int stride, int dilation, int pad_top, int pad_left, int pad_bottom, int pad_right,
+                                      float slope, void* stream) {
+  PV_CHECK(x_dev && w_host && out_dev, PREMVOS_ERR_INVALID_ARG, "premvos_conv2d_forward: null argument");
+  PV_CHECK(batch > 0 && cin > 0 && cout > 0 && height > 0 && width > 0 && kh > 0 && kw > 0 && dilation > 0, PREMVOS_ERR_INVALID_ARG,
+           "premvos_conv2d_forward: non-positive size");
+  PV_CHECK(stride == 1 || stride == 2, PREMVOS_ERR_UNSUPPORTED, "premvos_conv2d_forward: stride must be 1 or 2 (got %d)", stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (height + pad_top + pad_bottom - dilation * (kh - 1) - 1) / stride + 1;
+  const int Wo = (width + pad_left + pad_right - dilation * (kw - 1) - 1) / stride + 1;
+  PV_CHECK(Ho > 0 && Wo > 0, PREMVOS_ERR_INVALID_ARG, "premvos_conv2d_forward: empty output");
+  Scratch sc;
+  CView in, out, res;
+  PV_TRY(sc.cview(&in, batch, cin, height, width));
+  PV_TRY(sc.cview(&out, batch, cout, Ho, Wo));
+  PV_TRY(nchw_to_cp8(x_dev, in, st));
+  ConvOut o;
+  o.cp = out;
+  if (residual_dev) {
+    PV_TRY(sc.cview(&res, batch, cout, Ho, Wo));
+    PV_TRY(nchw_to_cp8(residual_dev, res, st));
+    o.res = res;
+  }
+  ConvWeightsUmma w;
+  PV_TRY(pack_conv_weights_umma(&w, w_host, bias_host, cout, cin, kh, kw));
+  ConvGeom g;
+  g.stride = stride; g.dil = dilation; g.pad_t = pad_top; g.pad_l = pad_left; g.pad_b = pad_bottom; g.pad_r = pad_right;
+  g.slope = slope;
+  ConvPlanUmma plan;
+  int r = plan_conv_umma(&plan, in, o, w, g);
+  if (r == 0) r = launch_conv_umma(plan, st);
+  if (r == 0) r = cp8_to_nchw(out, 0, out_dev, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  free_conv_weights_umma(&w);
+  if (r == 0 && e != cudaSuccess) r = fail((int)e, "premvos_conv2d_forward: %s", cudaGetErrorString(e));
+  return r;
+}

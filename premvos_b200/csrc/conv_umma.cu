@@ -1,25 +1,29 @@
-// Tensor-core convolution for sm_100a: implicit GEMM on tcgen05.mma with TMA-fed shared memory and
-// the accumulator in tensor memory (TMEM).
+// Tensor-core convolution for sm_100a: implicit GEMM on tcgen05.mma, operands staged in shared memory
+// by TMA, accumulators in tensor memory (TMEM).
 //
-// GEMM view of a stride-1 RxS convolution on channels-last activations:
-//     D[m, n] = sum_{tap=(r,s)} sum_{c} A_tap[m, c] * W[tap][n][c]
-//   m = output pixel inside a TH x TW tile (TH*TW = 128 = UMMA M), n = output channel, c = input channel.
-// im2col never materialises: the A tile of tap (r,s) is ONE 4-D TMA box {64 ch, TW, TH, 1} of the
-// input tensor at pixel offset ((s-S/2)*dil, (r-R/2)*dil); out-of-image pixels and channels beyond
-// the view are zero-filled by the TMA unit, which is exactly the convolution's zero padding (and the
-// K tail).  The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, i.e. the
-// canonical K-major UMMA operand layout.
+// Activation layout ("CP8", CView in common.cuh): split-bf16 planes (x = hi + lo) stored channel-chunk
+// planar, [N][C/8][H][W][8].  One 8-channel chunk of one pixel is 16 bytes -- exactly one row of a UMMA
+// "core matrix" in the un-swizzled K-major operand layout, so a TMA box {8 ch, BW px, BH px, KC chunks}
+// lands in shared memory as [KC][BH][BW][8ch] and IS a valid A operand with
+//      SBO (next 8 pixels = next tile row) = BW*16 B,    LBO (next 8 channels) = BH*BW*16 B.
+// im2col never materialises, and for stride-1 convolutions not even per tap: the box is the output
+// tile (16*MT rows x 8 cols) PLUS its halo, loaded ONCE per 16-channel k-block; the R*S taps are R*S
+// descriptors whose start address is shifted by ((r*dil)*BW + s*dil)*16 B.  Shared-memory fill traffic
+// for A drops from 9x to ~1.4x of the tile ("halo mode").  Strided / strongly dilated / 1x1
+// convolutions use one box per (tap, k-block) ("tap mode"; stride 2 = TMA elementStrides).
+// Out-of-image pixels and channels beyond the view are zero-filled by the TMA unit = zero padding.
 //
-// Numerics: activations and weights are stored as SPLIT bf16 -- x = hi + lo with hi = bf16(x),
-// lo = bf16(x - hi) (16 mantissa bits in total).  Each K step issues three kind::f16 MMAs into the
-// same fp32 TMEM accumulator:  hi*hi + hi*lo + lo*hi  (the dropped lo*lo term is ~2^-16 relative).
-// This keeps the 1e-3 parity contract with a large margin at 1.5x the cost of a single TF32 pass
-// (bf16 runs at twice the TF32 rate) instead of TF32's 2^-11 operand rounding.
+// Weights are pre-packed on the host into the exact shared-memory image of every (n-tile, tap,
+// k-block) stage, [KC][BN][8ch] (SBO = 128 B, LBO = BN*16 B), and fetched with 1-D bulk copies.
 //
-// Warp roles (256 threads, 1 CTA/SM): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp_id % 4):
-// tcgen05.ld -> +bias -> LeakyReLU/ReLU -> split to hi/lo -> 16-byte stores into the output view
-// (which may be a channel range of a DenseNet slab).
+// Numerics: x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits).  Each K step issues
+// three kind::f16 MMAs into the same fp32 TMEM accumulator: lo*hi + hi*lo + hi*hi (the dropped lo*lo
+// term is ~2^-16 relative).  1e-3 parity with a wide margin; fp32 accumulate.
+//
+// CTA = 256 threads: warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator,
+// warps 4..7 epilogue (TMEM lane quarter = warp % 4).  M = 128*MT pixels per CTA (MT accumulators
+// share every weight stage), N = BN <= 128.  ~80 KB shared memory and <= 256 TMEM columns per CTA so
+// two CTAs co-reside per SM: one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -31,11 +35,8 @@ namespace premvos {
 
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int KBLK = 64;           // bf16 channels per pipeline stage = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int A_TILE_BYTES = TILE_M * KBLK * 2;  // 16 KB
 constexpr int UMMA_THREADS = 256;
+constexpr int MAX_A_STAGES = 4, MAX_W_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -75,11 +76,16 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -105,32 +111,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms (1024 B) stacked along M/N.
-// bits [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64)
-// | [46,48) version=1 (sm_100) | [61,64) layout=2 (SWIZZLE_128B)      (cute/arch/mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
+// Un-swizzled ("interleaved") K-major operand descriptor: core matrix = 8 rows x 16 B, rows 16 B apart.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (byte distance between the two 8-element K halves of one MMA)
+//   | [32,46) SBO>>4 (byte distance between 8-row groups along M/N) | [46,48) version = 1 (sm_100)
+//   | [61,64) layout = 0 (SWIZZLE_NONE)     (cute/arch/mma_sm100_desc.hpp, mma_traits_sm100.hpp:194)
+// The MMA issuer assembles it from a constant high word and (LBO | address >> 4) in the low word.
 // kind::f16 instruction descriptor: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major,
 // N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -138,47 +134,54 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 struct UmmaConvArgs {
-  int tiles_x, tiles_y;      // tiles per image
-  int TW, TH;                // tile shape, TW*TH == 128
-  int H, W;                  // output (== input) spatial size
-  int in_coff;               // first input channel inside the pixel
-  int kblocks;               // ceil(Cin / 64)
-  int R, S, dil;
-  int BN;                    // N tile (multiple of 32, <= 256)
-  int Cout;
-  int stages;
-  const float* bias;         // [CoutP]
-  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; float* out_f32;  // split and/or fp32 output
-  int out_cs, out_coff;
-  float slope;
+  int tiles_x, tiles_y, MT;  // tiles per image; MT accumulators (16 rows x 8 cols each, stacked in y) per CTA
+  int Ho, Wo;                // output size
+  int stride, R, S, dil, pad_t, pad_l;
+  int halo;                  // 1: one A box per k-block serves all taps; 0: one A box per (tap, k-block)
+  int merged_x;              // 1: tensor map dim 0 = W*8 elements (stride-1 layers); 0: dims {8, W, ...}
+  int box_w, box_h;          // A box (pixels) as it lies in shared memory
+  int KC, kblocks;           // 8-channel chunks per k-block (even); k-blocks
+  int BN, Cout;
+  int a_stages, w_stages;
+  int a_plane, w_plane;      // bytes of one (hi or lo) plane of a stage, rounded up to 128
+  int a_box_bytes, w_box_bytes;  // bytes one TMA / bulk copy actually transfers per plane
+  const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;  // packed [ntile][tap][kblock][KC][BN][8]
+  const float* bias;         // [ntiles*BN]
+  float slope;               // LeakyReLU slope (1 = identity, 0 = ReLU)
+  // outputs: CP8 split planes and/or fp32 channels-last
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_chunks, out_c0;
+  float* out_f32; int out_cs, out_coff;
+  const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo; int res_chunks, res_c0;  // optional residual
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(UMMA_THREADS, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                 const UmmaConvArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle (TMA write and UMMA read agree on address bits)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int w_tile_bytes = a.BN * KBLK * 2;
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * w_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + a.stages;
-  uint64_t* tmem_full_bar = empty_bar + a.stages;
+__global__ void __launch_bounds__(UMMA_THREADS, 2)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const UmmaConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = a_smem + (size_t)a.a_stages * 2 * a.a_plane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + (size_t)a.w_stages * 2 * a.w_plane);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + MAX_A_STAGES;
+  uint64_t* w_full = bars + 2 * MAX_A_STAGES;
+  uint64_t* w_empty = w_full + MAX_W_STAGES;
+  uint64_t* tmem_full_bar = w_empty + MAX_W_STAGES;
   uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
-  const int n_img = tile / (a.tiles_x * a.tiles_y);
-  const int trem = tile - n_img * a.tiles_x * a.tiles_y;
-  const int ty0 = (trem / a.tiles_x) * a.TH, tx0 = (trem % a.tiles_x) * a.TW;
-  const int n0 = blockIdx.y * a.BN;
-  const int kiters = a.R * a.S * a.kblocks;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int n_img = tile / tiles_per_img;
+  const int trem = tile - n_img * tiles_per_img;
+  const int ty0 = (trem / a.tiles_x) * 16 * a.MT, tx0 = (trem % a.tiles_x) * 8;
+  const int ntile = blockIdx.y;
+  const int taps = a.R * a.S;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
-    for (int s = 0; s < a.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
+    for (int s = 0; s < a.a_stages; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < a.w_stages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
@@ -189,103 +192,163 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_addr_slot;
 
   if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    const uint32_t tx_bytes = (uint32_t)stage_bytes;
-    int it = 0;
-    for (int tap = 0; tap < a.R * a.S; tap++) {
-      const int r = tap / a.S, s = tap - r * a.S;
-      const int ix = tx0 + (s - a.S / 2) * a.dil, iy = ty0 + (r - a.R / 2) * a.dil;
-      for (int kb = 0; kb < a.kblocks; kb++, it++) {
-        const int st = it % a.stages;
-        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
-        mbar_wait(&empty_bar[st], ph ^ 1u);
-        uint8_t* sp = smem + (size_t)st * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[st], tx_bytes);
-        tma_load_4d(&tmA_hi, &full_bar[st], sp, a.in_coff + kb * KBLK, ix, iy, n_img);
-        tma_load_4d(&tmA_lo, &full_bar[st], sp + A_TILE_BYTES, a.in_coff + kb * KBLK, ix, iy, n_img);
-        tma_load_3d(&tmW_hi, &full_bar[st], sp + 2 * A_TILE_BYTES, kb * KBLK, n0, tap);
-        tma_load_3d(&tmW_lo, &full_bar[st], sp + 2 * A_TILE_BYTES + w_tile_bytes, kb * KBLK, n0, tap);
+    // ===== TMA producer =====  (no integer division in the loop: ring indices and phases are carried)
+    uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0;
+    const size_t w_stage_elems = (size_t)a.KC * a.BN * 8;
+    const __nv_bfloat16* wh = a.w_hi + (size_t)ntile * taps * a.kblocks * w_stage_elems;
+    const __nv_bfloat16* wl = a.w_lo + (size_t)ntile * taps * a.kblocks * w_stage_elems;
+    const size_t w_tap_stride = (size_t)a.kblocks * w_stage_elems;
+    const int bx = tx0 * a.stride - a.pad_l, by = ty0 * a.stride - a.pad_t;
+    auto load_a = [&](int kc0, int px, int py) {
+      mbar_wait(&a_empty[a_st], a_ph ^ 1u);
+      uint8_t* dst = a_smem + (size_t)a_st * 2 * a.a_plane;
+      mbar_arrive_expect_tx(&a_full[a_st], 2u * (uint32_t)a.a_box_bytes);
+      if (a.merged_x) {
+        tma_load_4d(&tmA_hi, &a_full[a_st], dst, px * 8, py, kc0, n_img);
+        tma_load_4d(&tmA_lo, &a_full[a_st], dst + a.a_plane, px * 8, py, kc0, n_img);
+      } else {
+        tma_load_5d(&tmA_hi, &a_full[a_st], dst, 0, px, py, kc0, n_img);
+        tma_load_5d(&tmA_lo, &a_full[a_st], dst + a.a_plane, 0, px, py, kc0, n_img);
+      }
+      if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
+    };
+    for (int kb = 0; kb < a.kblocks; kb++) {
+      if (a.halo) load_a(kb * a.KC, bx, by);
+      const __nv_bfloat16* wh_t = wh + (size_t)kb * w_stage_elems;
+      const __nv_bfloat16* wl_t = wl + (size_t)kb * w_stage_elems;
+      for (int r = 0; r < a.R; r++)
+        for (int s = 0; s < a.S; s++) {
+          if (!a.halo) load_a(kb * a.KC, bx + s * a.dil, by + r * a.dil);
+          mbar_wait(&w_empty[w_st], w_ph ^ 1u);
+          uint8_t* dst = w_smem + (size_t)w_st * 2 * a.w_plane;
+          mbar_arrive_expect_tx(&w_full[w_st], 2u * (uint32_t)a.w_box_bytes);
+          bulk_load_1d(dst, wh_t, (uint32_t)a.w_box_bytes, &w_full[w_st]);
+          bulk_load_1d(dst + a.w_plane, wl_t, (uint32_t)a.w_box_bytes, &w_full[w_st]);
+          wh_t += w_tap_stride; wl_t += w_tap_stride;
+          if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====  the whole warp walks the (warp-uniform) loop, one elected lane issues
+    const uint32_t idesc = make_idesc_bf16(128, a.BN);
+    const uint32_t a_sbo = (uint32_t)a.box_w * 16u, a_lbo = (uint32_t)a.box_h * a.box_w * 16u;
+    const uint32_t w_sbo = 128u, w_lbo = (uint32_t)a.BN * 16u;
+    // descriptor = constant high word (SBO, version) + low word (LBO | start address >> 4)
+    const uint32_t a_hi32 = (a_sbo >> 4) | (1u << 14), w_hi32 = (w_sbo >> 4) | (1u << 14);
+    const uint32_t a_lo32 = (a_lbo >> 4) << 16, w_lo32 = (w_lbo >> 4) << 16;
+    const uint32_t a_base = smem_u32(a_smem), w_base = smem_u32(w_smem);
+    const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = 2u * (uint32_t)a.w_plane;
+    const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = 16u * a_sbo;
+    const uint32_t tap_row = a.halo ? (uint32_t)(a.dil * a.box_w) * 16u : 0u, tap_col = a.halo ? (uint32_t)a.dil * 16u : 0u;
+    uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0;
+    uint32_t accum = 0;
+    const int ksteps = a.KC / 2;
+    for (int kb = 0; kb < a.kblocks; kb++) {
+      uint32_t row_off = 0;
+      for (int r = 0; r < a.R; r++, row_off += tap_row) {
+        uint32_t tap_off = row_off;
+        for (int s = 0; s < a.S; s++, tap_off += tap_col) {
+          if (!a.halo || (r | s) == 0) {
+            mbar_wait(&a_full[a_st], a_ph);
+            cur_a = a_st;
+            a_addr_stage = a_base + a_st * a_stage_bytes;
+            if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
+          }
+          mbar_wait(&w_full[w_st], w_ph);
+          tc_fence_after();
+          if (lane == 0) {
+            uint32_t aa0 = a_addr_stage + tap_off, ww = w_base + w_st * w_stage_bytes;
+            for (int ks = 0; ks < ksteps; ks++, aa0 += a_kstep, ww += w_kstep) {
+              const uint64_t dWh = ((uint64_t)w_hi32 << 32) | (w_lo32 + ((ww & 0x3FFFFu) >> 4));
+              const uint64_t dWl = ((uint64_t)w_hi32 << 32) | (w_lo32 + (((ww + (uint32_t)a.w_plane) & 0x3FFFFu) >> 4));
+              uint32_t aa = aa0, d = tmem_base;
+              for (int mt = 0; mt < a.MT; mt++, aa += a_mstep, d += (uint32_t)a.BN) {
+                const uint64_t dAh = ((uint64_t)a_hi32 << 32) | (a_lo32 + ((aa & 0x3FFFFu) >> 4));
+                const uint64_t dAl = ((uint64_t)a_hi32 << 32) | (a_lo32 + (((aa + (uint32_t)a.a_plane) & 0x3FFFFu) >> 4));
+                umma_bf16(d, dAl, dWh, idesc, accum);
+                umma_bf16(d, dAh, dWl, idesc, 1u);
+                umma_bf16(d, dAh, dWh, idesc, 1u);
+              }
+              accum = 1u;
+            }
+            umma_commit(&w_empty[w_st]);  // frees the weight slot once these MMAs have read it
+            if (!a.halo || (r == a.R - 1 && s == a.S - 1)) umma_commit(&a_empty[cur_a]);
+          }
+          __syncwarp();
+          if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+        }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_bf16(TILE_M, a.BN);
-    for (int it = 0; it < kiters; it++) {
-      const int st = it % a.stages;
-      const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
-      mbar_wait(&full_bar[st], ph);
-      tc_fence_after();
-      const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-      const uint64_t dA_hi = make_sw128_desc(sa), dA_lo = make_sw128_desc(sa + A_TILE_BYTES);
-      const uint64_t dW_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES), dW_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + w_tile_bytes);
-#pragma unroll
-      for (int k = 0; k < KBLK / UMMA_K; k++) {
-        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance inside the 128-byte swizzle row
-        umma_bf16(tmem_base, dA_lo + koff, dW_hi + koff, idesc, (it | k) != 0);
-        umma_bf16(tmem_base, dA_hi + koff, dW_lo + koff, idesc, 1u);
-        umma_bf16(tmem_base, dA_hi + koff, dW_hi + koff, idesc, 1u);
-      }
-      umma_commit(&empty_bar[st]);  // frees the smem slot once these MMAs have read it
-    }
-    umma_commit(tmem_full_bar);     // accumulator complete
+    if (lane == 0) umma_commit(tmem_full_bar);  // accumulators complete
+    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;         // accumulator row == pixel inside the tile
-    const int oy = ty0 + m / a.TW, ox = tx0 + m % a.TW;
-    const bool in_img = oy < a.H && ox < a.W;
-    const size_t pix = ((size_t)n_img * a.H + oy) * a.W + ox;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;  // accumulator row == pixel inside the 16x8 sub-tile
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    for (int c0 = 0; c0 < a.BN; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      const int co0 = n0 + c0;
-      if (in_img && co0 < a.Cout) {
-      float f[32];
+    const long hw = (long)a.Ho * a.Wo;
+    for (int mt = 0; mt < a.MT; mt++) {
+      const int oy = ty0 + mt * 16 + (m >> 3), ox = tx0 + (m & 7);
+      const bool in_img = oy < a.Ho && ox < a.Wo;
+      const long pix = (long)oy * a.Wo + ox;
+      for (int c0 = 0; c0 < a.BN; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0), v);
+        tmem_ld_wait();
+        const int co0 = ntile * a.BN + c0;
+        if (!in_img || co0 >= a.Cout) continue;
+        float f[16];
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        float t = __uint_as_float(v[j]) + __ldg(a.bias + co0 + j);
-        f[j] = t > 0.f ? t : t * a.slope;
-      }
-      const bool full = co0 + 32 <= a.Cout;
-      if (a.out_hi) {
-        __nv_bfloat16* ph = a.out_hi + pix * a.out_cs + a.out_coff + co0;
-        __nv_bfloat16* pl = a.out_lo + pix * a.out_cs + a.out_coff + co0;
-        if (full) {
-          uint32_t hw[16], lw[16];
+        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + __ldg(a.bias + co0 + j);
+        if (a.res_hi) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
-            __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
-            __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
-            hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
+          for (int h = 0; h < 2; h++) {
+            if (co0 + 8 * h >= a.Cout) continue;
+            const long ri = (((long)n_img * a.res_chunks + a.res_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+            const uint4 rh = *reinterpret_cast<const uint4*>(a.res_hi + ri);
+            const uint4 rl = *reinterpret_cast<const uint4*>(a.res_lo + ri);
+            const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            reinterpret_cast<uint4*>(ph)[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-            reinterpret_cast<uint4*>(pl)[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
-          }
-        } else {
-          for (int j = 0; j < 32 && co0 + j < a.Cout; j++) {
-            __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-            ph[j] = h;
-            pl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
+            for (int j = 0; j < 4; j++) {
+              f[8 * h + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+              f[8 * h + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+            }
           }
         }
-      }
-      if (a.out_f32) {
-        float* pf = a.out_f32 + pix * a.out_cs + a.out_coff + co0;
-        if (full) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(pf)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 32 && co0 + j < a.Cout; j++) pf[j] = f[j];
+        for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+        if (a.out_hi) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (co0 + 8 * h >= a.Cout) continue;  // chunk entirely beyond Cout (padding channels inside a chunk are exact zeros)
+            uint32_t hw4[4], lw4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float x0 = f[8 * h + 2 * j], x1 = f[8 * h + 2 * j + 1];
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+              hw4[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lw4[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            const long oi = (((long)n_img * a.out_chunks + a.out_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+            *reinterpret_cast<uint4*>(a.out_hi + oi) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+            *reinterpret_cast<uint4*>(a.out_lo + oi) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+          }
         }
-      }
+        if (a.out_f32) {
+          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff + co0;
+          if (co0 + 16 <= a.Cout && ((a.out_cs | a.out_coff) & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) reinterpret_cast<float4*>(pf)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (co0 + j < a.Cout) pf[j] = f[j];
+          }
+        }
       }
     }
   }
@@ -312,14 +375,17 @@ int get_encode_fn(EncodeTiledFn* out) {
   return 0;
 }
 
-int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
-  EncodeTiledFn fn;
+int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* estr) {
+  EncodeTiledFn fn = nullptr;
   PV_TRY(get_encode_fn(&fn));
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  PV_CHECK(r == CUDA_SUCCESS, PREMVOS_ERR_INVALID_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  PV_CHECK(r == CUDA_SUCCESS, PREMVOS_ERR_INVALID_ARG,
+           "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu, box %u %u %u %u)", (int)r, rank,
+           (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+           box[0], box[1], box[2], box[3]);
   return 0;
 }
 
@@ -330,35 +396,42 @@ inline void split_bf16(float x, __nv_bfloat16* hi, __nv_bfloat16* lo) {
 
 }  // namespace
 
-int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S) {
+int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
+                           const int* cin_map, int cin_phys) {
   out->R = R; out->S = S; out->Cin = Cin; out->Cout = Cout;
-  out->KP = round_up(Cin, KBLK);
-  int bn = round_up(Cout, 32);
+  const int phys = cin_map ? cin_phys : Cin;   // physical input channels (after the view's chunk padding)
+  out->CinPhys = phys;
+  out->KC = 2;
+  const int chunks = (phys + 7) / 8;
+  out->kblocks = (chunks + out->KC - 1) / out->KC;
+  int bn = round_up(Cout, 16);
   if (bn > 128) bn = 128;
   out->BN = bn;
-  out->CoutP = round_up(Cout, bn);
-  size_t n = (size_t)R * S * out->CoutP * out->KP;
+  out->ntiles = (Cout + bn - 1) / bn;
+  const int KP = out->kblocks * out->KC * 8;
+  const size_t stage_elems = (size_t)out->KC * bn * 8;
+  const size_t n = (size_t)out->ntiles * R * S * out->kblocks * stage_elems;
   std::vector<__nv_bfloat16> hi(n, __float2bfloat16_rn(0.f)), lo(n, __float2bfloat16_rn(0.f));
-  std::vector<float> b(out->CoutP, 0.f);
+  std::vector<float> b((size_t)out->ntiles * bn, 0.f);
   for (int co = 0; co < Cout; co++) {
     b[co] = host_b ? host_b[co] : 0.f;
-    for (int ci = 0; ci < Cin; ci++)
+    const int nt = co / bn, row = co - nt * bn;
+    for (int ci = 0; ci < Cin; ci++) {
+      const int pc = cin_map ? cin_map[ci] : ci;
+      if (pc < 0 || pc >= KP) return fail(PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: channel map out of range");
+      const int kb = pc / (out->KC * 8), kc = (pc / 8) % out->KC, e = pc & 7;
       for (int t = 0; t < R * S; t++) {
-        size_t idx = ((size_t)t * out->CoutP + co) * out->KP + ci;
+        const size_t idx = ((((size_t)nt * R * S + t) * out->kblocks + kb) * out->KC + kc) * bn * 8 + (size_t)row * 8 + e;
         split_bf16(host_w[((size_t)co * Cin + ci) * R * S + t], &hi[idx], &lo[idx]);
       }
+    }
   }
   PV_CUDA(cudaMalloc((void**)&out->w_hi, n * 2));
   PV_CUDA(cudaMalloc((void**)&out->w_lo, n * 2));
-  PV_CUDA(cudaMalloc((void**)&out->bias, out->CoutP * sizeof(float)));
+  PV_CUDA(cudaMalloc((void**)&out->bias, b.size() * sizeof(float)));
   PV_CUDA(cudaMemcpy(out->w_hi, hi.data(), n * 2, cudaMemcpyHostToDevice));
   PV_CUDA(cudaMemcpy(out->w_lo, lo.data(), n * 2, cudaMemcpyHostToDevice));
-  PV_CUDA(cudaMemcpy(out->bias, b.data(), out->CoutP * sizeof(float), cudaMemcpyHostToDevice));
-  cuuint64_t dims[3] = {(cuuint64_t)out->KP, (cuuint64_t)out->CoutP, (cuuint64_t)(R * S)};
-  cuuint64_t strides[2] = {(cuuint64_t)out->KP * 2, (cuuint64_t)out->KP * out->CoutP * 2};
-  cuuint32_t box[3] = {(cuuint32_t)KBLK, (cuuint32_t)out->BN, 1};
-  PV_TRY(encode_map((CUtensorMap*)out->map_hi, out->w_hi, 3, dims, strides, box));
-  PV_TRY(encode_map((CUtensorMap*)out->map_lo, out->w_lo, 3, dims, strides, box));
+  PV_CUDA(cudaMemcpy(out->bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -367,50 +440,95 @@ void free_conv_weights_umma(ConvWeightsUmma* w) {
   w->w_hi = w->w_lo = nullptr; w->bias = nullptr;
 }
 
-bool conv_umma_supported(int Cin, int Cout, int R, int S, int stride) {
-  return stride == 1 && R == S && (R == 1 || R == 3) && Cin >= 16 && Cout >= 16;
-}
-
 // Plans one convolution launch: tensor maps of the input view are encoded here (host only, no device work).
-int plan_conv_umma(ConvPlanUmma* plan, const TView& in, const TView& out, const ConvWeightsUmma& w, int dil, float slope) {
-  PV_CHECK(in.split() && (out.split() || out.p), PREMVOS_ERR_INVALID_ARG, "conv_umma: input must be split-bf16");
-  PV_CHECK(in.C == w.Cin && out.C == w.Cout && in.N == out.N && in.H == out.H && in.W == out.W, PREMVOS_ERR_INVALID_ARG,
-           "conv_umma: shape mismatch");
-  PV_CHECK((in.cs % 8) == 0 && (out.cs % 8) == 0 && ((out.coff) % 8) == 0, PREMVOS_ERR_INVALID_ARG,
-           "conv_umma: views must be 16-byte addressable (cs=%d/%d coff=%d)", in.cs, out.cs, out.coff);
-  int TW = 1;
-  while (TW < in.W && TW < 32) TW <<= 1;   // 8..32 wide tiles; narrow images get taller tiles
-  if (TW < 8) TW = 8;
-  int TH = TILE_M / TW;
+int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g) {
+  PV_CHECK(in.hi && in.lo, PREMVOS_ERR_INVALID_ARG, "conv_umma: null input view");
+  PV_CHECK(round_up(in.C, 8) == round_up(w.CinPhys, 8), PREMVOS_ERR_INVALID_ARG,
+           "conv_umma: input view has %d channels, weights were packed for %d", in.C, w.CinPhys);
+  PV_CHECK(g.stride == 1 || g.stride == 2, PREMVOS_ERR_UNSUPPORTED, "conv_umma: stride %d", g.stride);
+  const int Ho = (in.H + g.pad_t + g.pad_b - g.dil * (w.R - 1) - 1) / g.stride + 1;
+  const int Wo = (in.W + g.pad_l + g.pad_r - g.dil * (w.S - 1) - 1) / g.stride + 1;
+  PV_CHECK(Ho > 0 && Wo > 0, PREMVOS_ERR_INVALID_ARG, "conv_umma: empty output");
+  if (out.cp.hi) {
+    PV_CHECK(out.cp.N == in.N && out.cp.H == Ho && out.cp.W == Wo && out.cp.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
+             "conv_umma: CP8 output view is [%d,%d,%d,%d], expected [%d,%d,%d,%d]", out.cp.N, out.cp.C, out.cp.H, out.cp.W, in.N,
+             w.Cout, Ho, Wo);
+  }
+  if (out.f32.p) {
+    PV_CHECK(out.f32.N == in.N && out.f32.H == Ho && out.f32.W == Wo && out.f32.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
+             "conv_umma: fp32 output view shape mismatch");
+  }
+  PV_CHECK(out.cp.hi || out.f32.p, PREMVOS_ERR_INVALID_ARG, "conv_umma: no output");
+  if (out.res.hi)
+    PV_CHECK(out.res.N == in.N && out.res.H == Ho && out.res.W == Wo && out.res.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
+             "conv_umma: residual view shape mismatch");
+
   UmmaConvArgs& a = *reinterpret_cast<UmmaConvArgs*>(plan->args);
   static_assert(sizeof(UmmaConvArgs) <= sizeof(plan->args), "ConvPlanUmma::args too small");
-  a.TW = TW; a.TH = TH;
-  a.tiles_x = (in.W + TW - 1) / TW; a.tiles_y = (in.H + TH - 1) / TH;
-  a.H = in.H; a.W = in.W; a.in_coff = in.coff; a.kblocks = (in.C + KBLK - 1) / KBLK;
-  a.R = w.R; a.S = w.S; a.dil = dil; a.BN = w.BN; a.Cout = w.Cout;
-  a.bias = w.bias;
-  a.out_hi = out.hi; a.out_lo = out.lo; a.out_f32 = out.split() ? nullptr : out.p;
-  a.out_cs = out.cs; a.out_coff = out.coff; a.slope = slope;
+  memset(&a, 0, sizeof(a));
+  const int taps = w.R * w.S;
+  a.tiles_x = (Wo + 7) / 8;
+  // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
+  const long ctas_mt2 = (long)a.tiles_x * ((Ho + 31) / 32) * in.N * w.ntiles;
+  a.MT = (ctas_mt2 >= 2 * 148 && Ho > 16) ? 2 : 1;
+  a.tiles_y = (Ho + 16 * a.MT - 1) / (16 * a.MT);
+  a.Ho = Ho; a.Wo = Wo;
+  a.stride = g.stride; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
+  a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
+  // halo mode when it moves fewer bytes into shared memory than per-tap boxes
+  const int halo_w = 8 + (w.S - 1) * g.dil, halo_h = 16 * a.MT + (w.R - 1) * g.dil;
+  const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * a.MT;
+  a.halo = (g.stride == 1 && taps > 1 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256 &&
+            halo_px * w.KC * 16 <= 36 * 1024) ? 1 : 0;
+  a.merged_x = (g.stride == 1) ? 1 : 0;
+  a.box_w = a.halo ? halo_w : 8;
+  a.box_h = a.halo ? halo_h : 16 * a.MT;
+  a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
+  a.a_plane = round_up(a.a_box_bytes, 128);
+  a.w_box_bytes = w.KC * w.BN * 16;
+  a.w_plane = round_up(a.w_box_bytes, 128);
+  a.a_stages = a.halo ? 2 : 4;
+  a.w_stages = 4;
+  // grow the weight ring while two CTAs still fit one SM
+  while (a.w_stages < MAX_W_STAGES &&
+         a.a_stages * 2 * a.a_plane + (a.w_stages + 1) * 2 * a.w_plane + 1024 <= 110 * 1024)
+    a.w_stages++;
+  plan->smem_bytes = a.a_stages * 2 * a.a_plane + a.w_stages * 2 * a.w_plane + 128 /*align slack*/ + 512 /*barriers*/;
+  PV_CHECK(plan->smem_bytes <= SMEM_LIMIT, PREMVOS_ERR_UNSUPPORTED, "conv_umma: %d bytes of shared memory needed", plan->smem_bytes);
+  a.w_hi = w.w_hi; a.w_lo = w.w_lo; a.bias = w.bias; a.slope = g.slope;
+  a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
+  a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
+  a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
   uint32_t cols = 32;
-  while ((int)cols < w.BN) cols <<= 1;
+  while ((int)cols < a.MT * w.BN) cols <<= 1;
   a.tmem_cols = cols;
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * w.BN * KBLK * 2;
-  int stages = (SMEM_LIMIT - 2048) / stage_bytes;
-  if (stages > 6) stages = 6;
-  a.stages = stages;
-  plan->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   plan->grid_x = a.tiles_x * a.tiles_y * in.N;
-  plan->grid_y = w.CoutP / w.BN;
-  // input tensor maps: dims {channels addressable = coff + C, W, H, N}; box {64, TW, TH, 1}
-  cuuint64_t dims[4] = {(cuuint64_t)(in.coff + in.C), (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
-  cuuint64_t strides[3] = {(cuuint64_t)in.cs * 2, (cuuint64_t)in.W * in.cs * 2, (cuuint64_t)in.H * in.W * in.cs * 2};
-  cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-  PV_TRY(encode_map((CUtensorMap*)plan->map_a_hi, in.hi, 4, dims, strides, box));
-  PV_TRY(encode_map((CUtensorMap*)plan->map_a_lo, in.lo, 4, dims, strides, box));
-  memcpy(plan->map_w_hi, w.map_hi, 128);
-  memcpy(plan->map_w_lo, w.map_lo, 128);
-  plan->flops = 2.0 * in.N * in.H * in.W * (double)w.Cout * w.Cin * w.R * w.S;
-  plan->bytes = 4.0 * ((double)in.pixels() * in.C + (double)out.pixels() * w.Cout + (double)w.R * w.S * w.Cin * w.Cout);
+  plan->grid_y = w.ntiles;
+
+  // input tensor maps over the view's chunk planes: [N][chunks][H][W][8]
+  const int vchunks = (in.C + 7) / 8;
+  const size_t plane_bytes = (size_t)in.H * in.W * 16;
+  __nv_bfloat16* bases[2] = {in.hi + (size_t)in.c0 * in.H * in.W * 8, in.lo + (size_t)in.c0 * in.H * in.W * 8};
+  CUtensorMap* maps[2] = {(CUtensorMap*)plan->map_a_hi, (CUtensorMap*)plan->map_a_lo};
+  for (int k = 0; k < 2; k++) {
+    if (a.merged_x) {
+      cuuint64_t dims[4] = {(cuuint64_t)in.W * 8, (cuuint64_t)in.H, (cuuint64_t)vchunks, (cuuint64_t)in.N};
+      cuuint64_t strides[3] = {(cuuint64_t)in.W * 16, plane_bytes, plane_bytes * in.chunks};
+      cuuint32_t box[4] = {(cuuint32_t)a.box_w * 8, (cuuint32_t)a.box_h, (cuuint32_t)w.KC, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      PV_TRY(encode_map(maps[k], bases[k], 4, dims, strides, box, estr));
+    } else {
+      cuuint64_t dims[5] = {8, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)vchunks, (cuuint64_t)in.N};
+      cuuint64_t strides[4] = {16, (cuuint64_t)in.W * 16, plane_bytes, plane_bytes * in.chunks};
+      cuuint32_t box[5] = {8, (cuuint32_t)(a.box_w * g.stride), (cuuint32_t)(a.box_h * g.stride), (cuuint32_t)w.KC, 1};
+      cuuint32_t estr[5] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1, 1};
+      PV_TRY(encode_map(maps[k], bases[k], 5, dims, strides, box, estr));
+    }
+  }
+  const double opx = (double)in.N * Ho * Wo;
+  plan->flops = 2.0 * opx * (double)w.Cout * w.Cin * taps;
+  plan->bytes = 4.0 * ((double)in.N * in.H * in.W * w.Cin + opx * w.Cout + (double)taps * w.Cin * w.Cout);
+  plan->halo = a.halo; plan->MT = a.MT;
   return 0;
 }
 
@@ -423,8 +541,7 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st) {
   const UmmaConvArgs& a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
   prof_before(st);
   conv_umma_kernel<<<dim3(plan.grid_x, plan.grid_y), UMMA_THREADS, plan.smem_bytes, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo),
-      *reinterpret_cast<const CUtensorMap*>(plan.map_w_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_w_lo), a);
+      *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
   return after_launch("conv_umma_kernel", st, plan.flops, plan.bytes);
 }
 

@@ -62,9 +62,12 @@ struct premvos_pwc {
   DeconvWeights w_deconv[7], w_upfeat[7];
   ConvWeightsSimt w_dc[6];
   SmallConvWeights w_dc7;
-  // tensor-core mode: decoder + context convolutions on tcgen05 (split-bf16 slabs)
-  ConvWeightsUmma wt_dec[7][5], wt_dc[6];
-  ConvPlanUmma plan_dec[7][5], plan_dc[6];
+  // tensor-core mode: every convolution on tcgen05, activations in CP8 split-bf16 planes
+  CView c_img, c_pyr[7][3], c_slab[7], c_warp[7], c_ctxA, c_ctxB;
+  TView head[7], dc7out;   // fp32 channels-last [B,h,w,16]: {flow 2, upfeat phases 8} / {dc_conv7 2}
+  ConvWeightsUmma wt_pyr[7][3], wt_dec[7][5], wt_head[7], wt_dc[6], wt_dc7;
+  ConvPlanUmma pl_pyr[7][3], pl_dec[7][5], pl_head[7], pl_dc[6], pl_dc7;
+  float* d_deconv_w[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // deconvL weights [2][2][4][4] (64 floats) + bias [2]
 
   cudaStream_t stream = nullptr;  // internal stream (forward_host, capture)
   cudaGraph_t graph = nullptr;
@@ -136,7 +139,11 @@ int alloc_view(premvos_pwc* n, TView* v, int N, int H, int W, int C, int cs, boo
 
 const float* P(premvos_pwc* n, const std::string& k) { return n->params[k].data(); }
 
+int pack_weights_tc(premvos_pwc* n);
+int alloc_activations_tc(premvos_pwc* n);
+
 int pack_all_weights(premvos_pwc* n) {
+  if (n->opt_tensor_cores) return pack_weights_tc(n);
   for (int L = 1; L <= 6; L++)
     for (int j = 0; j < 3; j++) {
       std::string k = std::string(PYR_NAMES[L][j]) + ".0";
@@ -147,10 +154,7 @@ int pack_all_weights(premvos_pwc* n) {
     int cin = level_od(L);
     for (int i = 0; i < 5; i++) {
       std::string k = "conv" + std::to_string(L) + "_" + std::to_string(i) + ".0";
-      if (n->opt_tensor_cores)
-        PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3));
-      else
-        PV_TRY(pack_conv_weights_simt(&n->w_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3));
+      PV_TRY(pack_conv_weights_simt(&n->w_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3));
       cin += DEC_OUT[i];
     }
     std::string pf = "predict_flow" + std::to_string(L);
@@ -165,17 +169,17 @@ int pack_all_weights(premvos_pwc* n) {
   int cin = level_od(2) + 448;
   for (int i = 0; i < 6; i++) {
     std::string k = "dc_conv" + std::to_string(i + 1) + ".0";
-    if (n->opt_tensor_cores)
-      PV_TRY(pack_conv_weights_umma(&n->wt_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
-    else
-      PV_TRY(pack_conv_weights_simt(&n->w_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
+    PV_TRY(pack_conv_weights_simt(&n->w_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
     cin = DC_OUT[i];
   }
   PV_TRY(pack_small_conv_weights(&n->w_dc7, P(n, "dc_conv7.weight"), P(n, "dc_conv7.bias"), 2, 32));
   return 0;
 }
 
+int alloc_io(premvos_pwc* n);
+
 int alloc_activations(premvos_pwc* n) {
+  if (n->opt_tensor_cores) return alloc_activations_tc(n);
   const int B = n->B;
   PV_TRY(alloc_view(n, &n->img, 2 * B, n->H, n->W, 3, 4));
   for (int L = 1; L <= 6; L++) {
@@ -185,33 +189,127 @@ int alloc_activations(premvos_pwc* n) {
   for (int L = 6; L >= 2; L--) {
     int h = n->H >> L, w = n->W >> L;
     int ctot = level_od(L) + 448;
-    PV_TRY(alloc_view(n, &n->slab[L], B, h, w, ctot, round_up(ctot, 8), n->opt_tensor_cores != 0));
+    PV_TRY(alloc_view(n, &n->slab[L], B, h, w, ctot, round_up(ctot, 8)));
     PV_TRY(alloc_view(n, &n->flow[L], B, h, w, 2, 4));
     if (L != 6) PV_TRY(alloc_view(n, &n->warpbuf[L], B, h, w, LEVEL_CH[L], round_up(LEVEL_CH[L], 4)));
   }
-  PV_TRY(alloc_view(n, &n->ctxA, B, n->H >> 2, n->W >> 2, 128, 128, n->opt_tensor_cores != 0));
-  PV_TRY(alloc_view(n, &n->ctxB, B, n->H >> 2, n->W >> 2, 128, 128, n->opt_tensor_cores != 0));
-  if (n->opt_tensor_cores) {  // one launch plan (tensor maps + arguments) per tensor-core layer
-    for (int L = 6; L >= 2; L--) {
-      const int ctot = level_od(L) + 448;
-      for (int i = 0; i < 5; i++) {
-        TView in = n->slab[L].slice(DEC_IN_OFF[i], ctot - DEC_IN_OFF[i]);
-        TView out = n->slab[L].slice(DEC_OUT_OFF[i], DEC_OUT[i]);
-        PV_TRY(plan_conv_umma(&n->plan_dec[L][i], in, out, n->wt_dec[L][i], 1, 0.1f));
-        n->tensor_core_layers++;
+  PV_TRY(alloc_view(n, &n->ctxA, B, n->H >> 2, n->W >> 2, 128, 128));
+  PV_TRY(alloc_view(n, &n->ctxB, B, n->H >> 2, n->W >> 2, 128, 128));
+  return alloc_io(n);
+}
+
+// ---- tensor-core mode: slab layout (chunk planes) ---------------------------------------------------
+//   [conv_4 4 | conv_3 8 | conv_2 12 | conv_1 16 | conv_0 16 | corr 11 (81 ch + 7 zeros) | c1 C_L/8 |
+//    up 1 (up_flow 2, up_feat 2, 4 zeros)]        -- every segment starts on a chunk boundary; the weight
+// packer maps the reference's input-channel order (PWCNet.py:201-205) onto these physical channels.
+const int CORR_CHUNK = 56, C1_CHUNK = 67;
+int up_chunk(int L) { return C1_CHUNK + LEVEL_CH[L] / 8; }
+int slab_chunks(int L) { return L == 6 ? C1_CHUNK : up_chunk(L) + 1; }
+
+// physical channel (relative to a view that starts at dense channel `in_off`) of every reference input channel
+std::vector<int> slab_cin_map(int L, int in_off) {
+  std::vector<int> m;
+  for (int r = in_off; r < 448; r++) m.push_back(r - in_off);
+  const int base = 448 - in_off;
+  for (int r = 0; r < 81; r++) m.push_back(base + r);
+  if (L != 6) {
+    for (int r = 0; r < LEVEL_CH[L]; r++) m.push_back(base + 88 + r);
+    for (int r = 0; r < 4; r++) m.push_back(base + 88 + LEVEL_CH[L] + r);
+  }
+  return m;
+}
+
+int pack_weights_tc(premvos_pwc* n) {
+  for (int L = 1; L <= 6; L++)
+    for (int j = 0; j < 3; j++) {
+      std::string k = std::string(PYR_NAMES[L][j]) + ".0";
+      int cin = (j == 0) ? LEVEL_CH[L - 1] : LEVEL_CH[L];
+      if (L == 1 && j == 0) {
+        const int map3[3] = {0, 1, 2};
+        PV_TRY(pack_conv_weights_umma(&n->wt_pyr[L][j], P(n, k + ".weight"), P(n, k + ".bias"), LEVEL_CH[L], cin, 3, 3, map3, 8));
+      } else {
+        PV_TRY(pack_conv_weights_umma(&n->wt_pyr[L][j], P(n, k + ".weight"), P(n, k + ".bias"), LEVEL_CH[L], cin, 3, 3));
       }
     }
-    TView in = n->slab[2].slice(0, level_od(2) + 448);
-    TView bufs[2] = {n->ctxA, n->ctxB};
-    for (int i = 0; i < 6; i++) {
-      TView out = bufs[i & 1].slice(0, DC_OUT[i]);
-      PV_TRY(plan_conv_umma(&n->plan_dc[i], in, out, n->wt_dc[i], DC_DIL[i], 0.1f));
-      n->tensor_core_layers++;
-      in = out;
+  for (int L = 6; L >= 2; L--) {
+    const int phys_total = slab_chunks(L) * 8;
+    int cin = level_od(L);
+    for (int i = 0; i < 5; i++) {
+      std::string k = "conv" + std::to_string(L) + "_" + std::to_string(i) + ".0";
+      std::vector<int> map = slab_cin_map(L, DEC_IN_OFF[i]);
+      PV_CHECK((int)map.size() == cin, PREMVOS_ERR_INVALID_ARG, "internal: slab map size %d != %d", (int)map.size(), cin);
+      PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3, map.data(),
+                                    phys_total - DEC_IN_OFF[i]));
+      cin += DEC_OUT[i];
     }
+    // head = predict_flowL (2 ch) fused with upfeatL: ConvTranspose2d(cin, 2, 4, 2, 1) == 3x3 convolution with
+    // 8 outputs ((py*2+px)*2+co) at the input resolution followed by a pixel shuffle:
+    //   out[2y+py, 2x+px, co] = sum_{r,s} in[y+r-1, x+s-1] * Wd[ci][co][3-2r+py][3-2s+px]   (taps outside 0..3 vanish)
+    const int hc = (L != 2) ? 10 : 2;
+    std::vector<float> hw((size_t)hc * cin * 9, 0.f), hb(hc, 0.f);
+    std::string pf = "predict_flow" + std::to_string(L);
+    const float* pw = P(n, pf + ".weight");
+    std::copy(pw, pw + (size_t)2 * cin * 9, hw.begin());
+    hb[0] = P(n, pf + ".bias")[0]; hb[1] = P(n, pf + ".bias")[1];
+    if (L != 2) {
+      std::string uk = "upfeat" + std::to_string(L);
+      const float* uw = P(n, uk + ".weight");  // [cin][2][4][4]
+      const float* ub = P(n, uk + ".bias");
+      for (int py = 0; py < 2; py++)
+        for (int px = 0; px < 2; px++)
+          for (int co = 0; co < 2; co++) {
+            const int oc = 2 + (py * 2 + px) * 2 + co;
+            hb[oc] = ub[co];
+            for (int ci = 0; ci < cin; ci++)
+              for (int r = 0; r < 3; r++)
+                for (int s2 = 0; s2 < 3; s2++) {
+                  const int ky = 3 - 2 * r + py, kx = 3 - 2 * s2 + px;
+                  if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;
+                  hw[((size_t)oc * cin + ci) * 9 + r * 3 + s2] = uw[(((size_t)ci * 2 + co) * 4 + ky) * 4 + kx];
+                }
+          }
+      std::string dk = "deconv" + std::to_string(L);
+      std::vector<float> dw(66);  // [ci 2][co 2][4][4] + bias [2]
+      std::copy(P(n, dk + ".weight"), P(n, dk + ".weight") + 64, dw.begin());
+      dw[64] = P(n, dk + ".bias")[0]; dw[65] = P(n, dk + ".bias")[1];
+      PV_CUDA(cudaMalloc((void**)&n->d_deconv_w[L], 66 * sizeof(float)));
+      PV_CUDA(cudaMemcpy(n->d_deconv_w[L], dw.data(), 66 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    std::vector<int> map = slab_cin_map(L, 0);
+    PV_TRY(pack_conv_weights_umma(&n->wt_head[L], hw.data(), hb.data(), hc, cin, 3, 3, map.data(), phys_total));
   }
-  size_t xin = (size_t)B * 6 * n->H * n->W * sizeof(float);
-  size_t fout = (size_t)B * 2 * (n->H / 4) * (n->W / 4) * sizeof(float);
+  int cin = level_od(2) + 448;
+  for (int i = 0; i < 6; i++) {
+    std::string k = "dc_conv" + std::to_string(i + 1) + ".0";
+    if (i == 0) {
+      std::vector<int> map = slab_cin_map(2, 0);
+      PV_TRY(pack_conv_weights_umma(&n->wt_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3, map.data(),
+                                    slab_chunks(2) * 8));
+    } else {
+      PV_TRY(pack_conv_weights_umma(&n->wt_dc[i], P(n, k + ".weight"), P(n, k + ".bias"), DC_OUT[i], cin, 3, 3));
+    }
+    cin = DC_OUT[i];
+  }
+  PV_TRY(pack_conv_weights_umma(&n->wt_dc7, P(n, "dc_conv7.weight"), P(n, "dc_conv7.bias"), 2, 32, 3, 3));
+  return 0;
+}
+
+int alloc_cview(premvos_pwc* n, CView* v, int N, int H, int W, int chunks) {
+  v->N = N; v->H = H; v->W = W; v->chunks = chunks; v->c0 = 0; v->C = chunks * 8;
+  const size_t bytes = (size_t)N * chunks * H * W * 8 * sizeof(__nv_bfloat16);
+  for (int k = 0; k < 2; k++) {
+    void* p = nullptr;
+    PV_CUDA(cudaMalloc(&p, bytes));
+    PV_CUDA(cudaMemset(p, 0, bytes));
+    n->allocs.push_back(p);
+    (k == 0 ? v->hi : v->lo) = (__nv_bfloat16*)p;
+  }
+  return 0;
+}
+
+int alloc_io(premvos_pwc* n) {
+  size_t xin = (size_t)n->B * 6 * n->H * n->W * sizeof(float);
+  size_t fout = (size_t)n->B * 2 * (n->H / 4) * (n->W / 4) * sizeof(float);
   PV_CUDA(cudaMalloc((void**)&n->x_in, xin));
   PV_CUDA(cudaMalloc((void**)&n->flow_out, fout));
   n->allocs.push_back(n->x_in);
@@ -219,12 +317,100 @@ int alloc_activations(premvos_pwc* n) {
   return 0;
 }
 
+int alloc_activations_tc(premvos_pwc* n) {
+  const int B = n->B;
+  PV_TRY(alloc_cview(n, &n->c_img, 2 * B, n->H, n->W, 1));
+  for (int L = 1; L <= 6; L++)
+    for (int j = 0; j < 3; j++) {
+      PV_TRY(alloc_cview(n, &n->c_pyr[L][j], 2 * B, n->H >> L, n->W >> L, (LEVEL_CH[L] + 7) / 8));
+      n->c_pyr[L][j].C = LEVEL_CH[L];
+    }
+  for (int L = 6; L >= 2; L--) {
+    const int h = n->H >> L, w = n->W >> L;
+    PV_TRY(alloc_cview(n, &n->c_slab[L], B, h, w, slab_chunks(L)));
+    PV_TRY(alloc_view(n, &n->head[L], B, h, w, 16, 16));
+    if (L != 6) {
+      PV_TRY(alloc_cview(n, &n->c_warp[L], B, h, w, LEVEL_CH[L] / 8));
+    }
+  }
+  PV_TRY(alloc_cview(n, &n->c_ctxA, B, n->H >> 2, n->W >> 2, 16));
+  PV_TRY(alloc_cview(n, &n->c_ctxB, B, n->H >> 2, n->W >> 2, 16));
+  PV_TRY(alloc_view(n, &n->dc7out, B, n->H >> 2, n->W >> 2, 16, 16));
+  // one launch plan (tensor maps + arguments) per layer
+  auto plan = [&](ConvPlanUmma* pl, const CView& in, const CView* out_cp, const TView* out_f32, const ConvWeightsUmma& w,
+                  const ConvGeom& g) {
+    ConvOut o;
+    if (out_cp) o.cp = *out_cp;
+    if (out_f32) o.f32 = *out_f32;
+    n->tensor_core_layers++;
+    return plan_conv_umma(pl, in, o, w, g);
+  };
+  CView cur = n->c_img.slice(0, 8);
+  for (int L = 1; L <= 6; L++) {
+    ConvGeom g2 = ConvGeom::same3x3(1, 0.1f);
+    g2.stride = 2;
+    PV_TRY(plan(&n->pl_pyr[L][0], cur, &n->c_pyr[L][0], nullptr, n->wt_pyr[L][0], g2));
+    PV_TRY(plan(&n->pl_pyr[L][1], n->c_pyr[L][0], &n->c_pyr[L][1], nullptr, n->wt_pyr[L][1], ConvGeom::same3x3(1, 0.1f)));
+    PV_TRY(plan(&n->pl_pyr[L][2], n->c_pyr[L][1], &n->c_pyr[L][2], nullptr, n->wt_pyr[L][2], ConvGeom::same3x3(1, 0.1f)));
+    cur = n->c_pyr[L][2];
+  }
+  for (int L = 6; L >= 2; L--) {
+    const int tot = slab_chunks(L);
+    for (int i = 0; i < 5; i++) {
+      CView in = n->c_slab[L].slice(DEC_IN_OFF[i] / 8, (tot - DEC_IN_OFF[i] / 8) * 8);
+      CView out = n->c_slab[L].slice(DEC_OUT_OFF[i] / 8, DEC_OUT[i]);
+      PV_TRY(plan(&n->pl_dec[L][i], in, &out, nullptr, n->wt_dec[L][i], ConvGeom::same3x3(1, 0.1f)));
+    }
+    CView all = n->c_slab[L].slice(0, tot * 8);
+    TView ho = n->head[L].slice(0, n->wt_head[L].Cout);
+    PV_TRY(plan(&n->pl_head[L], all, nullptr, &ho, n->wt_head[L], ConvGeom::same3x3(1, 1.0f)));
+  }
+  CView in = n->c_slab[2].slice(0, slab_chunks(2) * 8);
+  CView bufs[2] = {n->c_ctxA, n->c_ctxB};
+  for (int i = 0; i < 6; i++) {
+    CView out = bufs[i & 1].slice(0, DC_OUT[i]);
+    PV_TRY(plan(&n->pl_dc[i], in, &out, nullptr, n->wt_dc[i], ConvGeom::same3x3(DC_DIL[i], 0.1f)));
+    in = out;
+  }
+  TView d7 = n->dc7out.slice(0, 2);
+  PV_TRY(plan(&n->pl_dc7, in, nullptr, &d7, n->wt_dc7, ConvGeom::same3x3(1, 1.0f)));
+  return alloc_io(n);
+}
+
+int run_middle_tc(premvos_pwc* n, cudaStream_t st) {
+  const int B = n->B;
+  for (int L = 1; L <= 6; L++)  // feature pyramid, both frames at once (PWCNet.py:183-194)
+    for (int j = 0; j < 3; j++) PV_TRY(launch_conv_umma(n->pl_pyr[L][j], st));
+  for (int L = 6; L >= 2; L--) {
+    const int CL = LEVEL_CH[L];
+    CView c1 = n->c_pyr[L][2].batch_range(0, B);
+    CView c2 = n->c_pyr[L][2].batch_range(B, B);
+    CView& slab = n->c_slab[L];
+    CView f2 = c2, c1_slot;  // c1 slot stays null at level 6 (x = corr6 only, PWCNet.py:201)
+    if (L != 6) {
+      PV_TRY(warp_cp8(c2, slab.slice(up_chunk(L), 8), 0, WARP_SCALE[L], n->c_warp[L], st));  // :211,225,239,255
+      f2 = n->c_warp[L];
+      c1_slot = slab.slice(C1_CHUNK, CL);
+    }
+    PV_TRY(corr81_cp8(c1, f2, slab.slice(CORR_CHUNK, 81), c1_slot, 0.1f, st));  // corr + LeakyReLU (:197-198)
+    for (int i = 0; i < 5; i++) PV_TRY(launch_conv_umma(n->pl_dec[L][i], st));
+    PV_TRY(launch_conv_umma(n->pl_head[L], st));  // predict_flowL + upfeatL
+    if (L != 2)
+      PV_TRY(level_up_cp8(n->head[L], n->d_deconv_w[L], n->d_deconv_w[L] + 64, n->c_slab[L - 1].slice(up_chunk(L - 1), 8), st));
+  }
+  for (int i = 0; i < 6; i++) PV_TRY(launch_conv_umma(n->pl_dc[i], st));  // context network (:266)
+  PV_TRY(launch_conv_umma(n->pl_dc7, st));
+  return 0;
+}
+
 // ---- the network ---------------------------------------------------------------------------------
 int run_front(premvos_pwc* n, const float* x_dev, cudaStream_t st) {
+  if (n->opt_tensor_cores) return pack_pair_input_cp8(x_dev, n->B, n->H, n->W, n->c_img, st);
   return pack_pair_input(x_dev, n->B, n->H, n->W, n->img, st);
 }
 
 int run_middle(premvos_pwc* n, cudaStream_t st) {
+  if (n->opt_tensor_cores) return run_middle_tc(n, st);
   const int B = n->B;
   // feature pyramid, both frames at once (PWCNet.py:183-194)
   TView cur = n->img;
@@ -253,8 +439,7 @@ int run_middle(premvos_pwc* n, cudaStream_t st) {
     for (int i = 0; i < 5; i++) {
       TView in = slab.slice(DEC_IN_OFF[i], ctot - DEC_IN_OFF[i]);
       TView out = slab.slice(DEC_OUT_OFF[i], DEC_OUT[i]);
-      if (n->opt_tensor_cores) PV_TRY(launch_conv_umma(n->plan_dec[L][i], st));
-      else PV_TRY(conv2d_simt(in, out, n->w_dec[L][i], 1, 1, 0.1f, st));
+      PV_TRY(conv2d_simt(in, out, n->w_dec[L][i], 1, 1, 0.1f, st));
     }
     TView all = slab.slice(0, ctot);
     TView flow = n->flow[L].slice(0, 2);
@@ -271,14 +456,15 @@ int run_middle(premvos_pwc* n, cudaStream_t st) {
   TView bufs[2] = {n->ctxA, n->ctxB};
   for (int i = 0; i < 6; i++) {
     TView out = bufs[i & 1].slice(0, DC_OUT[i]);
-    if (n->opt_tensor_cores) PV_TRY(launch_conv_umma(n->plan_dc[i], st));
-    else PV_TRY(conv2d_simt(in, out, n->w_dc[i], 1, DC_DIL[i], 0.1f, st));
+    PV_TRY(conv2d_simt(in, out, n->w_dc[i], 1, DC_DIL[i], 0.1f, st));
     in = out;
   }
   return 0;
 }
 
 int run_back(premvos_pwc* n, float* flow_dev, cudaStream_t st) {
+  if (n->opt_tensor_cores)  // flow2 + dc_conv7(...) (PWCNet.py:267), NCHW out
+    return flow_finish(n->head[2].slice(0, 2), n->dc7out.slice(0, 2), flow_dev, st);
   TView dc6 = n->ctxB.slice(0, 32);
   TView flow2 = n->flow[2].slice(0, 2);
   TView none;
@@ -398,39 +584,46 @@ extern "C" int premvos_pwc_tensor_core_layers(const premvos_pwc_t* n) { return n
 extern "C" int premvos_pwc_get_tensor(premvos_pwc_t* n, const char* name, float* host_out, int64_t* numel) {
   PV_CHECK(n && name && numel, PREMVOS_ERR_INVALID_ARG, "premvos_pwc_get_tensor: null argument");
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_pwc_get_tensor: network not finalized");
+  const bool tc = n->opt_tensor_cores != 0;
   std::string k(name);
-  TView v;
-  bool found = false;
+  TView v;       // fp32 channels-last source ...
+  CView cv;      // ... or CP8 source (+ channel offset inside its first chunk plane)
+  int ch_off = 0;
+  bool found = false, is_cp = false;
   auto lvl = [&](size_t pos) { return (k.size() > pos && k[pos] >= '1' && k[pos] <= '6') ? k[pos] - '0' : -1; };
   if (k.size() == 3 && k[0] == 'c' && (k[1] == '1' || k[1] == '2') && lvl(2) > 0) {
     int L = lvl(2);
-    v = n->pyr[L][2].batch_range(k[1] == '1' ? 0 : n->B, n->B);
+    if (tc) { cv = n->c_pyr[L][2].batch_range(k[1] == '1' ? 0 : n->B, n->B); is_cp = true; }
+    else v = n->pyr[L][2].batch_range(k[1] == '1' ? 0 : n->B, n->B);
     found = true;
   } else if (k.rfind("corr", 0) == 0 && lvl(4) >= 2) {
-    v = n->slab[lvl(4)].slice(BASE_OFF, 81); found = true;
+    if (tc) { cv = n->c_slab[lvl(4)].slice(CORR_CHUNK, 81); is_cp = true; }
+    else v = n->slab[lvl(4)].slice(BASE_OFF, 81);
+    found = true;
   } else if (k.rfind("warp", 0) == 0 && lvl(4) >= 2 && lvl(4) <= 5) {
-    v = n->warpbuf[lvl(4)]; found = true;
+    if (tc) { cv = n->c_warp[lvl(4)]; is_cp = true; }
+    else v = n->warpbuf[lvl(4)];
+    found = true;
   } else if (k.rfind("flow", 0) == 0 && lvl(4) >= 2) {
-    v = n->flow[lvl(4)].slice(0, 2); found = true;
-  } else if (k.rfind("up_flow", 0) == 0 && lvl(7) >= 3) {
+    v = tc ? n->head[lvl(4)].slice(0, 2) : n->flow[lvl(4)].slice(0, 2); found = true;
+  } else if ((k.rfind("up_flow", 0) == 0 || k.rfind("up_feat", 0) == 0) && lvl(7) >= 3) {
     int L = lvl(7);
-    v = n->slab[L - 1].slice(BASE_OFF + 81 + LEVEL_CH[L - 1], 2); found = true;
-  } else if (k.rfind("up_feat", 0) == 0 && lvl(7) >= 3) {
-    int L = lvl(7);
-    v = n->slab[L - 1].slice(BASE_OFF + 81 + LEVEL_CH[L - 1] + 2, 2); found = true;
-  } else if (k.rfind("slab", 0) == 0 && lvl(4) >= 2) {
-    int L = lvl(4);
-    v = n->slab[L].slice(0, level_od(L) + 448); found = true;
+    const int off = k[3] == 'f' && k[4] == 'l' ? 0 : 2;
+    if (tc) { cv = n->c_slab[L - 1].slice(up_chunk(L - 1), 2); ch_off = off; is_cp = true; }
+    else v = n->slab[L - 1].slice(BASE_OFF + 81 + LEVEL_CH[L - 1] + off, 2);
+    found = true;
   } else if (k == "dc6") {
-    v = n->ctxB.slice(0, 32); found = true;
+    if (tc) { cv = n->c_ctxB.slice(0, 32); is_cp = true; }
+    else v = n->ctxB.slice(0, 32);
+    found = true;
   }
   if (!found) return fail(PREMVOS_ERR_INVALID_ARG, "premvos_pwc_get_tensor: unknown tensor '%s'", name);
-  *numel = (int64_t)v.N * v.C * v.H * v.W;
+  *numel = is_cp ? (int64_t)cv.N * cv.C * cv.H * cv.W : (int64_t)v.N * v.C * v.H * v.W;
   if (!host_out) return 0;
   PV_CUDA(cudaDeviceSynchronize());
   float* dtmp = nullptr;
   PV_CUDA(cudaMalloc((void**)&dtmp, (size_t)(*numel) * sizeof(float)));
-  int r = view_to_nchw(v, dtmp, nullptr);
+  int r = is_cp ? cp8_to_nchw(cv, ch_off, dtmp, nullptr) : view_to_nchw(v, dtmp, nullptr);
   if (r == 0) {
     cudaError_t e = cudaMemcpy(host_out, dtmp, (size_t)(*numel) * sizeof(float), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) r = fail((int)e, "premvos_pwc_get_tensor: %s", cudaGetErrorString(e));
@@ -454,9 +647,15 @@ extern "C" void premvos_pwc_destroy(premvos_pwc_t* n) {
     free_deconv_weights(&n->w_upfeat[L]);
   }
   for (int i = 0; i < 6; i++) free_conv_weights_simt(&n->w_dc[i]);
-  for (int L = 2; L <= 6; L++)
+  for (int L = 1; L <= 6; L++)
+    for (int j = 0; j < 3; j++) free_conv_weights_umma(&n->wt_pyr[L][j]);
+  for (int L = 2; L <= 6; L++) {
     for (int i = 0; i < 5; i++) free_conv_weights_umma(&n->wt_dec[L][i]);
+    free_conv_weights_umma(&n->wt_head[L]);
+    if (n->d_deconv_w[L]) cudaFree(n->d_deconv_w[L]);
+  }
   for (int i = 0; i < 6; i++) free_conv_weights_umma(&n->wt_dc[i]);
+  free_conv_weights_umma(&n->wt_dc7);
   free_small_conv_weights(&n->w_dc7);
   if (n->stream) cudaStreamDestroy(n->stream);
   delete n;

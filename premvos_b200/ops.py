@@ -1,0 +1,43 @@
+"""Single-op entry points of the CUDA library (bring-up / parity hooks).  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def conv2d(x: torch.Tensor, weight, bias=None, stride=1, dilation=1, padding=(0, 0, 0, 0), slope=1.0,
+           residual: torch.Tensor = None) -> torch.Tensor:
+    """act(conv2d(x, weight) + bias + residual) on the tcgen05 tensor-core path (premvos_conv2d_forward).
+
+    x: CUDA float32 [N,Cin,H,W]; weight: [Cout,Cin,kh,kw] (host numpy / CPU tensor); padding =
+    (top, left, bottom, right) zeros; act = LeakyReLU(slope) (1 = identity, 0 = ReLU)."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise TypeError("x must be a CUDA float32 tensor (premvos_b200 has no CPU path)")
+    x = x.contiguous()
+    w = np.ascontiguousarray(weight.detach().cpu().numpy() if isinstance(weight, torch.Tensor) else weight, dtype=np.float32)
+    b = None if bias is None else np.ascontiguousarray(
+        bias.detach().cpu().numpy() if isinstance(bias, torch.Tensor) else bias, dtype=np.float32)
+    N, Cin, H, W = x.shape
+    Cout, Cin2, kh, kw = w.shape
+    if Cin2 != Cin:
+        raise ValueError("weight has %d input channels, x has %d" % (Cin2, Cin))
+    pt, pl, pb, pr = padding
+    Ho = (H + pt + pb - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (W + pl + pr - dilation * (kw - 1) - 1) // stride + 1
+    out = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    res_ptr = None
+    if residual is not None:
+        residual = residual.contiguous()
+        if tuple(residual.shape) != tuple(out.shape):
+            raise ValueError("residual shape %s != output shape %s" % (tuple(residual.shape), tuple(out.shape)))
+        res_ptr = residual.data_ptr()
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_conv2d_forward(
+            x.data_ptr(), w.ctypes.data_as(ctypes.c_void_p), None if b is None else b.ctypes.data_as(ctypes.c_void_p),
+            res_ptr, out.data_ptr(), N, Cin, H, W, Cout, kh, kw, stride, dilation, pt, pl, pb, pr, float(slope), st))
+    return out

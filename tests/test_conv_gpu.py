@@ -1,0 +1,82 @@
+"""GPU parity of the tensor-core convolution (premvos_conv2d_forward) against a plain PyTorch fp32/fp64
+CPU convolution of the same op.  Tolerance: the split-bf16 x3 scheme keeps ~16 mantissa bits per operand,
+so 1e-4 relative (||d||_inf / ||ref||_inf) is required here -- ten times tighter than the 1e-3 contract."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from premvos_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _ref(x, w, b, stride, dil, pad, slope, res):
+    pt, pl, pb, pr = pad
+    xp = F.pad(x.double(), (pl, pr, pt, pb))
+    y = F.conv2d(xp, w.double(), None if b is None else b.double(), stride=stride, dilation=dil)
+    if res is not None:
+        y = y + res.double()
+    return torch.where(y > 0, y, y * slope).float()
+
+
+CASES = [
+    # (N, Cin, H, W, Cout, k, stride, dil, pad(t,l,b,r), slope, residual)   -- what each case exercises
+    (1, 16, 16, 8, 16, 3, 1, 1, (1, 1, 1, 1), 0.1, False),      # one exact tile, halo mode
+    (2, 40, 37, 29, 72, 3, 1, 1, (1, 1, 1, 1), 0.1, False),     # ragged tiles, K tail (40 = 5 chunks), N tail
+    (1, 565, 28, 64, 128, 3, 1, 1, (1, 1, 1, 1), 0.1, False),   # PWC dc_conv1 shape (K = 565)
+    (1, 128, 40, 48, 128, 3, 1, 2, (2, 2, 2, 2), 0.1, False),   # dilation 2 (halo)
+    (1, 128, 40, 48, 96, 3, 1, 4, (4, 4, 4, 4), 0.1, False),    # dilation 4 (halo)
+    (1, 96, 40, 48, 64, 3, 1, 8, (8, 8, 8, 8), 0.1, False),     # dilation 8
+    (1, 64, 40, 48, 32, 3, 1, 16, (16, 16, 16, 16), 0.1, False),  # dilation 16 (tap mode)
+    (2, 3, 64, 64, 16, 3, 2, 1, (1, 1, 1, 1), 0.1, False),      # PWC conv1a: Cin 3, stride 2
+    (2, 32, 33, 47, 64, 3, 2, 1, (1, 1, 1, 1), 0.1, False),     # stride 2, odd sizes
+    (1, 64, 31, 45, 64, 3, 2, 1, (0, 0, 1, 1), 0.0, False),     # ResNet stride-2 3x3: pad (0,1) + VALID, ReLU
+    (1, 64, 30, 44, 256, 1, 1, 1, (0, 0, 0, 0), 1.0, False),    # 1x1, two N tiles, no activation
+    (1, 256, 30, 44, 64, 1, 1, 1, (0, 0, 0, 0), 0.0, True),     # 1x1 + residual + ReLU (bottleneck tail)
+    (1, 256, 29, 43, 512, 1, 2, 1, (0, 0, 0, 0), 1.0, False),   # 1x1 stride-2 shortcut
+    (1, 196, 7, 16, 196, 3, 1, 1, (1, 1, 1, 1), 0.1, False),    # PWC level 6: 196 channels (24.5 chunks)
+    (1, 529, 7, 16, 10, 3, 1, 1, (1, 1, 1, 1), 1.0, False),     # flow head: Cout 10 -> N = 16
+    (4, 117, 112, 256, 128, 3, 1, 1, (1, 1, 1, 1), 0.1, False),  # bench-size level 2 layer: MT = 2 tiles
+    (1, 3, 75, 131, 64, 7, 2, 1, (2, 2, 3, 3), 0.0, False),     # ResNet stem 7x7 s2, pad (2,3)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d_k%d_s%d_d%d" % c[:8])
+def test_conv2d_matches_torch(case):
+    N, Cin, H, W, Cout, k, stride, dil, pad, slope, use_res = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho = (H + pad[0] + pad[2] - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + pad[1] + pad[3] - dil * (k - 1) - 1) // stride + 1
+    res = torch.randn(N, Cout, Ho, Wo, generator=g) if use_res else None
+    ref = _ref(x, w, b, stride, dil, pad, slope, res)
+    got = ops.conv2d(x.cuda(), w, b, stride, dil, pad, slope, None if res is None else res.cuda()).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(got.numpy(), ref.numpy()) < TOL
+
+
+def test_conv2d_linearity_and_zero_padding_at_full_size():
+    # size-independent properties at the bench resolution
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 32, 112, 256, generator=g).cuda()
+    w = torch.randn(32, 32, 3, 3, generator=g) / 17.0
+    y1 = ops.conv2d(x, w, None, 1, 1, (1, 1, 1, 1), 1.0)
+    y2 = ops.conv2d(2.0 * x, w, None, 1, 1, (1, 1, 1, 1), 1.0)
+    assert torch.allclose(y2, 2.0 * y1, rtol=1e-4, atol=1e-5)          # exact up to the hi/lo split rounding
+    # an explicitly padded input with VALID geometry gives the same answer as implicit zero padding
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    y3 = ops.conv2d(xp, w, None, 1, 1, (0, 0, 0, 0), 1.0)
+    assert torch.equal(y3, y1)
+
+
+def test_conv2d_errors_are_loud():
+    x = torch.zeros(1, 8, 8, 8, device="cuda")
+    with pytest.raises(_lib.PremvosError):
+        ops.conv2d(x, np.zeros((8, 8, 3, 3), np.float32), None, stride=3)
+    with pytest.raises(ValueError):
+        ops.conv2d(x, np.zeros((8, 4, 3, 3), np.float32))
