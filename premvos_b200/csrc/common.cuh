@@ -174,9 +174,8 @@ struct CView {
 
 // ---- convolution on tcgen05 tensor cores (split-bf16 x3, fp32 accumulate), conv_umma.cu ----------
 struct ConvWeightsUmma {
-  __nv_bfloat16* w_hi = nullptr;  // device, packed shared-memory images [ntile][tap][kblock][KC][BN][8]
-  __nv_bfloat16* w_lo = nullptr;
-  float* bias = nullptr;          // device [ntiles*BN]
+  __nv_bfloat16* w = nullptr;  // device, packed shared-memory images [ntile][kblock][tap][hi|lo][KC][BN][8]
+  float* bias = nullptr;       // device [ntiles*BN]
   int R = 3, S = 3, Cin = 0, CinPhys = 0, Cout = 0, KC = 2, kblocks = 0, BN = 0, ntiles = 0;
 };
 struct ConvGeom {
@@ -200,7 +199,7 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
 // host_w: torch Conv2d layout [Cout][Cin][R][S].  cin_map (optional): physical channel (inside the input
 // view) of every reference input channel, cin_phys = physical channel count of that view.
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
-                           const int* cin_map = nullptr, int cin_phys = 0);
+                           const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0);
 void free_conv_weights_umma(ConvWeightsUmma* w);
 int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g);
 int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st);

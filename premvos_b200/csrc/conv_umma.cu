@@ -26,6 +26,7 @@
 // two CTAs co-reside per SM: one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -142,10 +143,13 @@ struct UmmaConvArgs {
   int box_w, box_h;          // A box (pixels) as it lies in shared memory
   int KC, kblocks;           // 8-channel chunks per k-block (even); k-blocks
   int BN, Cout;
+  int TPS;                   // taps per weight stage (divides R*S): one bulk copy fetches TPS taps x {hi, lo}
   int a_stages, w_stages;
-  int a_plane, w_plane;      // bytes of one (hi or lo) plane of a stage, rounded up to 128
-  int a_box_bytes, w_box_bytes;  // bytes one TMA / bulk copy actually transfers per plane
-  const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;  // packed [ntile][tap][kblock][KC][BN][8]
+  int a_plane;               // bytes of one (hi or lo) A plane of a stage, rounded up to 128
+  int a_box_bytes;           // bytes one A TMA actually transfers
+  int w_plane;               // bytes of one (hi or lo) plane of one tap = KC*BN*16
+  int w_stage;               // bytes of a weight stage (TPS * 2 * w_plane), rounded up to 128
+  const __nv_bfloat16* w;    // packed [ntile][kblock][tap][plane hi|lo][KC][BN][8]
   const float* bias;         // [ntiles*BN]
   float slope;               // LeakyReLU slope (1 = identity, 0 = ReLU)
   // outputs: CP8 split planes and/or fp32 channels-last
@@ -161,7 +165,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint8_t* a_smem = smem;
   uint8_t* w_smem = a_smem + (size_t)a.a_stages * 2 * a.a_plane;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + (size_t)a.w_stages * 2 * a.w_plane);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + (size_t)a.w_stages * a.w_stage);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + MAX_A_STAGES;
   uint64_t* w_full = bars + 2 * MAX_A_STAGES;
@@ -194,10 +198,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====  (no integer division in the loop: ring indices and phases are carried)
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0;
-    const size_t w_stage_elems = (size_t)a.KC * a.BN * 8;
-    const __nv_bfloat16* wh = a.w_hi + (size_t)ntile * taps * a.kblocks * w_stage_elems;
-    const __nv_bfloat16* wl = a.w_lo + (size_t)ntile * taps * a.kblocks * w_stage_elems;
-    const size_t w_tap_stride = (size_t)a.kblocks * w_stage_elems;
+    const uint32_t w_bytes = (uint32_t)a.TPS * 2u * (uint32_t)a.w_plane;   // one bulk copy
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)ntile * a.kblocks * taps * 2 * a.w_plane;
     const int bx = tx0 * a.stride - a.pad_l, by = ty0 * a.stride - a.pad_t;
     auto load_a = [&](int kc0, int px, int py) {
       mbar_wait(&a_empty[a_st], a_ph ^ 1u);
@@ -214,18 +216,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     };
     for (int kb = 0; kb < a.kblocks; kb++) {
       if (a.halo) load_a(kb * a.KC, bx, by);
-      const __nv_bfloat16* wh_t = wh + (size_t)kb * w_stage_elems;
-      const __nv_bfloat16* wl_t = wl + (size_t)kb * w_stage_elems;
+      int tin = 0;  // tap index inside the current weight stage
       for (int r = 0; r < a.R; r++)
         for (int s = 0; s < a.S; s++) {
           if (!a.halo) load_a(kb * a.KC, bx + s * a.dil, by + r * a.dil);
-          mbar_wait(&w_empty[w_st], w_ph ^ 1u);
-          uint8_t* dst = w_smem + (size_t)w_st * 2 * a.w_plane;
-          mbar_arrive_expect_tx(&w_full[w_st], 2u * (uint32_t)a.w_box_bytes);
-          bulk_load_1d(dst, wh_t, (uint32_t)a.w_box_bytes, &w_full[w_st]);
-          bulk_load_1d(dst + a.w_plane, wl_t, (uint32_t)a.w_box_bytes, &w_full[w_st]);
-          wh_t += w_tap_stride; wl_t += w_tap_stride;
-          if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+          if (tin == 0) {
+            mbar_wait(&w_empty[w_st], w_ph ^ 1u);
+            mbar_arrive_expect_tx(&w_full[w_st], w_bytes);
+            bulk_load_1d(w_smem + (size_t)w_st * a.w_stage, wsrc, w_bytes, &w_full[w_st]);
+            wsrc += w_bytes;
+            if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+          }
+          if (++tin == a.TPS) tin = 0;
         }
     }
   } else if (warp == 1) {
@@ -237,11 +239,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_hi32 = (a_sbo >> 4) | (1u << 14), w_hi32 = (w_sbo >> 4) | (1u << 14);
     const uint32_t a_lo32 = (a_lbo >> 4) << 16, w_lo32 = (w_lbo >> 4) << 16;
     const uint32_t a_base = smem_u32(a_smem), w_base = smem_u32(w_smem);
-    const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = 2u * (uint32_t)a.w_plane;
+    const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = (uint32_t)a.w_stage;
     const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = 16u * a_sbo;
     const uint32_t tap_row = a.halo ? (uint32_t)(a.dil * a.box_w) * 16u : 0u, tap_col = a.halo ? (uint32_t)a.dil * 16u : 0u;
-    uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0;
+    uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0, w_addr_tap = 0;
     uint32_t accum = 0;
+    int tin = 0;  // tap index inside the current weight stage
     const int ksteps = a.KC / 2;
     for (int kb = 0; kb < a.kblocks; kb++) {
       uint32_t row_off = 0;
@@ -254,10 +257,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             a_addr_stage = a_base + a_st * a_stage_bytes;
             if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
           }
-          mbar_wait(&w_full[w_st], w_ph);
+          if (tin == 0) {
+            mbar_wait(&w_full[w_st], w_ph);
+            w_addr_tap = w_base + w_st * w_stage_bytes;
+          }
           tc_fence_after();
+          const bool w_done = (tin == a.TPS - 1);
           if (lane == 0) {
-            uint32_t aa0 = a_addr_stage + tap_off, ww = w_base + w_st * w_stage_bytes;
+            uint32_t aa0 = a_addr_stage + tap_off, ww = w_addr_tap;
             for (int ks = 0; ks < ksteps; ks++, aa0 += a_kstep, ww += w_kstep) {
               const uint64_t dWh = ((uint64_t)w_hi32 << 32) | (w_lo32 + ((ww & 0x3FFFFu) >> 4));
               const uint64_t dWl = ((uint64_t)w_hi32 << 32) | (w_lo32 + (((ww + (uint32_t)a.w_plane) & 0x3FFFFu) >> 4));
@@ -271,11 +278,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               }
               accum = 1u;
             }
-            umma_commit(&w_empty[w_st]);  // frees the weight slot once these MMAs have read it
+            if (w_done) umma_commit(&w_empty[w_st]);  // frees the weight slot once these MMAs have read it
             if (!a.halo || (r == a.R - 1 && s == a.S - 1)) umma_commit(&a_empty[cur_a]);
           }
           __syncwarp();
-          if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+          w_addr_tap += 2u * (uint32_t)a.w_plane;
+          if (w_done) {
+            tin = 0;
+            if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+          } else {
+            tin++;
+          }
         }
       }
     }
@@ -396,22 +409,34 @@ inline void split_bf16(float x, __nv_bfloat16* hi, __nv_bfloat16* lo) {
 
 }  // namespace
 
+// Channels per k-block (KC chunks of 8).  Bigger stages amortise the fixed cost of a TMA request; halo-mode
+// 3x3 layers keep the A box small instead (its halo is loaded once per k-block and serves all taps).
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
-                           const int* cin_map, int cin_phys) {
+                           const int* cin_map, int cin_phys, int kc_hint) {
   out->R = R; out->S = S; out->Cin = Cin; out->Cout = Cout;
   const int phys = cin_map ? cin_phys : Cin;   // physical input channels (after the view's chunk padding)
   out->CinPhys = phys;
-  out->KC = 2;
   const int chunks = (phys + 7) / 8;
-  out->kblocks = (chunks + out->KC - 1) / out->KC;
+  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? 4 : 8);
+  kc = env_int("PREMVOS_KC", kc);
+  if (kc > round_up(chunks, 2)) kc = round_up(chunks, 2);
+  PV_CHECK(kc >= 2 && (kc % 2) == 0 && kc <= 16, PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: KC=%d", kc);
+  out->KC = kc;
+  out->kblocks = (chunks + kc - 1) / kc;
   int bn = round_up(Cout, 16);
   if (bn > 128) bn = 128;
   out->BN = bn;
   out->ntiles = (Cout + bn - 1) / bn;
-  const int KP = out->kblocks * out->KC * 8;
-  const size_t stage_elems = (size_t)out->KC * bn * 8;
-  const size_t n = (size_t)out->ntiles * R * S * out->kblocks * stage_elems;
-  std::vector<__nv_bfloat16> hi(n, __float2bfloat16_rn(0.f)), lo(n, __float2bfloat16_rn(0.f));
+  const int KP = out->kblocks * kc * 8;
+  const int taps = R * S;
+  const size_t plane_elems = (size_t)kc * bn * 8;   // one (tap, k-block) operand image of one plane
+  const size_t n = (size_t)out->ntiles * out->kblocks * taps * 2 * plane_elems;
+  std::vector<__nv_bfloat16> w(n, __float2bfloat16_rn(0.f));
   std::vector<float> b((size_t)out->ntiles * bn, 0.f);
   for (int co = 0; co < Cout; co++) {
     b[co] = host_b ? host_b[co] : 0.f;
@@ -419,25 +444,24 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
     for (int ci = 0; ci < Cin; ci++) {
       const int pc = cin_map ? cin_map[ci] : ci;
       if (pc < 0 || pc >= KP) return fail(PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: channel map out of range");
-      const int kb = pc / (out->KC * 8), kc = (pc / 8) % out->KC, e = pc & 7;
-      for (int t = 0; t < R * S; t++) {
-        const size_t idx = ((((size_t)nt * R * S + t) * out->kblocks + kb) * out->KC + kc) * bn * 8 + (size_t)row * 8 + e;
-        split_bf16(host_w[((size_t)co * Cin + ci) * R * S + t], &hi[idx], &lo[idx]);
+      const int kb = pc / (kc * 8), kcc = (pc / 8) % kc, e = pc & 7;
+      for (int t = 0; t < taps; t++) {
+        // [ntile][kblock][tap][plane][KC][BN][8]
+        const size_t base = ((((size_t)nt * out->kblocks + kb) * taps + t) * 2) * plane_elems + ((size_t)kcc * bn + row) * 8 + e;
+        split_bf16(host_w[((size_t)co * Cin + ci) * taps + t], &w[base], &w[base + plane_elems]);
       }
     }
   }
-  PV_CUDA(cudaMalloc((void**)&out->w_hi, n * 2));
-  PV_CUDA(cudaMalloc((void**)&out->w_lo, n * 2));
+  PV_CUDA(cudaMalloc((void**)&out->w, n * 2));
   PV_CUDA(cudaMalloc((void**)&out->bias, b.size() * sizeof(float)));
-  PV_CUDA(cudaMemcpy(out->w_hi, hi.data(), n * 2, cudaMemcpyHostToDevice));
-  PV_CUDA(cudaMemcpy(out->w_lo, lo.data(), n * 2, cudaMemcpyHostToDevice));
+  PV_CUDA(cudaMemcpy(out->w, w.data(), n * 2, cudaMemcpyHostToDevice));
   PV_CUDA(cudaMemcpy(out->bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
   return 0;
 }
 
 void free_conv_weights_umma(ConvWeightsUmma* w) {
-  cudaFree(w->w_hi); cudaFree(w->w_lo); cudaFree(w->bias);
-  w->w_hi = w->w_lo = nullptr; w->bias = nullptr;
+  cudaFree(w->w); cudaFree(w->bias);
+  w->w = nullptr; w->bias = nullptr;
 }
 
 // Plans one convolution launch: tensor maps of the input view are encoded here (host only, no device work).
@@ -471,6 +495,8 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
   const long ctas_mt2 = (long)a.tiles_x * ((Ho + 31) / 32) * in.N * w.ntiles;
   a.MT = (ctas_mt2 >= 2 * 148 && Ho > 16) ? 2 : 1;
+  a.MT = env_int("PREMVOS_MT", a.MT);
+  PV_CHECK(a.MT == 1 || a.MT == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", a.MT);
   a.tiles_y = (Ho + 16 * a.MT - 1) / (16 * a.MT);
   a.Ho = Ho; a.Wo = Wo;
   a.stride = g.stride; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
@@ -479,23 +505,32 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const int halo_w = 8 + (w.S - 1) * g.dil, halo_h = 16 * a.MT + (w.R - 1) * g.dil;
   const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * a.MT;
   a.halo = (g.stride == 1 && taps > 1 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256 &&
-            halo_px * w.KC * 16 <= 36 * 1024) ? 1 : 0;
+            halo_px * w.KC * 16 <= 48 * 1024) ? 1 : 0;
   a.merged_x = (g.stride == 1) ? 1 : 0;
   a.box_w = a.halo ? halo_w : 8;
   a.box_h = a.halo ? halo_h : 16 * a.MT;
   a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
   a.a_plane = round_up(a.a_box_bytes, 128);
-  a.w_box_bytes = w.KC * w.BN * 16;
-  a.w_plane = round_up(a.w_box_bytes, 128);
-  a.a_stages = a.halo ? 2 : 4;
-  a.w_stages = 4;
-  // grow the weight ring while two CTAs still fit one SM
-  while (a.w_stages < MAX_W_STAGES &&
-         a.a_stages * 2 * a.a_plane + (a.w_stages + 1) * 2 * a.w_plane + 1024 <= 110 * 1024)
+  a.w_plane = w.KC * w.BN * 16;
+  // taps per weight stage: as many as fit ~48 KB (fewer, larger bulk copies: a TMA request has a fixed cost)
+  int tps = 1;
+  for (int t = 1; t <= taps; t++)
+    if (taps % t == 0 && (t <= w.S || t % w.S == 0) && t * 2 * a.w_plane <= 48 * 1024) tps = t;
+  tps = env_int("PREMVOS_TPS", tps);
+  PV_CHECK(tps >= 1 && taps % tps == 0, PREMVOS_ERR_INVALID_ARG, "conv_umma: TPS=%d does not divide %d taps", tps, taps);
+  a.TPS = tps;
+  a.w_stage = round_up(tps * 2 * a.w_plane, 128);
+  a.a_stages = a.halo ? 2 : 3;
+  a.w_stages = 2;
+  const int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
+  while (a.w_stages < MAX_W_STAGES && a.w_stages * tps < 2 * taps + 2 &&
+         a.a_stages * 2 * a.a_plane + (a.w_stages + 1) * a.w_stage + 1024 <= budget)
     a.w_stages++;
-  plan->smem_bytes = a.a_stages * 2 * a.a_plane + a.w_stages * 2 * a.w_plane + 128 /*align slack*/ + 512 /*barriers*/;
+  while (!a.halo && a.a_stages < MAX_A_STAGES && a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 2 * a.a_plane + 1024 <= budget)
+    a.a_stages++;
+  plan->smem_bytes = a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 128 /*align slack*/ + 512 /*barriers*/;
   PV_CHECK(plan->smem_bytes <= SMEM_LIMIT, PREMVOS_ERR_UNSUPPORTED, "conv_umma: %d bytes of shared memory needed", plan->smem_bytes);
-  a.w_hi = w.w_hi; a.w_lo = w.w_lo; a.bias = w.bias; a.slope = g.slope;
+  a.w = w.w; a.bias = w.bias; a.slope = g.slope;
   a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
   a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
