@@ -143,6 +143,8 @@ struct UmmaConvArgs {
   int box_w, box_h;          // A box (pixels) as it lies in shared memory
   int KC, kblocks;           // 8-channel chunks per k-block (even); k-blocks
   int BN, Cout;
+  int NACC;                  // accumulator replicas (1..3): product p of {lo*hi, hi*lo, hi*hi} accumulates into replica p % NACC;
+                             // independent accumulators let the tensor pipe overlap the otherwise serial MMA chain
   int TPS;                   // taps per weight stage (divides R*S): one bulk copy fetches TPS taps x {hi, lo}
   int a_stages, w_stages;
   int a_plane;               // bytes of one (hi or lo) A plane of a stage, rounded up to 128
@@ -246,6 +248,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint32_t accum = 0;
     int tin = 0;  // tap index inside the current weight stage
     const int ksteps = a.KC / 2;
+    const uint32_t rep_cols = (uint32_t)(a.MT * a.BN);
+    const uint32_t rep1 = a.NACC > 1 ? rep_cols : 0u, rep2 = a.NACC > 2 ? 2u * rep_cols : 0u;
     for (int kb = 0; kb < a.kblocks; kb++) {
       uint32_t row_off = 0;
       for (int r = 0; r < a.R; r++, row_off += tap_row) {
@@ -273,8 +277,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint64_t dAh = ((uint64_t)a_hi32 << 32) | (a_lo32 + ((aa & 0x3FFFFu) >> 4));
                 const uint64_t dAl = ((uint64_t)a_hi32 << 32) | (a_lo32 + (((aa + (uint32_t)a.a_plane) & 0x3FFFFu) >> 4));
                 umma_bf16(d, dAl, dWh, idesc, accum);
-                umma_bf16(d, dAh, dWl, idesc, 1u);
-                umma_bf16(d, dAh, dWh, idesc, 1u);
+                umma_bf16(d + rep1, dAh, dWl, idesc, a.NACC > 1 ? accum : 1u);
+                umma_bf16(d + rep2, dAh, dWh, idesc, a.NACC > 2 ? accum : 1u);
               }
               accum = 1u;
             }
@@ -308,8 +312,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int c0 = 0; c0 < a.BN; c0 += 16) {
         uint32_t v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0), v);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0);
+        tmem_ld16(taddr, v);
         tmem_ld_wait();
+        for (int rep = 1; rep < a.NACC; rep++) {
+          uint32_t v2[16];
+          tmem_ld16(taddr + (uint32_t)(rep * a.MT * a.BN), v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
         const int co0 = ntile * a.BN + c0;
         if (!in_img || co0 >= a.Cout) continue;
         float f[16];
@@ -492,38 +504,51 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   memset(&a, 0, sizeof(a));
   const int taps = w.R * w.S;
   a.tiles_x = (Wo + 7) / 8;
-  // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
-  const long ctas_mt2 = (long)a.tiles_x * ((Ho + 31) / 32) * in.N * w.ntiles;
-  a.MT = (ctas_mt2 >= 2 * 148 && Ho > 16) ? 2 : 1;
-  a.MT = env_int("PREMVOS_MT", a.MT);
-  PV_CHECK(a.MT == 1 || a.MT == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", a.MT);
-  a.tiles_y = (Ho + 16 * a.MT - 1) / (16 * a.MT);
   a.Ho = Ho; a.Wo = Wo;
   a.stride = g.stride; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
   a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
-  // halo mode when it moves fewer bytes into shared memory than per-tap boxes
-  const int halo_w = 8 + (w.S - 1) * g.dil, halo_h = 16 * a.MT + (w.R - 1) * g.dil;
-  const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * a.MT;
-  a.halo = (g.stride == 1 && taps > 1 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256 &&
-            halo_px * w.KC * 16 <= 48 * 1024) ? 1 : 0;
   a.merged_x = (g.stride == 1) ? 1 : 0;
-  a.box_w = a.halo ? halo_w : 8;
-  a.box_h = a.halo ? halo_h : 16 * a.MT;
-  a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
-  a.a_plane = round_up(a.a_box_bytes, 128);
   a.w_plane = w.KC * w.BN * 16;
-  // taps per weight stage: as many as fit ~48 KB (fewer, larger bulk copies: a TMA request has a fixed cost)
-  int tps = 1;
-  for (int t = 1; t <= taps; t++)
-    if (taps % t == 0 && (t <= w.S || t % w.S == 0) && t * 2 * a.w_plane <= 48 * 1024) tps = t;
-  tps = env_int("PREMVOS_TPS", tps);
-  PV_CHECK(tps >= 1 && taps % tps == 0, PREMVOS_ERR_INVALID_ARG, "conv_umma: TPS=%d does not divide %d taps", tps, taps);
-  a.TPS = tps;
-  a.w_stage = round_up(tps * 2 * a.w_plane, 128);
-  a.a_stages = a.halo ? 2 : 3;
-  a.w_stages = 2;
+  // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
+  const long ctas_mt2 = (long)a.tiles_x * ((Ho + 31) / 32) * in.N * w.ntiles;
+  int mt_pref = (ctas_mt2 >= 2 * 148 && Ho > 16) ? 2 : 1;
+  mt_pref = env_int("PREMVOS_MT", mt_pref);
+  PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
+  const int tps_env = env_int("PREMVOS_TPS", 0);
+  PV_CHECK(tps_env == 0 || taps % tps_env == 0, PREMVOS_ERR_INVALID_ARG, "conv_umma: TPS=%d does not divide %d taps", tps_env, taps);
+  // candidate configurations in order of preference; the first whose minimal pipeline fits shared memory wins
+  bool found = false;
+  for (int cand = 0; cand < 4 && !found; cand++) {
+    const int mt = (cand & 1) ? 1 : mt_pref;
+    const bool want_halo = cand < 2;
+    if ((cand & 1) && mt_pref == 1) continue;
+    const int halo_w = 8 + (w.S - 1) * g.dil, halo_h = 16 * mt + (w.R - 1) * g.dil;
+    const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * mt;
+    // halo mode only when it moves fewer bytes into shared memory than per-tap boxes
+    const bool halo_ok = g.stride == 1 && taps > 1 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
+    if (want_halo && !halo_ok) continue;
+    a.MT = mt;
+    a.halo = want_halo ? 1 : 0;
+    a.box_w = a.halo ? halo_w : 8;
+    a.box_h = a.halo ? halo_h : 16 * mt;
+    a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
+    a.a_plane = round_up(a.a_box_bytes, 128);
+    a.a_stages = a.halo ? 2 : 3;
+    // taps per weight stage: fewer, larger bulk copies (a TMA request has a fixed cost), <= 48 KB each
+    for (int t = taps; t >= 1 && !found; t--) {
+      if (taps % t != 0 || !(t <= w.S || t % w.S == 0)) continue;
+      if (tps_env ? (t != tps_env) : (t > 1 && t * 2 * a.w_plane > 48 * 1024)) continue;
+      a.TPS = t;
+      a.w_stage = round_up(t * 2 * a.w_plane, 128);
+      a.w_stages = 2;
+      if (a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 1024 <= SMEM_LIMIT) found = true;
+    }
+  }
+  PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);
+  a.tiles_y = (Ho + 16 * a.MT - 1) / (16 * a.MT);
+  // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
   const int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
-  while (a.w_stages < MAX_W_STAGES && a.w_stages * tps < 2 * taps + 2 &&
+  while (a.w_stages < MAX_W_STAGES && a.w_stages * a.TPS < 2 * taps + 2 &&
          a.a_stages * 2 * a.a_plane + (a.w_stages + 1) * a.w_stage + 1024 <= budget)
     a.w_stages++;
   while (!a.halo && a.a_stages < MAX_A_STAGES && a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 2 * a.a_plane + 1024 <= budget)
@@ -534,8 +559,10 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
   a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
+  a.NACC = env_int("PREMVOS_NACC", 1);
+  PV_CHECK(a.NACC >= 1 && a.NACC <= 3 && a.NACC * a.MT * w.BN <= 512, PREMVOS_ERR_INVALID_ARG, "conv_umma: NACC=%d does not fit TMEM", a.NACC);
   uint32_t cols = 32;
-  while ((int)cols < a.MT * w.BN) cols <<= 1;
+  while ((int)cols < a.NACC * a.MT * w.BN) cols <<= 1;
   a.tmem_cols = cols;
   plan->grid_x = a.tiles_x * a.tiles_y * in.N;
   plan->grid_y = w.ntiles;

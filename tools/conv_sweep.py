@@ -28,7 +28,7 @@ SHAPES = {
 
 def run(name, env):
     N, Cin, H, W, Cout, k, stride, dil = SHAPES[name]
-    for key in ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT"):
+    for key in ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_NACC"):
         os.environ.pop(key, None)
     os.environ.update({k2: str(v) for k2, v in env.items() if v is not None})
     x = torch.randn(N, Cin, H, W, device="cuda")
@@ -50,13 +50,10 @@ def run(name, env):
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SHAPES)
     for name in names:
-        k = SHAPES[name][5]
-        kcs = [None, 2, 4, 8]
-        tpss = [None, 1, 3, 9] if k == 3 else [None]
-        mts = [None, 1, 2]
         print("==", name, SHAPES[name])
-        for kc, tps, mt in itertools.product(kcs, tpss, mts):
-            if (kc is None) != (tps is None and k == 3) and k == 3:
-                continue
-            us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt})
-            print("  KC=%s TPS=%s MT=%s: %s %s" % (kc, tps, mt, "%.1f us" % us if us else "--", note), flush=True)
+        k = SHAPES[name][5]
+        for kc, tps in ([(2, 3), (4, 3), (8, 1)] if k == 3 else [(2, None), (8, None)]):
+            for mt in (1, 2):
+                for nacc in (1, 2, 3):
+                    us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt, "PREMVOS_NACC": nacc})
+                    print("  KC=%s TPS=%s MT=%s NACC=%s: %s %s" % (kc, tps, mt, nacc, "%.1f us" % us if us else "--", note), flush=True)
