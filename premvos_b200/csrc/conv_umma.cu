@@ -67,6 +67,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// one lane of the (converged) warp; the ELECT form lets ptxas keep MMA/TMA operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -184,7 +190,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int ntile = blockIdx.y;
   const int taps = a.R * a.S;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && lane == 0) {  // one-time setup
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
     for (int s = 0; s < a.a_stages; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < a.w_stages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -195,37 +201,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_addr_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_addr_slot, 0);
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====  (no integer division in the loop: ring indices and phases are carried)
+  if (warp == 0) {
+    // ===== TMA producer =====  the whole warp walks the warp-uniform loop, one elected lane issues the copies
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0;
     const uint32_t w_bytes = (uint32_t)a.TPS * 2u * (uint32_t)a.w_plane;   // one bulk copy
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)ntile * a.kblocks * taps * 2 * a.w_plane;
     const int bx = tx0 * a.stride - a.pad_l, by = ty0 * a.stride - a.pad_t;
-    auto load_a = [&](int kc0, int px, int py) {
-      mbar_wait(&a_empty[a_st], a_ph ^ 1u);
-      uint8_t* dst = a_smem + (size_t)a_st * 2 * a.a_plane;
-      mbar_arrive_expect_tx(&a_full[a_st], 2u * (uint32_t)a.a_box_bytes);
-      if (a.merged_x) {
-        tma_load_4d(&tmA_hi, &a_full[a_st], dst, px * 8, py, kc0, n_img);
-        tma_load_4d(&tmA_lo, &a_full[a_st], dst + a.a_plane, px * 8, py, kc0, n_img);
-      } else {
-        tma_load_5d(&tmA_hi, &a_full[a_st], dst, 0, px, py, kc0, n_img);
-        tma_load_5d(&tmA_lo, &a_full[a_st], dst + a.a_plane, 0, px, py, kc0, n_img);
-      }
-      if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
-    };
     for (int kb = 0; kb < a.kblocks; kb++) {
-      if (a.halo) load_a(kb * a.KC, bx, by);
       int tin = 0;  // tap index inside the current weight stage
       for (int r = 0; r < a.R; r++)
         for (int s = 0; s < a.S; s++) {
-          if (!a.halo) load_a(kb * a.KC, bx + s * a.dil, by + r * a.dil);
+          if (!a.halo || (r | s) == 0) {
+            const int px = a.halo ? bx : bx + s * a.dil, py = a.halo ? by : by + r * a.dil;
+            mbar_wait(&a_empty[a_st], a_ph ^ 1u);
+            if (elect_one()) {
+              uint8_t* dst = a_smem + (size_t)a_st * 2 * a.a_plane;
+              mbar_arrive_expect_tx(&a_full[a_st], 2u * (uint32_t)a.a_box_bytes);
+              if (a.merged_x) {
+                tma_load_4d(&tmA_hi, &a_full[a_st], dst, px * 8, py, kb * a.KC, n_img);
+                tma_load_4d(&tmA_lo, &a_full[a_st], dst + a.a_plane, px * 8, py, kb * a.KC, n_img);
+              } else {
+                tma_load_5d(&tmA_hi, &a_full[a_st], dst, 0, px, py, kb * a.KC, n_img);
+                tma_load_5d(&tmA_lo, &a_full[a_st], dst + a.a_plane, 0, px, py, kb * a.KC, n_img);
+              }
+            }
+            __syncwarp();
+            if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
+          }
           if (tin == 0) {
             mbar_wait(&w_empty[w_st], w_ph ^ 1u);
-            mbar_arrive_expect_tx(&w_full[w_st], w_bytes);
-            bulk_load_1d(w_smem + (size_t)w_st * a.w_stage, wsrc, w_bytes, &w_full[w_st]);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&w_full[w_st], w_bytes);
+              bulk_load_1d(w_smem + (size_t)w_st * a.w_stage, wsrc, w_bytes, &w_full[w_st]);
+            }
+            __syncwarp();
             wsrc += w_bytes;
             if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
           }
@@ -267,7 +278,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
           tc_fence_after();
           const bool w_done = (tin == a.TPS - 1);
-          if (lane == 0) {
+          if (elect_one()) {
             uint32_t aa0 = a_addr_stage + tap_off, ww = w_addr_tap;
             for (int ks = 0; ks < ksteps; ks++, aa0 += a_kstep, ww += w_kstep) {
               const uint64_t dWh = ((uint64_t)w_hi32 << 32) | (w_lo32 + ((ww & 0x3FFFFu) >> 4));
@@ -296,7 +307,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
     }
-    if (lane == 0) umma_commit(tmem_full_bar);  // accumulators complete
+    if (elect_one()) umma_commit(tmem_full_bar);  // accumulators complete
     __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue =====
