@@ -49,6 +49,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -149,6 +152,7 @@ struct UmmaConvArgs {
   int box_w, box_h;          // A box (pixels) as it lies in shared memory
   int KC, kblocks;           // 8-channel chunks per k-block (even); k-blocks
   int BN, Cout;
+  int dbg;                   // ablation switches (PREMVOS_DBG): 1 = producer skips the copies, 2 = issuer skips the MMAs
   int NACC;                  // accumulator replicas (1..3): product p of {lo*hi, hi*lo, hi*hi} accumulates into replica p % NACC;
                              // independent accumulators let the tensor pipe overlap the otherwise serial MMA chain
   int TPS;                   // taps per weight stage (divides R*S): one bulk copy fetches TPS taps x {hi, lo}
@@ -216,7 +220,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (!a.halo || (r | s) == 0) {
             const int px = a.halo ? bx : bx + s * a.dil, py = a.halo ? by : by + r * a.dil;
             mbar_wait(&a_empty[a_st], a_ph ^ 1u);
-            if (elect_one()) {
+            if (a.dbg & 1) {
+              if (elect_one()) mbar_arrive(&a_full[a_st]);
+            } else if (elect_one()) {
               uint8_t* dst = a_smem + (size_t)a_st * 2 * a.a_plane;
               mbar_arrive_expect_tx(&a_full[a_st], 2u * (uint32_t)a.a_box_bytes);
               if (a.merged_x) {
@@ -232,7 +238,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
           if (tin == 0) {
             mbar_wait(&w_empty[w_st], w_ph ^ 1u);
-            if (elect_one()) {
+            if (a.dbg & 1) {
+              if (elect_one()) mbar_arrive(&w_full[w_st]);
+            } else if (elect_one()) {
               mbar_arrive_expect_tx(&w_full[w_st], w_bytes);
               bulk_load_1d(w_smem + (size_t)w_st * a.w_stage, wsrc, w_bytes, &w_full[w_st]);
             }
@@ -255,32 +263,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = (uint32_t)a.w_stage;
     const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = 16u * a_sbo;
     const uint32_t tap_row = a.halo ? (uint32_t)(a.dil * a.box_w) * 16u : 0u, tap_col = a.halo ? (uint32_t)a.dil * 16u : 0u;
-    uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0, w_addr_tap = 0;
+    uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0;
     uint32_t accum = 0;
-    int tin = 0;  // tap index inside the current weight stage
     const int ksteps = a.KC / 2;
     const uint32_t rep_cols = (uint32_t)(a.MT * a.BN);
     const uint32_t rep1 = a.NACC > 1 ? rep_cols : 0u, rep2 = a.NACC > 2 ? 2u * rep_cols : 0u;
+    // One barrier handshake per weight stage (TPS taps): all of its MMAs are issued in one go, one commit
+    // releases the stage.  (A per-tap handshake costs ~500 cycles of mbarrier/commit latency -- more than the
+    // MMAs of one tap.)  Tap mode additionally waits for / releases one A stage per tap.
+    const int wgroups = taps / a.TPS;
     for (int kb = 0; kb < a.kblocks; kb++) {
-      uint32_t row_off = 0;
-      for (int r = 0; r < a.R; r++, row_off += tap_row) {
-        uint32_t tap_off = row_off;
-        for (int s = 0; s < a.S; s++, tap_off += tap_col) {
-          if (!a.halo || (r | s) == 0) {
+      int r = 0, s = 0;
+      uint32_t row_off = 0, tap_off = 0;
+      for (int wg = 0; wg < wgroups; wg++) {
+        if (a.halo && wg == 0) {
+          mbar_wait(&a_full[a_st], a_ph);
+          cur_a = a_st;
+          a_addr_stage = a_base + a_st * a_stage_bytes;
+          if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
+        }
+        mbar_wait(&w_full[w_st], w_ph);
+        tc_fence_after();
+        uint32_t w_addr_tap = w_base + w_st * w_stage_bytes;
+        for (int t = 0; t < a.TPS; t++) {
+          if (!a.halo) {
             mbar_wait(&a_full[a_st], a_ph);
+            tc_fence_after();
             cur_a = a_st;
             a_addr_stage = a_base + a_st * a_stage_bytes;
             if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
           }
-          if (tin == 0) {
-            mbar_wait(&w_full[w_st], w_ph);
-            w_addr_tap = w_base + w_st * w_stage_bytes;
-          }
-          tc_fence_after();
-          const bool w_done = (tin == a.TPS - 1);
           if (elect_one()) {
             uint32_t aa0 = a_addr_stage + tap_off, ww = w_addr_tap;
-            for (int ks = 0; ks < ksteps; ks++, aa0 += a_kstep, ww += w_kstep) {
+            for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aa0 += a_kstep, ww += w_kstep) {
               const uint64_t dWh = ((uint64_t)w_hi32 << 32) | (w_lo32 + ((ww & 0x3FFFFu) >> 4));
               const uint64_t dWl = ((uint64_t)w_hi32 << 32) | (w_lo32 + (((ww + (uint32_t)a.w_plane) & 0x3FFFFu) >> 4));
               uint32_t aa = aa0, d = tmem_base;
@@ -293,18 +308,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               }
               accum = 1u;
             }
-            if (w_done) umma_commit(&w_empty[w_st]);  // frees the weight slot once these MMAs have read it
-            if (!a.halo || (r == a.R - 1 && s == a.S - 1)) umma_commit(&a_empty[cur_a]);
+            if (!a.halo) umma_commit(&a_empty[cur_a]);
           }
           __syncwarp();
           w_addr_tap += 2u * (uint32_t)a.w_plane;
-          if (w_done) {
-            tin = 0;
-            if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
-          } else {
-            tin++;
-          }
+          if (++s == a.S) { s = 0; r++; row_off += tap_row; tap_off = row_off; } else { tap_off += tap_col; }
         }
+        if (elect_one()) {
+          umma_commit(&w_empty[w_st]);                                   // frees the weight slot once read
+          if (a.halo && wg == wgroups - 1) umma_commit(&a_empty[cur_a]);  // ... and the halo box after the last tap
+        }
+        __syncwarp();
+        if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
       }
     }
     if (elect_one()) umma_commit(tmem_full_bar);  // accumulators complete
@@ -445,7 +460,9 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   const int phys = cin_map ? cin_phys : Cin;   // physical input channels (after the view's chunk padding)
   out->CinPhys = phys;
   const int chunks = (phys + 7) / 8;
-  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? 4 : 8);
+  // measured on B200 (tools/conv_sweep.py): 3x3 with a wide N tile runs best with 16-channel k-blocks and two
+  // co-resident CTAs per SM; narrow N tiles and 1x1 layers want longer k-blocks (fewer barrier handshakes)
+  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? (Cout >= 64 ? 2 : 4) : 8);
   kc = env_int("PREMVOS_KC", kc);
   if (kc > round_up(chunks, 2)) kc = round_up(chunks, 2);
   PV_CHECK(kc >= 2 && (kc % 2) == 0 && kc <= 16, PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: KC=%d", kc);
@@ -522,7 +539,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.w_plane = w.KC * w.BN * 16;
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
   const long ctas_mt2 = (long)a.tiles_x * ((Ho + 31) / 32) * in.N * w.ntiles;
-  int mt_pref = (ctas_mt2 >= 2 * 148 && Ho > 16) ? 2 : 1;
+  int mt_pref = (ctas_mt2 >= 2 * 148 && Ho > 16 && g.dil < 4) ? 2 : 1;
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
   const int tps_env = env_int("PREMVOS_TPS", 0);
@@ -548,7 +565,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     // taps per weight stage: fewer, larger bulk copies (a TMA request has a fixed cost), <= 48 KB each
     for (int t = taps; t >= 1 && !found; t--) {
       if (taps % t != 0 || !(t <= w.S || t % w.S == 0)) continue;
-      if (tps_env ? (t != tps_env) : (t > 1 && t * 2 * a.w_plane > 48 * 1024)) continue;
+      if (tps_env ? (t != tps_env) : (t > 1 && t * 2 * a.w_plane > 24 * 1024)) continue;
       a.TPS = t;
       a.w_stage = round_up(t * 2 * a.w_plane, 128);
       a.w_stages = 2;
@@ -558,8 +575,10 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);
   a.tiles_y = (Ho + 16 * a.MT - 1) / (16 * a.MT);
   // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
-  const int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
-  while (a.w_stages < MAX_W_STAGES && a.w_stages * a.TPS < 2 * taps + 2 &&
+  int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
+  if (env_int("PREMVOS_BUDGET_KB", 0) > 0) budget = env_int("PREMVOS_BUDGET_KB", 0) * 1024;
+  if (a.halo && budget > 120 * 1024) a.a_stages = 3;
+  while (a.w_stages < MAX_W_STAGES && a.w_stages * a.TPS < 3 * taps &&
          a.a_stages * 2 * a.a_plane + (a.w_stages + 1) * a.w_stage + 1024 <= budget)
     a.w_stages++;
   while (!a.halo && a.a_stages < MAX_A_STAGES && a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 2 * a.a_plane + 1024 <= budget)
@@ -570,6 +589,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
   a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
+  a.dbg = env_int("PREMVOS_DBG", 0);
   a.NACC = env_int("PREMVOS_NACC", 1);
   PV_CHECK(a.NACC >= 1 && a.NACC <= 3 && a.NACC * a.MT * w.BN <= 512, PREMVOS_ERR_INVALID_ARG, "conv_umma: NACC=%d does not fit TMEM", a.NACC);
   uint32_t cols = 32;

@@ -219,6 +219,12 @@ std::vector<int> slab_cin_map(int L, int in_off) {
   return m;
 }
 
+// true when a decoder layer of level L launches fewer 128-pixel tiles than the GPU has SMs
+bool small_grid(const premvos_pwc* n, int L) {
+  const long tiles = (long)n->B * (((n->H >> L) + 15) / 16) * (((n->W >> L) + 7) / 8);
+  return tiles < 148;
+}
+
 int pack_weights_tc(premvos_pwc* n) {
   for (int L = 1; L <= 6; L++)
     for (int j = 0; j < 3; j++) {
@@ -238,8 +244,9 @@ int pack_weights_tc(premvos_pwc* n) {
       std::string k = "conv" + std::to_string(L) + "_" + std::to_string(i) + ".0";
       std::vector<int> map = slab_cin_map(L, DEC_IN_OFF[i]);
       PV_CHECK((int)map.size() == cin, PREMVOS_ERR_INVALID_ARG, "internal: slab map size %d != %d", (int)map.size(), cin);
+      // levels 6..4 launch fewer CTAs than there are SMs: latency-bound K loops want long k-blocks
       PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3, map.data(),
-                                    phys_total - DEC_IN_OFF[i]));
+                                    phys_total - DEC_IN_OFF[i], small_grid(n, L) ? 8 : 0));
       cin += DEC_OUT[i];
     }
     // head = predict_flowL (2 ch) fused with upfeatL: ConvTranspose2d(cin, 2, 4, 2, 1) == 3x3 convolution with
@@ -276,7 +283,8 @@ int pack_weights_tc(premvos_pwc* n) {
       PV_CUDA(cudaMemcpy(n->d_deconv_w[L], dw.data(), 66 * sizeof(float), cudaMemcpyHostToDevice));
     }
     std::vector<int> map = slab_cin_map(L, 0);
-    PV_TRY(pack_conv_weights_umma(&n->wt_head[L], hw.data(), hb.data(), hc, cin, 3, 3, map.data(), phys_total));
+    PV_TRY(pack_conv_weights_umma(&n->wt_head[L], hw.data(), hb.data(), hc, cin, 3, 3, map.data(), phys_total,
+                                  small_grid(n, L) ? 8 : 0));
   }
   int cin = level_od(2) + 448;
   for (int i = 0; i < 6; i++) {

@@ -28,7 +28,7 @@ SHAPES = {
 
 def run(name, env):
     N, Cin, H, W, Cout, k, stride, dil = SHAPES[name]
-    for key in ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_NACC"):
+    for key in ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_NACC", "PREMVOS_DBG", "PREMVOS_BUDGET_KB"):
         os.environ.pop(key, None)
     os.environ.update({k2: str(v) for k2, v in env.items() if v is not None})
     x = torch.randn(N, Cin, H, W, device="cuda")
@@ -52,8 +52,8 @@ if __name__ == "__main__":
     for name in names:
         print("==", name, SHAPES[name])
         k = SHAPES[name][5]
-        for kc, tps in ([(2, 3), (4, 3), (8, 1)] if k == 3 else [(2, None), (8, None)]):
+        for kc, tps in ([(2, 1), (2, 3), (4, 1), (4, 3)] if k == 3 else [(4, None), (8, None)]):
             for mt in (1, 2):
-                for nacc in (1, 2, 3):
-                    us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt, "PREMVOS_NACC": nacc})
-                    print("  KC=%s TPS=%s MT=%s NACC=%s: %s %s" % (kc, tps, mt, nacc, "%.1f us" % us if us else "--", note), flush=True)
+                for bud in (110, 160, 226):
+                    us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt, "PREMVOS_BUDGET_KB": bud})
+                    print("  KC=%s TPS=%s MT=%s NACC=%s: %s %s" % (kc, tps, mt, bud, "%.1f us" % us if us else "--", note), flush=True)
