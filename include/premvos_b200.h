@@ -17,6 +17,9 @@
  *   premvos_pwc_*          <- models.pwc_dc_net(path) / PWCDCNet.forward, models/PWCNet.py:179-272,
  *                             496-505, driven by script_pwc_multi.py:33-70 (one device round trip
  *                             per frame pair)
+ *   premvos_propnet_*      <- tensorpack OfflinePredictor `pred_func(img)` over proposal_net/train.py's
+ *                             Model (train.py:107-309, 653-657), called by eval.py:61-110 / train.py:508
+ *   premvos_conv2d_forward <- one nn.Conv2d / tensorpack Conv2D layer (bring-up hook)
  */
 #ifndef PREMVOS_B200_H
 #define PREMVOS_B200_H
@@ -128,6 +131,69 @@ int premvos_pwc_set_option(premvos_pwc_t* net, const char* key, int value);
  * "up_feat6".."up_feat3", "dc6".  *numel receives the element count; pass host_out = NULL to query. */
 int premvos_pwc_get_tensor(premvos_pwc_t* net, const char* name, float* host_out, int64_t* numel);
 void premvos_pwc_destroy(premvos_pwc_t* net);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index-exact pieces of the proposal network as single ops (host pointers; parity hooks).
+ * premvos_topk_host <- tf.nn.top_k(scores, k, sorted=False) (proposal_net/model.py:189-190): the k (<= 1024)
+ *   largest of n scores; returned ordered by (score descending, index ascending).
+ * premvos_nms_host  <- tf.image.non_max_suppression(boxes, scores, max_output_size, iou_threshold)
+ *   (model.py:205-209, 466-467), n <= 1024 boxes [n,4] (either corner order): greedy by descending score, ties
+ *   broken by the lower index, a box is dropped when its IoU with a kept box is > iou_threshold; IoU in fp32 with
+ *   TensorFlow's operation order, so the selected INDICES are bit-exact with the oracle on identical inputs.
+ * --------------------------------------------------------------------------------------------- */
+int premvos_topk_host(const float* scores, int n, int k, int* indices_out, int* count_out);
+int premvos_nms_host(const float* boxes, const float* scores, int n, float iou_threshold, int max_output_size,
+                     int* selected_out, int* count_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Proposal network forward: ResNet-101 C4 Faster R-CNN, class-agnostic, with the second classification
+ * head -- the graph `train.py --forward --agnostic --second_head` builds (proposal_net/train.py:107-189,
+ * 274-295; basemodel.py:12-99; model.py:18-51, 114-139, 170-217, 301-395, 439-491, 552-565) and that
+ * tensorpack's OfflinePredictor exposes as `pred_func(img)` (train.py:653-657, 508; eval.py:61-110).
+ *
+ * Life cycle: create(H, W of the ALREADY RESIZED image, num_class = 2, second_num_class = 81)
+ *   [-> set_option("num_blocks0".."num_blocks3", count): ResNet depth, default 3,4,23,3 (config.py:61)]
+ *   -> set_param(name, host fp32, numel) for every tensorpack variable, names and layouts as in a
+ *      tensorpack checkpoint: "conv0/W" (HWIO), "conv0/bn/gamma|beta|mean/EMA|variance/EMA",
+ *      "group{0..3}/block{i}/{conv1,conv2,conv3,convshortcut}/...", "rpn/conv0/{W,b}", "rpn/class/{W,b}",
+ *      "rpn/box/{W,b}", "fastrcnn/{class,box}/{W,b}" (FullyConnected: [in,out]), "secondclassification/class/{W,b}"
+ *   -> finalize() (folds the frozen BatchNorms, packs weights, allocates every buffer, plans every launch)
+ *   -> forward*() -> destroy().
+ *
+ * img : fp32 [H, W, 3], BGR, 0..255, un-normalised (the graph normalises, basemodel.py:12-26).
+ * Results = the six tensors of get_model_output_names() (train.py:52-62), at most 20 rows
+ * (RESULTS_PER_IM, config.py:123): final_boxes [n,4] x1y1x2y2 in resized-image coordinates, final_probs [n],
+ * final_labels [n] (int64, always 1 when class-agnostic), final_posterior [n,2], second_final_labels [n]
+ * (int64), second_final_posterior [n,second_num_class].  Row order: ascending proposal index (the reference
+ * leaves it unspecified: tf.nn.top_k(sorted=False), model.py:485-488).  The reference's quirk of gathering
+ * label_probs with the CATEGORY index (train.py:287-288) is reproduced.
+ *
+ * premvos_propnet_forward       : img is a DEVICE pointer; enqueues on `stream`, does not synchronise;
+ *                                 fetch with premvos_propnet_read_results (synchronises `stream`).
+ * premvos_propnet_forward_host  : img and all outputs are HOST pointers; copies, runs, synchronises.
+ * Any output pointer except n_out may be NULL.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct premvos_propnet premvos_propnet_t;
+
+int premvos_propnet_create(premvos_propnet_t** out, int height, int width, int num_class, int second_num_class);
+int premvos_propnet_set_option(premvos_propnet_t* net, const char* key, int value);
+int premvos_propnet_set_param(premvos_propnet_t* net, const char* name, const float* host_data, int64_t numel);
+int premvos_propnet_finalize(premvos_propnet_t* net);
+int premvos_propnet_forward(premvos_propnet_t* net, const float* img_dev, void* stream);
+int premvos_propnet_read_results(premvos_propnet_t* net, void* stream, int* n_out, float* final_boxes, float* final_probs,
+                                 int64_t* final_labels, float* final_posterior, int64_t* second_final_labels,
+                                 float* second_final_posterior);
+int premvos_propnet_forward_host(premvos_propnet_t* net, const float* img_host, int* n_out, float* final_boxes,
+                                 float* final_probs, int64_t* final_labels, float* final_posterior,
+                                 int64_t* second_final_labels, float* second_final_posterior);
+int premvos_propnet_launches_per_forward(const premvos_propnet_t* net);
+/* Test hook: intermediates of the LAST forward as fp32 (CP8 activations are returned NCHW; index tensors are
+ * converted to fp32).  Names: "conv0", "pool0", "block<i>", "featuremap", "rpn_hidden", "rpn_out" ([fh,fw,80]:
+ * 15 logits + 60 deltas), "rpn_scores", "rpn_decoded_boxes", "topk_indices", "nms_keep", "proposal_boxes",
+ * "proposal_scores", "roi_resized", "feature_fastrcnn", "pooled", "head_logits", "fastrcnn_all_probs",
+ * "fastrcnn_all_boxes", "final_box_index", "cell_anchors".  Pass host_out = NULL to query *numel. */
+int premvos_propnet_get_tensor(premvos_propnet_t* net, const char* name, float* host_out, int64_t* numel);
+void premvos_propnet_destroy(premvos_propnet_t* net);
 
 #ifdef __cplusplus
 }

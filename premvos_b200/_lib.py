@@ -15,6 +15,10 @@ EXPORTS = [
     "premvos_pwc_create", "premvos_pwc_set_param", "premvos_pwc_finalize", "premvos_pwc_forward",
     "premvos_pwc_forward_host", "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
     "premvos_pwc_get_tensor", "premvos_pwc_destroy", "premvos_pwc_tensor_core_layers",
+    "premvos_propnet_create", "premvos_propnet_set_option", "premvos_propnet_set_param", "premvos_propnet_finalize",
+    "premvos_propnet_forward", "premvos_propnet_read_results", "premvos_propnet_forward_host",
+    "premvos_propnet_launches_per_forward", "premvos_propnet_get_tensor", "premvos_propnet_destroy",
+    "premvos_topk_host", "premvos_nms_host",
 ]
 
 _lib = None
@@ -56,6 +60,19 @@ def lib() -> ctypes.CDLL:
     L.premvos_pwc_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
     L.premvos_pwc_destroy.argtypes = [c_void_p]
     L.premvos_pwc_destroy.restype = None
+    L.premvos_topk_host.argtypes = [c_void_p, c_int, c_int, c_void_p, P(c_int)]
+    L.premvos_nms_host.argtypes = [c_void_p, c_void_p, c_int, ctypes.c_float, c_int, c_void_p, P(c_int)]
+    L.premvos_propnet_create.argtypes = [P(c_void_p), c_int, c_int, c_int, c_int]
+    L.premvos_propnet_set_option.argtypes = [c_void_p, c_char_p, c_int]
+    L.premvos_propnet_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
+    L.premvos_propnet_finalize.argtypes = [c_void_p]
+    L.premvos_propnet_forward.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.premvos_propnet_read_results.argtypes = [c_void_p, c_void_p, P(c_int)] + [c_void_p] * 6
+    L.premvos_propnet_forward_host.argtypes = [c_void_p, c_void_p, P(c_int)] + [c_void_p] * 6
+    L.premvos_propnet_launches_per_forward.argtypes = [c_void_p]
+    L.premvos_propnet_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
+    L.premvos_propnet_destroy.argtypes = [c_void_p]
+    L.premvos_propnet_destroy.restype = None
     _lib = L
     return L
 

@@ -221,6 +221,33 @@ int flow_finish(const TView& a, const TView& b, float* out_nchw, cudaStream_t st
 int nchw_to_cp8(const float* src, const CView& dst, cudaStream_t st);
 int cp8_to_nchw(const CView& src, int ch_off, float* dst, cudaStream_t st);
 
+// ---- detection-side kernels of the proposal network, det_ops.cu ---------------------------------------
+int det_preprocess(const float* img_hwc_dev, const CView& out, cudaStream_t st);           // basemodel.py:12-26
+int det_maxpool3x3s2(const CView& in, const CView& out, cudaStream_t st);                  // basemodel.py:81-82
+int det_rpn_decode(const float* rpn, int cs, int fh, int fw, int na, const float* cell_anchors, float stride, float clip,
+                   float* scores, float* boxes, cudaStream_t st);                          // model.py:114-139
+// k best of n scores as (index, score) sorted by (score desc, index asc); k <= 1024
+int det_topk(const float* scores, int n, int k, int* out_idx, float* out_score, int* out_count, cudaStream_t st);
+int det_gather_clip_valid(const float* boxes, const int* idx, const float* score, const int* count, float img_h, float img_w,
+                          float min_size, float* out_boxes, float* out_scores, int* out_src, int* out_count, cudaStream_t st);
+// greedy NMS over <= 1024 boxes already sorted by descending score; keep[] = positions, TensorFlow IoU arithmetic
+int det_nms(const float* boxes_sorted, const int* count, float thr, int max_out, uint32_t* mask_scratch /*[1024*32]*/, int* keep,
+            int* keep_count, cudaStream_t st);
+int det_gather_proposals(const float* boxes, const float* scores, const int* keep, const int* keep_count, int max_out,
+                         float* out_boxes, float* out_scores, cudaStream_t st);
+int det_roi_align(const CView& fm, const float* rois, float spatial_scale, int out_size, const CView& out, cudaStream_t st);
+int det_gap_fc(const CView& feat, const float* Wt, const float* bias, int nout, float* pooled_out, float* out, cudaStream_t st);
+struct DetTailArgs {
+  const float* logits; int nfc, nsecond;
+  const float* prop_boxes; const int* prop_count;
+  float img_h, img_w, clip, score_thresh, nms_thresh;
+  int max_rois, results_per_im;
+  float* all_probs; float* all_boxes; float* second_probs;
+  int* n_out; float* final_boxes; float* final_probs; int64_t* final_labels; float* final_posterior;
+  int64_t* second_final_labels; float* second_final_posterior; int* final_box_index;
+};
+int det_frcnn_tail(const DetTailArgs& a, cudaStream_t st);                                  // train.py:275-295
+
 // ---- layout / format conversion, layout.cu ---------------------------------------------------------
 // NCHW fp32 [N,C,H,W] -> channels-last view (fp32 or split)
 int nchw_to_view(const float* src, const TView& dst, cudaStream_t st);

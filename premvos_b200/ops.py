@@ -41,3 +41,27 @@ def conv2d(x: torch.Tensor, weight, bias=None, stride=1, dilation=1, padding=(0,
             x.data_ptr(), w.ctypes.data_as(ctypes.c_void_p), None if b is None else b.ctypes.data_as(ctypes.c_void_p),
             res_ptr, out.data_ptr(), N, Cin, H, W, Cout, kh, kw, stride, dilation, pt, pl, pb, pr, float(slope), st))
     return out
+
+
+def top_k(scores: np.ndarray, k: int) -> np.ndarray:
+    """tf.nn.top_k indices (proposal_net/model.py:189-190), ordered by (score desc, index asc); k <= 1024."""
+    s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1)
+    out = np.zeros(1024, np.int32)
+    n = ctypes.c_int()
+    _lib.check(_lib.lib().premvos_topk_host(s.ctypes.data_as(ctypes.c_void_p), s.size, int(k),
+                                            out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+    return out[:n.value].copy()
+
+
+def non_max_suppression(boxes: np.ndarray, scores: np.ndarray, max_output_size: int, iou_threshold: float) -> np.ndarray:
+    """tf.image.non_max_suppression (proposal_net/model.py:205-209, 466-467) for <= 1024 boxes -> int32 indices."""
+    b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+    s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1)
+    if b.shape[0] != s.size:
+        raise ValueError("boxes and scores disagree: %d vs %d" % (b.shape[0], s.size))
+    out = np.zeros(1024, np.int32)
+    n = ctypes.c_int()
+    _lib.check(_lib.lib().premvos_nms_host(b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), s.size,
+                                           float(iou_threshold), int(max_output_size), out.ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.byref(n)))
+    return out[:n.value].copy()

@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's proposal call surface, backed by the CUDA library.
+
+Reference surface reproduced here (paths relative to code/proposal_net):
+  pred_func(img) -> (final_boxes, final_probs, final_labels, final_posterior, second_final_labels,
+                     second_final_posterior)                      train.py:52-62, 653-657 (OfflinePredictor)
+  detect_one_image(img, model_func) -> [SecondDetectionResult]     eval.py:24-26, 61-110
+  CustomResize(800, 1333)                                          common.py:35-62
+  convert_results_to_json(results, img_idx)                        train.py:388-428
+
+All tensor arithmetic runs in libpremvos_b200.so; there is no TensorFlow, PyTorch-op or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict, namedtuple
+
+import numpy as np
+
+from . import _lib
+from .synth import propnet_param_shapes
+
+SHORT_EDGE_SIZE, MAX_SIZE, RESULTS_PER_IM = 800, 1333, 20
+
+SecondDetectionResult = namedtuple(
+    "SecondDetectionResult",
+    ["box", "score", "class_id", "posterior", "mask", "second_class_id", "second_posterior", "feature_fastrcnn_pooled"])
+
+
+class ProposalNet:
+    """The `--forward --agnostic --second_head` graph.  `load_params(dict)` takes tensorpack variable names
+    (as `get_model_loader(path)` would restore them); device handles are created per resized-image shape."""
+
+    def __init__(self, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81):
+        self.num_blocks = tuple(num_blocks)
+        self.num_class = num_class
+        self.second_num_class = second_num_class
+        self._shapes = propnet_param_shapes(self.num_blocks, num_class, second_num_class)
+        self._params = OrderedDict()
+        self._handles = {}
+
+    def load_params(self, params):
+        missing = [k for k in self._shapes if k not in params]
+        unexpected = [k for k in params if k not in self._shapes]
+        if missing or unexpected:
+            raise RuntimeError("proposal_net variables: missing %s, unexpected %s" % (missing[:5], unexpected[:5]))
+        for k, shp in self._shapes.items():
+            v = np.ascontiguousarray(params[k], dtype=np.float32)
+            if tuple(v.shape) != tuple(shp):
+                raise RuntimeError("size mismatch for %s: got %s, expected %s" % (k, tuple(v.shape), tuple(shp)))
+            self._params[k] = v
+        self._drop_handles()
+        return self
+
+    def _drop_handles(self):
+        for h in self._handles.values():
+            _lib.lib().premvos_propnet_destroy(h)
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            self._drop_handles()
+        except Exception:
+            pass
+
+    def _handle(self, H, W):
+        key = (H, W)
+        if key in self._handles:
+            return self._handles[key]
+        if not self._params:
+            raise RuntimeError("ProposalNet: load_params() first")
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(L.premvos_propnet_create(ctypes.byref(h), H, W, self.num_class, self.second_num_class))
+        try:
+            for g, nb in enumerate(self.num_blocks):
+                _lib.check(L.premvos_propnet_set_option(h, b"num_blocks%d" % g, int(nb)))
+            for k, v in self._params.items():
+                _lib.check(L.premvos_propnet_set_param(h, k.encode(), v.ctypes.data_as(ctypes.c_void_p), v.size))
+            _lib.check(L.premvos_propnet_finalize(h))
+        except Exception:
+            L.premvos_propnet_destroy(h)
+            raise
+        self._handles[key] = h
+        return h
+
+    def launches_per_forward(self, H, W):
+        return int(_lib.lib().premvos_propnet_launches_per_forward(self._handle(H, W)))
+
+    # -- pred_func -----------------------------------------------------------------------------------
+    def __call__(self, img):
+        """img: [h,w,3] BGR uint8 or float32 (0..255), already resized (eval.py:75-78)."""
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected an [h,w,3] BGR image, got %s" % (img.shape,))
+        H, W = img.shape[:2]
+        h = self._handle(H, W)
+        n = ctypes.c_int()
+        boxes = np.zeros((RESULTS_PER_IM, 4), np.float32)
+        probs = np.zeros((RESULTS_PER_IM,), np.float32)
+        labels = np.zeros((RESULTS_PER_IM,), np.int64)
+        post = np.zeros((RESULTS_PER_IM, self.num_class), np.float32)
+        slabels = np.zeros((RESULTS_PER_IM,), np.int64)
+        spost = np.zeros((RESULTS_PER_IM, max(self.second_num_class, 1)), np.float32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(_lib.lib().premvos_propnet_forward_host(h, vp(img), ctypes.byref(n), vp(boxes), vp(probs), vp(labels),
+                                                           vp(post), vp(slabels), vp(spost)))
+        m = n.value
+        return (boxes[:m].copy(), probs[:m].copy(), labels[:m].copy(), post[:m].copy(), slabels[:m].copy(),
+                spost[:m, :self.second_num_class].copy())
+
+    def get_tensor(self, name, H, W):
+        L = _lib.lib()
+        h = self._handle(H, W)
+        n = ctypes.c_int64()
+        _lib.check(L.premvos_propnet_get_tensor(h, name.encode(), None, ctypes.byref(n)))
+        buf = np.empty(n.value, dtype=np.float32)
+        if n.value:
+            _lib.check(L.premvos_propnet_get_tensor(h, name.encode(), buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+        return buf
+
+
+def custom_resize_shape(h, w, size=SHORT_EDGE_SIZE, max_size=MAX_SIZE):
+    """CustomResize._get_augment_params (common.py:49-62)"""
+    scale = size * 1.0 / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh = newh * scale
+        neww = neww * scale
+    return int(newh + 0.5), int(neww + 0.5)
+
+
+def clip_boxes(boxes, shape):
+    """common.py:107-119"""
+    orig_shape = boxes.shape
+    boxes = boxes.reshape([-1, 4])
+    h, w = shape
+    boxes[:, [0, 1]] = np.maximum(boxes[:, [0, 1]], 0)
+    boxes[:, 2] = np.minimum(boxes[:, 2], w)
+    boxes[:, 3] = np.minimum(boxes[:, 3], h)
+    return boxes.reshape(orig_shape)
+
+
+def detect_one_image(img, model_func, size=SHORT_EDGE_SIZE, max_size=MAX_SIZE):
+    """eval.py:61-110 for USE_SECOND_HEAD without masks / feature extraction."""
+    import cv2
+    orig_shape = img.shape[:2]
+    newh, neww = custom_resize_shape(orig_shape[0], orig_shape[1], size, max_size)
+    resized_img = cv2.resize(img, (neww, newh), interpolation=cv2.INTER_LINEAR)
+    scale = (resized_img.shape[0] * 1.0 / img.shape[0] + resized_img.shape[1] * 1.0 / img.shape[1]) / 2
+    boxes, probs, labels, posteriors, second_labels, second_posteriors = model_func(resized_img)
+    boxes = boxes / scale
+    boxes = clip_boxes(boxes, orig_shape)
+    masks = [None] * len(boxes)
+    features = [None for _ in range(labels.size)]
+    return [SecondDetectionResult(*args) for args in
+            zip(boxes, probs, labels, posteriors, masks, second_labels, second_posteriors, features)]
+
+
+def convert_results_to_json(results, img_idx=None):
+    """train.py:388-428: [{'bbox': [x, y, w, h] (1 decimal), 'score': (2 decimals)}]"""
+    img_res = []
+    for r in results:
+        box = np.array(r.box, dtype=np.float64)
+        box[2] -= box[0]
+        box[3] -= box[1]
+        img_res.append({"bbox": list(map(lambda x: float(round(x, 1)), box)), "score": float(round(float(r.score), 2))})
+    return img_res

@@ -121,3 +121,89 @@ def synthetic_pwc_input(batch: int, h_: int, w_: int, seed: int = 1) -> np.ndarr
         for k, f in enumerate((f1, f2)):
             out[b, 3 * k:3 * k + 3] = np.transpose(f[:, :, ::-1].astype(np.float32) / np.float32(255.0), (2, 0, 1))
     return out
+
+
+# ---- proposal network (tensorpack variable names, proposal_net/basemodel.py + model.py) -----------------
+def propnet_param_shapes(num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81):
+    t = OrderedDict()
+
+    def conv_bn(scope, k, cin, cout):
+        t[scope + "/W"] = (k, k, cin, cout)  # HWIO
+        for v in ("gamma", "beta", "mean/EMA", "variance/EMA"):
+            t[scope + "/bn/" + v] = (cout,)
+
+    conv_bn("conv0", 7, 3, 64)
+    cin = 64
+    for g, (ch, nb) in enumerate(zip((64, 128, 256, 512), num_blocks)):
+        for b in range(nb):
+            s = "group%d/block%d" % (g, b)
+            conv_bn(s + "/conv1", 1, cin, ch)
+            conv_bn(s + "/conv2", 3, ch, ch)
+            conv_bn(s + "/conv3", 1, ch, ch * 4)
+            if cin != ch * 4:
+                conv_bn(s + "/convshortcut", 1, cin, ch * 4)
+            cin = ch * 4
+    t["rpn/conv0/W"] = (3, 3, 1024, 1024)
+    t["rpn/conv0/b"] = (1024,)
+    t["rpn/class/W"] = (1, 1, 1024, 15)
+    t["rpn/class/b"] = (15,)
+    t["rpn/box/W"] = (1, 1, 1024, 60)
+    t["rpn/box/b"] = (60,)
+    t["fastrcnn/class/W"] = (2048, num_class)
+    t["fastrcnn/class/b"] = (num_class,)
+    t["fastrcnn/box/W"] = (2048, (num_class - 1) * 4)
+    t["fastrcnn/box/b"] = ((num_class - 1) * 4,)
+    if second_num_class:
+        t["secondclassification/class/W"] = (2048, second_num_class)
+        t["secondclassification/class/b"] = (second_num_class,)
+    return t
+
+
+def propnet_synthetic_params(seed=0, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81):
+    """Seeded weights with trained-net-like statistics: He-normal convolutions, BatchNorm gamma/variance near 1
+    (+-10 %), small beta/mean; the last BN of every bottleneck is damped (gamma ~0.25) so that activations neither
+    explode nor vanish through 33 residual blocks; head weights wide enough that scores spread over (0,1) and few
+    decisions sit on a threshold."""
+    rng = np.random.default_rng(seed)
+    P = OrderedDict()
+    for name, shape in propnet_param_shapes(num_blocks, num_class, second_num_class).items():
+        if name.endswith("/W") and len(shape) == 4:
+            fan_in = shape[0] * shape[1] * shape[2]
+            std = np.sqrt(2.0 / fan_in)
+            if name.startswith("rpn/class"):
+                std = 3.0 / np.sqrt(fan_in)
+            elif name.startswith("rpn/box"):
+                std = 0.3 / np.sqrt(fan_in)
+            P[name] = (rng.standard_normal(shape) * std).astype(np.float32)
+        elif name.endswith("/W"):
+            std = {"fastrcnn/class/W": 4.0, "fastrcnn/box/W": 1.0}.get(name, 3.0) / np.sqrt(shape[0])
+            P[name] = (rng.standard_normal(shape) * std).astype(np.float32)
+        elif name.endswith("/b"):
+            P[name] = (rng.standard_normal(shape) * 0.05).astype(np.float32)
+        elif name.endswith("bn/gamma"):
+            base = 0.25 if "/conv3/" in name else 1.0
+            P[name] = (base * (1.0 + 0.1 * rng.uniform(-1, 1, shape))).astype(np.float32)
+        elif name.endswith("bn/beta"):
+            P[name] = (0.05 * rng.standard_normal(shape)).astype(np.float32)
+        elif name.endswith("bn/mean/EMA"):
+            P[name] = (0.05 * rng.standard_normal(shape)).astype(np.float32)
+        elif name.endswith("bn/variance/EMA"):
+            P[name] = (1.0 + 0.1 * rng.uniform(-1, 1, shape)).astype(np.float32)
+        else:
+            raise AssertionError(name)
+    return P
+
+
+def synthetic_bgr_frame(h, w, seed=2):
+    """uint8 BGR frame [h,w,3]: low-pass filtered noise (smooth texture) plus a few bright rectangles."""
+    rng = np.random.default_rng(seed)
+    coarse = rng.uniform(0, 255, (h // 8 + 2, w // 8 + 2, 3))
+    img = np.kron(coarse, np.ones((8, 8, 1)))[:h, :w]
+    k = np.ones(5) / 5.0
+    for ax in (0, 1):
+        img = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), ax, img)
+    for _ in range(6):
+        y0, x0 = int(rng.integers(0, max(1, h - 20))), int(rng.integers(0, max(1, w - 20)))
+        hh, ww = int(rng.integers(10, max(11, h // 3))), int(rng.integers(10, max(11, w // 3)))
+        img[y0:y0 + hh, x0:x0 + ww] = rng.uniform(0, 255, 3)
+    return np.clip(img + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
