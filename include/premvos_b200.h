@@ -19,6 +19,8 @@
  *                             per frame pair)
  *   premvos_propnet_*      <- tensorpack OfflinePredictor `pred_func(img)` over proposal_net/train.py's
  *                             Model (train.py:107-309, 653-657), called by eval.py:61-110 / train.py:508
+ *   premvos_refnet_*       <- refinement_net Engine: `engine.trainer.validation_step(feed_dict, extraction_keys)` per
+ *                             proposal (core/Trainer.py:128-133), as driven by MergeTrack/refinement_net_functions.py:38-65
  *   premvos_conv2d_forward <- one nn.Conv2d / tensorpack Conv2D layer (bring-up hook)
  */
 #ifndef PREMVOS_B200_H
@@ -194,6 +196,46 @@ int premvos_propnet_launches_per_forward(const premvos_propnet_t* net);
  * "fastrcnn_all_boxes", "final_box_index", "cell_anchors".  Pass host_out = NULL to query *numel. */
 int premvos_propnet_get_tensor(premvos_propnet_t* net, const char* name, float* host_out, int64_t* numel);
 void premvos_propnet_destroy(premvos_propnet_t* net);
+
+/* ---------------------------------------------------------------------------------------------
+ * Refinement network forward: DeepLabv3+ (Xception-65, output stride 16, ASPP 6/12/18, decoder stride 4) on box crops
+ * with a 4th guidance channel -- the graph refinement_net/configs/{run,live} build (network/deeplab/DeepLabV3Plus.py:13-39,
+ * deeplab/model.py:200-707, deeplab/core/xception.py:70-560, network/SegmentationOutputLayers.py:35-61,106-135) together
+ * with its in-graph input pipeline (datasets/Dataset.py:141-186, datasets/Resize.py:150-193) and the per-proposal loop of
+ * MergeTrack/refinement_net_functions.py:38-65 / forwarding/FewShotSegmentationForwarder.py:85-155, which calls
+ * `engine.trainer.validation_step(feed_dict, extraction_keys)` once per proposal with the whole frame in the feed.
+ *
+ * Life cycle: create(max_batch proposals per launch group, input_size = 385 ("input_size_train", configs/run:27),
+ *   middle_units = 16 (Xception-65; fewer only for tests)) -> set_param(name, host fp32, numel) for every slim variable,
+ *   names and layouts as in the TF checkpoint: "xception_65/entry_flow/conv1_1/weights" (HWIO, 4 input channels),
+ *   ".../BatchNorm/{gamma,beta,moving_mean,moving_variance}",
+ *   "xception_65/<flow>/block<b>/unit_<u>/xception_module/separable_conv<i>_depthwise/depthwise_weights" ([3,3,C,1]),
+ *   ".../separable_conv<i>_pointwise/weights", ".../shortcut/weights", "image_pooling/...", "aspp0/...",
+ *   "aspp{1,2,3}_{depthwise,pointwise}/...", "concat_projection/...", "decoder/feature_projection0/...",
+ *   "decoder/decoder_conv{0,1}_{depthwise,pointwise}/...", "logits/features/{weights,biases}"
+ *   -> finalize() -> forward_host()* -> destroy().
+ *
+ * forward_host: frame = uint8 RGB [height, width, 3] (as scipy imread returns it; the reference divides by 255,
+ *   FewShotFeedSegmentationDataset.py:37); boxes = [num_boxes, 4] fp32 x, y, w, h (proposal['bbox']).  Any number of
+ *   boxes (processed max_batch at a time).  Outputs, all HOST pointers:
+ *     masks        uint8 [num_boxes, height, width], 0/1 = SEGMENTATION_MASK_ORIGINAL_SIZE
+ *     conf_scores  fp32  [num_boxes] = mean over the frame of 2*p' - 1, p' = p where mask else 1 - p
+ *                  (refinement_net_functions.py:58-62)
+ *     posteriors   fp32  [num_boxes, height, width] = SEGMENTATION_POSTERIORS_ORIGINAL_SIZE, or NULL to skip the copy
+ * --------------------------------------------------------------------------------------------- */
+typedef struct premvos_refnet premvos_refnet_t;
+
+int premvos_refnet_create(premvos_refnet_t** out, int max_batch, int input_size, int middle_units);
+int premvos_refnet_set_param(premvos_refnet_t* net, const char* name, const float* host_data, int64_t numel);
+int premvos_refnet_finalize(premvos_refnet_t* net);
+int premvos_refnet_forward_host(premvos_refnet_t* net, const unsigned char* frame_rgb, int height, int width,
+                                const float* boxes_xywh, int num_boxes, unsigned char* masks_out, float* conf_scores_out,
+                                float* posteriors_out);
+int premvos_refnet_launches_per_forward(const premvos_refnet_t* net);
+/* Test hook (state of the LAST batch): "net_input", "xception_out", "low_level", "aspp_concat", "aspp_out", "decoder_in",
+ * "decoder_out" (NCHW), "logits" ([max_batch,h,w,16] channels-last, classes in channels 0..1), "crops" ([max_batch,4]). */
+int premvos_refnet_get_tensor(premvos_refnet_t* net, const char* name, float* host_out, int64_t* numel);
+void premvos_refnet_destroy(premvos_refnet_t* net);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,8 @@ EXPORTS = [
     "premvos_propnet_forward", "premvos_propnet_read_results", "premvos_propnet_forward_host",
     "premvos_propnet_launches_per_forward", "premvos_propnet_get_tensor", "premvos_propnet_destroy",
     "premvos_topk_host", "premvos_nms_host",
+    "premvos_refnet_create", "premvos_refnet_set_param", "premvos_refnet_finalize", "premvos_refnet_forward_host",
+    "premvos_refnet_launches_per_forward", "premvos_refnet_get_tensor", "premvos_refnet_destroy",
 ]
 
 _lib = None
@@ -60,6 +62,14 @@ def lib() -> ctypes.CDLL:
     L.premvos_pwc_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
     L.premvos_pwc_destroy.argtypes = [c_void_p]
     L.premvos_pwc_destroy.restype = None
+    L.premvos_refnet_create.argtypes = [P(c_void_p), c_int, c_int, c_int]
+    L.premvos_refnet_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
+    L.premvos_refnet_finalize.argtypes = [c_void_p]
+    L.premvos_refnet_forward_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.premvos_refnet_launches_per_forward.argtypes = [c_void_p]
+    L.premvos_refnet_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
+    L.premvos_refnet_destroy.argtypes = [c_void_p]
+    L.premvos_refnet_destroy.restype = None
     L.premvos_topk_host.argtypes = [c_void_p, c_int, c_int, c_void_p, P(c_int)]
     L.premvos_nms_host.argtypes = [c_void_p, c_void_p, c_int, ctypes.c_float, c_int, c_void_p, P(c_int)]
     L.premvos_propnet_create.argtypes = [P(c_void_p), c_int, c_int, c_int, c_int]

@@ -193,7 +193,7 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
   alignas(64) unsigned char map_a_hi[128];
   alignas(64) unsigned char map_a_lo[128];
   alignas(16) unsigned char args[256];
-  int grid_x = 0, grid_y = 0, smem_bytes = 0, halo = 0, MT = 0;
+  int grid_x = 0, grid_y = 0, smem_bytes = 0, halo = 0, MT = 0, N = 0;
   double flops = 0, bytes = 0;
 };
 // host_w: torch Conv2d layout [Cout][Cin][R][S].  cin_map (optional): physical channel (inside the input
@@ -202,7 +202,8 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
                            const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0);
 void free_conv_weights_umma(ConvWeightsUmma* w);
 int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g);
-int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st);
+// active_n >= 0: process only the first active_n images of the planned batch
+int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n = -1);
 
 // ---- CP8 companions of the tensor-core path, cp8_ops.cu -----------------------------------------------
 // x: NCHW fp32 [B,6,H,W] -> img CP8 [2B, 1 chunk, H, W] (ch 0..2 = BGR of image 1 for n < B, image 2 for n >= B)
@@ -247,6 +248,21 @@ struct DetTailArgs {
   int64_t* second_final_labels; float* second_final_posterior; int* final_box_index;
 };
 int det_frcnn_tail(const DetTailArgs& a, cudaStream_t st);                                  // train.py:275-295
+
+// ---- refinement-network kernels, refine_ops.cu ------------------------------------------------------------
+// frame uint8 RGB [H,W,3] + boxes [N,4] (x,y,w,h) -> network input CP8 [N,1 chunk,S,S] (RGB in [-1,1], guidance -1/+1) + crop boxes
+int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float* boxes_xywh, int N, int S, const CView& out, int* crops,
+                      cudaStream_t st);
+// w: [9][round_up(C,8)] with BN scale folded, bias [round_up(C,8)]; input coordinate = o*stride + tap*rate - pad
+int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const float* bias, int stride, int rate, int pad, bool pre_relu,
+                     bool post_relu, int n_active, cudaStream_t st);
+int resize_bilinear_ac_cp8(const CView& in, const CView& out, int n_active, cudaStream_t st);   // align_corners=True
+int broadcast_vec_cp8(const float* vec, int C, bool relu, const CView& out, int n_active, cudaStream_t st);
+int gap_fc_relu(const CView& feat, const float* Wt /*[C][nout]*/, const float* bias, int nout, bool relu, float* out, int n_active,
+                cudaStream_t st);
+// logits fp32 channels-last [N,h,w,cs] -> per-proposal full-frame masks (0/1), optional posteriors, sum of (2p'-1) over the frame
+int refine_output(const TView& logits, const int* crops, int N, int S, int H, int W, unsigned char* mask, float* posterior,
+                  double* conf_sum, cudaStream_t st);
 
 // ---- layout / format conversion, layout.cu ---------------------------------------------------------
 // NCHW fp32 [N,C,H,W] -> channels-last view (fp32 or split)

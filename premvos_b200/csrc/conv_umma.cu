@@ -621,21 +621,26 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const double opx = (double)in.N * Ho * Wo;
   plan->flops = 2.0 * opx * (double)w.Cout * w.Cin * taps;
   plan->bytes = 4.0 * ((double)in.N * in.H * in.W * w.Cin + opx * w.Cout + (double)taps * w.Cin * w.Cout);
-  plan->halo = a.halo; plan->MT = a.MT;
+  plan->halo = a.halo; plan->MT = a.MT; plan->N = in.N;
   return 0;
 }
 
-int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st) {
+int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   static bool attr_set = false;
   if (!attr_set) {
     PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   const UmmaConvArgs& a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
+  // the image index is the slowest part of the tile index: a shorter grid processes the first active_n images
+  int grid_x = plan.grid_x;
+  if (active_n >= 0 && active_n < plan.N) grid_x = plan.grid_x / plan.N * active_n;
+  if (grid_x == 0) return 0;
   prof_before(st);
-  conv_umma_kernel<<<dim3(plan.grid_x, plan.grid_y), UMMA_THREADS, plan.smem_bytes, st>>>(
+  conv_umma_kernel<<<dim3(grid_x, plan.grid_y), UMMA_THREADS, plan.smem_bytes, st>>>(
       *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
-  return after_launch("conv_umma_kernel", st, plan.flops, plan.bytes);
+  const double frac = (double)grid_x / plan.grid_x;
+  return after_launch("conv_umma_kernel", st, plan.flops * frac, plan.bytes * frac);
 }
 
 }  // namespace premvos

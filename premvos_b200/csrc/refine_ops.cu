@@ -1,0 +1,344 @@
+// Bandwidth-bound kernels of the refinement network (DeepLabv3+ / Xception-65 on box crops), CP8 activations:
+//   * crop + resize + guidance + normalisation chain that builds the 4-channel network input for every proposal of
+//     a frame in one launch (the reference re-feeds the whole frame over PCIe per proposal and runs the guidance
+//     mask through a CPU py_func, datasets/Dataset.py:141-186, Resize.py:150-193);
+//   * depthwise 3x3 convolution (stride, atrous rate, fixed_padding) with the unit's leading ReLU, the folded
+//     BatchNorm and the optional trailing ReLU fused (deeplab/core/xception.py:92-190, 251-275);
+//   * bilinear resize with align_corners=True (deeplab/model.py:399-400, 570-571), plane broadcast (image pooling);
+//   * the output layer: legacy-TF1 bilinear resize of the logits to the input size, softmax, argmax, nearest /
+//     bilinear resize to the crop size, zero padding back to the frame (network/SegmentationOutputLayers.py:35-61,
+//     106-135) and the conf_score reduction of MergeTrack/refinement_net_functions.py:58-62 -- one kernel, the
+//     only thing that leaves the device is a uint8 mask per proposal and one float.
+#include "cp8.cuh"
+
+namespace premvos {
+
+using namespace cp8;
+
+namespace {
+
+// legacy TF1 resize coordinate (align_corners=False, no half-pixel centres): in = out * (in_size / out_size)
+__device__ __forceinline__ void legacy_axis(int o, float scale, int in_size, int* lo, int* hi, float* lerp) {
+  const float src = __fmul_rn((float)o, scale);
+  const int l = (int)floorf(src);
+  *lo = l;
+  *hi = min(l + 1, in_size - 1);
+  *lerp = __fsub_rn(src, (float)l);
+}
+
+// ---- network input ----------------------------------------------------------------------------------------------
+struct PreArgs {
+  const unsigned char* frame; int H, W;   // uint8 RGB frame
+  const float* boxes;                      // [N][4] x, y, w, h (proposal 'bbox')
+  int N, S;                                // S = network input size (385)
+  CV out;                                  // [N][1 chunk][S][S]: ch 0..2 RGB in [-1,1], ch 3 guidance -1/+1
+  int* crops;                              // [N][4] y0 x0 y1 x1 (CROP_BOXES_y0x0y1x1)
+};
+
+__device__ __forceinline__ void crop_of(const float* b, int H, int W, int* cy0, int* cx0, int* cy1, int* cx1, int* gy0, int* gx0,
+                                        int* gy1, int* gx1) {
+  // FewShotFeedSegmentationDataset.py:40-43 (fp32 placeholder), tf.round / np.round = half to even
+  const float y0 = b[1], x0 = b[0], y1 = __fadd_rn(b[3], b[1]), x1 = __fadd_rn(b[2], b[0]);
+  *gy0 = (int)rintf(y0); *gx0 = (int)rintf(x0); *gy1 = (int)rintf(y1); *gx1 = (int)rintf(x1);
+  *cy0 = max(*gy0 - 50, 0); *cx0 = max(*gx0 - 50, 0); *cy1 = min(*gy1 + 50, H); *cx1 = min(*gx1 + 50, W);   // Resize.py:151-164
+}
+
+__global__ void __launch_bounds__(256) refine_input_kernel(PreArgs a) {
+  const long total = (long)a.N * a.S * a.S;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % a.S), y = (int)((idx / a.S) % a.S), n = (int)(idx / ((long)a.S * a.S));
+  int cy0, cx0, cy1, cx1, gy0, gx0, gy1, gx1;
+  crop_of(a.boxes + n * 4, a.H, a.W, &cy0, &cx0, &cy1, &cx1, &gy0, &gx0, &gy1, &gx1);
+  if (x == 0 && y == 0) { a.crops[n * 4] = cy0; a.crops[n * 4 + 1] = cx0; a.crops[n * 4 + 2] = cy1; a.crops[n * 4 + 3] = cx1; }
+  const int ch = cy1 - cy0, cw = cx1 - cx0;
+  F8 f = zero8();
+  if (ch > 0 && cw > 0) {
+    // image: tf.image.resize_images bilinear (Util.py:25), then (v - mean) / std, then DeepLab's (n*std + mean)*255 and 2/255*u - 1
+    int ylo, yhi, xlo, xhi; float yl, xl;
+    legacy_axis(y, __fdiv_rn((float)ch, (float)a.S), ch, &ylo, &yhi, &yl);
+    legacy_axis(x, __fdiv_rn((float)cw, (float)a.S), cw, &xlo, &xhi, &xl);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      auto px = [&](int yy, int xx) { return (float)((double)a.frame[((long)(cy0 + yy) * a.W + (cx0 + xx)) * 3 + c] / 255.0); };
+      const float tl = px(ylo, xlo), tr = px(ylo, xhi), bl = px(yhi, xlo), br = px(yhi, xhi);
+      const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), xl)), bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), xl));
+      const float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+      const float nrm = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+      const float u = __fmul_rn(__fadd_rn(__fmul_rn(nrm, stdv[c]), mean[c]), 255.f);
+      f.v[c] = __fsub_rn(__fmul_rn(2.0f / 255.0f, u), 1.0f);
+    }
+    // guidance: nearest-neighbour resize of the box mask (Util.py:27-28, BoundingBox.py:15-19)
+    const int sy = min((int)floorf(__fmul_rn((float)y, __fdiv_rn((float)ch, (float)a.S))), ch - 1) + cy0;
+    const int sx = min((int)floorf(__fmul_rn((float)x, __fdiv_rn((float)cw, (float)a.S))), cw - 1) + cx0;
+    const float g = (sy >= max(gy0, 0) && sy < gy1 && sx >= max(gx0, 0) && sx < gx1) ? 1.f : 0.f;
+    f.v[3] = __fsub_rn(__fmul_rn(2.0f / 255.0f, __fmul_rn(g, 255.f)), 1.0f);
+  }
+  st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, 0, y, x), f);
+}
+
+// ---- depthwise 3x3 -----------------------------------------------------------------------------------------------
+struct DwArgs {
+  CV in, out;
+  const float* w;     // [9][Cpad] (BatchNorm scale folded in), Cpad = 8 * chunks
+  const float* bias;  // [Cpad]
+  int stride, rate, pad;   // input coordinate = o*stride + t*rate - pad
+  int pre_relu, post_relu, n_active;
+};
+
+__global__ void __launch_bounds__(256) depthwise3x3_kernel(DwArgs a) {
+  const int nch = (a.in.C + 7) / 8;
+  const long total = (long)a.n_active * nch * a.out.H * a.out.W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % a.out.W), oy = (int)((idx / a.out.W) % a.out.H);
+  const int ch = (int)((idx / ((long)a.out.W * a.out.H)) % nch), n = (int)(idx / ((long)a.out.W * a.out.H * nch));
+  const int cpad = nch * 8;
+  F8 acc = zero8();
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const int iy = oy * a.stride + r * a.rate - a.pad;
+    if (iy < 0 || iy >= a.in.H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const int ix = ox * a.stride + s * a.rate - a.pad;
+      if (ix < 0 || ix >= a.in.W) continue;
+      F8 v = ld_chunk(a.in.hi, a.in.lo, cv_elem(a.in, n, ch, iy, ix));
+      const float4 w0 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float x = a.pre_relu ? fmaxf(v.v[j], 0.f) : v.v[j];
+        acc.v[j] = fmaf(x, wv[j], acc.v[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float t = acc.v[j] + a.bias[ch * 8 + j];
+    acc.v[j] = a.post_relu ? fmaxf(t, 0.f) : t;
+  }
+  st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, ch, oy, ox), acc);
+}
+
+// ---- bilinear resize, align_corners=True ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_ac_kernel(CV in, CV out, int n_active) {
+  const int nch = (in.C + 7) / 8;
+  const long total = (long)n_active * nch * out.H * out.W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % out.W), oy = (int)((idx / out.W) % out.H);
+  const int ch = (int)((idx / ((long)out.W * out.H)) % nch), n = (int)(idx / ((long)out.W * out.H * nch));
+  const float sy = out.H > 1 ? __fdiv_rn((float)(in.H - 1), (float)(out.H - 1)) : __fdiv_rn((float)in.H, (float)out.H);
+  const float sx = out.W > 1 ? __fdiv_rn((float)(in.W - 1), (float)(out.W - 1)) : __fdiv_rn((float)in.W, (float)out.W);
+  int ylo, yhi, xlo, xhi; float yl, xl;
+  legacy_axis(oy, sy, in.H, &ylo, &yhi, &yl);
+  legacy_axis(ox, sx, in.W, &xlo, &xhi, &xl);
+  const F8 tl = ld_chunk(in.hi, in.lo, cv_elem(in, n, ch, ylo, xlo)), tr = ld_chunk(in.hi, in.lo, cv_elem(in, n, ch, ylo, xhi));
+  const F8 bl = ld_chunk(in.hi, in.lo, cv_elem(in, n, ch, yhi, xlo)), br = ld_chunk(in.hi, in.lo, cv_elem(in, n, ch, yhi, xhi));
+  F8 r;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float top = __fadd_rn(tl.v[j], __fmul_rn(__fsub_rn(tr.v[j], tl.v[j]), xl));
+    const float bot = __fadd_rn(bl.v[j], __fmul_rn(__fsub_rn(br.v[j], bl.v[j]), xl));
+    r.v[j] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+  }
+  st_chunk(out.hi, out.lo, cv_elem(out, n, ch, oy, ox), r);
+}
+
+// vec [N][C] (fp32, optional ReLU) -> every pixel of out (image-level feature, model.py:397-400)
+__global__ void __launch_bounds__(256) broadcast_kernel(const float* __restrict__ vec, int C, int relu, CV out, int n_active) {
+  const int nch = (C + 7) / 8;
+  const long total = (long)n_active * nch * out.H * out.W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % out.W), oy = (int)((idx / out.W) % out.H);
+  const int ch = (int)((idx / ((long)out.W * out.H)) % nch), n = (int)(idx / ((long)out.W * out.H * nch));
+  F8 f = zero8();
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (ch * 8 + j < C) {
+      const float v = vec[(long)n * C + ch * 8 + j];
+      f.v[j] = relu ? fmaxf(v, 0.f) : v;
+    }
+  st_chunk(out.hi, out.lo, cv_elem(out, n, ch, oy, ox), f);
+}
+
+// ---- output layer -----------------------------------------------------------------------------------------------------
+struct OutArgs {
+  const float* logits; int lh, lw, lcs;   // fp32 channels-last [N][lh][lw][lcs], classes 0/1
+  const int* crops;                        // [N][4]
+  int N, S, H, W;
+  unsigned char* mask;                     // [N][H][W] 0/1
+  float* posterior;                        // [N][H][W] or null
+  double* conf_sum;                        // [N] sum over the frame of 2*p' - 1
+};
+
+// logits at input resolution (SegmentationOutputLayers.py:36): legacy bilinear of the [lh,lw] logits
+__device__ __forceinline__ void logits_at(const OutArgs& a, int n, int y, int x, float* l0, float* l1) {
+  int ylo, yhi, xlo, xhi; float yl, xl;
+  legacy_axis(y, __fdiv_rn((float)a.lh, (float)a.S), a.lh, &ylo, &yhi, &yl);
+  legacy_axis(x, __fdiv_rn((float)a.lw, (float)a.S), a.lw, &xlo, &xhi, &xl);
+  const float* base = a.logits + (long)n * a.lh * a.lw * a.lcs;
+  const float* ptl = base + ((long)ylo * a.lw + xlo) * a.lcs; const float* ptr = base + ((long)ylo * a.lw + xhi) * a.lcs;
+  const float* pbl = base + ((long)yhi * a.lw + xlo) * a.lcs; const float* pbr = base + ((long)yhi * a.lw + xhi) * a.lcs;
+  float o[2];
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const float top = __fadd_rn(ptl[c], __fmul_rn(__fsub_rn(ptr[c], ptl[c]), xl));
+    const float bot = __fadd_rn(pbl[c], __fmul_rn(__fsub_rn(pbr[c], pbl[c]), xl));
+    o[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+  }
+  *l0 = o[0]; *l1 = o[1];
+}
+__device__ __forceinline__ float fg_prob(float l0, float l1) {  // softmax(...)[1], max-subtracted like tf.nn.softmax
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  return e1 / (e0 + e1);
+}
+
+__global__ void __launch_bounds__(256) refine_output_kernel(OutArgs a) {
+  __shared__ double red[8];
+  const int n = blockIdx.y;
+  const long hw = (long)a.H * a.W;
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double contrib = 0.0;
+  if (p < hw) {
+    const int y = (int)(p / a.W), x = (int)(p % a.W);
+    const int cy0 = a.crops[n * 4], cx0 = a.crops[n * 4 + 1], cy1 = a.crops[n * 4 + 2], cx1 = a.crops[n * 4 + 3];
+    unsigned char m = 0;
+    float post = 0.f;
+    if (y >= cy0 && y < cy1 && x >= cx0 && x < cx1) {
+      const int ch = cy1 - cy0, cw = cx1 - cx0, yy = y - cy0, xx = x - cx0;
+      // class map: nearest-neighbour resize S x S -> crop size (:120-125), argmax of the logits (first max wins)
+      const int sy = min((int)floorf(__fmul_rn((float)yy, __fdiv_rn((float)a.S, (float)ch))), a.S - 1);
+      const int sx = min((int)floorf(__fmul_rn((float)xx, __fdiv_rn((float)a.S, (float)cw))), a.S - 1);
+      float l0, l1;
+      logits_at(a, n, sy, sx, &l0, &l1);
+      m = l1 > l0 ? 1 : 0;
+      // posterior: bilinear (legacy) resize of softmax(logits)[..., 1] from S x S to the crop size
+      int ylo, yhi, xlo, xhi; float yl, xl;
+      legacy_axis(yy, __fdiv_rn((float)a.S, (float)ch), a.S, &ylo, &yhi, &yl);
+      legacy_axis(xx, __fdiv_rn((float)a.S, (float)cw), a.S, &xlo, &xhi, &xl);
+      float q[4];
+      const int ys[2] = {ylo, yhi}, xs[2] = {xlo, xhi};
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          logits_at(a, n, ys[i], xs[j], &l0, &l1);
+          q[i * 2 + j] = fg_prob(l0, l1);
+        }
+      const float top = __fadd_rn(q[0], __fmul_rn(__fsub_rn(q[1], q[0]), xl)), bot = __fadd_rn(q[2], __fmul_rn(__fsub_rn(q[3], q[2]), xl));
+      post = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+    }
+    a.mask[(long)n * hw + p] = m;
+    if (a.posterior) a.posterior[(long)n * hw + p] = post;
+    const float c = m ? post : __fsub_rn(1.0f, post);          // refinement_net_functions.py:58-61
+    contrib = (double)__fsub_rn(__fmul_rn(2.0f, c), 1.0f);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; i++) s += red[i];
+    atomicAdd(a.conf_sum + n, s);
+  }
+}
+
+// global average pool + FC with optional ReLU (image pooling branch: mean -> 1x1 conv + BN + ReLU)
+__global__ void __launch_bounds__(256) gap_fc_relu_kernel(CV feat, const float* __restrict__ Wt, const float* __restrict__ bias, int nout,
+                                                          int relu, float* __restrict__ out) {
+  extern __shared__ float pooled[];
+  const int n = blockIdx.x, C = feat.C, nch = (C + 7) / 8, hw = feat.H * feat.W;
+  for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
+    F8 s = zero8();
+    for (int p = 0; p < hw; p++) {
+      const F8 v = ld_chunk(feat.hi, feat.lo, (((long)n * feat.chunks + feat.c0 + ch) * hw + p) * 8);
+#pragma unroll
+      for (int j = 0; j < 8; j++) s.v[j] += v.v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (ch * 8 + j < C) pooled[ch * 8 + j] = s.v[j] / (float)hw;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = wid; o < nout; o += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(pooled[c], Wt[(long)c * nout + o], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const float v = acc + bias[o];
+      out[(long)n * nout + o] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+
+}  // namespace
+
+int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float* boxes_xywh, int N, int S, const CView& out, int* crops,
+                      cudaStream_t st) {
+  PV_CHECK(out.H == S && out.W == S && N <= out.N, PREMVOS_ERR_INVALID_ARG, "refine_make_input: shape mismatch");
+  PreArgs a{frame_rgb, H, W, boxes_xywh, N, S, dev(out), crops};
+  const long total = (long)N * S * S;
+  if (total == 0) return 0;
+  prof_before(st);
+  refine_input_kernel<<<blocks_for(total), 256, 0, st>>>(a);
+  return after_launch("refine_input_kernel", st, 60.0 * total, (double)total * (12.0 + 32.0));
+}
+
+int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const float* bias, int stride, int rate, int pad, bool pre_relu,
+                     bool post_relu, int n_active, cudaStream_t st) {
+  PV_CHECK(in.C == out.C && in.N == out.N, PREMVOS_ERR_INVALID_ARG, "depthwise3x3_cp8: shape mismatch");
+  DwArgs a{dev(in), dev(out), w, bias, stride, rate, pad, pre_relu ? 1 : 0, post_relu ? 1 : 0, n_active};
+  const long total = (long)n_active * in.vchunks() * out.H * out.W;
+  if (total == 0) return 0;
+  prof_before(st);
+  depthwise3x3_kernel<<<blocks_for(total), 256, 0, st>>>(a);
+  const double frac = (double)n_active / in.N;
+  return after_launch("depthwise3x3_kernel", st, 18.0 * total * 8, 4.0 * frac * ((double)in.pixels() + (double)out.pixels()) * in.C);
+}
+
+int resize_bilinear_ac_cp8(const CView& in, const CView& out, int n_active, cudaStream_t st) {
+  PV_CHECK(in.C == out.C && in.N == out.N, PREMVOS_ERR_INVALID_ARG, "resize_bilinear_ac_cp8: shape mismatch");
+  const long total = (long)n_active * in.vchunks() * out.H * out.W;
+  if (total == 0) return 0;
+  prof_before(st);
+  resize_ac_kernel<<<blocks_for(total), 256, 0, st>>>(dev(in), dev(out), n_active);
+  return after_launch("resize_ac_kernel", st, 6.0 * total * 8, 4.0 * (double)n_active * in.C * ((double)in.H * in.W + (double)out.H * out.W));
+}
+
+int broadcast_vec_cp8(const float* vec, int C, bool relu, const CView& out, int n_active, cudaStream_t st) {
+  const long total = (long)n_active * ((C + 7) / 8) * out.H * out.W;
+  if (total == 0) return 0;
+  prof_before(st);
+  broadcast_kernel<<<blocks_for(total), 256, 0, st>>>(vec, C, relu ? 1 : 0, dev(out), n_active);
+  return after_launch("broadcast_kernel", st, 0.0, 32.0 * total);
+}
+
+int gap_fc_relu(const CView& feat, const float* Wt, const float* bias, int nout, bool relu, float* out, int n_active, cudaStream_t st) {
+  if (n_active == 0) return 0;
+  prof_before(st);
+  gap_fc_relu_kernel<<<n_active, 256, round_up(feat.C, 8) * sizeof(float), st>>>(dev(feat), Wt, bias, nout, relu ? 1 : 0, out);
+  return after_launch("gap_fc_relu_kernel", st, 2.0 * n_active * feat.C * nout, 4.0 * (double)n_active * feat.H * feat.W * feat.C);
+}
+
+int refine_output(const TView& logits, const int* crops, int N, int S, int H, int W, unsigned char* mask, float* posterior,
+                  double* conf_sum, cudaStream_t st) {
+  PV_CHECK(logits.p && logits.coff == 0 && N <= logits.N, PREMVOS_ERR_INVALID_ARG, "refine_output: bad logits view");
+  if (N == 0) return 0;
+  OutArgs a{logits.p, logits.H, logits.W, logits.cs, crops, N, S, H, W, mask, posterior, conf_sum};
+  PV_CUDA(cudaMemsetAsync(conf_sum, 0, (size_t)N * sizeof(double), st));
+  dim3 grid(blocks_for((long)H * W), N);
+  prof_before(st);
+  refine_output_kernel<<<grid, 256, 0, st>>>(a);
+  return after_launch("refine_output_kernel", st, 100.0 * N * H * W, (double)N * H * W * (posterior ? 5.0 : 1.0));
+}
+
+}  // namespace premvos

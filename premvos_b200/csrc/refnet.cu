@@ -1,0 +1,447 @@
+// Refinement network forward (DeepLabv3+ with an Xception-65 backbone on 385x385 box crops, 4 input channels =
+// RGB + box guidance): host-side orchestration and C ABI.
+//
+// Restates refinement_net's inference path (network/deeplab/DeepLabV3Plus.py:13-39, deeplab/model.py:200-707,
+// deeplab/core/xception.py:70-560, network/SegmentationOutputLayers.py:35-61,106-135, datasets/Dataset.py:141-186,
+// datasets/Resize.py:150-193) as a fixed list of launches over pre-allocated CP8 buffers:
+//   * all proposals of a frame are cropped/resized on the device from ONE uploaded uint8 frame and run as a batch
+//     (the reference runs batch 1 and re-feeds the whole float frame per proposal, configs/run:16-17);
+//   * every BatchNorm (frozen: "freeze_batchnorm": true, eps 1e-3 in the backbone, 1e-5 in ASPP/decoder) is folded
+//     into the preceding depthwise / pointwise / regular convolution;
+//   * separable convolution = depthwise kernel (unit ReLU in, BN, optional ReLU out fused) + pointwise 1x1 GEMM on
+//     tcgen05 (conv_umma.cu) whose epilogue adds the unit's shortcut;
+//   * ASPP branches and the decoder concat write straight into chunk ranges of one buffer (no tf.concat copies);
+//   * the output layer, the paste-back into the frame and the conf_score reduction are one kernel.
+#include <math.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace premvos;
+
+namespace {
+
+struct BlockSpec { const char* scope; int depth[3]; int skip; /*0 none 1 conv 2 sum*/ bool act_in_sep; int units; int stride; };
+const float XC_EPS = 1e-3f, ASPP_EPS = 1e-5f;
+
+typedef std::function<int(cudaStream_t, int)> Step;
+
+}  // namespace
+
+struct premvos_refnet {
+  int NB = 0, S = 0, middle_units = 16, n_classes = 2;
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> params;
+  std::map<std::string, std::vector<int64_t>> shapes;
+  std::vector<void*> allocs;
+  std::vector<std::unique_ptr<ConvWeightsUmma>> conv_weights;
+  std::vector<std::unique_ptr<ConvPlanUmma>> conv_plans;
+  std::vector<Step> steps;
+  std::map<std::string, CView> named;   // test hook
+  cudaStream_t stream = nullptr;
+  CView input;
+  TView logits;
+  float* boxes_dev = nullptr; int* crops = nullptr; double* conf_sum = nullptr;
+  unsigned char* frame_dev = nullptr; size_t frame_cap = 0;
+  unsigned char* mask_dev = nullptr; size_t mask_cap = 0;
+  float* post_dev = nullptr; size_t post_cap = 0;
+  int launches_per_forward = 0;
+};
+
+namespace {
+
+std::vector<BlockSpec> block_specs(int middle_units) {
+  return {{"entry_flow/block1", {128, 128, 128}, 1, false, 1, 2},   {"entry_flow/block2", {256, 256, 256}, 1, false, 1, 2},
+          {"entry_flow/block3", {728, 728, 728}, 1, false, 1, 2},   {"middle_flow/block1", {728, 728, 728}, 2, false, middle_units, 1},
+          {"exit_flow/block1", {728, 1024, 1024}, 1, false, 1, 2},  {"exit_flow/block2", {1536, 1536, 2048}, 0, true, 1, 1}};
+}
+
+int64_t numel_of(const std::vector<int64_t>& s) {
+  int64_t n = 1;
+  for (auto d : s) n *= d;
+  return n;
+}
+
+void build_shape_table(premvos_refnet* n) {
+  auto bn = [&](const std::string& s, int c) {
+    for (const char* v : {"gamma", "beta", "moving_mean", "moving_variance"}) n->shapes[s + "/BatchNorm/" + v] = {c};
+  };
+  auto conv = [&](const std::string& s, int k, int cin, int cout) { n->shapes[s + "/weights"] = {k, k, cin, cout}; bn(s, cout); };
+  auto sep = [&](const std::string& s, int cin, int cout) {
+    n->shapes[s + "_depthwise/depthwise_weights"] = {3, 3, cin, 1};
+    bn(s + "_depthwise", cin);
+    conv(s + "_pointwise", 1, cin, cout);
+  };
+  const std::string x = "xception_65/";
+  conv(x + "entry_flow/conv1_1", 3, 4, 32);
+  conv(x + "entry_flow/conv1_2", 3, 32, 64);
+  int cin = 64;
+  for (const BlockSpec& b : block_specs(n->middle_units))
+    for (int u = 0; u < b.units; u++) {
+      const std::string s = x + b.scope + "/unit_" + std::to_string(u + 1) + "/xception_module";
+      int c = cin;
+      for (int i = 0; i < 3; i++) { sep(s + "/separable_conv" + std::to_string(i + 1), c, b.depth[i]); c = b.depth[i]; }
+      if (b.skip == 1) conv(s + "/shortcut", 1, cin, b.depth[2]);
+      cin = b.depth[2];
+    }
+  conv("image_pooling", 1, cin, 256);
+  conv("aspp0", 1, cin, 256);
+  for (int i = 1; i <= 3; i++) sep("aspp" + std::to_string(i), cin, 256);
+  conv("concat_projection", 1, 1280, 256);
+  conv("decoder/feature_projection0", 1, 256, 48);
+  sep("decoder/decoder_conv0", 304, 256);
+  sep("decoder/decoder_conv1", 256, 256);
+  n->shapes["logits/features/weights"] = {1, 1, 256, n->n_classes};
+  n->shapes["logits/features/biases"] = {n->n_classes};
+}
+
+template <typename T>
+int dev_alloc(premvos_refnet* n, T** p, size_t count) {
+  PV_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  PV_CUDA(cudaMemset(*p, 0, count * sizeof(T)));
+  n->allocs.push_back(*p);
+  return 0;
+}
+
+int alloc_cview(premvos_refnet* n, CView* v, int C, int H, int W) {
+  v->N = n->NB; v->H = H; v->W = W; v->chunks = (C + 7) / 8; v->c0 = 0; v->C = C;
+  const size_t elems = (size_t)v->N * v->chunks * H * W * 8;
+  PV_TRY(dev_alloc(n, &v->hi, elems));
+  PV_TRY(dev_alloc(n, &v->lo, elems));
+  return 0;
+}
+
+// BatchNorm inference folded to (scale, shift): slim.batch_norm, (x - mean) * rsqrt(var + eps) * gamma + beta
+void bn_fold(premvos_refnet* n, const std::string& scope, float eps, std::vector<float>* scale, std::vector<float>* shift) {
+  const std::vector<float>&g = n->params[scope + "/BatchNorm/gamma"], &b = n->params[scope + "/BatchNorm/beta"];
+  const std::vector<float>&m = n->params[scope + "/BatchNorm/moving_mean"], &v = n->params[scope + "/BatchNorm/moving_variance"];
+  scale->resize(g.size()); shift->resize(g.size());
+  for (size_t i = 0; i < g.size(); i++) {
+    (*scale)[i] = g[i] / sqrtf(v[i] + eps);
+    (*shift)[i] = b[i] - m[i] * (*scale)[i];
+  }
+}
+
+// regular / pointwise convolution (+ folded BN or bias) on tcgen05; appends the launch to the step list
+int add_conv(premvos_refnet* n, const std::string& scope, bool bn, float eps, const CView& in, const ConvOut& out, ConvGeom g,
+             const int* cin_map = nullptr, int cin_phys = 0) {
+  const std::vector<int64_t>& ws = n->shapes[scope + "/weights"];
+  const int kh = (int)ws[0], kw = (int)ws[1], cin = (int)ws[2], cout = (int)ws[3];
+  const std::vector<float>& W = n->params[scope + "/weights"];
+  std::vector<float> w((size_t)cout * cin * kh * kw), scale(cout, 1.f), shift(cout, 0.f);
+  if (bn) bn_fold(n, scope, eps, &scale, &shift);
+  else if (n->params.count(scope + "/biases")) shift = n->params[scope + "/biases"];
+  for (int y = 0; y < kh; y++)
+    for (int x = 0; x < kw; x++)
+      for (int i = 0; i < cin; i++)
+        for (int o = 0; o < cout; o++)
+          w[(((size_t)o * cin + i) * kh + y) * kw + x] = W[(((size_t)y * kw + x) * cin + i) * cout + o] * scale[o];
+  n->conv_weights.emplace_back(new ConvWeightsUmma());
+  n->conv_plans.emplace_back(new ConvPlanUmma());
+  ConvWeightsUmma* cw = n->conv_weights.back().get();
+  ConvPlanUmma* pl = n->conv_plans.back().get();
+  PV_TRY(pack_conv_weights_umma(cw, w.data(), shift.data(), cout, cin, kh, kw, cin_map, cin_phys));
+  PV_TRY(plan_conv_umma(pl, in, out, *cw, g));
+  n->steps.push_back([pl](cudaStream_t st, int na) { return launch_conv_umma(*pl, st, na); });
+  return 0;
+}
+
+// depthwise 3x3 + folded BN (+ ReLU in / out)
+int add_depthwise(premvos_refnet* n, const std::string& scope, float eps, const CView& in, const CView& out, int stride, int rate,
+                  bool pre_relu, bool post_relu) {
+  const int C = in.C, cpad = round_up(C, 8);
+  const std::vector<float>& W = n->params[scope + "/depthwise_weights"];  // [3][3][C][1]
+  std::vector<float> scale, shift, w((size_t)9 * cpad, 0.f), b(cpad, 0.f);
+  bn_fold(n, scope, eps, &scale, &shift);
+  for (int t = 0; t < 9; t++)
+    for (int c = 0; c < C; c++) w[(size_t)t * cpad + c] = W[(size_t)t * C + c] * scale[c];
+  for (int c = 0; c < C; c++) b[c] = shift[c];
+  float *dw = nullptr, *db = nullptr;
+  PV_TRY(dev_alloc(n, &dw, w.size())); PV_TRY(dev_alloc(n, &db, b.size()));
+  PV_CUDA(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  PV_CUDA(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  CView i2 = in, o2 = out;
+  n->steps.push_back([=](cudaStream_t st, int na) { return depthwise3x3_cp8(i2, o2, dw, db, stride, rate, rate, pre_relu, post_relu, na, st); });
+  return 0;
+}
+
+int build_network(premvos_refnet* n) {
+  const int S = n->S;
+  PV_TRY(alloc_cview(n, &n->input, 8, S, S));
+  const std::string x = "xception_65/";
+  const int map4[4] = {0, 1, 2, 3};
+  // root: conv2d_same 3x3 s2 (explicit pad 1,1 + VALID) and 3x3 s1 SAME (xception.py:430-433)
+  const int S1 = (S + 2 - 3) / 2 + 1;
+  CView c11, c12;
+  PV_TRY(alloc_cview(n, &c11, 32, S1, S1));
+  PV_TRY(alloc_cview(n, &c12, 64, S1, S1));
+  {
+    ConvGeom g; g.stride = 2; g.pad_t = g.pad_l = g.pad_b = g.pad_r = 1; g.slope = 0.f;
+    ConvOut o; o.cp = c11;
+    PV_TRY(add_conv(n, x + "entry_flow/conv1_1", true, XC_EPS, n->input, o, g, map4, 8));
+    ConvOut o2; o2.cp = c12;
+    PV_TRY(add_conv(n, x + "entry_flow/conv1_2", true, XC_EPS, c11, o2, ConvGeom::same3x3(1, 0.f)));
+  }
+  CView cur = c12, low_level;
+  const int target = 16 / 2;  // output_stride 16, halved by the stride-2 root conv (xception.py:424-429)
+  int current_stride = 1, rate = 1;
+  for (const BlockSpec& b : block_specs(n->middle_units))
+    for (int u = 0; u < b.units; u++) {
+      const std::string s = x + b.scope + "/unit_" + std::to_string(u + 1) + "/xception_module";
+      int stride = b.stride, unit_rate = 1;
+      if (current_stride == target) { stride = 1; unit_rate = rate; rate *= b.stride; }   // xception.py:341-355
+      else current_stride *= b.stride;
+      const int Ho = stride == 2 ? (cur.H - 1) / 2 + 1 : cur.H, Wo = stride == 2 ? (cur.W - 1) / 2 + 1 : cur.W;
+      CView sc;
+      if (b.skip == 1) {  // 1x1 stride-s shortcut + BN, no activation
+        PV_TRY(alloc_cview(n, &sc, b.depth[2], Ho, Wo));
+        ConvGeom g; g.stride = stride;
+        ConvOut o; o.cp = sc;
+        PV_TRY(add_conv(n, s + "/shortcut", true, XC_EPS, cur, o, g));
+      }
+      CView t = cur;
+      for (int i = 0; i < 3; i++) {
+        const int st_i = i == 2 ? stride : 1;
+        const int h_i = st_i == 2 ? Ho : t.H, w_i = st_i == 2 ? Wo : t.W;
+        const std::string ss = s + "/separable_conv" + std::to_string(i + 1);
+        CView d, p;
+        PV_TRY(alloc_cview(n, &d, t.C, h_i, w_i));
+        PV_TRY(alloc_cview(n, &p, b.depth[i], h_i, w_i));
+        PV_TRY(add_depthwise(n, ss + "_depthwise", XC_EPS, t, d, st_i, unit_rate, !b.act_in_sep, b.act_in_sep));
+        ConvGeom g; g.slope = b.act_in_sep ? 0.f : 1.f;
+        ConvOut o; o.cp = p;
+        if (i == 2 && b.skip == 1) o.res = sc;
+        if (i == 2 && b.skip == 2) o.res = cur;
+        PV_TRY(add_conv(n, ss + "_pointwise", true, XC_EPS, d, o, g));
+        if (std::string(b.scope) == "entry_flow/block2" && i == 1) low_level = p;   // feature_extractor.py:89-94
+        t = p;
+      }
+      cur = t;
+    }
+  n->named["xception_out"] = cur;
+  n->named["low_level"] = low_level;
+  const int fh = cur.H, fw = cur.W;
+  // ---- ASPP (model.py:361-435) ----
+  CView cat, aspp_out;
+  PV_TRY(alloc_cview(n, &cat, 1280, fh, fw));
+  PV_TRY(alloc_cview(n, &aspp_out, 256, fh, fw));
+  {
+    // image pooling: global mean -> 1x1 conv + BN + ReLU -> broadcast
+    std::vector<float> scale, shift;
+    bn_fold(n, "image_pooling", ASPP_EPS, &scale, &shift);
+    const std::vector<float>& W = n->params["image_pooling/weights"];  // [1][1][2048][256] == [in][out]
+    std::vector<float> w(W.size());
+    const int cin = cur.C;
+    for (int i = 0; i < cin; i++)
+      for (int o = 0; o < 256; o++) w[(size_t)i * 256 + o] = W[(size_t)i * 256 + o] * scale[o];
+    float *dw = nullptr, *db = nullptr, *vec = nullptr;
+    PV_TRY(dev_alloc(n, &dw, w.size())); PV_TRY(dev_alloc(n, &db, (size_t)256)); PV_TRY(dev_alloc(n, &vec, (size_t)n->NB * 256));
+    PV_CUDA(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    PV_CUDA(cudaMemcpy(db, shift.data(), 256 * 4, cudaMemcpyHostToDevice));
+    CView feat = cur, dst = cat.slice(0, 256);
+    n->steps.push_back([=](cudaStream_t st, int na) {
+      PV_TRY(gap_fc_relu(feat, dw, db, 256, true, vec, na, st));
+      return broadcast_vec_cp8(vec, 256, false, dst, na, st);
+    });
+  }
+  {
+    ConvGeom g; g.slope = 0.f;
+    ConvOut o; o.cp = cat.slice(32, 256);
+    PV_TRY(add_conv(n, "aspp0", true, ASPP_EPS, cur, o, g));
+    const int rates[3] = {6, 12, 18};
+    for (int i = 1; i <= 3; i++) {
+      CView d;
+      PV_TRY(alloc_cview(n, &d, cur.C, fh, fw));
+      PV_TRY(add_depthwise(n, "aspp" + std::to_string(i) + "_depthwise", ASPP_EPS, cur, d, 1, rates[i - 1], false, true));
+      ConvOut o2; o2.cp = cat.slice(32 * (i + 1), 256);
+      PV_TRY(add_conv(n, "aspp" + std::to_string(i) + "_pointwise", true, ASPP_EPS, d, o2, g));
+    }
+    ConvOut o3; o3.cp = aspp_out;
+    PV_TRY(add_conv(n, "concat_projection", true, ASPP_EPS, cat, o3, g));
+  }
+  n->named["aspp_concat"] = cat;
+  n->named["aspp_out"] = aspp_out;
+  // ---- decoder (model.py:503-598) ----
+  const int dh = (int)(((float)S - 1.0f) * 0.25f + 1.0f);
+  CView low48, dec_in, d0, p0, d1, p1;
+  PV_TRY(alloc_cview(n, &low48, 48, low_level.H, low_level.W));
+  PV_TRY(alloc_cview(n, &dec_in, 304, dh, dh));
+  PV_TRY(alloc_cview(n, &d0, 304, dh, dh)); PV_TRY(alloc_cview(n, &p0, 256, dh, dh));
+  PV_TRY(alloc_cview(n, &d1, 256, dh, dh)); PV_TRY(alloc_cview(n, &p1, 256, dh, dh));
+  {
+    ConvGeom g; g.slope = 0.f;
+    ConvOut o; o.cp = low48;
+    PV_TRY(add_conv(n, "decoder/feature_projection0", true, ASPP_EPS, low_level, o, g));
+    CView a_src = aspp_out, a_dst = dec_in.slice(0, 256), l_src = low48, l_dst = dec_in.slice(32, 48);
+    n->steps.push_back([=](cudaStream_t st, int na) {
+      PV_TRY(resize_bilinear_ac_cp8(a_src, a_dst, na, st));
+      return resize_bilinear_ac_cp8(l_src, l_dst, na, st);
+    });
+    PV_TRY(add_depthwise(n, "decoder/decoder_conv0_depthwise", ASPP_EPS, dec_in, d0, 1, 1, false, true));
+    ConvOut o0; o0.cp = p0;
+    PV_TRY(add_conv(n, "decoder/decoder_conv0_pointwise", true, ASPP_EPS, d0, o0, g));
+    PV_TRY(add_depthwise(n, "decoder/decoder_conv1_depthwise", ASPP_EPS, p0, d1, 1, 1, false, true));
+    ConvOut o1; o1.cp = p1;
+    PV_TRY(add_conv(n, "decoder/decoder_conv1_pointwise", true, ASPP_EPS, d1, o1, g));
+  }
+  n->named["decoder_in"] = dec_in;
+  n->named["decoder_out"] = p1;
+  // logits: 1x1 conv with bias, no BN (model.py:639-659); the resize to [dh, dw] (:295-297) is the identity
+  n->logits.N = n->NB; n->logits.H = dh; n->logits.W = dh; n->logits.cs = 16; n->logits.coff = 0; n->logits.C = n->n_classes;
+  PV_TRY(dev_alloc(n, &n->logits.p, (size_t)n->NB * dh * dh * 16));
+  {
+    ConvGeom g;
+    ConvOut o; o.f32 = n->logits;
+    PV_TRY(add_conv(n, "logits/features", false, 0.f, p1, o, g));
+  }
+  PV_TRY(dev_alloc(n, &n->boxes_dev, (size_t)n->NB * 4));
+  PV_TRY(dev_alloc(n, &n->crops, (size_t)n->NB * 4));
+  PV_TRY(dev_alloc(n, &n->conf_sum, (size_t)n->NB));
+  return 0;
+}
+
+int ensure(void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  PV_CUDA(cudaMalloc(p, need));
+  *cap = need;
+  return 0;
+}
+
+int run_batch(premvos_refnet* n, int na, cudaStream_t st) {
+  for (auto& s : n->steps) PV_TRY(s(st, na));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int premvos_refnet_create(premvos_refnet_t** out, int max_batch, int input_size, int middle_units) {
+  PV_CHECK(out, PREMVOS_ERR_INVALID_ARG, "premvos_refnet_create: out is null");
+  *out = nullptr;
+  PV_CHECK(max_batch >= 1 && max_batch <= 256 && input_size >= 33 && input_size <= 1025 && middle_units >= 0 && middle_units <= 16,
+           PREMVOS_ERR_INVALID_ARG, "premvos_refnet_create: max_batch in [1,256], input_size in [33,1025], middle_units in [0,16]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PREMVOS_ERR_NO_DEVICE, "premvos_refnet_create: no CUDA device visible");
+  premvos_refnet* n = new premvos_refnet();
+  n->NB = max_batch; n->S = input_size; n->middle_units = middle_units;
+  build_shape_table(n);
+  *out = n;
+  return 0;
+}
+
+extern "C" int premvos_refnet_set_param(premvos_refnet_t* n, const char* name, const float* host_data, int64_t numel) {
+  PV_CHECK(n && name && host_data, PREMVOS_ERR_INVALID_ARG, "premvos_refnet_set_param: null argument");
+  PV_CHECK(!n->finalized, PREMVOS_ERR_NOT_READY, "premvos_refnet_set_param: network already finalized");
+  auto it = n->shapes.find(name);
+  if (it == n->shapes.end()) return fail(PREMVOS_ERR_UNKNOWN_PARAM, "premvos_refnet_set_param: unexpected variable '%s'", name);
+  const int64_t want = numel_of(it->second);
+  if (numel != want)
+    return fail(PREMVOS_ERR_BAD_SHAPE, "premvos_refnet_set_param: '%s' has %lld elements, expected %lld", name, (long long)numel, (long long)want);
+  n->params[name].assign(host_data, host_data + numel);
+  return 0;
+}
+
+extern "C" int premvos_refnet_finalize(premvos_refnet_t* n) {
+  PV_CHECK(n, PREMVOS_ERR_INVALID_ARG, "premvos_refnet_finalize: null handle");
+  PV_CHECK(!n->finalized, PREMVOS_ERR_NOT_READY, "premvos_refnet_finalize: already finalized");
+  for (auto& kv : n->shapes)
+    if (!n->params.count(kv.first)) return fail(PREMVOS_ERR_NOT_READY, "premvos_refnet_finalize: missing variable '%s'", kv.first.c_str());
+  PV_CUDA(cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking));
+  PV_TRY(build_network(n));
+  n->params.clear();
+  const int64_t before = g_launch_count.load();
+  PV_TRY(run_batch(n, n->NB, n->stream));  // warm-up on the zero-initialised input: validates every launch configuration
+  PV_CUDA(cudaStreamSynchronize(n->stream));
+  n->launches_per_forward = (int)(g_launch_count.load() - before) + 2;
+  n->finalized = true;
+  return 0;
+}
+
+// The batched equivalent of MergeTrack/refinement_net_functions.py:do_refinement's inner loop: one frame, n proposal boxes.
+extern "C" int premvos_refnet_forward_host(premvos_refnet_t* n, const unsigned char* frame_rgb, int height, int width, const float* boxes_xywh,
+                                           int num_boxes, unsigned char* masks_out, float* conf_scores_out, float* posteriors_out) {
+  PV_CHECK(n && frame_rgb && (num_boxes == 0 || (boxes_xywh && masks_out && conf_scores_out)), PREMVOS_ERR_INVALID_ARG,
+           "premvos_refnet_forward_host: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_refnet_forward_host: call premvos_refnet_finalize first");
+  PV_CHECK(height > 0 && width > 0 && num_boxes >= 0, PREMVOS_ERR_INVALID_ARG, "premvos_refnet_forward_host: bad sizes");
+  if (num_boxes == 0) return 0;
+  cudaStream_t st = n->stream;
+  const size_t hw = (size_t)height * width;
+  PV_TRY(ensure((void**)&n->frame_dev, &n->frame_cap, hw * 3));
+  PV_TRY(ensure((void**)&n->mask_dev, &n->mask_cap, hw * n->NB));
+  if (posteriors_out) PV_TRY(ensure((void**)&n->post_dev, &n->post_cap, hw * n->NB * sizeof(float)));
+  PV_CUDA(cudaMemcpyAsync(n->frame_dev, frame_rgb, hw * 3, cudaMemcpyHostToDevice, st));
+  std::vector<double> sums(n->NB);
+  for (int b0 = 0; b0 < num_boxes; b0 += n->NB) {
+    const int na = std::min(n->NB, num_boxes - b0);
+    PV_CUDA(cudaMemcpyAsync(n->boxes_dev, boxes_xywh + (size_t)b0 * 4, (size_t)na * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    PV_TRY(refine_make_input(n->frame_dev, height, width, n->boxes_dev, na, n->S, n->input, n->crops, st));
+    PV_TRY(run_batch(n, na, st));
+    PV_TRY(refine_output(n->logits, n->crops, na, n->S, height, width, n->mask_dev, posteriors_out ? n->post_dev : nullptr, n->conf_sum, st));
+    PV_CUDA(cudaMemcpyAsync(masks_out + (size_t)b0 * hw, n->mask_dev, hw * na, cudaMemcpyDeviceToHost, st));
+    if (posteriors_out)
+      PV_CUDA(cudaMemcpyAsync(posteriors_out + (size_t)b0 * hw, n->post_dev, hw * na * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PV_CUDA(cudaMemcpyAsync(sums.data(), n->conf_sum, (size_t)na * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PV_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < na; i++) conf_scores_out[b0 + i] = (float)(sums[i] / (double)hw);
+  }
+  return 0;
+}
+
+extern "C" int premvos_refnet_launches_per_forward(const premvos_refnet_t* n) { return n ? n->launches_per_forward : 0; }
+
+// Test hook (state of the LAST batch): "net_input" [NB,8,S,S], "xception_out", "low_level", "aspp_concat", "aspp_out",
+// "decoder_in", "decoder_out" (CP8 -> NCHW), "logits" (fp32 [NB,h,w,16] channels-last), "crops" ([NB,4] as fp32).
+extern "C" int premvos_refnet_get_tensor(premvos_refnet_t* n, const char* name, float* host_out, int64_t* numel) {
+  PV_CHECK(n && name && numel, PREMVOS_ERR_INVALID_ARG, "premvos_refnet_get_tensor: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_refnet_get_tensor: network not finalized");
+  PV_CUDA(cudaDeviceSynchronize());
+  std::string k(name);
+  if (k == "logits") {
+    *numel = (int64_t)n->NB * n->logits.H * n->logits.W * 16;
+    if (host_out) PV_CUDA(cudaMemcpy(host_out, n->logits.p, (size_t)(*numel) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  if (k == "crops") {
+    *numel = (int64_t)n->NB * 4;
+    if (host_out) {
+      std::vector<int> t((size_t)n->NB * 4);
+      PV_CUDA(cudaMemcpy(t.data(), n->crops, t.size() * 4, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < t.size(); i++) host_out[i] = (float)t[i];
+    }
+    return 0;
+  }
+  CView cv;
+  if (k == "net_input") cv = n->input;
+  else if (n->named.count(k)) cv = n->named[k];
+  else return fail(PREMVOS_ERR_INVALID_ARG, "premvos_refnet_get_tensor: unknown tensor '%s'", name);
+  *numel = (int64_t)cv.N * cv.C * cv.H * cv.W;
+  if (!host_out) return 0;
+  float* dtmp = nullptr;
+  PV_CUDA(cudaMalloc((void**)&dtmp, (size_t)(*numel) * sizeof(float)));
+  int r = cp8_to_nchw(cv, 0, dtmp, nullptr);
+  if (r == 0) {
+    cudaError_t e = cudaMemcpy(host_out, dtmp, (size_t)(*numel) * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) r = fail((int)e, "premvos_refnet_get_tensor: %s", cudaGetErrorString(e));
+  }
+  cudaFree(dtmp);
+  return r;
+}
+
+extern "C" void premvos_refnet_destroy(premvos_refnet_t* n) {
+  if (!n) return;
+  cudaDeviceSynchronize();
+  for (void* p : n->allocs) cudaFree(p);
+  for (auto& w : n->conv_weights) free_conv_weights_umma(w.get());
+  if (n->frame_dev) cudaFree(n->frame_dev);
+  if (n->mask_dev) cudaFree(n->mask_dev);
+  if (n->post_dev) cudaFree(n->post_dev);
+  if (n->stream) cudaStreamDestroy(n->stream);
+  delete n;
+}

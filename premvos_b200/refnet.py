@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's refinement call surface, backed by the CUDA library.
+
+Reference surface reproduced here:
+  refinement_net_init() -> engine                                  MergeTrack/refinement_net_functions.py:19-24
+  do_refinement(proposals, image_fn, engine) -> proposals          MergeTrack/refinement_net_functions.py:38-65
+  engine.valid_data.set_up_data_for_image(image, boxes)            refinement_net/datasets/few_shot_segmentation/
+  engine.valid_data.get_feed_dict_for_next_step(image_data, idx)     FewShotFeedSegmentationDataset.py:35-51, FeedDataset.py
+  engine.trainer.validation_step(feed_dict=..., extraction_keys=[...]) -> {'extractions': {...}}
+                                                                    refinement_net/core/Trainer.py:128-133,150-169
+  COCO RLE 'segmentation' records                                  pycocotools.mask.encode as used at :52-56
+
+All tensor arithmetic (crop/resize, DeepLabv3+, output layer, conf_score) runs in libpremvos_b200.so; the proposals of a
+frame are run as one batch instead of one session.run per proposal.  No TensorFlow, no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+from .synth import refnet_param_shapes
+
+# refinement_net/core/Extractions.py:1-6, datasets/DataKeys.py
+EXTRACTIONS = "extractions"
+SEGMENTATION_POSTERIORS_ORIGINAL_SIZE = "segmentation_posteriors_original_size"
+SEGMENTATION_MASK_ORIGINAL_SIZE = "segmentation_mask_original_size"
+OBJ_TAGS = "obj_tags"
+IMAGES = "images"
+BBOXES_y0x0y1x1 = "bboxes_y0x0y1x1"
+
+
+class RefinementNet:
+    def __init__(self, max_batch=16, input_size=385, middle_units=16):
+        self.max_batch, self.input_size, self.middle_units = max_batch, input_size, middle_units
+        self._shapes = refnet_param_shapes(middle_units)
+        self._handle = None
+        self._params = None
+
+    def load_params(self, params):
+        missing = [k for k in self._shapes if k not in params]
+        unexpected = [k for k in params if k not in self._shapes]
+        if missing or unexpected:
+            raise RuntimeError("refinement_net variables: missing %s, unexpected %s" % (missing[:5], unexpected[:5]))
+        for k, shp in self._shapes.items():
+            if tuple(np.shape(params[k])) != tuple(shp):
+                raise RuntimeError("size mismatch for %s: got %s, expected %s" % (k, tuple(np.shape(params[k])), tuple(shp)))
+        self._params = OrderedDict((k, np.ascontiguousarray(params[k], dtype=np.float32)) for k in self._shapes)
+        self.close()
+        return self
+
+    def close(self):
+        if self._handle is not None:
+            _lib.lib().premvos_refnet_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _h(self):
+        if self._handle is not None:
+            return self._handle
+        if self._params is None:
+            raise RuntimeError("RefinementNet: load_params() first")
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(L.premvos_refnet_create(ctypes.byref(h), self.max_batch, self.input_size, self.middle_units))
+        try:
+            for k, v in self._params.items():
+                _lib.check(L.premvos_refnet_set_param(h, k.encode(), v.ctypes.data_as(ctypes.c_void_p), v.size))
+            _lib.check(L.premvos_refnet_finalize(h))
+        except Exception:
+            L.premvos_refnet_destroy(h)
+            raise
+        self._handle = h
+        return h
+
+    def refine(self, image_rgb_uint8, boxes_xywh, want_posteriors=False):
+        """-> masks uint8 [n,H,W] (0/1), conf_scores float32 [n], posteriors float32 [n,H,W] or None"""
+        img = np.ascontiguousarray(image_rgb_uint8)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected a uint8 RGB image [H,W,3], got %s %s" % (img.dtype, img.shape))
+        boxes = np.ascontiguousarray(boxes_xywh, dtype=np.float32).reshape(-1, 4)
+        n, (H, W) = boxes.shape[0], img.shape[:2]
+        masks = np.zeros((n, H, W), np.uint8)
+        conf = np.zeros((n,), np.float32)
+        post = np.zeros((n, H, W), np.float32) if want_posteriors else None
+        vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(_lib.lib().premvos_refnet_forward_host(self._h(), vp(img), H, W, vp(boxes), n, vp(masks), vp(conf), vp(post)))
+        return masks, conf, post
+
+    def get_tensor(self, name):
+        L = _lib.lib()
+        n = ctypes.c_int64()
+        _lib.check(L.premvos_refnet_get_tensor(self._h(), name.encode(), None, ctypes.byref(n)))
+        buf = np.empty(n.value, dtype=np.float32)
+        _lib.check(L.premvos_refnet_get_tensor(self._h(), name.encode(), buf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n)))
+        return buf
+
+
+# ---- COCO RLE (pycocotools maskApi.c: rleEncode + rleToString / rleFrString) ---------------------------------
+def rle_encode(mask):
+    m = np.asarray(mask)
+    h, w = m.shape
+    flat = np.ascontiguousarray(m.T).reshape(-1) != 0            # column-major
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    bounds = np.concatenate([[0], change, [flat.size]])
+    counts = np.diff(bounds).tolist()
+    if flat.size and flat[0]:
+        counts = [0] + counts                                      # runs start with a zero-run
+    out = []
+    for i, x in enumerate(counts):
+        x = int(x)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(chr(c + 48))
+    return {"size": [h, w], "counts": "".join(out)}
+
+
+def rle_decode(rle):
+    h, w = rle["size"]
+    s = rle["counts"]
+    if isinstance(s, bytes):
+        s = s.decode("ascii")
+    counts, p = [], 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = ord(s[p]) - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    flat = np.zeros(h * w, np.uint8)
+    pos, v = 0, 0
+    for c in counts:
+        flat[pos:pos + c] = v
+        pos += c
+        v = 1 - v
+    return flat.reshape(w, h).T
+
+
+# ---- the MergeTrack surface -----------------------------------------------------------------------------------
+class _ValidData:
+    """engine.valid_data (FewShotFeedSegmentationDataset): dict-of-dicts protocol kept as is."""
+
+    def set_up_data_for_image(self, image, boxes):
+        obj_data = {}
+        for box_id, box in enumerate(boxes):
+            x0, y0, x1, y1 = box
+            obj_data[box_id] = {IMAGES: image, BBOXES_y0x0y1x1: [y0, x0, y1 + y0, x1 + x0], OBJ_TAGS: str(box_id), "_xywh": list(box)}
+        return obj_data if obj_data else None
+
+    def get_feed_dict_for_next_step(self, image_data, idx):
+        return image_data[idx]
+
+
+class _Trainer:
+    def __init__(self, net):
+        self.net = net
+
+    def validation_step(self, feed_dict=None, extraction_keys=()):
+        """One proposal, like the reference's session.run (core/Trainer.py:128-133): arrays shaped [1, ...] in lists."""
+        masks, conf, post = self.net.refine(feed_dict[IMAGES], [feed_dict["_xywh"]], want_posteriors=True)
+        ex = {SEGMENTATION_MASK_ORIGINAL_SIZE: [masks.astype(np.int64)], SEGMENTATION_POSTERIORS_ORIGINAL_SIZE: [post],
+              OBJ_TAGS: [np.array([feed_dict[OBJ_TAGS].encode("utf-8")])]}
+        return {EXTRACTIONS: {k: v for k, v in ex.items() if k in extraction_keys}, "measures": {}, "loss": 0.0}
+
+
+class Engine:
+    def __init__(self, net: RefinementNet):
+        self.net = net
+        self.valid_data = _ValidData()
+        self.trainer = _Trainer(net)
+
+
+def refinement_net_init(params=None, **kw) -> Engine:
+    """refinement_net_functions.py:19-24.  `params`: slim variables (the reference restores
+    weights/PReMVOS_weights/refinement_net/specific_weights; pass the loaded dict here)."""
+    net = RefinementNet(**kw)
+    if params is not None:
+        net.load_params(params)
+    return Engine(net)
+
+
+def do_refinement(proposals, image_fn, refinement_net: Engine):
+    """refinement_net_functions.py:38-65, all proposals of the frame in one batched call.  `image_fn`: file name or RGB array."""
+    if isinstance(image_fn, np.ndarray):
+        image = image_fn
+    else:
+        import cv2
+        image = cv2.imread(image_fn, cv2.IMREAD_COLOR)[:, :, ::-1]
+    boxes = [prop["bbox"] for prop in proposals]
+    if not boxes:
+        return proposals
+    masks, conf, _ = refinement_net.net.refine(image, boxes)
+    for prop, m, c in zip(proposals, masks, conf):
+        prop["segmentation"] = rle_encode(m * 255)
+        prop["conf_score"] = str(c)
+    return proposals

@@ -207,3 +207,88 @@ def synthetic_bgr_frame(h, w, seed=2):
         hh, ww = int(rng.integers(10, max(11, h // 3))), int(rng.integers(10, max(11, w // 3)))
         img[y0:y0 + hh, x0:x0 + ww] = rng.uniform(0, 255, 3)
     return np.clip(img + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
+
+
+# ---- refinement network (slim variable names, refinement_net/network/deeplab) -----------------------------
+def refnet_param_shapes(middle_units=16, n_classes=2):
+    t = OrderedDict()
+
+    def bn(scope, c):
+        for v in ("gamma", "beta", "moving_mean", "moving_variance"):
+            t[scope + "/BatchNorm/" + v] = (c,)
+
+    def conv(scope, k, cin, cout):
+        t[scope + "/weights"] = (k, k, cin, cout)
+        bn(scope, cout)
+
+    def sep(scope, cin, cout):
+        t[scope + "_depthwise/depthwise_weights"] = (3, 3, cin, 1)
+        bn(scope + "_depthwise", cin)
+        conv(scope + "_pointwise", 1, cin, cout)
+
+    blocks = [("entry_flow/block1", [128, 128, 128], "conv", 1), ("entry_flow/block2", [256, 256, 256], "conv", 1),
+              ("entry_flow/block3", [728, 728, 728], "conv", 1), ("middle_flow/block1", [728, 728, 728], "sum", middle_units),
+              ("exit_flow/block1", [728, 1024, 1024], "conv", 1), ("exit_flow/block2", [1536, 1536, 2048], "none", 1)]
+    x = "xception_65/"
+    conv(x + "entry_flow/conv1_1", 3, 4, 32)
+    conv(x + "entry_flow/conv1_2", 3, 32, 64)
+    cin = 64
+    for scope, depths, skip, units in blocks:
+        for u in range(units):
+            s = "%s%s/unit_%d/xception_module" % (x, scope, u + 1)
+            c = cin
+            for i, d in enumerate(depths):
+                sep("%s/separable_conv%d" % (s, i + 1), c, d)
+                c = d
+            if skip == "conv":
+                conv(s + "/shortcut", 1, cin, depths[-1])
+            cin = depths[-1]
+    conv("image_pooling", 1, cin, 256)
+    conv("aspp0", 1, cin, 256)
+    for i in (1, 2, 3):
+        sep("aspp%d" % i, cin, 256)
+    conv("concat_projection", 1, 1280, 256)
+    conv("decoder/feature_projection0", 1, 256, 48)
+    sep("decoder/decoder_conv0", 304, 256)
+    sep("decoder/decoder_conv1", 256, 256)
+    t["logits/features/weights"] = (1, 1, 256, n_classes)
+    t["logits/features/biases"] = (n_classes,)
+    return t
+
+
+def refnet_synthetic_params(seed=0, middle_units=16, n_classes=2):
+    """Seeded DeepLabv3+/Xception-65 variables with trained-net-like statistics (He-normal kernels, BN gamma and
+    variance near 1, small beta / mean; the BN closing a residual unit is damped so 20 stacked units stay O(1))."""
+    rng = np.random.default_rng(seed)
+    P = OrderedDict()
+    for name, shape in refnet_param_shapes(middle_units, n_classes).items():
+        if name.endswith("depthwise_weights"):
+            P[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / 9.0)).astype(np.float32)
+        elif name.endswith("/weights"):
+            fan_in = shape[0] * shape[1] * shape[2]
+            std = np.sqrt(2.0 / fan_in)
+            if name.startswith("logits/"):
+                std = 4.0 / np.sqrt(fan_in)
+            P[name] = (rng.standard_normal(shape) * std).astype(np.float32)
+        elif name.endswith("/biases"):
+            P[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+        elif name.endswith("/gamma"):
+            base = 0.3 if "separable_conv3_pointwise" in name and "exit_flow/block2" not in name else 1.0
+            P[name] = (base * (1.0 + 0.1 * rng.uniform(-1, 1, shape))).astype(np.float32)
+        elif name.endswith("/beta") or name.endswith("/moving_mean"):
+            P[name] = (0.05 * rng.standard_normal(shape)).astype(np.float32)
+        elif name.endswith("/moving_variance"):
+            P[name] = (1.0 + 0.1 * rng.uniform(-1, 1, shape)).astype(np.float32)
+        else:
+            raise AssertionError(name)
+    return P
+
+
+def synthetic_boxes(n, h, w, seed=3, min_size=40, max_size=300):
+    """n proposal boxes [x, y, w, h] (float, like the 1-decimal JSON boxes): sizes ~U(min,max), clipped to the frame."""
+    rng = np.random.default_rng(seed)
+    bw = rng.uniform(min_size, min(max_size, w - 2), n)
+    bh = rng.uniform(min_size, min(max_size, h - 2), n)
+    x0 = rng.uniform(0, w - bw)
+    y0 = rng.uniform(0, h - bh)
+    return np.round(np.stack([x0, y0, bw, bh], 1), 1).astype(np.float32)
