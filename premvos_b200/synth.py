@@ -263,7 +263,9 @@ def refnet_synthetic_params(seed=0, middle_units=16, n_classes=2):
     P = OrderedDict()
     for name, shape in refnet_param_shapes(middle_units, n_classes).items():
         if name.endswith("depthwise_weights"):
-            P[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / 9.0)).astype(np.float32)
+            # variance-preserving: a ReLU follows the depthwise conv only in exit_flow/block2, ASPP and the decoder
+            relu_after = ("exit_flow/block2" in name) or name.startswith("aspp") or name.startswith("decoder")
+            P[name] = (rng.standard_normal(shape) * np.sqrt((2.0 if relu_after else 1.0) / 9.0)).astype(np.float32)
         elif name.endswith("/weights"):
             fan_in = shape[0] * shape[1] * shape[2]
             std = np.sqrt(2.0 / fan_in)

@@ -46,8 +46,9 @@ def _check(P, blocks, net, frame, boxes, S, check_inter=True):
         diff = masks[i] != mask_ref
         if diff.any():   # only pixels whose foreground posterior is within tolerance of 0.5 may flip
             lgS = O.tf_resize_bilinear(logits[0].permute(2, 0, 1), S, S)
+            # the flipped pixels must be ones whose two logits are closer than the tolerance allows to resolve
             margin = float((lgS[1] - lgS[0]).abs().min())
-            assert diff.sum() <= 1e-4 * diff.size and margin < 1e-2, (int(diff.sum()), margin)
+            assert diff.sum() <= 1e-4 * diff.size and margin < 4 * TOL * float(lgS.abs().max()), (int(diff.sum()), margin)
         cs = O.conf_score(mask_ref, post_ref)
         report.append(("conf_score[%d]" % i, abs(float(conf[i]) - float(cs)) / max(abs(float(cs)), 1e-6)))
     print("\n".join("%-20s %.3e" % r for r in report))
