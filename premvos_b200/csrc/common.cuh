@@ -188,12 +188,18 @@ struct ConvOut {
   CView cp;    // CP8 split output (optional)
   TView f32;   // fp32 channels-last output (optional; small heads)
   CView res;   // optional residual added before the activation (same shape as the output)
+  // channel routing (fused heads): output channels [0, cp_channels) go to `cp` (cp_channels < 0: all of them);
+  // channels [f32_first, Cout) go to `f32` at channel index c - f32_first
+  int cp_channels = -1, f32_first = 0;
+  bool f32_linear = false;      // fp32 outputs skip the activation
+  bool f32_accumulate = false;  // fp32 outputs are added to the buffer's current contents
 };
 struct ConvPlanUmma {  // everything one launch needs; built once per layer at finalize time
   alignas(64) unsigned char map_a_hi[128];
   alignas(64) unsigned char map_a_lo[128];
-  alignas(16) unsigned char args[256];
-  int grid_x = 0, grid_y = 0, smem_bytes = 0, halo = 0, MT = 0, N = 0;
+  alignas(16) unsigned char args[320];
+  int grid_x = 0, grid_y = 0, grid_z = 1, smem_bytes = 0, halo = 0, MT = 0, N = 0;
+  void* scratch = nullptr;   // split-K partial sums (owned by the plan, see free_conv_plan_umma)
   double flops = 0, bytes = 0;
 };
 // host_w: torch Conv2d layout [Cout][Cin][R][S].  cin_map (optional): physical channel (inside the input
@@ -201,6 +207,8 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
                            const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0);
 void free_conv_weights_umma(ConvWeightsUmma* w);
+struct ConvPlanUmma;
+void free_conv_plan_umma(ConvPlanUmma* plan);
 int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g);
 // active_n >= 0: process only the first active_n images of the planned batch
 int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n = -1);

@@ -60,6 +60,7 @@ extern "C" int premvos_conv2d_forward(const float* x_dev, const float* w_host, c
   if (r == 0) r = cp8_to_nchw(out, 0, out_dev, st);
   cudaError_t e = cudaStreamSynchronize(st);
   free_conv_weights_umma(&w);
+  free_conv_plan_umma(&plan);
   if (r == 0 && e != cudaSuccess) r = fail((int)e, "premvos_conv2d_forward: %s", cudaGetErrorString(e));
   return r;
 }

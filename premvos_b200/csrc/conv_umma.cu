@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -167,8 +168,15 @@ struct UmmaConvArgs {
   // outputs: CP8 split planes and/or fp32 channels-last
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_chunks, out_c0;
   float* out_f32; int out_cs, out_coff;
+  // channel routing: [0, cp_cout) -> CP8 planes (activated); [f32_first, Cout) -> fp32 channels-last at channel c - f32_first
+  int cp_cout, f32_first, f32_linear /*1: no activation on the fp32 outputs*/, f32_accum /*1: add to what is there*/;
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo; int res_chunks, res_c0;  // optional residual
   uint32_t tmem_cols;
+  // split-K (grids smaller than the machine): blockIdx.z owns k-blocks [z*kb_per, (z+1)*kb_per) and stores raw fp32
+  // partial sums; conv_finish_kernel adds them in a fixed order (deterministic) and applies the epilogue
+  int ksplit, kb_per, cout_pad;
+  float* partial;            // [ksplit][N*Ho*Wo][cout_pad]
+  long partial_stride;       // elements per split
 };
 
 __global__ void __launch_bounds__(UMMA_THREADS, 2)
@@ -193,6 +201,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int ty0 = (trem / a.tiles_x) * 16 * a.MT, tx0 = (trem % a.tiles_x) * 8;
   const int ntile = blockIdx.y;
   const int taps = a.R * a.S;
+  const int kb_begin = a.ksplit > 1 ? (int)blockIdx.z * a.kb_per : 0;
+  const int kb_end = a.ksplit > 1 ? min(a.kblocks, kb_begin + a.kb_per) : a.kblocks;
 
   if (warp == 0 && lane == 0) {  // one-time setup
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
@@ -211,9 +221,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // ===== TMA producer =====  the whole warp walks the warp-uniform loop, one elected lane issues the copies
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0;
     const uint32_t w_bytes = (uint32_t)a.TPS * 2u * (uint32_t)a.w_plane;   // one bulk copy
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)ntile * a.kblocks * taps * 2 * a.w_plane;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)ntile * a.kblocks + kb_begin) * taps * 2 * a.w_plane;
     const int bx = tx0 * a.stride - a.pad_l, by = ty0 * a.stride - a.pad_t;
-    for (int kb = 0; kb < a.kblocks; kb++) {
+    for (int kb = kb_begin; kb < kb_end; kb++) {
       int tin = 0;  // tap index inside the current weight stage
       for (int r = 0; r < a.R; r++)
         for (int s = 0; s < a.S; s++) {
@@ -272,7 +282,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // releases the stage.  (A per-tap handshake costs ~500 cycles of mbarrier/commit latency -- more than the
     // MMAs of one tap.)  Tap mode additionally waits for / releases one A stage per tap.
     const int wgroups = taps / a.TPS;
-    for (int kb = 0; kb < a.kblocks; kb++) {
+    for (int kb = kb_begin; kb < kb_end; kb++) {
       int r = 0, s = 0;
       uint32_t row_off = 0, tap_off = 0;
       for (int wg = 0; wg < wgroups; wg++) {
@@ -349,6 +359,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         }
         const int co0 = ntile * a.BN + c0;
+        if (a.ksplit > 1) {  // raw partial sums; bias / residual / activation happen in conv_finish_kernel
+          if (in_img) {
+            float* pp = a.partial + (long)blockIdx.z * a.partial_stride + ((long)n_img * hw + pix) * a.cout_pad + co0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              reinterpret_cast<float4*>(pp)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+          continue;
+        }
         if (!in_img || co0 >= a.Cout) continue;
         float f[16];
 #pragma unroll
@@ -368,12 +388,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
           }
         }
+        if (a.out_f32 && a.f32_linear) {  // fp32 outputs without activation (fused flow heads)
+          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (co0 + j >= a.f32_first && co0 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+        }
 #pragma unroll
         for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
         if (a.out_hi) {
 #pragma unroll
           for (int h = 0; h < 2; h++) {
-            if (co0 + 8 * h >= a.Cout) continue;  // chunk entirely beyond Cout (padding channels inside a chunk are exact zeros)
+            if (co0 + 8 * h >= a.cp_cout) continue;  // chunk beyond the CP8 range (padding channels inside a chunk are exact zeros)
             uint32_t hw4[4], lw4[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -389,15 +415,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             *reinterpret_cast<uint4*>(a.out_lo + oi) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
           }
         }
-        if (a.out_f32) {
-          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff + co0;
-          if (co0 + 16 <= a.Cout && ((a.out_cs | a.out_coff) & 3) == 0) {
+        if (a.out_f32 && !a.f32_linear) {
+          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
+          if (a.f32_first == 0 && !a.f32_accum && co0 + 16 <= a.Cout && ((a.out_cs | a.out_coff) & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 4; j++) reinterpret_cast<float4*>(pf)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; j++)
-              if (co0 + j < a.Cout) pf[j] = f[j];
+              if (co0 + j >= a.f32_first && co0 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
           }
         }
       }
@@ -406,6 +432,69 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// Sums the split-K partials in split order and applies the same epilogue as the fused path (bias, residual, LeakyReLU/ReLU,
+// CP8 split store and/or fp32 channels-last store).  One thread per (pixel, 8-channel chunk).
+__global__ void __launch_bounds__(256) conv_finish_kernel(const UmmaConvArgs a, int n_active) {
+  const long hw = (long)a.Ho * a.Wo;
+  const int cchunks = (a.Cout + 7) / 8;
+  const long total = (long)n_active * hw * cchunks;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long pg = idx % ((long)n_active * hw);   // pixel fastest -> coalesced CP8 stores
+  const int c8 = (int)(idx / ((long)n_active * hw));
+  const int n_img = (int)(pg / hw);
+  const long pix = pg - (long)n_img * hw;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = 0.f;
+  for (int z = 0; z < a.ksplit; z++) {
+    const float* pp = a.partial + (long)z * a.partial_stride + pg * a.cout_pad + c8 * 8;
+    const float4 p0 = reinterpret_cast<const float4*>(pp)[0], p1 = reinterpret_cast<const float4*>(pp)[1];
+    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] += __ldg(a.bias + c8 * 8 + j);
+  if (a.res_hi) {
+    const long ri = (((long)n_img * a.res_chunks + a.res_c0 + c8) * hw + pix) * 8;
+    const uint4 rh = *reinterpret_cast<const uint4*>(a.res_hi + ri);
+    const uint4 rl = *reinterpret_cast<const uint4*>(a.res_lo + ri);
+    const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      f[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+      f[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+    }
+  }
+  float* pf = a.out_f32 ? a.out_f32 + pg * a.out_cs + a.out_coff - a.f32_first + c8 * 8 : nullptr;
+  if (pf && a.f32_linear) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (c8 * 8 + j >= a.f32_first && c8 * 8 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+  if (a.out_hi && c8 * 8 < a.cp_cout) {
+    uint32_t hw4[4], lw4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float x0 = f[2 * j], x1 = f[2 * j + 1];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      hw4[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw4[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const long oi = (((long)n_img * a.out_chunks + a.out_c0 + c8) * hw + pix) * 8;
+    *reinterpret_cast<uint4*>(a.out_hi + oi) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+    *reinterpret_cast<uint4*>(a.out_lo + oi) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+  }
+  if (pf && !a.f32_linear) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (c8 * 8 + j >= a.f32_first && c8 * 8 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -499,6 +588,11 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   return 0;
 }
 
+void free_conv_plan_umma(ConvPlanUmma* plan) {
+  if (plan->scratch) cudaFree(plan->scratch);
+  plan->scratch = nullptr;
+}
+
 void free_conv_weights_umma(ConvWeightsUmma* w) {
   cudaFree(w->w); cudaFree(w->bias);
   w->w = nullptr; w->bias = nullptr;
@@ -513,13 +607,17 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const int Ho = (in.H + g.pad_t + g.pad_b - g.dil * (w.R - 1) - 1) / g.stride + 1;
   const int Wo = (in.W + g.pad_l + g.pad_r - g.dil * (w.S - 1) - 1) / g.stride + 1;
   PV_CHECK(Ho > 0 && Wo > 0, PREMVOS_ERR_INVALID_ARG, "conv_umma: empty output");
+  const int cp_cout = out.cp.hi ? (out.cp_channels >= 0 ? out.cp_channels : w.Cout) : 0;
+  const int f32_first = out.f32.p ? out.f32_first : 0;
+  PV_CHECK(cp_cout <= w.Cout && (cp_cout == w.Cout || cp_cout % 8 == 0) && f32_first >= 0 && f32_first <= w.Cout, PREMVOS_ERR_INVALID_ARG,
+           "conv_umma: bad channel routing (cp %d, f32 from %d, Cout %d)", cp_cout, f32_first, w.Cout);
   if (out.cp.hi) {
-    PV_CHECK(out.cp.N == in.N && out.cp.H == Ho && out.cp.W == Wo && out.cp.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
+    PV_CHECK(out.cp.N == in.N && out.cp.H == Ho && out.cp.W == Wo && out.cp.C == cp_cout, PREMVOS_ERR_INVALID_ARG,
              "conv_umma: CP8 output view is [%d,%d,%d,%d], expected [%d,%d,%d,%d]", out.cp.N, out.cp.C, out.cp.H, out.cp.W, in.N,
              w.Cout, Ho, Wo);
   }
   if (out.f32.p) {
-    PV_CHECK(out.f32.N == in.N && out.f32.H == Ho && out.f32.W == Wo && out.f32.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
+    PV_CHECK(out.f32.N == in.N && out.f32.H == Ho && out.f32.W == Wo && out.f32.C == w.Cout - f32_first, PREMVOS_ERR_INVALID_ARG,
              "conv_umma: fp32 output view shape mismatch");
   }
   PV_CHECK(out.cp.hi || out.f32.p, PREMVOS_ERR_INVALID_ARG, "conv_umma: no output");
@@ -588,6 +686,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.w = w.w; a.bias = w.bias; a.slope = g.slope;
   a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
   a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
+  a.cp_cout = cp_cout; a.f32_first = f32_first; a.f32_linear = out.f32_linear ? 1 : 0; a.f32_accum = out.f32_accumulate ? 1 : 0;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
   a.dbg = env_int("PREMVOS_DBG", 0);
   a.NACC = env_int("PREMVOS_NACC", 1);
@@ -597,6 +696,26 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.tmem_cols = cols;
   plan->grid_x = a.tiles_x * a.tiles_y * in.N;
   plan->grid_y = w.ntiles;
+  // split-K when the grid cannot fill the machine: the K loop of a CTA is a serial chain of barrier handshakes
+  a.ksplit = 1; a.kb_per = a.kblocks; a.cout_pad = w.ntiles * w.BN; a.partial = nullptr; a.partial_stride = 0;
+  {
+    const long ctas = (long)plan->grid_x * plan->grid_y;
+    int split = 1;
+    if (ctas * 2 <= 148 && a.kblocks >= 4) {
+      split = (int)std::min<long>(std::min<long>(a.kblocks / 2, 148 / ctas), 16);
+    }
+    split = env_int("PREMVOS_KSPLIT", split);
+    if (split > a.kblocks) split = a.kblocks;
+    if (split > 1) {
+      a.kb_per = (a.kblocks + split - 1) / split;
+      a.ksplit = (a.kblocks + a.kb_per - 1) / a.kb_per;   // every split owns at least one k-block
+      a.partial_stride = (long)in.N * Ho * Wo * a.cout_pad;
+      PV_CUDA(cudaMalloc((void**)&a.partial, (size_t)a.ksplit * a.partial_stride * sizeof(float)));
+      PV_CUDA(cudaMemset(a.partial, 0, (size_t)a.ksplit * a.partial_stride * sizeof(float)));
+      plan->scratch = a.partial;
+    }
+  }
+  plan->grid_z = a.ksplit;
 
   // input tensor maps over the view's chunk planes: [N][chunks][H][W][8]
   const int vchunks = (in.C + 7) / 8;
@@ -637,10 +756,18 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   if (active_n >= 0 && active_n < plan.N) grid_x = plan.grid_x / plan.N * active_n;
   if (grid_x == 0) return 0;
   prof_before(st);
-  conv_umma_kernel<<<dim3(grid_x, plan.grid_y), UMMA_THREADS, plan.smem_bytes, st>>>(
+  conv_umma_kernel<<<dim3(grid_x, plan.grid_y, plan.grid_z), UMMA_THREADS, plan.smem_bytes, st>>>(
       *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
   const double frac = (double)grid_x / plan.grid_x;
-  return after_launch("conv_umma_kernel", st, plan.flops * frac, plan.bytes * frac);
+  PV_TRY(after_launch("conv_umma_kernel", st, plan.flops * frac, plan.bytes * frac));
+  if (plan.grid_z > 1) {
+    const int na = (active_n >= 0 && active_n < plan.N) ? active_n : plan.N;
+    const long total = (long)na * a.Ho * a.Wo * ((a.Cout + 7) / 8);
+    prof_before(st);
+    conv_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, na);
+    PV_TRY(after_launch("conv_finish_kernel", st, 0.0, (double)total * 32.0 * (a.ksplit + 1)));
+  }
+  return 0;
 }
 
 }  // namespace premvos

@@ -362,7 +362,11 @@ int run_network(premvos_propnet* n, cudaStream_t st) {
   return 0;
 }
 
-void free_layer(ConvLayer* L) { if (L->used) free_conv_weights_umma(&L->w); }
+void free_layer(ConvLayer* L) {
+  if (!L->used) return;
+  free_conv_weights_umma(&L->w);
+  free_conv_plan_umma(&L->plan);
+}
 
 }  // namespace
 

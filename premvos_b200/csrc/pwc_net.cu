@@ -240,39 +240,33 @@ int pack_weights_tc(premvos_pwc* n) {
   for (int L = 6; L >= 2; L--) {
     const int phys_total = slab_chunks(L) * 8;
     int cin = level_od(L);
-    for (int i = 0; i < 5; i++) {
-      std::string k = "conv" + std::to_string(L) + "_" + std::to_string(i) + ".0";
-      std::vector<int> map = slab_cin_map(L, DEC_IN_OFF[i]);
-      PV_CHECK((int)map.size() == cin, PREMVOS_ERR_INVALID_ARG, "internal: slab map size %d != %d", (int)map.size(), cin);
-      // levels 6..4 launch fewer CTAs than there are SMs: latency-bound K loops want long k-blocks
-      PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3, map.data(),
-                                    phys_total - DEC_IN_OFF[i], small_grid(n, L) ? 8 : 0));
-      cin += DEC_OUT[i];
-    }
+    const int cin_all = cin + 448;               // input channels of predict_flowL / upfeatL (the whole slab)
     // head = predict_flowL (2 ch) fused with upfeatL: ConvTranspose2d(cin, 2, 4, 2, 1) == 3x3 convolution with
     // 8 outputs ((py*2+px)*2+co) at the input resolution followed by a pixel shuffle:
     //   out[2y+py, 2x+px, co] = sum_{r,s} in[y+r-1, x+s-1] * Wd[ci][co][3-2r+py][3-2s+px]   (taps outside 0..3 vanish)
     const int hc = (L != 2) ? 10 : 2;
-    std::vector<float> hw((size_t)hc * cin * 9, 0.f), hb(hc, 0.f);
-    std::string pf = "predict_flow" + std::to_string(L);
-    const float* pw = P(n, pf + ".weight");
-    std::copy(pw, pw + (size_t)2 * cin * 9, hw.begin());
-    hb[0] = P(n, pf + ".bias")[0]; hb[1] = P(n, pf + ".bias")[1];
+    std::vector<float> hw((size_t)hc * cin_all * 9, 0.f), hb(hc, 0.f);
+    {
+      std::string pf = "predict_flow" + std::to_string(L);
+      const float* pw = P(n, pf + ".weight");
+      std::copy(pw, pw + (size_t)2 * cin_all * 9, hw.begin());
+      hb[0] = P(n, pf + ".bias")[0]; hb[1] = P(n, pf + ".bias")[1];
+    }
     if (L != 2) {
       std::string uk = "upfeat" + std::to_string(L);
-      const float* uw = P(n, uk + ".weight");  // [cin][2][4][4]
+      const float* uw = P(n, uk + ".weight");  // [cin_all][2][4][4]
       const float* ub = P(n, uk + ".bias");
       for (int py = 0; py < 2; py++)
         for (int px = 0; px < 2; px++)
           for (int co = 0; co < 2; co++) {
             const int oc = 2 + (py * 2 + px) * 2 + co;
             hb[oc] = ub[co];
-            for (int ci = 0; ci < cin; ci++)
+            for (int ci = 0; ci < cin_all; ci++)
               for (int r = 0; r < 3; r++)
                 for (int s2 = 0; s2 < 3; s2++) {
                   const int ky = 3 - 2 * r + py, kx = 3 - 2 * s2 + px;
                   if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;
-                  hw[((size_t)oc * cin + ci) * 9 + r * 3 + s2] = uw[(((size_t)ci * 2 + co) * 4 + ky) * 4 + kx];
+                  hw[((size_t)oc * cin_all + ci) * 9 + r * 3 + s2] = uw[(((size_t)ci * 2 + co) * 4 + ky) * 4 + kx];
                 }
           }
       std::string dk = "deconv" + std::to_string(L);
@@ -282,9 +276,37 @@ int pack_weights_tc(premvos_pwc* n) {
       PV_CUDA(cudaMalloc((void**)&n->d_deconv_w[L], 66 * sizeof(float)));
       PV_CUDA(cudaMemcpy(n->d_deconv_w[L], dw.data(), 66 * sizeof(float), cudaMemcpyHostToDevice));
     }
-    std::vector<int> map = slab_cin_map(L, 0);
-    PV_TRY(pack_conv_weights_umma(&n->wt_head[L], hw.data(), hb.data(), hc, cin, 3, 3, map.data(), phys_total,
-                                  small_grid(n, L) ? 8 : 0));
+    for (int i = 0; i < 5; i++) {
+      std::string k = "conv" + std::to_string(L) + "_" + std::to_string(i) + ".0";
+      std::vector<int> map = slab_cin_map(L, DEC_IN_OFF[i]);
+      PV_CHECK((int)map.size() == cin, PREMVOS_ERR_INVALID_ARG, "internal: slab map size %d != %d", (int)map.size(), cin);
+      // levels 6..4 launch fewer CTAs than there are SMs: split-K with 32-channel k-blocks
+      const int kc = small_grid(n, L) ? 4 : 0;
+      if (i < 4) {
+        PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], P(n, k + ".weight"), P(n, k + ".bias"), DEC_OUT[i], cin, 3, 3, map.data(),
+                                      phys_total - DEC_IN_OFF[i], kc));
+      } else {
+        // convL_4 reads everything the flow head reads except its own 32 outputs: the head's partial sums over those
+        // `cin` channels ride along as hc extra (linear) output channels; the head proper only adds the 32-channel rest
+        const int co = DEC_OUT[4] + hc;
+        std::vector<float> w4((size_t)co * cin * 9), b4(co);
+        std::copy(P(n, k + ".weight"), P(n, k + ".weight") + (size_t)DEC_OUT[4] * cin * 9, w4.begin());
+        std::copy(P(n, k + ".bias"), P(n, k + ".bias") + DEC_OUT[4], b4.begin());
+        for (int o = 0; o < hc; o++) {
+          b4[DEC_OUT[4] + o] = hb[o];
+          for (int ci = 0; ci < cin; ci++)
+            for (int t = 0; t < 9; t++)
+              w4[((size_t)(DEC_OUT[4] + o) * cin + ci) * 9 + t] = hw[((size_t)o * cin_all + DEC_OUT[4] + ci) * 9 + t];
+        }
+        PV_TRY(pack_conv_weights_umma(&n->wt_dec[L][i], w4.data(), b4.data(), co, cin, 3, 3, map.data(), phys_total - DEC_IN_OFF[i], kc));
+        std::vector<float> wr((size_t)hc * DEC_OUT[4] * 9);
+        for (int o = 0; o < hc; o++)
+          for (int ci = 0; ci < DEC_OUT[4]; ci++)
+            for (int t = 0; t < 9; t++) wr[((size_t)o * DEC_OUT[4] + ci) * 9 + t] = hw[((size_t)o * cin_all + ci) * 9 + t];
+        PV_TRY(pack_conv_weights_umma(&n->wt_head[L], wr.data(), nullptr, hc, DEC_OUT[4], 3, 3));
+      }
+      cin += DEC_OUT[i];
+    }
   }
   int cin = level_od(2) + 448;
   for (int i = 0; i < 6; i++) {
@@ -364,14 +386,27 @@ int alloc_activations_tc(premvos_pwc* n) {
   }
   for (int L = 6; L >= 2; L--) {
     const int tot = slab_chunks(L);
+    const int hc = n->wt_head[L].Cout;
+    TView ho = n->head[L].slice(0, hc);
     for (int i = 0; i < 5; i++) {
       CView in = n->c_slab[L].slice(DEC_IN_OFF[i] / 8, (tot - DEC_IN_OFF[i] / 8) * 8);
       CView out = n->c_slab[L].slice(DEC_OUT_OFF[i] / 8, DEC_OUT[i]);
-      PV_TRY(plan(&n->pl_dec[L][i], in, &out, nullptr, n->wt_dec[L][i], ConvGeom::same3x3(1, 0.1f)));
+      if (i < 4) {
+        PV_TRY(plan(&n->pl_dec[L][i], in, &out, nullptr, n->wt_dec[L][i], ConvGeom::same3x3(1, 0.1f)));
+      } else {  // convL_4 + the flow head's partial sums (linear, fp32) in one launch
+        ConvOut o;
+        o.cp = out; o.cp_channels = DEC_OUT[4];
+        o.f32 = ho; o.f32_first = DEC_OUT[4]; o.f32_linear = true;
+        n->tensor_core_layers++;
+        PV_TRY(plan_conv_umma(&n->pl_dec[L][i], in, o, n->wt_dec[L][i], ConvGeom::same3x3(1, 0.1f)));
+      }
     }
-    CView all = n->c_slab[L].slice(0, tot * 8);
-    TView ho = n->head[L].slice(0, n->wt_head[L].Cout);
-    PV_TRY(plan(&n->pl_head[L], all, nullptr, &ho, n->wt_head[L], ConvGeom::same3x3(1, 1.0f)));
+    {  // head remainder: the 32 channels convL_4 just produced, accumulated onto the partial sums
+      ConvOut o;
+      o.f32 = ho; o.f32_linear = true; o.f32_accumulate = true;
+      n->tensor_core_layers++;
+      PV_TRY(plan_conv_umma(&n->pl_head[L], n->c_slab[L].slice(0, DEC_OUT[4]), o, n->wt_head[L], ConvGeom::same3x3(1, 1.0f)));
+    }
   }
   CView in = n->c_slab[2].slice(0, slab_chunks(2) * 8);
   CView bufs[2] = {n->c_ctxA, n->c_ctxB};
@@ -664,6 +699,14 @@ extern "C" void premvos_pwc_destroy(premvos_pwc_t* n) {
   }
   for (int i = 0; i < 6; i++) free_conv_weights_umma(&n->wt_dc[i]);
   free_conv_weights_umma(&n->wt_dc7);
+  for (int L = 1; L <= 6; L++)
+    for (int j = 0; j < 3; j++) free_conv_plan_umma(&n->pl_pyr[L][j]);
+  for (int L = 2; L <= 6; L++) {
+    for (int i = 0; i < 5; i++) free_conv_plan_umma(&n->pl_dec[L][i]);
+    free_conv_plan_umma(&n->pl_head[L]);
+  }
+  for (int i = 0; i < 6; i++) free_conv_plan_umma(&n->pl_dc[i]);
+  free_conv_plan_umma(&n->pl_dc7);
   free_small_conv_weights(&n->w_dc7);
   if (n->stream) cudaStreamDestroy(n->stream);
   delete n;

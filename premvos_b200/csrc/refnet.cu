@@ -439,6 +439,7 @@ extern "C" void premvos_refnet_destroy(premvos_refnet_t* n) {
   cudaDeviceSynchronize();
   for (void* p : n->allocs) cudaFree(p);
   for (auto& w : n->conv_weights) free_conv_weights_umma(w.get());
+  for (auto& pl : n->conv_plans) free_conv_plan_umma(pl.get());
   if (n->frame_dev) cudaFree(n->frame_dev);
   if (n->mask_dev) cudaFree(n->mask_dev);
   if (n->post_dev) cudaFree(n->post_dev);

@@ -41,6 +41,8 @@ CASES = [
     (1, 529, 7, 16, 10, 3, 1, 1, (1, 1, 1, 1), 1.0, False),     # flow head: Cout 10 -> N = 16
     (4, 117, 112, 256, 128, 3, 1, 1, (1, 1, 1, 1), 0.1, False),  # bench-size level 2 layer: MT = 2 tiles
     (1, 3, 75, 131, 64, 7, 2, 1, (2, 2, 3, 3), 0.0, False),     # ResNet stem 7x7 s2, pad (2,3)
+    (2, 661, 14, 32, 96, 3, 1, 1, (1, 1, 1, 1), 0.1, False),    # PWC level 5: 8 CTAs -> split-K + finish kernel
+    (1, 2048, 9, 9, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, True),     # tiny grid 1x1 with residual through the split-K path
 ]
 
 
