@@ -147,11 +147,14 @@ def test_pwc_full_size_against_oracle_and_properties(tc):
     f0 = net(xd[:1])
     f0b = net(xd[:1])
     assert torch.equal(f0, f0b), "forward is not deterministic"
-    # batch independence: a batch-2 handle gives the same per-pair results
+    # batch independence: a batch-2 handle gives the same per-pair results.  In tensor-core mode the planner may pick a
+    # different (deterministic) split-K factor for the low pyramid levels at another batch size, i.e. another fp32
+    # summation order -- equal within rounding, not bit for bit.
+    btol = 1e-4 if tc else 1e-6
     f01 = net(xd)
-    assert rel_err(f01[:1].cpu().numpy(), f0.cpu().numpy()) < 1e-6
+    assert rel_err(f01[:1].cpu().numpy(), f0.cpu().numpy()) < btol
     f1 = net(xd[1:])
-    assert rel_err(f01[1:].cpu().numpy(), f1.cpu().numpy()) < 1e-6
+    assert rel_err(f01[1:].cpu().numpy(), f1.cpu().numpy()) < btol
     # host entry point == device entry point
     fh = net.forward_host(x[:1].copy())
     assert np.array_equal(fh, f0.cpu().numpy())
