@@ -198,7 +198,7 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
   alignas(64) unsigned char map_a_hi[128];
   alignas(64) unsigned char map_a_lo[128];
   alignas(16) unsigned char args[320];
-  int grid_x = 0, grid_y = 0, grid_z = 1, smem_bytes = 0, halo = 0, MT = 0, N = 0;
+  int grid_x = 0, grid_y = 0, grid_z = 1, smem_bytes = 0, halo = 0, MT = 0, N = 0, ctas_per_sm = 1;
   void* scratch = nullptr;   // split-K partial sums (owned by the plan, see free_conv_plan_umma)
   double flops = 0, bytes = 0;
 };

@@ -177,6 +177,9 @@ struct UmmaConvArgs {
   int ksplit, kb_per, cout_pad;
   float* partial;            // [ksplit][N*Ho*Wo][cout_pad]
   long partial_stride;       // elements per split
+  // persistent scheduling: work item t = ((z * ntiles + ntile) * n_images + n) * tiles_per_img + tile, CTA b takes b, b+grid, ...
+  int ntiles, n_images, total_work;
+  int nbuf;                  // TMEM accumulator buffers (2: the epilogue of item i overlaps the MMAs of item i+1)
 };
 
 __global__ void __launch_bounds__(UMMA_THREADS, 2)
@@ -190,25 +193,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* a_empty = bars + MAX_A_STAGES;
   uint64_t* w_full = bars + 2 * MAX_A_STAGES;
   uint64_t* w_empty = w_full + MAX_W_STAGES;
-  uint64_t* tmem_full_bar = w_empty + MAX_W_STAGES;
-  uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = w_empty + MAX_W_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
-  const int n_img = tile / tiles_per_img;
-  const int trem = tile - n_img * tiles_per_img;
-  const int ty0 = (trem / a.tiles_x) * 16 * a.MT, tx0 = (trem % a.tiles_x) * 8;
-  const int ntile = blockIdx.y;
   const int taps = a.R * a.S;
-  const int kb_begin = a.ksplit > 1 ? (int)blockIdx.z * a.kb_per : 0;
-  const int kb_end = a.ksplit > 1 ? min(a.kblocks, kb_begin + a.kb_per) : a.kblocks;
+  // decode of a work item (once per item, the only integer divisions in the kernel)
+  struct Work { int n_img, ty0, tx0, ntile, z, kb_begin, kb_end; };
+  auto decode = [&](int t) {
+    Work w;
+    const int tile = t % tiles_per_img;
+    int r = t / tiles_per_img;
+    w.n_img = r % a.n_images; r /= a.n_images;
+    w.ntile = r % a.ntiles;
+    w.z = r / a.ntiles;
+    w.ty0 = (tile / a.tiles_x) * 16 * a.MT;
+    w.tx0 = (tile % a.tiles_x) * 8;
+    w.kb_begin = a.ksplit > 1 ? w.z * a.kb_per : 0;
+    w.kb_end = a.ksplit > 1 ? min(a.kblocks, w.kb_begin + a.kb_per) : a.kblocks;
+    return w;
+  };
 
   if (warp == 0 && lane == 0) {  // one-time setup
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
     for (int s = 0; s < a.a_stages; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < a.w_stages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_addr_slot, a.tmem_cols);
@@ -221,9 +233,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // ===== TMA producer =====  the whole warp walks the warp-uniform loop, one elected lane issues the copies
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0;
     const uint32_t w_bytes = (uint32_t)a.TPS * 2u * (uint32_t)a.w_plane;   // one bulk copy
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)ntile * a.kblocks + kb_begin) * taps * 2 * a.w_plane;
-    const int bx = tx0 * a.stride - a.pad_l, by = ty0 * a.stride - a.pad_t;
-    for (int kb = kb_begin; kb < kb_end; kb++) {
+    for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
+    const Work wk = decode(t);
+    const int n_img = wk.n_img;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)wk.ntile * a.kblocks + wk.kb_begin) * taps * 2 * a.w_plane;
+    const int bx = wk.tx0 * a.stride - a.pad_l, by = wk.ty0 * a.stride - a.pad_t;
+    for (int kb = wk.kb_begin; kb < wk.kb_end; kb++) {
       int tin = 0;  // tap index inside the current weight stage
       for (int r = 0; r < a.R; r++)
         for (int s = 0; s < a.S; s++) {
@@ -261,6 +276,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (++tin == a.TPS) tin = 0;
         }
     }
+    }  // work loop
   } else if (warp == 1) {
     // ===== MMA issuer =====  the whole warp walks the (warp-uniform) loop, one elected lane issues
     const uint32_t idesc = make_idesc_bf16(128, a.BN);
@@ -274,7 +290,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = 16u * a_sbo;
     const uint32_t tap_row = a.halo ? (uint32_t)(a.dil * a.box_w) * 16u : 0u, tap_col = a.halo ? (uint32_t)a.dil * 16u : 0u;
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0;
-    uint32_t accum = 0;
+    uint32_t buf = 0, empty_ph = 0;   // bit b = phase of tmem_empty_bar[b]
     const int ksteps = a.KC / 2;
     const uint32_t rep_cols = (uint32_t)(a.MT * a.BN);
     const uint32_t rep1 = a.NACC > 1 ? rep_cols : 0u, rep2 = a.NACC > 2 ? 2u * rep_cols : 0u;
@@ -282,7 +298,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // releases the stage.  (A per-tap handshake costs ~500 cycles of mbarrier/commit latency -- more than the
     // MMAs of one tap.)  Tap mode additionally waits for / releases one A stage per tap.
     const int wgroups = taps / a.TPS;
-    for (int kb = kb_begin; kb < kb_end; kb++) {
+    for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
+    const Work wk = decode(t);
+    // the accumulator buffer must have been drained by the epilogue of the item that used it last
+    mbar_wait(&tmem_empty_bar[buf], ((empty_ph >> buf) & 1u) ^ 1u);
+    empty_ph ^= 1u << buf;
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + buf * rep_cols * (uint32_t)a.NACC;
+    uint32_t accum = 0;
+    for (int kb = wk.kb_begin; kb < wk.kb_end; kb++) {
       int r = 0, s = 0;
       uint32_t row_off = 0, tap_off = 0;
       for (int wg = 0; wg < wgroups; wg++) {
@@ -308,7 +332,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aa0 += a_kstep, ww += w_kstep) {
               const uint64_t dWh = ((uint64_t)w_hi32 << 32) | (w_lo32 + ((ww & 0x3FFFFu) >> 4));
               const uint64_t dWl = ((uint64_t)w_hi32 << 32) | (w_lo32 + (((ww + (uint32_t)a.w_plane) & 0x3FFFFu) >> 4));
-              uint32_t aa = aa0, d = tmem_base;
+              uint32_t aa = aa0, d = tmem_acc;
               for (int mt = 0; mt < a.MT; mt++, aa += a_mstep, d += (uint32_t)a.BN) {
                 const uint64_t dAh = ((uint64_t)a_hi32 << 32) | (a_lo32 + ((aa & 0x3FFFFu) >> 4));
                 const uint64_t dAl = ((uint64_t)a_hi32 << 32) | (a_lo32 + (((aa + (uint32_t)a.a_plane) & 0x3FFFFu) >> 4));
@@ -332,15 +356,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
       }
     }
-    if (elect_one()) umma_commit(tmem_full_bar);  // accumulators complete
+    if (elect_one()) umma_commit(&tmem_full_bar[buf]);  // accumulators of this item complete
     __syncwarp();
+    if (a.nbuf > 1) buf ^= 1u;
+    }  // work loop
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;  // accumulator row == pixel inside the 16x8 sub-tile
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const long hw = (long)a.Ho * a.Wo;
+    uint32_t buf = 0, full_ph = 0;    // bit b = phase of tmem_full_bar[b]
+    const uint32_t buf_cols = (uint32_t)(a.MT * a.BN * a.NACC);
+    for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
+    const Work wk = decode(t);
+    const int n_img = wk.n_img, ty0 = wk.ty0, tx0 = wk.tx0, ntile = wk.ntile;
+    mbar_wait(&tmem_full_bar[buf], (full_ph >> buf) & 1u);
+    full_ph ^= 1u << buf;
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + buf * buf_cols;
     for (int mt = 0; mt < a.MT; mt++) {
       const int oy = ty0 + mt * 16 + (m >> 3), ox = tx0 + (m & 7);
       const bool in_img = oy < a.Ho && ox < a.Wo;
@@ -348,7 +381,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int c0 = 0; c0 < a.BN; c0 += 16) {
         uint32_t v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0);
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0);
+        const bool last_ld = (mt == a.MT - 1) && (c0 + 16 >= a.BN);
         tmem_ld16(taddr, v);
         tmem_ld_wait();
         for (int rep = 1; rep < a.NACC; rep++) {
@@ -358,10 +392,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         }
+        if (last_ld) {  // every accumulator column of this item is in registers: hand the TMEM buffer back to the issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
         const int co0 = ntile * a.BN + c0;
         if (a.ksplit > 1) {  // raw partial sums; bias / residual / activation happen in conv_finish_kernel
           if (in_img) {
-            float* pp = a.partial + (long)blockIdx.z * a.partial_stride + ((long)n_img * hw + pix) * a.cout_pad + co0;
+            float* pp = a.partial + (long)wk.z * a.partial_stride + ((long)n_img * hw + pix) * a.cout_pad + co0;
 #pragma unroll
             for (int j = 0; j < 4; j++)
               reinterpret_cast<float4*>(pp)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -428,6 +467,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
     }
+    if (a.nbuf > 1) buf ^= 1u;
+    }  // work loop
   }
   tc_fence_before();
   __syncthreads();
@@ -716,6 +757,16 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     }
   }
   plan->grid_z = a.ksplit;
+  a.ntiles = w.ntiles; a.n_images = in.N;
+  a.total_work = plan->grid_x * plan->grid_y * a.ksplit;
+  // two CTAs per SM when shared memory and TMEM allow it; a second accumulator buffer when TMEM allows that too
+  const int cps = (plan->smem_bytes <= 112 * 1024 && a.NACC * a.MT * w.BN <= 256) ? 2 : 1;
+  a.nbuf = (2 * a.NACC * a.MT * w.BN <= (cps == 2 ? 256 : 512)) ? 2 : 1;
+  a.nbuf = env_int("PREMVOS_NBUF", a.nbuf);
+  cols = 32;
+  while ((int)cols < a.nbuf * a.NACC * a.MT * w.BN) cols <<= 1;
+  a.tmem_cols = cols;
+  plan->ctas_per_sm = cps;
 
   // input tensor maps over the view's chunk planes: [N][chunks][H][W][8]
   const int vchunks = (in.C + 7) / 8;
@@ -750,15 +801,25 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
     PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  const UmmaConvArgs& a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
-  // the image index is the slowest part of the tile index: a shorter grid processes the first active_n images
-  int grid_x = plan.grid_x;
-  if (active_n >= 0 && active_n < plan.N) grid_x = plan.grid_x / plan.N * active_n;
-  if (grid_x == 0) return 0;
+  // persistent CTAs: at most ctas_per_sm per SM, each walks the work items b, b + grid, ...  A smaller active batch
+  // just shortens the list (the image index is a digit of the work index).
+  UmmaConvArgs a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
+  if (active_n >= 0 && active_n < plan.N) {
+    a.total_work = a.total_work / plan.N * active_n;
+    a.n_images = active_n;
+  }
+  if (a.total_work == 0) return 0;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PV_CUDA(cudaGetDevice(&dev));
+    PV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = std::min(a.total_work, num_sms * plan.ctas_per_sm);
   prof_before(st);
-  conv_umma_kernel<<<dim3(grid_x, plan.grid_y, plan.grid_z), UMMA_THREADS, plan.smem_bytes, st>>>(
+  conv_umma_kernel<<<grid, UMMA_THREADS, plan.smem_bytes, st>>>(
       *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
-  const double frac = (double)grid_x / plan.grid_x;
+  const double frac = (double)a.n_images / plan.N;
   PV_TRY(after_launch("conv_umma_kernel", st, plan.flops * frac, plan.bytes * frac));
   if (plan.grid_z > 1) {
     const int na = (active_n >= 0 && active_n < plan.N) ? active_n : plan.N;
