@@ -145,7 +145,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 struct UmmaConvArgs {
-  int tiles_x, tiles_y, MT;  // tiles per image; MT accumulators (16 rows x 8 cols each, stacked in y) per CTA
+  int tiles_x, tiles_y, MT;  // tiles per image; MT accumulators (16 rows x 8 cols each) per CTA ...
+  int mt_horizontal;         // ... side by side in x (1) or stacked in y (0), whichever pads the image less
   int Ho, Wo;                // output size
   int stride, R, S, dil, pad_t, pad_l;
   int halo;                  // 1: one A box per k-block serves all taps; 0: one A box per (tap, k-block)
@@ -209,8 +210,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     w.n_img = r % a.n_images; r /= a.n_images;
     w.ntile = r % a.ntiles;
     w.z = r / a.ntiles;
-    w.ty0 = (tile / a.tiles_x) * 16 * a.MT;
-    w.tx0 = (tile % a.tiles_x) * 8;
+    w.ty0 = (tile / a.tiles_x) * (a.mt_horizontal ? 16 : 16 * a.MT);
+    w.tx0 = (tile % a.tiles_x) * (a.mt_horizontal ? 8 * a.MT : 8);
     w.kb_begin = a.ksplit > 1 ? w.z * a.kb_per : 0;
     w.kb_end = a.ksplit > 1 ? min(a.kblocks, w.kb_begin + a.kb_per) : a.kblocks;
     return w;
@@ -287,7 +288,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_lo32 = (a_lbo >> 4) << 16, w_lo32 = (w_lbo >> 4) << 16;
     const uint32_t a_base = smem_u32(a_smem), w_base = smem_u32(w_smem);
     const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = (uint32_t)a.w_stage;
-    const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = 16u * a_sbo;
+    const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = a.mt_horizontal ? 128u : 16u * a_sbo;
     const uint32_t tap_row = a.halo ? (uint32_t)(a.dil * a.box_w) * 16u : 0u, tap_col = a.halo ? (uint32_t)a.dil * 16u : 0u;
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0;
     uint32_t buf = 0, empty_ph = 0;   // bit b = phase of tmem_empty_bar[b]
@@ -375,7 +376,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base + buf * buf_cols;
     for (int mt = 0; mt < a.MT; mt++) {
-      const int oy = ty0 + mt * 16 + (m >> 3), ox = tx0 + (m & 7);
+      const int oy = ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
       const bool in_img = oy < a.Ho && ox < a.Wo;
       const long pix = (long)oy * a.Wo + ox;
       for (int c0 = 0; c0 < a.BN; c0 += 16) {
@@ -670,14 +671,16 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   static_assert(sizeof(UmmaConvArgs) <= sizeof(plan->args), "ConvPlanUmma::args too small");
   memset(&a, 0, sizeof(a));
   const int taps = w.R * w.S;
-  a.tiles_x = (Wo + 7) / 8;
   a.Ho = Ho; a.Wo = Wo;
   a.stride = g.stride; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
   a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
   a.merged_x = (g.stride == 1) ? 1 : 0;
   a.w_plane = w.KC * w.BN * 16;
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
-  const long ctas_mt2 = (long)a.tiles_x * ((Ho + 31) / 32) * in.N * w.ntiles;
+  // two sub-tiles per CTA either stacked (32 x 8 pixels) or side by side (16 x 16): take the one that pads less
+  const long tiles_v = (long)((Wo + 7) / 8) * ((Ho + 31) / 32), tiles_h = (long)((Wo + 15) / 16) * ((Ho + 15) / 16);
+  const bool horiz = tiles_h < tiles_v;
+  const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
   int mt_pref = (ctas_mt2 >= 2 * 148 && Ho > 16 && g.dil < 4) ? 2 : 1;
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
@@ -689,15 +692,17 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     const int mt = (cand & 1) ? 1 : mt_pref;
     const bool want_halo = cand < 2;
     if ((cand & 1) && mt_pref == 1) continue;
-    const int halo_w = 8 + (w.S - 1) * g.dil, halo_h = 16 * mt + (w.R - 1) * g.dil;
+    const bool hz = horiz && mt == 2;
+    const int halo_w = (hz ? 16 : 8) + (w.S - 1) * g.dil, halo_h = (hz ? 16 : 16 * mt) + (w.R - 1) * g.dil;
     const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * mt;
     // halo mode only when it moves fewer bytes into shared memory than per-tap boxes
     const bool halo_ok = g.stride == 1 && taps > 1 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
     if (want_halo && !halo_ok) continue;
     a.MT = mt;
+    a.mt_horizontal = hz ? 1 : 0;
     a.halo = want_halo ? 1 : 0;
-    a.box_w = a.halo ? halo_w : 8;
-    a.box_h = a.halo ? halo_h : 16 * mt;
+    a.box_w = a.halo ? halo_w : (hz ? 16 : 8);
+    a.box_h = a.halo ? halo_h : (hz ? 16 : 16 * mt);
     a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
     a.a_plane = round_up(a.a_box_bytes, 128);
     a.a_stages = a.halo ? 2 : 3;
@@ -712,7 +717,9 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     }
   }
   PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);
-  a.tiles_y = (Ho + 16 * a.MT - 1) / (16 * a.MT);
+  const int tile_w = a.mt_horizontal ? 16 : 8, tile_h = a.mt_horizontal ? 16 : 16 * a.MT;
+  a.tiles_x = (Wo + tile_w - 1) / tile_w;
+  a.tiles_y = (Ho + tile_h - 1) / tile_h;
   // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
   int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
   if (env_int("PREMVOS_BUDGET_KB", 0) > 0) budget = env_int("PREMVOS_BUDGET_KB", 0) * 1024;

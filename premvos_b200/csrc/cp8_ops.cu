@@ -62,6 +62,34 @@ __global__ void __launch_bounds__(256) pack_pair_cp8_kernel(const float* __restr
   st_chunk(img.hi, img.lo, (((long)n * img.chunks + img.c0) * hw + p) * 8, f);
 }
 
+// im2col of the FIRST pyramid convolution (3x3, stride 2, pad 1, 3 input channels: PWCNet.py:50): the 27 inputs of every
+// output pixel are gathered here so that conv1a becomes a 1x1 GEMM with K = 27 (4 chunk planes, channel (r*3+s)*3 + c).
+// Same bytes written as a plain 8-channel full-resolution image, but the convolution reads them once instead of through
+// nine strided TMA boxes.
+__global__ void __launch_bounds__(256) pack_pair_im2col_kernel(const float* __restrict__ x, CV img, int B, int H, int W) {
+  const int Ho = img.H, Wo = img.W;
+  const long total = 2L * B * 4 * Ho * Wo;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
+  const int ch = (int)((idx / ((long)Wo * Ho)) % 4), n = (int)(idx / ((long)Wo * Ho * 4));
+  const int b = n % B, im = n / B;
+  const float* src = x + ((long)b * 6 + im * 3) * H * W;
+  F8 f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = ch * 8 + j;          // (r*3+s)*3 + c
+    float v = 0.f;
+    if (k < 27) {
+      const int c = k % 3, tap = k / 3, r = tap / 3, s = tap % 3;
+      const int iy = 2 * oy + r - 1, ix = 2 * ox + s - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = src[(long)c * H * W + (long)iy * W + ix];
+    }
+    f.v[j] = v;
+  }
+  st_chunk(img.hi, img.lo, cv_elem(img, n, ch, oy, ox), f);
+}
+
 // ---- PWCDCNet.warp (PWCNet.py:140-176) -------------------------------------------------------------
 struct WarpCp8Args { CV x, flow, out; int flow_ch; float scale; };
 
@@ -304,6 +332,14 @@ int pack_pair_input_cp8(const float* x_nchw, int B, int H, int W, const CView& i
   prof_before(st);
   pack_pair_cp8_kernel<<<blocks_for(total), 256, 0, st>>>(x_nchw, dev(img), B);
   return after_launch("pack_pair_cp8_kernel", st, 0.0, (double)total * (12.0 + 32.0));
+}
+
+int pack_pair_im2col_cp8(const float* x_nchw, int B, int H, int W, const CView& img, cudaStream_t st) {
+  PV_CHECK(img.N == 2 * B && img.H == H / 2 && img.W == W / 2 && img.C == 32, PREMVOS_ERR_INVALID_ARG, "pack_pair_im2col_cp8: shape mismatch");
+  const long total = 2L * B * 4 * img.H * img.W;
+  prof_before(st);
+  pack_pair_im2col_kernel<<<blocks_for(total), 256, 0, st>>>(x_nchw, dev(img), B, H, W);
+  return after_launch("pack_pair_im2col_kernel", st, 0.0, (double)B * 6 * H * W * 4 + (double)total * 32.0);
 }
 
 int warp_cp8(const CView& x2, const CView& flow, int flow_ch, float flow_scale, const CView& out, cudaStream_t st) {

@@ -231,8 +231,13 @@ int pack_weights_tc(premvos_pwc* n) {
       std::string k = std::string(PYR_NAMES[L][j]) + ".0";
       int cin = (j == 0) ? LEVEL_CH[L - 1] : LEVEL_CH[L];
       if (L == 1 && j == 0) {
-        const int map3[3] = {0, 1, 2};
-        PV_TRY(pack_conv_weights_umma(&n->wt_pyr[L][j], P(n, k + ".weight"), P(n, k + ".bias"), LEVEL_CH[L], cin, 3, 3, map3, 8));
+        // conv1a runs as a 1x1 GEMM over the im2col image written by pack_pair_im2col_cp8: K index (r*3+s)*3 + c
+        const float* w3 = P(n, k + ".weight");  // [16][3][3][3]
+        std::vector<float> w1((size_t)LEVEL_CH[1] * 27);
+        for (int co = 0; co < LEVEL_CH[1]; co++)
+          for (int c = 0; c < 3; c++)
+            for (int t = 0; t < 9; t++) w1[(size_t)co * 27 + t * 3 + c] = w3[((size_t)co * 3 + c) * 9 + t];
+        PV_TRY(pack_conv_weights_umma(&n->wt_pyr[L][j], w1.data(), P(n, k + ".bias"), LEVEL_CH[L], 27, 1, 1));
       } else {
         PV_TRY(pack_conv_weights_umma(&n->wt_pyr[L][j], P(n, k + ".weight"), P(n, k + ".bias"), LEVEL_CH[L], cin, 3, 3));
       }
@@ -349,7 +354,8 @@ int alloc_io(premvos_pwc* n) {
 
 int alloc_activations_tc(premvos_pwc* n) {
   const int B = n->B;
-  PV_TRY(alloc_cview(n, &n->c_img, 2 * B, n->H, n->W, 1));
+  PV_TRY(alloc_cview(n, &n->c_img, 2 * B, n->H / 2, n->W / 2, 4));
+  n->c_img.C = 32;
   for (int L = 1; L <= 6; L++)
     for (int j = 0; j < 3; j++) {
       PV_TRY(alloc_cview(n, &n->c_pyr[L][j], 2 * B, n->H >> L, n->W >> L, (LEVEL_CH[L] + 7) / 8));
@@ -375,10 +381,14 @@ int alloc_activations_tc(premvos_pwc* n) {
     n->tensor_core_layers++;
     return plan_conv_umma(pl, in, o, w, g);
   };
-  CView cur = n->c_img.slice(0, 8);
+  CView cur = n->c_img.slice(0, 27);
   for (int L = 1; L <= 6; L++) {
     ConvGeom g2 = ConvGeom::same3x3(1, 0.1f);
     g2.stride = 2;
+    if (L == 1) {  // 1x1 over the im2col image (the stride and the padding were applied by the packing kernel)
+      g2 = ConvGeom();
+      g2.slope = 0.1f;
+    }
     PV_TRY(plan(&n->pl_pyr[L][0], cur, &n->c_pyr[L][0], nullptr, n->wt_pyr[L][0], g2));
     PV_TRY(plan(&n->pl_pyr[L][1], n->c_pyr[L][0], &n->c_pyr[L][1], nullptr, n->wt_pyr[L][1], ConvGeom::same3x3(1, 0.1f)));
     PV_TRY(plan(&n->pl_pyr[L][2], n->c_pyr[L][1], &n->c_pyr[L][2], nullptr, n->wt_pyr[L][2], ConvGeom::same3x3(1, 0.1f)));
@@ -448,7 +458,7 @@ int run_middle_tc(premvos_pwc* n, cudaStream_t st) {
 
 // ---- the network ---------------------------------------------------------------------------------
 int run_front(premvos_pwc* n, const float* x_dev, cudaStream_t st) {
-  if (n->opt_tensor_cores) return pack_pair_input_cp8(x_dev, n->B, n->H, n->W, n->c_img, st);
+  if (n->opt_tensor_cores) return pack_pair_im2col_cp8(x_dev, n->B, n->H, n->W, n->c_img, st);
   return pack_pair_input(x_dev, n->B, n->H, n->W, n->img, st);
 }
 
