@@ -211,7 +211,13 @@ def main():
     sets = max(2, -(-300 // (B * 11)))          # > 2x the 126 MB L2 in total
     host_inputs = make_inputs(B, sets)
     dev_inputs = [torch.from_numpy(x).cuda() for x in host_inputs]
-    pinned = [torch.from_numpy(x).pin_memory() for x in host_inputs]
+    # end-to-end inputs: what the stage-1 driver has in hand after decoding + cv2.resize (script_pwc_multi.py:34-45) --
+    # uint8 RGB frames; BGR / 255 / planar run on the device (premvos_pwc_forward_host_u8)
+    def to_frames(x):
+        f = np.clip(np.rint(x * 255.0), 0, 255).astype(np.uint8)          # [B,6,H,W] BGR planes -> [B,2,H,W,3] RGB
+        f = f.reshape(x.shape[0], 2, 3, H_NET, W_NET)[:, :, ::-1]
+        return np.ascontiguousarray(np.transpose(f, (0, 1, 3, 4, 2)))
+    pinned = [torch.from_numpy(to_frames(x)).pin_memory() for x in host_inputs]
     out_pinned = torch.empty((B, 2, H_NET // 4, W_NET // 4), dtype=torch.float32).pin_memory()
 
     def barrier():
@@ -247,16 +253,16 @@ def main():
 
     # ---- end-to-end arm: host buffers in, host flow out, every step ----
     for i in range(2):
-        net.forward_host(pinned[i % sets].numpy(), out_pinned.numpy())
+        net.forward_host_u8(pinned[i % sets].numpy(), out_pinned.numpy())
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        net.forward_host(pinned[i % sets].numpy(), out_pinned.numpy())
+        net.forward_host_u8(pinned[i % sets].numpy(), out_pinned.numpy())
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     e2e = world * B * args.steps / e2e_s
-    h2d = B * 6 * H_NET * W_NET * 4
+    h2d = B * 2 * H_NET * W_NET * 3
     d2h = B * 2 * (H_NET // 4) * (W_NET // 4) * 4
 
     # ---- per-launch profile of one step (rank 0) -> roofline of the dominant kernel ----
@@ -314,7 +320,9 @@ def main():
                            "batch_per_gpu_per_step": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "weights": "seeded He-normal (reference init), 9.37M params",
                            "l2": "inputs rotate over %d device buffers (%d MB > 126 MB L2)" % (sets, sets * B * 11)},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "call": "premvos_pwc_forward_host_u8: pinned uint8 RGB frame pairs in (as decoded + resized by the "
+                                "stage-1 driver), fp32 flow out, synchronous per step"},
                 "gpu_launches": int(launches), "launches_per_forward": net.launches_per_forward(B, H_NET, W_NET),
                 "tensor_core_layers": tc_layers, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
                 "other_configs": other}

@@ -119,6 +119,11 @@ int premvos_pwc_set_param(premvos_pwc_t* net, const char* name, const float* hos
 int premvos_pwc_finalize(premvos_pwc_t* net);
 int premvos_pwc_forward(premvos_pwc_t* net, const float* x_dev, float* flow_dev, void* stream);
 int premvos_pwc_forward_host(premvos_pwc_t* net, const float* x_host, float* flow_host);
+/* The stage-1 unit of work (calculate_flow, script_pwc_multi.py:33-70) on decoded frames: frames = HOST uint8 RGB
+ * [batch, 2, height, width, 3] (frame 1 then frame 2 of every pair, already cv2.resize'd to multiples of 64, :38-45);
+ * the BGR swap, /255 (float32(double(u)/255.0)), planar layout (:47-56) happen on the device.  Same result, bit for bit, as
+ * premvos_pwc_forward_host on the float tensor the reference builds; a quarter of its host->device bytes. */
+int premvos_pwc_forward_host_u8(premvos_pwc_t* net, const unsigned char* frames_rgb_host, float* flow_host);
 /* Number of kernel launches one forward() performs (nodes of the captured graph). */
 int premvos_pwc_launches_per_forward(const premvos_pwc_t* net);
 /* Number of convolution layers of this handle that run on the tcgen05 tensor-core path (0 = pure

@@ -13,7 +13,7 @@ EXPORTS = [
     "premvos_profile_end",
     "premvos_corr_output_shape", "premvos_corr_forward", "premvos_conv2d_forward",
     "premvos_pwc_create", "premvos_pwc_set_param", "premvos_pwc_finalize", "premvos_pwc_forward",
-    "premvos_pwc_forward_host", "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
+    "premvos_pwc_forward_host", "premvos_pwc_forward_host_u8", "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
     "premvos_pwc_get_tensor", "premvos_pwc_destroy", "premvos_pwc_tensor_core_layers",
     "premvos_propnet_create", "premvos_propnet_set_option", "premvos_propnet_set_param", "premvos_propnet_finalize",
     "premvos_propnet_forward", "premvos_propnet_read_results", "premvos_propnet_forward_host",
@@ -56,6 +56,7 @@ def lib() -> ctypes.CDLL:
     L.premvos_pwc_finalize.argtypes = [c_void_p]
     L.premvos_pwc_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.premvos_pwc_forward_host.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.premvos_pwc_forward_host_u8.argtypes = [c_void_p, c_void_p, c_void_p]
     L.premvos_pwc_launches_per_forward.argtypes = [c_void_p]
     L.premvos_pwc_tensor_core_layers.argtypes = [c_void_p]
     L.premvos_pwc_set_option.argtypes = [c_void_p, c_char_p, c_int]

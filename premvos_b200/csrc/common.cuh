@@ -216,6 +216,8 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n = -
 // ---- CP8 companions of the tensor-core path, cp8_ops.cu -----------------------------------------------
 // x: NCHW fp32 [B,6,H,W] -> img CP8 [2B, 1 chunk, H, W] (ch 0..2 = BGR of image 1 for n < B, image 2 for n >= B)
 int pack_pair_input_cp8(const float* x_nchw, int B, int H, int W, const CView& img, cudaStream_t st);
+// uint8 RGB frame pairs [B][2][H][W][3] -> x NCHW fp32 [B][6][H][W] (BGR / 255, script_pwc_multi.py:47-56)
+int frames_u8_to_x(const unsigned char* frames_rgb, float* x_nchw, int B, int H, int W, cudaStream_t st);
 // same input -> im2col of the first 3x3/stride-2 convolution: img CP8 [2B, 4 chunks, H/2, W/2], channel (r*3+s)*3 + c (27 of 32 used)
 int pack_pair_im2col_cp8(const float* x_nchw, int B, int H, int W, const CView& img, cudaStream_t st);
 // PWCDCNet.warp on CP8 features; flow = channels [flow_ch, flow_ch+2) of chunk plane flow.c0

@@ -90,6 +90,20 @@ __global__ void __launch_bounds__(256) pack_pair_im2col_kernel(const float* __re
   st_chunk(img.hi, img.lo, cv_elem(img, n, ch, oy, ox), f);
 }
 
+// uint8 RGB frames [B][2][H][W][3] -> the network input the reference builds on the host (script_pwc_multi.py:47-56):
+// fp32 NCHW [B][6][H][W], BGR, float32(double(u) / 255.0)
+__global__ void __launch_bounds__(256) frames_u8_to_x_kernel(const unsigned char* __restrict__ fr, float* __restrict__ x, int B, int H, int W) {
+  const long hw = (long)H * W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * 2 * hw) return;
+  const long p = idx % hw;
+  const int im = (int)((idx / hw) % 2), b = (int)(idx / (2 * hw));
+  const unsigned char* s = fr + (((long)b * 2 + im) * hw + p) * 3;
+  float* d = x + ((long)b * 6 + im * 3) * hw + p;
+#pragma unroll
+  for (int c = 0; c < 3; c++) d[(long)c * hw] = (float)((double)s[2 - c] / 255.0);
+}
+
 // ---- PWCDCNet.warp (PWCNet.py:140-176) -------------------------------------------------------------
 struct WarpCp8Args { CV x, flow, out; int flow_ch; float scale; };
 
@@ -340,6 +354,13 @@ int pack_pair_im2col_cp8(const float* x_nchw, int B, int H, int W, const CView& 
   prof_before(st);
   pack_pair_im2col_kernel<<<blocks_for(total), 256, 0, st>>>(x_nchw, dev(img), B, H, W);
   return after_launch("pack_pair_im2col_kernel", st, 0.0, (double)B * 6 * H * W * 4 + (double)total * 32.0);
+}
+
+int frames_u8_to_x(const unsigned char* frames_rgb, float* x_nchw, int B, int H, int W, cudaStream_t st) {
+  const long total = (long)B * 2 * H * W;
+  prof_before(st);
+  frames_u8_to_x_kernel<<<blocks_for(total), 256, 0, st>>>(frames_rgb, x_nchw, B, H, W);
+  return after_launch("frames_u8_to_x_kernel", st, 0.0, (double)total * 15.0);
 }
 
 int warp_cp8(const CView& x2, const CView& flow, int flow_ch, float flow_scale, const CView& out, cudaStream_t st) {

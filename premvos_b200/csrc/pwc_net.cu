@@ -75,6 +75,7 @@ struct premvos_pwc {
   int graph_nodes = 0;
   float* x_in = nullptr;      // device staging for forward_host
   float* flow_out = nullptr;  // device staging for forward_host
+  unsigned char* frames_u8 = nullptr;  // device staging for forward_host_u8
   int launches_per_forward = 0;
   int tensor_core_layers = 0;
 };
@@ -348,6 +349,8 @@ int alloc_io(premvos_pwc* n) {
   PV_CUDA(cudaMalloc((void**)&n->x_in, xin));
   PV_CUDA(cudaMalloc((void**)&n->flow_out, fout));
   n->allocs.push_back(n->x_in);
+  PV_CUDA(cudaMalloc((void**)&n->frames_u8, (size_t)n->B * 2 * n->H * n->W * 3));
+  n->allocs.push_back(n->frames_u8);
   n->allocs.push_back(n->flow_out);
   return 0;
 }
@@ -624,6 +627,21 @@ extern "C" int premvos_pwc_forward_host(premvos_pwc_t* n, const float* x_host, f
   size_t xin = (size_t)n->B * 6 * n->H * n->W * sizeof(float);
   size_t fout = (size_t)n->B * 2 * (n->H / 4) * (n->W / 4) * sizeof(float);
   PV_CUDA(cudaMemcpyAsync(n->x_in, x_host, xin, cudaMemcpyHostToDevice, n->stream));
+  PV_TRY(enqueue_forward(n, n->x_in, n->flow_out, n->stream));
+  PV_CUDA(cudaMemcpyAsync(flow_host, n->flow_out, fout, cudaMemcpyDeviceToHost, n->stream));
+  PV_CUDA(cudaStreamSynchronize(n->stream));
+  return 0;
+}
+
+// Stage-1 unit of work of the reference (calculate_flow, script_pwc_multi.py:33-70) minus file I/O and cv2.resize: takes the
+// uint8 RGB frames (already resized to multiples of 64), does BGR / 255 / planar on the device.  4x less H2D traffic.
+extern "C" int premvos_pwc_forward_host_u8(premvos_pwc_t* n, const unsigned char* frames_rgb_host, float* flow_host) {
+  PV_CHECK(n && frames_rgb_host && flow_host, PREMVOS_ERR_INVALID_ARG, "premvos_pwc_forward_host_u8: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_pwc_forward_host_u8: call premvos_pwc_finalize first");
+  const size_t fin = (size_t)n->B * 2 * n->H * n->W * 3;
+  const size_t fout = (size_t)n->B * 2 * (n->H / 4) * (n->W / 4) * sizeof(float);
+  PV_CUDA(cudaMemcpyAsync(n->frames_u8, frames_rgb_host, fin, cudaMemcpyHostToDevice, n->stream));
+  PV_TRY(frames_u8_to_x(n->frames_u8, n->x_in, n->B, n->H, n->W, n->stream));
   PV_TRY(enqueue_forward(n, n->x_in, n->flow_out, n->stream));
   PV_CUDA(cudaMemcpyAsync(flow_host, n->flow_out, fout, cudaMemcpyDeviceToHost, n->stream));
   PV_CUDA(cudaStreamSynchronize(n->stream));

@@ -224,6 +224,22 @@ class PWCDCNet:
                                                        oa.ctypes.data_as(ctypes.c_void_p)))
         return out
 
+    def forward_host_u8(self, frames: np.ndarray, out: np.ndarray = None) -> np.ndarray:
+        """End-to-end call on decoded frames: uint8 RGB [B,2,H,W,3] (H, W multiples of 64) -> flow2 [B,2,H/4,W/4].
+        BGR / 255 / planar layout (script_pwc_multi.py:47-56) run on the device; identical bits to forward_host."""
+        fa = frames.numpy() if isinstance(frames, torch.Tensor) else frames
+        if fa.dtype != np.uint8 or not fa.flags["C_CONTIGUOUS"] or fa.ndim != 5 or fa.shape[1] != 2 or fa.shape[4] != 3:
+            raise ValueError("frames must be C-contiguous uint8 [B,2,H,W,3]")
+        B, _, H, W, _ = fa.shape
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (script_pwc_multi.py:38-45), got %dx%d" % (H, W))
+        if out is None:
+            out = np.empty((B, 2, H // 4, W // 4), dtype=np.float32)
+        oa = out.numpy() if isinstance(out, torch.Tensor) else out
+        h = self._handle(B, H, W)
+        _lib.check(_lib.lib().premvos_pwc_forward_host_u8(h, fa.ctypes.data_as(ctypes.c_void_p), oa.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
     def get_tensor(self, name: str, B, H, W) -> np.ndarray:
         """Test hook: intermediate of the last forward, NCHW (see include/premvos_b200.h)."""
         L = _lib.lib()
@@ -314,6 +330,15 @@ def calculate_flow(net: PWCDCNet, im1_fn, im2_fn):
             raise FileNotFoundError(fn)
         return im[:, :, ::-1]  # scipy.ndimage.imread returned RGB
 
-    x, (H, W, H_, W_) = preprocess_frames(_read(im1_fn), _read(im2_fn))
-    flo = net.forward_host(x)[0]
+    im1, im2 = _read(im1_fn), _read(im2_fn)
+    H, W = im1.shape[:2]
+    H_ = int(math.ceil(H / 64.0) * 64)
+    W_ = int(math.ceil(W / 64.0) * 64)
+    if im1.dtype == np.uint8 and im2.dtype == np.uint8:
+        # decoded frames stay uint8 until they are on the device (a quarter of the upload of the float tensor)
+        frames = np.ascontiguousarray(np.stack([cv2.resize(im[:, :, :3], (W_, H_)) for im in (im1, im2)])[None])
+        flo = net.forward_host_u8(frames)[0]
+    else:
+        x, _ = preprocess_frames(im1, im2)
+        flo = net.forward_host(x)[0]
     return postprocess_flow(flo, H, W, H_, W_)

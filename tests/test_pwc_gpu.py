@@ -180,6 +180,18 @@ def test_calculate_flow_end_to_end():
     assert rel_err(got, ref) < TOL
 
 
+def test_forward_host_u8_equals_float_path():
+    f1, f2 = synth.synthetic_frame_pair(128, 192, seed=4)
+    net = _net(3)
+    x, _ = pwc.preprocess_frames(f1, f2)                       # the float tensor the reference uploads
+    frames = np.ascontiguousarray(np.stack([f1, f2])[None])
+    a = net.forward_host(x)
+    b = net.forward_host_u8(frames)
+    np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):
+        net.forward_host_u8(frames.astype(np.float32))
+
+
 def test_errors_are_loud():
     net = _net(0)
     with pytest.raises(ValueError):
