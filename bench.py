@@ -197,6 +197,7 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     args.warmup = max(args.warmup, 3)
     B = args.batch
