@@ -270,8 +270,8 @@ int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const fl
                      bool post_relu, int n_active, cudaStream_t st);
 int resize_bilinear_ac_cp8(const CView& in, const CView& out, int n_active, cudaStream_t st);   // align_corners=True
 int broadcast_vec_cp8(const float* vec, int C, bool relu, const CView& out, int n_active, cudaStream_t st);
-int gap_fc_relu(const CView& feat, const float* Wt /*[C][nout]*/, const float* bias, int nout, bool relu, float* out, int n_active,
-                cudaStream_t st);
+int gap_fc_relu(const CView& feat, const float* Wt /*[C][nout]*/, const float* bias, int nout, bool relu, float* pooled_scratch /*[N][C]*/,
+                float* out, int n_active, cudaStream_t st);
 // logits fp32 channels-last [N,h,w,cs] -> per-proposal full-frame masks (0/1), optional posteriors, sum of (2p'-1) over the frame
 int refine_output(const TView& logits, const int* crops, int N, int S, int H, int W, unsigned char* mask, float* posterior,
                   double* conf_sum, cudaStream_t st);

@@ -13,7 +13,7 @@ struct Scratch {
   ~Scratch() { for (void* p : ptrs) cudaFree(p); }
   int cview(CView* v, int N, int C, int H, int W) {
     v->N = N; v->H = H; v->W = W; v->chunks = (C + 7) / 8; v->c0 = 0; v->C = C;
-    const size_t bytes = (size_t)N * v->chunks * H * W * 8 * sizeof(__nv_bfloat16);
+    const size_t bytes = (size_t)N * v->chunks * H * W * 8 * sizeof(__nv_bfloat16) + 128;  // slack for flattened 1x1 layers
     for (int k = 0; k < 2; k++) {
       void* p = nullptr;
       PV_CUDA(cudaMalloc(&p, bytes));

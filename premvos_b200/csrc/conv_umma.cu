@@ -180,6 +180,8 @@ struct UmmaConvArgs {
   long partial_stride;       // elements per split
   // persistent scheduling: work item t = ((z * ntiles + ntile) * n_images + n) * tiles_per_img + tile, CTA b takes b, b+grid, ...
   int ntiles, n_images, total_work;
+  int flat_hw;               // > 0: 1x1 stride-1 layer run over the FLATTENED pixel list of each plane (tiles of 128 consecutive
+                             // pixels, no 2-D tile padding); value = real H*W, geometry fields describe an [ceil(HW/8)][8] image
   int nbuf;                  // TMEM accumulator buffers (2: the epilogue of item i overlaps the MMAs of item i+1)
 };
 
@@ -365,7 +367,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // ===== epilogue =====
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;  // accumulator row == pixel inside the 16x8 sub-tile
-    const long hw = (long)a.Ho * a.Wo;
+    const long hw = a.flat_hw > 0 ? (long)a.flat_hw : (long)a.Ho * a.Wo;
     uint32_t buf = 0, full_ph = 0;    // bit b = phase of tmem_full_bar[b]
     const uint32_t buf_cols = (uint32_t)(a.MT * a.BN * a.NACC);
     for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
@@ -377,8 +379,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t tmem_acc = tmem_base + buf * buf_cols;
     for (int mt = 0; mt < a.MT; mt++) {
       const int oy = ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
-      const bool in_img = oy < a.Ho && ox < a.Wo;
       const long pix = (long)oy * a.Wo + ox;
+      const bool in_img = a.flat_hw > 0 ? pix < hw : (oy < a.Ho && ox < a.Wo);
       for (int c0 = 0; c0 < a.BN; c0 += 16) {
         uint32_t v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
@@ -479,7 +481,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // Sums the split-K partials in split order and applies the same epilogue as the fused path (bias, residual, LeakyReLU/ReLU,
 // CP8 split store and/or fp32 channels-last store).  One thread per (pixel, 8-channel chunk).
 __global__ void __launch_bounds__(256) conv_finish_kernel(const UmmaConvArgs a, int n_active) {
-  const long hw = (long)a.Ho * a.Wo;
+  const long hw = a.flat_hw > 0 ? (long)a.flat_hw : (long)a.Ho * a.Wo;
   const int cchunks = (a.Cout + 7) / 8;
   const long total = (long)n_active * hw * cchunks;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -671,17 +673,23 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   static_assert(sizeof(UmmaConvArgs) <= sizeof(plan->args), "ConvPlanUmma::args too small");
   memset(&a, 0, sizeof(a));
   const int taps = w.R * w.S;
-  a.Ho = Ho; a.Wo = Wo;
+  // 1x1 / stride 1 / no padding: the spatial structure is irrelevant -> tile the flattened pixel list (needs the
+  // 128 bytes of slack every activation buffer is allocated with: the last 8-pixel row may straddle the plane end)
+  const bool flat = taps == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
+                    env_int("PREMVOS_FLAT", 1) != 0 && (long)in.H * in.W >= 8;
+  const int real_hw = Ho * Wo;
+  const int geoH = flat ? (real_hw + 7) / 8 : Ho, geoW = flat ? 8 : Wo;
+  a.Ho = geoH; a.Wo = geoW; a.flat_hw = flat ? real_hw : 0;
   a.stride = g.stride; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
   a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
   a.merged_x = (g.stride == 1) ? 1 : 0;
   a.w_plane = w.KC * w.BN * 16;
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
   // two sub-tiles per CTA either stacked (32 x 8 pixels) or side by side (16 x 16): take the one that pads less
-  const long tiles_v = (long)((Wo + 7) / 8) * ((Ho + 31) / 32), tiles_h = (long)((Wo + 15) / 16) * ((Ho + 15) / 16);
+  const long tiles_v = (long)((geoW + 7) / 8) * ((geoH + 31) / 32), tiles_h = (long)((geoW + 15) / 16) * ((geoH + 15) / 16);
   const bool horiz = tiles_h < tiles_v;
   const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
-  int mt_pref = (ctas_mt2 >= 2 * 148 && Ho > 16 && g.dil < 4) ? 2 : 1;
+  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && g.dil < 4) ? 2 : 1;
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
   const int tps_env = env_int("PREMVOS_TPS", 0);
@@ -718,8 +726,8 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   }
   PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);
   const int tile_w = a.mt_horizontal ? 16 : 8, tile_h = a.mt_horizontal ? 16 : 16 * a.MT;
-  a.tiles_x = (Wo + tile_w - 1) / tile_w;
-  a.tiles_y = (Ho + tile_h - 1) / tile_h;
+  a.tiles_x = (geoW + tile_w - 1) / tile_w;
+  a.tiles_y = (geoH + tile_h - 1) / tile_h;
   // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
   int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
   if (env_int("PREMVOS_BUDGET_KB", 0) > 0) budget = env_int("PREMVOS_BUDGET_KB", 0) * 1024;
@@ -781,7 +789,13 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   __nv_bfloat16* bases[2] = {in.hi + (size_t)in.c0 * in.H * in.W * 8, in.lo + (size_t)in.c0 * in.H * in.W * 8};
   CUtensorMap* maps[2] = {(CUtensorMap*)plan->map_a_hi, (CUtensorMap*)plan->map_a_lo};
   for (int k = 0; k < 2; k++) {
-    if (a.merged_x) {
+    if (flat) {
+      cuuint64_t dims[4] = {64, (cuuint64_t)geoH, (cuuint64_t)vchunks, (cuuint64_t)in.N};
+      cuuint64_t strides[3] = {128, plane_bytes, plane_bytes * in.chunks};
+      cuuint32_t box[4] = {(cuuint32_t)a.box_w * 8, (cuuint32_t)a.box_h, (cuuint32_t)w.KC, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      PV_TRY(encode_map(maps[k], bases[k], 4, dims, strides, box, estr));
+    } else if (a.merged_x) {
       cuuint64_t dims[4] = {(cuuint64_t)in.W * 8, (cuuint64_t)in.H, (cuuint64_t)vchunks, (cuuint64_t)in.N};
       cuuint64_t strides[3] = {(cuuint64_t)in.W * 16, plane_bytes, plane_bytes * in.chunks};
       cuuint32_t box[4] = {(cuuint32_t)a.box_w * 8, (cuuint32_t)a.box_h, (cuuint32_t)w.KC, 1};

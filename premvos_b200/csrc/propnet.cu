@@ -130,7 +130,7 @@ int dev_alloc(premvos_propnet* n, T** p, size_t count) {
 
 int alloc_cview(premvos_propnet* n, CView* v, int N, int C, int H, int W) {
   v->N = N; v->H = H; v->W = W; v->chunks = (C + 7) / 8; v->c0 = 0; v->C = C;
-  const size_t elems = (size_t)N * v->chunks * H * W * 8;
+  const size_t elems = (size_t)N * v->chunks * H * W * 8 + 64;  // + 128 B slack for flattened 1x1 layers (conv_umma.cu)
   PV_TRY(dev_alloc(n, &v->hi, elems));
   PV_TRY(dev_alloc(n, &v->lo, elems));
   return 0;

@@ -332,7 +332,8 @@ int pack_weights_tc(premvos_pwc* n) {
 
 int alloc_cview(premvos_pwc* n, CView* v, int N, int H, int W, int chunks) {
   v->N = N; v->H = H; v->W = W; v->chunks = chunks; v->c0 = 0; v->C = chunks * 8;
-  const size_t bytes = (size_t)N * chunks * H * W * 8 * sizeof(__nv_bfloat16);
+  // + 128 B: a flattened 1x1 layer may read the last 8-pixel row of the last plane past its end (conv_umma.cu)
+  const size_t bytes = (size_t)N * chunks * H * W * 8 * sizeof(__nv_bfloat16) + 128;
   for (int k = 0; k < 2; k++) {
     void* p = nullptr;
     PV_CUDA(cudaMalloc(&p, bytes));

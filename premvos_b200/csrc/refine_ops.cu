@@ -250,33 +250,44 @@ __global__ void __launch_bounds__(256) refine_output_kernel(OutArgs a) {
   }
 }
 
-// global average pool + FC with optional ReLU (image pooling branch: mean -> 1x1 conv + BN + ReLU)
-__global__ void __launch_bounds__(256) gap_fc_relu_kernel(CV feat, const float* __restrict__ Wt, const float* __restrict__ bias, int nout,
-                                                          int relu, float* __restrict__ out) {
-  extern __shared__ float pooled[];
-  const int n = blockIdx.x, C = feat.C, nch = (C + 7) / 8, hw = feat.H * feat.W;
-  for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
-    F8 s = zero8();
-    for (int p = 0; p < hw; p++) {
-      const F8 v = ld_chunk(feat.hi, feat.lo, (((long)n * feat.chunks + feat.c0 + ch) * hw + p) * 8);
+// global average pool: one warp per (image, chunk plane), lanes stride over the pixels
+__global__ void __launch_bounds__(256) gap_kernel(CV feat, float* __restrict__ pooled /*[N][C]*/, int n_active) {
+  const int nch = (feat.C + 7) / 8, hw = feat.H * feat.W;
+  const int gw = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (gw >= n_active * nch) return;
+  const int n = gw / nch, ch = gw - n * nch;
+  F8 s = zero8();
+  for (int p = lane; p < hw; p += 32) {
+    const F8 v = ld_chunk(feat.hi, feat.lo, (((long)n * feat.chunks + feat.c0 + ch) * hw + p) * 8);
 #pragma unroll
-      for (int j = 0; j < 8; j++) s.v[j] += v.v[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (ch * 8 + j < C) pooled[ch * 8 + j] = s.v[j] / (float)hw;
+    for (int j = 0; j < 8; j++) s.v[j] += v.v[j];
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int o = wid; o < nout; o += nw) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(pooled[c], Wt[(long)c * nout + o], acc);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-      const float v = acc + bias[o];
-      out[(long)n * nout + o] = relu ? fmaxf(v, 0.f) : v;
-    }
+  for (int j = 0; j < 8; j++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s.v[j] += __shfl_xor_sync(0xffffffffu, s.v[j], off);
+  }
+  if (lane < 8 && ch * 8 + lane < feat.C) {
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) if (j == lane) m = s.v[j];
+    pooled[(long)n * feat.C + ch * 8 + lane] = m / (float)hw;
+  }
+}
+
+// out[n][o] = act(pooled[n] . W[:, o] + bias[o]); one warp per output
+__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ pooled, int C, const float* __restrict__ Wt,
+                                                 const float* __restrict__ bias, int nout, int relu, float* __restrict__ out, int n_active) {
+  const int gw = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (gw >= n_active * nout) return;
+  const int n = gw / nout, o = gw - n * nout;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(pooled[(long)n * C + c], Wt[(long)c * nout + o], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    const float v = acc + bias[o];
+    out[(long)n * nout + o] = relu ? fmaxf(v, 0.f) : v;
   }
 }
 
@@ -322,11 +333,16 @@ int broadcast_vec_cp8(const float* vec, int C, bool relu, const CView& out, int 
   return after_launch("broadcast_kernel", st, 0.0, 32.0 * total);
 }
 
-int gap_fc_relu(const CView& feat, const float* Wt, const float* bias, int nout, bool relu, float* out, int n_active, cudaStream_t st) {
+int gap_fc_relu(const CView& feat, const float* Wt, const float* bias, int nout, bool relu, float* pooled_scratch, float* out,
+                int n_active, cudaStream_t st) {
   if (n_active == 0) return 0;
+  const long warps = (long)n_active * feat.vchunks();
   prof_before(st);
-  gap_fc_relu_kernel<<<n_active, 256, round_up(feat.C, 8) * sizeof(float), st>>>(dev(feat), Wt, bias, nout, relu ? 1 : 0, out);
-  return after_launch("gap_fc_relu_kernel", st, 2.0 * n_active * feat.C * nout, 4.0 * (double)n_active * feat.H * feat.W * feat.C);
+  gap_kernel<<<blocks_for(warps * 32), 256, 0, st>>>(dev(feat), pooled_scratch, n_active);
+  PV_TRY(after_launch("gap_kernel", st, 0.0, 4.0 * (double)n_active * feat.H * feat.W * feat.C));
+  prof_before(st);
+  fc_kernel<<<blocks_for((long)n_active * nout * 32), 256, 0, st>>>(pooled_scratch, feat.C, Wt, bias, nout, relu ? 1 : 0, out, n_active);
+  return after_launch("fc_kernel", st, 2.0 * n_active * feat.C * nout, 4.0 * (double)feat.C * nout);
 }
 
 int refine_output(const TView& logits, const int* crops, int N, int S, int H, int W, unsigned char* mask, float* posterior,

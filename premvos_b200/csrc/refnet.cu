@@ -110,7 +110,7 @@ int dev_alloc(premvos_refnet* n, T** p, size_t count) {
 
 int alloc_cview(premvos_refnet* n, CView* v, int C, int H, int W) {
   v->N = n->NB; v->H = H; v->W = W; v->chunks = (C + 7) / 8; v->c0 = 0; v->C = C;
-  const size_t elems = (size_t)v->N * v->chunks * H * W * 8;
+  const size_t elems = (size_t)v->N * v->chunks * H * W * 8 + 64;  // + 128 B slack for flattened 1x1 layers (conv_umma.cu)
   PV_TRY(dev_alloc(n, &v->hi, elems));
   PV_TRY(dev_alloc(n, &v->lo, elems));
   return 0;
@@ -239,13 +239,14 @@ int build_network(premvos_refnet* n) {
     const int cin = cur.C;
     for (int i = 0; i < cin; i++)
       for (int o = 0; o < 256; o++) w[(size_t)i * 256 + o] = W[(size_t)i * 256 + o] * scale[o];
-    float *dw = nullptr, *db = nullptr, *vec = nullptr;
+    float *dw = nullptr, *db = nullptr, *vec = nullptr, *pooled = nullptr;
     PV_TRY(dev_alloc(n, &dw, w.size())); PV_TRY(dev_alloc(n, &db, (size_t)256)); PV_TRY(dev_alloc(n, &vec, (size_t)n->NB * 256));
+    PV_TRY(dev_alloc(n, &pooled, (size_t)n->NB * cur.C));
     PV_CUDA(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     PV_CUDA(cudaMemcpy(db, shift.data(), 256 * 4, cudaMemcpyHostToDevice));
     CView feat = cur, dst = cat.slice(0, 256);
     n->steps.push_back([=](cudaStream_t st, int na) {
-      PV_TRY(gap_fc_relu(feat, dw, db, 256, true, vec, na, st));
+      PV_TRY(gap_fc_relu(feat, dw, db, 256, true, pooled, vec, na, st));
       return broadcast_vec_cp8(vec, 256, false, dst, na, st);
     });
   }

@@ -43,6 +43,8 @@ CASES = [
     (1, 3, 75, 131, 64, 7, 2, 1, (2, 2, 3, 3), 0.0, False),     # ResNet stem 7x7 s2, pad (2,3)
     (2, 661, 14, 32, 96, 3, 1, 1, (1, 1, 1, 1), 0.1, False),    # PWC level 5: 8 CTAs -> split-K + finish kernel
     (1, 2048, 9, 9, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, True),     # tiny grid 1x1 with residual through the split-K path
+    (3, 728, 25, 25, 728, 1, 1, 1, (0, 0, 0, 0), 1.0, True),    # Xception middle flow: flattened 1x1, 625 px (not a multiple of 8)
+    (2, 1024, 46, 83, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, False),  # ResNet group2 conv1: flattened, 3818 px
 ]
 
 
