@@ -123,6 +123,67 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(DwArgs a) {
   st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, ch, oy, ox), acc);
 }
 
+// rate-1 fast path: one thread = one chunk x 4 consecutive output pixels; every input row is loaded once into registers
+// (3*STRIDE + 3 columns) and the 9 weight vectors are loaded once per thread -> ~2x fewer L1 transactions per output
+template <int STRIDE>
+__global__ void __launch_bounds__(128, 3) depthwise3x3_x4_kernel(DwArgs a) {
+  constexpr int NC = 3 * STRIDE + 3;
+  const int nch = (a.in.C + 7) / 8;
+  const int wg = (a.out.W + 3) / 4;
+  const long total = (long)a.n_active * nch * a.out.H * wg;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int oxg = (int)(idx % wg), oy = (int)((idx / wg) % a.out.H);
+  const int ch = (int)((idx / ((long)wg * a.out.H)) % nch), n = (int)(idx / ((long)wg * a.out.H * nch));
+  const int cpad = nch * 8;
+  const int ox0 = oxg * 4, ix0 = ox0 * STRIDE - a.pad;
+  F8 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) acc[k] = zero8();
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const int iy = oy * STRIDE + r - a.pad;
+    if (iy < 0 || iy >= a.in.H) continue;
+    F8 v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const int ix = ix0 + c;
+      if (ix >= 0 && ix < a.in.W) {
+        v[c] = ld_chunk(a.in.hi, a.in.lo, cv_elem(a.in, n, ch, iy, ix));
+        if (a.pre_relu) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) v[c].v[j] = fmaxf(v[c].v[j], 0.f);
+        }
+      } else {
+        v[c] = zero8();
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const float4 w0 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[k].v[j] = fmaf(v[k * STRIDE + s].v[j], wv[j], acc[k].v[j]);
+    }
+  }
+  float bias[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) bias[j] = a.bias[ch * 8 + j];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (ox0 + k >= a.out.W) break;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float t = acc[k].v[j] + bias[j];
+      acc[k].v[j] = a.post_relu ? fmaxf(t, 0.f) : t;
+    }
+    st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, ch, oy, ox0 + k), acc[k]);
+  }
+}
+
 // ---- bilinear resize, align_corners=True ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) resize_ac_kernel(CV in, CV out, int n_active) {
   const int nch = (in.C + 7) / 8;
@@ -311,7 +372,13 @@ int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const fl
   const long total = (long)n_active * in.vchunks() * out.H * out.W;
   if (total == 0) return 0;
   prof_before(st);
-  depthwise3x3_kernel<<<blocks_for(total), 256, 0, st>>>(a);
+  if (rate == 1 && (stride == 1 || stride == 2)) {
+    const long t4 = (long)n_active * in.vchunks() * out.H * ((out.W + 3) / 4);
+    if (stride == 1) depthwise3x3_x4_kernel<1><<<blocks_for(t4, 128), 128, 0, st>>>(a);
+    else depthwise3x3_x4_kernel<2><<<blocks_for(t4, 128), 128, 0, st>>>(a);
+  } else {
+    depthwise3x3_kernel<<<blocks_for(total), 256, 0, st>>>(a);
+  }
   const double frac = (double)n_active / in.N;
   return after_launch("depthwise3x3_kernel", st, 18.0 * total * 8, 4.0 * frac * ((double)in.pixels() + (double)out.pixels()) * in.C);
 }
