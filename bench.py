@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="frame pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU per step")
     ap.add_argument("--fp32", action="store_true", help="fp32 SIMT convolutions instead of tensor cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the proposal_net / refinement_net context timings")
