@@ -595,7 +595,7 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   const int chunks = (phys + 7) / 8;
   // measured on B200 (tools/conv_sweep.py): 3x3 with a wide N tile runs best with 16-channel k-blocks and two
   // co-resident CTAs per SM; narrow N tiles and 1x1 layers want longer k-blocks (fewer barrier handshakes)
-  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? (Cout >= 64 ? 2 : 4) : 8);
+  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? 2 : 8);
   kc = env_int("PREMVOS_KC", kc);
   if (kc > round_up(chunks, 2)) kc = round_up(chunks, 2);
   PV_CHECK(kc >= 2 && (kc % 2) == 0 && kc <= 16, PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: KC=%d", kc);
@@ -689,7 +689,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const long tiles_v = (long)((geoW + 7) / 8) * ((geoH + 31) / 32), tiles_h = (long)((geoW + 15) / 16) * ((geoH + 15) / 16);
   const bool horiz = tiles_h < tiles_v;
   const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
-  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && g.dil < 4) ? 2 : 1;
+  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16) ? 2 : 1;
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
   const int tps_env = env_int("PREMVOS_TPS", 0);
@@ -698,13 +698,16 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   bool found = false;
   for (int cand = 0; cand < 4 && !found; cand++) {
     const int mt = (cand & 1) ? 1 : mt_pref;
+    const int halo_env = env_int("PREMVOS_HALO", -1);
     const bool want_halo = cand < 2;
+    if ((halo_env == 0 && want_halo) || (halo_env == 1 && !want_halo)) continue;   // tuning override
     if ((cand & 1) && mt_pref == 1) continue;
     const bool hz = horiz && mt == 2;
     const int halo_w = (hz ? 16 : 8) + (w.S - 1) * g.dil, halo_h = (hz ? 16 : 16 * mt) + (w.R - 1) * g.dil;
     const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * mt;
     // halo mode only when it moves fewer bytes into shared memory than per-tap boxes
-    const bool halo_ok = g.stride == 1 && taps > 1 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
+    // (measured: from dilation 4 on the halo box is so large that one CTA per SM remains; per-tap boxes win)
+    const bool halo_ok = g.stride == 1 && taps > 1 && g.dil < 4 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
     if (want_halo && !halo_ok) continue;
     a.MT = mt;
     a.mt_horizontal = hz ? 1 : 0;
@@ -714,14 +717,18 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
     a.a_plane = round_up(a.a_box_bytes, 128);
     a.a_stages = a.halo ? 2 : 3;
-    // taps per weight stage: fewer, larger bulk copies (a TMA request has a fixed cost), <= 48 KB each
-    for (int t = taps; t >= 1 && !found; t--) {
-      if (taps % t != 0 || !(t <= w.S || t % w.S == 0)) continue;
-      if (tps_env ? (t != tps_env) : (t > 1 && t * 2 * a.w_plane > 24 * 1024)) continue;
-      a.TPS = t;
-      a.w_stage = round_up(t * 2 * a.w_plane, 128);
-      a.w_stages = 2;
-      if (a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 1024 <= SMEM_LIMIT) found = true;
+    // taps per weight stage: fewer, larger bulk copies (a TMA request has a fixed cost) -- the largest group of <= 32 KB
+    // that still leaves room for two CTAs per SM; only if nothing fits 110 KB is the whole SM used
+    for (int pass = 0; pass < 2 && !found; pass++) {
+      const int limit = pass == 0 ? 110 * 1024 : SMEM_LIMIT;
+      for (int t = taps; t >= 1 && !found; t--) {
+        if (taps % t != 0 || !(t <= w.S || t % w.S == 0)) continue;
+        if (tps_env ? (t != tps_env) : (t > 1 && t * 2 * a.w_plane > 32 * 1024)) continue;
+        a.TPS = t;
+        a.w_stage = round_up(t * 2 * a.w_plane, 128);
+        a.w_stages = 2;
+        if (a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 1024 <= limit) found = true;
+      }
     }
   }
   PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);

@@ -21,6 +21,10 @@ SHAPES = {
     "conv3a": (8, 32, 112, 256, 64, 3, 2, 1),
     "conv6_4": (4, 529, 7, 16, 32, 3, 1, 1),
     "conv4_2": (4, 437, 28, 64, 96, 3, 1, 1),
+    "conv2_4h": (16, 533, 112, 256, 48, 3, 1, 1),
+    "dc_conv4": (16, 128, 112, 256, 96, 3, 1, 8),
+    "dc_conv3b": (16, 128, 112, 256, 128, 3, 1, 4),
+    "conv2_3": (16, 469, 112, 256, 64, 3, 1, 1),
     "res1x1": (1, 1024, 46, 83, 256, 1, 1, 1),
     "res1x1b": (1, 256, 46, 83, 1024, 1, 1, 1),
 }
@@ -28,7 +32,7 @@ SHAPES = {
 
 def run(name, env):
     N, Cin, H, W, Cout, k, stride, dil = SHAPES[name]
-    for key in ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_NACC", "PREMVOS_DBG", "PREMVOS_BUDGET_KB"):
+    for key in ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_NACC", "PREMVOS_DBG", "PREMVOS_BUDGET_KB", "PREMVOS_HALO"):
         os.environ.pop(key, None)
     os.environ.update({k2: str(v) for k2, v in env.items() if v is not None})
     x = torch.randn(N, Cin, H, W, device="cuda")
@@ -51,9 +55,8 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(SHAPES)
     for name in names:
         print("==", name, SHAPES[name])
-        k = SHAPES[name][5]
-        for kc, tps in ([(2, 1), (2, 3), (4, 1), (4, 3)] if k == 3 else [(4, None), (8, None)]):
+        for kc, tps in [(2, 1), (2, 3), (2, 9), (4, 1), (4, 3)]:
             for mt in (1, 2):
-                for bud in (110, 160, 226):
-                    us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt, "PREMVOS_BUDGET_KB": bud})
-                    print("  KC=%s TPS=%s MT=%s NACC=%s: %s %s" % (kc, tps, mt, bud, "%.1f us" % us if us else "--", note), flush=True)
+                for halo in (0, 1):
+                    us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt, "PREMVOS_HALO": halo})
+                    print("  KC=%s TPS=%s MT=%s NACC=%s: %s %s" % (kc, tps, mt, halo, "%.1f us" % us if us else "--", note), flush=True)
