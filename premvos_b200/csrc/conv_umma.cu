@@ -387,6 +387,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0);
         const bool last_ld = (mt == a.MT - 1) && (c0 + 16 >= a.BN);
         tmem_ld16(taddr, v);
+        // global loads of this group (bias, residual) are issued while the TMEM load is in flight
+        const int co0 = ntile * a.BN + c0;
+        const bool live = in_img && co0 < a.Cout && a.ksplit == 1;
+        float4 bv[4];
+        uint4 rres[4];
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + co0) + j);
+          if (a.res_hi) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              if (co0 + 8 * h >= a.Cout) continue;
+              const long ri = (((long)n_img * a.res_chunks + a.res_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+              rres[2 * h] = *reinterpret_cast<const uint4*>(a.res_hi + ri);
+              rres[2 * h + 1] = *reinterpret_cast<const uint4*>(a.res_lo + ri);
+            }
+          }
+        }
         tmem_ld_wait();
         for (int rep = 1; rep < a.NACC; rep++) {
           uint32_t v2[16];
@@ -400,7 +418,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
-        const int co0 = ntile * a.BN + c0;
         if (a.ksplit > 1) {  // raw partial sums; bias / residual / activation happen in conv_finish_kernel
           if (in_img) {
             float* pp = a.partial + (long)wk.z * a.partial_stride + ((long)n_img * hw + pix) * a.cout_pad + co0;
@@ -414,14 +431,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (!in_img || co0 >= a.Cout) continue;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + __ldg(a.bias + co0 + j);
+        for (int j = 0; j < 4; j++) {
+          f[4 * j] = __uint_as_float(v[4 * j]) + bv[j].x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv[j].y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv[j].z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+        }
         if (a.res_hi) {
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             if (co0 + 8 * h >= a.Cout) continue;
-            const long ri = (((long)n_img * a.res_chunks + a.res_c0 + (co0 >> 3) + h) * hw + pix) * 8;
-            const uint4 rh = *reinterpret_cast<const uint4*>(a.res_hi + ri);
-            const uint4 rl = *reinterpret_cast<const uint4*>(a.res_lo + ri);
+            const uint4 rh = rres[2 * h], rl = rres[2 * h + 1];
             const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
