@@ -160,11 +160,13 @@ __global__ void __launch_bounds__(256) warp_cp8_kernel(WarpCp8Args a) {
 // ---- 9x9 cost volume (corr_cuda_kernel.cu:59-127 semantics, pad 4, k 1, md 4, strides 1) ---------------
 // One CTA owns a 4x32 pixel tile; per 32-channel group the f1 tile and the f2 tile + 4-pixel halo are
 // staged in shared memory as fp32 (pitch 33 floats: 32 lanes = 32 consecutive pixels hit 32 banks).
-// 384 threads = 128 pixels x 3 groups of 27 displacements held in registers.
+// 288 threads = 32 pixel columns x 9 x-displacements; a thread owns its column's 4 pixels x all 9 y-displacements
+// (36 accumulators): per channel 4 f1 + 12 f2 shared-memory reads feed 36 FMAs (register reuse along y), and the
+// 32 lanes of a warp read 32 consecutive pixels = 32 different banks.
 constexpr int CT_H = 4, CT_W = 32, MD = 4, DW = 9;
 constexpr int HALO_H = CT_H + 2 * MD, HALO_W = CT_W + 2 * MD;  // 12 x 40
 constexpr int CK = 32, PITCH = CK + 1;
-constexpr int CORR_THREADS = 384;
+constexpr int CORR_THREADS = 288;
 constexpr size_t CORR_SMEM = (size_t)(HALO_H * HALO_W + CT_H * CT_W) * PITCH * sizeof(float);
 
 struct CorrCp8Args { CV f1, f2, out, c1; int has_c1; float slope; };
@@ -176,14 +178,15 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_cp8_kernel(CorrCp8Args a)
   const int tid = threadIdx.x;
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * CT_H, x0 = blockIdx.x * CT_W;
-  const int p = tid & 127, grp = tid >> 7;
-  const int py = p >> 5, px = p & 31;
+  const int px = tid & 31, dxi = tid >> 5;   // pixel column, x-displacement index (dx = dxi - 4)
   const int H = a.f1.H, W = a.f1.W, C = a.f1.C;
   const int nchunks = (C + 7) / 8;
 
-  float acc[27];
+  float acc[CT_H][DW];   // [pixel row][y-displacement]
 #pragma unroll
-  for (int i = 0; i < 27; i++) acc[i] = 0.f;
+  for (int i = 0; i < CT_H; i++)
+#pragma unroll
+    for (int j = 0; j < DW; j++) acc[i][j] = 0.f;
 
   for (int cg = 0; cg < nchunks; cg += 4) {  // 4 chunks = 32 channels per pass
     for (int i = tid; i < 4 * HALO_H * HALO_W; i += CORR_THREADS) {
@@ -218,16 +221,19 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_cp8_kernel(CorrCp8Args a)
       for (int j = 0; j < 8; j++) d[j] = f.v[j];
     }
     __syncthreads();
-    const float* q1 = s1 + p * PITCH;
-    const float* q2 = s2 + ((py + 3 * grp) * HALO_W + px) * PITCH;
-#pragma unroll 4
+    const float* q1 = s1 + px * PITCH;                 // f1 pixel (row r, column px) at q1[r * CT_W * PITCH]
+    const float* q2 = s2 + (px + dxi) * PITCH;         // f2 halo pixel (row r, column px + dxi) at q2[r * HALO_W * PITCH]
+#pragma unroll 2
     for (int c = 0; c < CK; c++) {
-      const float f = q1[c];
+      float f1v[CT_H], f2v[HALO_H];
 #pragma unroll
-      for (int dy = 0; dy < 3; dy++)
+      for (int r = 0; r < CT_H; r++) f1v[r] = q1[r * CT_W * PITCH + c];
 #pragma unroll
-        for (int dx = 0; dx < DW; dx++)
-          acc[dy * DW + dx] = fmaf(f, q2[(dy * HALO_W + dx) * PITCH + c], acc[dy * DW + dx]);
+      for (int r = 0; r < HALO_H; r++) f2v[r] = q2[r * HALO_W * PITCH + c];
+#pragma unroll
+      for (int r = 0; r < CT_H; r++)
+#pragma unroll
+        for (int dy = 0; dy < DW; dy++) acc[r][dy] = fmaf(f1v[r], f2v[r + dy], acc[r][dy]);
     }
     __syncthreads();
   }
@@ -235,14 +241,16 @@ __global__ void __launch_bounds__(CORR_THREADS) corr81_cp8_kernel(CorrCp8Args a)
   constexpr int OP = 89;
   float* so = smem;
 #pragma unroll
-  for (int i = 0; i < 27; i++) {
-    float v = acc[i] / (float)C;  // corr_cuda_kernel.cu:119-121
-    v = v > 0.f ? v : v * a.slope;
-    so[p * OP + grp * 27 + i] = v;
-  }
-  if (grp == 0) {
+  for (int r = 0; r < CT_H; r++)
 #pragma unroll
-    for (int i = 81; i < 88; i++) so[p * OP + i] = 0.f;
+    for (int dy = 0; dy < DW; dy++) {
+      float v = acc[r][dy] / (float)C;  // corr_cuda_kernel.cu:119-121
+      v = v > 0.f ? v : v * a.slope;
+      so[(r * CT_W + px) * OP + dy * DW + dxi] = v;   // output channel = (dy+4)*9 + (dx+4), corr_cuda_kernel.cu:94-95
+    }
+  if (dxi < 7) {
+#pragma unroll
+    for (int r = 0; r < CT_H; r++) so[(r * CT_W + px) * OP + 81 + dxi] = 0.f;
   }
   __syncthreads();
   for (int i = tid; i < 11 * CT_H * CT_W; i += CORR_THREADS) {
