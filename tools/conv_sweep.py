@@ -25,6 +25,11 @@ SHAPES = {
     "dc_conv4": (16, 128, 112, 256, 96, 3, 1, 8),
     "dc_conv3b": (16, 128, 112, 256, 128, 3, 1, 4),
     "conv2_3": (16, 469, 112, 256, 64, 3, 1, 1),
+    "xc_mid": (20, 728, 25, 25, 728, 1, 1, 1),
+    "xc_entry": (20, 128, 193, 193, 128, 1, 1, 1),
+    "xc_exit": (20, 1536, 25, 25, 2048, 1, 1, 1),
+    "head_c3": (100, 512, 7, 7, 2048, 1, 1, 1),
+    "head_c2": (100, 512, 7, 7, 512, 3, 1, 1),
     "res1x1": (1, 1024, 46, 83, 256, 1, 1, 1),
     "res1x1b": (1, 256, 46, 83, 1024, 1, 1, 1),
 }
@@ -55,8 +60,8 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(SHAPES)
     for name in names:
         print("==", name, SHAPES[name])
-        for kc, tps in [(2, 1), (2, 3), (2, 9), (4, 1), (4, 3)]:
+        k = SHAPES[name][5]
+        for kc, tps in ([(2, 3), (2, 9), (4, 3), (8, 1)] if k == 3 else [(2, None), (4, None), (8, None)]):
             for mt in (1, 2):
-                for halo in (0, 1):
-                    us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt, "PREMVOS_HALO": halo})
-                    print("  KC=%s TPS=%s MT=%s NACC=%s: %s %s" % (kc, tps, mt, halo, "%.1f us" % us if us else "--", note), flush=True)
+                us, note = run(name, {"PREMVOS_KC": kc, "PREMVOS_TPS": tps, "PREMVOS_MT": mt})
+                print("  KC=%s TPS=%s MT=%s NACC=0: %s %s" % (kc, tps, mt, "%.1f us" % us if us else "--", note), flush=True)
