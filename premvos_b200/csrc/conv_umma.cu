@@ -613,7 +613,7 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   const int chunks = (phys + 7) / 8;
   // measured on B200 (tools/conv_sweep.py): 3x3 with a wide N tile runs best with 16-channel k-blocks and two
   // co-resident CTAs per SM; narrow N tiles and 1x1 layers want longer k-blocks (fewer barrier handshakes)
-  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? 2 : 8);
+  int kc = kc_hint > 0 ? kc_hint : (R * S > 1 ? 2 : (phys <= 160 ? 2 : 4));
   kc = env_int("PREMVOS_KC", kc);
   if (kc > round_up(chunks, 2)) kc = round_up(chunks, 2);
   PV_CHECK(kc >= 2 && (kc % 2) == 0 && kc <= 16, PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: KC=%d", kc);
@@ -707,7 +707,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const long tiles_v = (long)((geoW + 7) / 8) * ((geoH + 31) / 32), tiles_h = (long)((geoW + 15) / 16) * ((geoH + 15) / 16);
   const bool horiz = tiles_h < tiles_v;
   const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
-  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16) ? 2 : 1;
+  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && taps > 1) ? 2 : 1;   // 1x1 layers measured best with one sub-tile
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
   const int tps_env = env_int("PREMVOS_TPS", 0);
