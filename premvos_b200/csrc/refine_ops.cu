@@ -9,6 +9,7 @@
 //     bilinear resize to the crop size, zero padding back to the frame (network/SegmentationOutputLayers.py:35-61,
 //     106-135) and the conf_score reduction of MergeTrack/refinement_net_functions.py:58-62 -- one kernel, the
 //     only thing that leaves the device is a uint8 mask per proposal and one float.
+#include <algorithm>
 #include "cp8.cuh"
 
 namespace premvos {
@@ -79,108 +80,137 @@ __global__ void __launch_bounds__(256) refine_input_kernel(PreArgs a) {
 }
 
 // ---- depthwise 3x3 -----------------------------------------------------------------------------------------------
+// One CTA = one output tile of one 8-channel chunk plane of one crop.  The input region of the tile (with its halo) is
+// read once with coalesced 8-byte loads, hi + lo are summed to fp32 (leading ReLU applied) and parked in shared memory
+// as [row][col][8 floats]; after that every thread works on 4 channels ("half" of a chunk) so that neighbouring threads
+// read neighbouring 16-byte words of shared memory (conflict-free) and write neighbouring 8-byte words of both planes.
+// Stride-1 / rate-1 layers (62 of the 68 depthwise layers of Xception-65 + decoder) take the FAST path: a thread owns a
+// vertical strip of RS outputs and slides a 3-row window down it, 3 LDS.128 per input row.  Tap order per output is
+// r-major, s-minor in both paths (same bits as a plain loop).
 struct DwArgs {
   CV in, out;
   const float* w;     // [9][Cpad] (BatchNorm scale folded in), Cpad = 8 * chunks
   const float* bias;  // [Cpad]
   int stride, rate, pad;   // input coordinate = o*stride + t*rate - pad
-  int pre_relu, post_relu, n_active;
+  int pre_relu, post_relu;
+  int TH, TW, ntx;         // output tile, tiles per row of tiles
+  int RH, RW;              // unclipped input region of a tile
+  int clip;                // 1: keep only the part of the region inside the image, taps test the bounds
 };
 
-__global__ void __launch_bounds__(256) depthwise3x3_kernel(DwArgs a) {
-  const int nch = (a.in.C + 7) / 8;
-  const long total = (long)a.n_active * nch * a.out.H * a.out.W;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ox = (int)(idx % a.out.W), oy = (int)((idx / a.out.W) % a.out.H);
-  const int ch = (int)((idx / ((long)a.out.W * a.out.H)) % nch), n = (int)(idx / ((long)a.out.W * a.out.H * nch));
-  const int cpad = nch * 8;
-  F8 acc = zero8();
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-    const int iy = oy * a.stride + r * a.rate - a.pad;
-    if (iy < 0 || iy >= a.in.H) continue;
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const int ix = ox * a.stride + s * a.rate - a.pad;
-      if (ix < 0 || ix >= a.in.W) continue;
-      F8 v = ld_chunk(a.in.hi, a.in.lo, cv_elem(a.in, n, ch, iy, ix));
-      const float4 w0 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8 + 4);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float x = a.pre_relu ? fmaxf(v.v[j], 0.f) : v.v[j];
-        acc.v[j] = fmaf(x, wv[j], acc.v[j]);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    float t = acc.v[j] + a.bias[ch * 8 + j];
-    acc.v[j] = a.post_relu ? fmaxf(t, 0.f) : t;
-  }
-  st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, ch, oy, ox), acc);
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t* hi, uint32_t* lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);   // one F2FP for the pair
+  const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __uint_as_float(hw << 16), x1 - __uint_as_float(hw & 0xffff0000u));
+  *hi = hw; *lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void st_half(const CV& o, long elem, int half, const float4& f) {
+  uint32_t h0, l0, h1, l1;
+  split2(f.x, f.y, &h0, &l0); split2(f.z, f.w, &h1, &l1);
+  *reinterpret_cast<uint2*>(o.hi + elem + half * 4) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(o.lo + elem + half * 4) = make_uint2(l0, l1);
+}
+__device__ __forceinline__ void fma4(float4& acc, const float4& v, const float4& w) {
+  acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y); acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
 }
 
-// rate-1 fast path: one thread = one chunk x 4 consecutive output pixels; every input row is loaded once into registers
-// (3*STRIDE + 3 columns) and the 9 weight vectors are loaded once per thread -> ~2x fewer L1 transactions per output
-template <int STRIDE>
-__global__ void __launch_bounds__(128, 3) depthwise3x3_x4_kernel(DwArgs a) {
-  constexpr int NC = 3 * STRIDE + 3;
-  const int nch = (a.in.C + 7) / 8;
-  const int wg = (a.out.W + 3) / 4;
-  const long total = (long)a.n_active * nch * a.out.H * wg;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int oxg = (int)(idx % wg), oy = (int)((idx / wg) % a.out.H);
-  const int ch = (int)((idx / ((long)wg * a.out.H)) % nch), n = (int)(idx / ((long)wg * a.out.H * nch));
-  const int cpad = nch * 8;
-  const int ox0 = oxg * 4, ix0 = ox0 * STRIDE - a.pad;
-  F8 acc[4];
+template <int RS, bool FAST>
+__global__ void __launch_bounds__(256) depthwise3x3_tile_kernel(DwArgs a) {
+  extern __shared__ float4 dw_sm[];   // [RH][RW][2 halves]
+  const int tile = blockIdx.x, ch = blockIdx.y, n = blockIdx.z;
+  const int oy0 = (tile / a.ntx) * a.TH, ox0 = (tile % a.ntx) * a.TW;
+  int ry0 = oy0 * a.stride - a.pad, rx0 = ox0 * a.stride - a.pad, RH = a.RH, RW = a.RW;
+  if (a.clip) {
+    const int y1 = min(ry0 + RH, a.in.H), x1 = min(rx0 + RW, a.in.W);
+    ry0 = max(ry0, 0); rx0 = max(rx0, 0);
+    RH = max(y1 - ry0, 0); RW = max(x1 - rx0, 0);
+  }
+  // ---- stage the input region: 8 independent 8-byte loads per plane in flight per thread ----
+  const long plane = cv_elem(a.in, n, ch, 0, 0);
+  const int total = RH * RW * 2;
+  const unsigned magic = (1u << 20) / (unsigned)max(RW, 1) + 1u;   // e / RW for e < 2^20 / RW (host-checked)
+  for (int base = threadIdx.x; base < total; base += 8 * blockDim.x) {
+    uint2 h[8], l[8];
 #pragma unroll
-  for (int k = 0; k < 4; k++) acc[k] = zero8();
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-    const int iy = oy * STRIDE + r - a.pad;
-    if (iy < 0 || iy >= a.in.H) continue;
-    F8 v[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const int ix = ix0 + c;
-      if (ix >= 0 && ix < a.in.W) {
-        v[c] = ld_chunk(a.in.hi, a.in.lo, cv_elem(a.in, n, ch, iy, ix));
-        if (a.pre_relu) {
-#pragma unroll
-          for (int j = 0; j < 8; j++) v[c].v[j] = fmaxf(v[c].v[j], 0.f);
-        }
-      } else {
-        v[c] = zero8();
+    for (int q = 0; q < 8; q++) {
+      const int idx = base + q * blockDim.x;
+      const int half = idx & 1, e = idx >> 1, ry = (int)(((unsigned)e * magic) >> 20), rx = e - ry * RW;
+      const int gy = ry0 + ry, gx = rx0 + rx;
+      h[q] = make_uint2(0u, 0u); l[q] = make_uint2(0u, 0u);
+      if (idx < total && gy >= 0 && gy < a.in.H && gx >= 0 && gx < a.in.W) {
+        const long el = plane + (long)(gy * a.in.W + gx) * 8 + half * 4;
+        h[q] = *reinterpret_cast<const uint2*>(a.in.hi + el);
+        l[q] = *reinterpret_cast<const uint2*>(a.in.lo + el);
       }
     }
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const float4 w0 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(a.w + (r * 3 + s) * cpad + ch * 8 + 4);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc[k].v[j] = fmaf(v[k * STRIDE + s].v[j], wv[j], acc[k].v[j]);
+    for (int q = 0; q < 8; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx >= total) break;
+      float4 f;
+      f.x = __uint_as_float(h[q].x << 16) + __uint_as_float(l[q].x << 16);
+      f.y = __uint_as_float(h[q].x & 0xffff0000u) + __uint_as_float(l[q].x & 0xffff0000u);
+      f.z = __uint_as_float(h[q].y << 16) + __uint_as_float(l[q].y << 16);
+      f.w = __uint_as_float(h[q].y & 0xffff0000u) + __uint_as_float(l[q].y & 0xffff0000u);
+      if (a.pre_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+      dw_sm[idx] = f;
     }
   }
-  float bias[8];
+  __syncthreads();
+  // ---- compute ----
+  const int cpad = ((a.in.C + 7) / 8) * 8;
+  const int units = FAST ? (a.TH / RS) * a.TW * 2 : a.TH * a.TW * 2;
+  const unsigned tw_magic = (1u << 20) / (unsigned)a.TW + 1u;
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    const int half = u & 1, p = u >> 1, ty = (int)(((unsigned)p * tw_magic) >> 20), tx = p - ty * a.TW;
+    const int ox = ox0 + tx;
+    if (ox >= a.out.W) continue;
+    float4 wv[9];
 #pragma unroll
-  for (int j = 0; j < 8; j++) bias[j] = a.bias[ch * 8 + j];
+    for (int t = 0; t < 9; t++) wv[t] = *reinterpret_cast<const float4*>(a.w + t * cpad + ch * 8 + half * 4);
+    const float4 bv = *reinterpret_cast<const float4*>(a.bias + ch * 8 + half * 4);
+    if (FAST) {
+      float4 acc[RS];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (ox0 + k >= a.out.W) break;
+      for (int k = 0; k < RS; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* base = dw_sm + ((long)(ty * RS) * RW + tx) * 2 + half;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const float t = acc[k].v[j] + bias[j];
-      acc[k].v[j] = a.post_relu ? fmaxf(t, 0.f) : t;
+      for (int j = 0; j < RS + 2; j++) {
+        const float4 v0 = base[(j * RW) * 2], v1 = base[(j * RW + 1) * 2], v2 = base[(j * RW + 2) * 2];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const int k = j - r;
+          if (k < 0 || k >= RS) continue;
+          fma4(acc[k], v0, wv[r * 3]); fma4(acc[k], v1, wv[r * 3 + 1]); fma4(acc[k], v2, wv[r * 3 + 2]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RS; k++) {
+        const int oy = oy0 + ty * RS + k;
+        if (oy >= a.out.H) break;
+        float4 t = make_float4(acc[k].x + bv.x, acc[k].y + bv.y, acc[k].z + bv.z, acc[k].w + bv.w);
+        if (a.post_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+        st_half(a.out, cv_elem(a.out, n, ch, oy, ox), half, t);
+      }
+    } else {
+      const int oy = oy0 + ty;
+      if (oy >= a.out.H) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int sy = oy * a.stride + r * a.rate - a.pad - ry0;
+        if (sy < 0 || sy >= RH) continue;
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          const int sx = ox * a.stride + s * a.rate - a.pad - rx0;
+          if (sx < 0 || sx >= RW) continue;
+          fma4(acc, dw_sm[(sy * RW + sx) * 2 + half], wv[r * 3 + s]);
+        }
+      }
+      float4 t = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
+      if (a.post_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+      st_half(a.out, cv_elem(a.out, n, ch, oy, ox), half, t);
     }
-    st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, ch, oy, ox0 + k), acc[k]);
   }
 }
 
@@ -368,17 +398,38 @@ int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float*
 int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const float* bias, int stride, int rate, int pad, bool pre_relu,
                      bool post_relu, int n_active, cudaStream_t st) {
   PV_CHECK(in.C == out.C && in.N == out.N, PREMVOS_ERR_INVALID_ARG, "depthwise3x3_cp8: shape mismatch");
-  DwArgs a{dev(in), dev(out), w, bias, stride, rate, pad, pre_relu ? 1 : 0, post_relu ? 1 : 0, n_active};
   const long total = (long)n_active * in.vchunks() * out.H * out.W;
   if (total == 0) return 0;
-  prof_before(st);
-  if (rate == 1 && (stride == 1 || stride == 2)) {
-    const long t4 = (long)n_active * in.vchunks() * out.H * ((out.W + 3) / 4);
-    if (stride == 1) depthwise3x3_x4_kernel<1><<<blocks_for(t4, 128), 128, 0, st>>>(a);
-    else depthwise3x3_x4_kernel<2><<<blocks_for(t4, 128), 128, 0, st>>>(a);
+  const bool fast = stride == 1 && rate == 1;
+  const int RS = (fast && out.H % 5 == 0) ? 5 : 4;
+  const int target = stride == 1 ? 32 : 16;
+  const int ntx = (out.W + target - 1) / target, TW = (out.W + ntx - 1) / ntx;
+  int TH, nty;
+  if (fast) {   // strips of RS rows; 5..8 strips per tile, least padding wins
+    const int strips = (out.H + RS - 1) / RS;
+    int best = 8, waste = 1 << 30;
+    for (int sp = 8; sp >= 5; sp--) {
+      const int wst = (strips + sp - 1) / sp * sp - strips;
+      if (wst < waste) { waste = wst; best = sp; }
+    }
+    if (strips < 5) best = strips;
+    TH = best * RS; nty = (strips + best - 1) / best;
   } else {
-    depthwise3x3_kernel<<<blocks_for(total), 256, 0, st>>>(a);
+    nty = (out.H + target - 1) / target; TH = (out.H + nty - 1) / nty;
   }
+  const int clip = rate > 2 ? 1 : 0;
+  const int RH = (TH - 1) * stride + 2 * rate + 1, RW = (TW - 1) * stride + 2 * rate + 1;
+  const size_t smem = (size_t)(clip ? std::min(RH, in.H) : RH) * (clip ? std::min(RW, in.W) : RW) * 32;
+  PV_CHECK(smem <= 200 * 1024 && (long)RH * RW * RW < (1 << 20) && (long)TH * TW * TW < (1 << 20), PREMVOS_ERR_UNSUPPORTED,
+           "depthwise3x3_cp8: tile does not fit shared memory");
+  const int units = fast ? (TH / RS) * TW * 2 : TH * TW * 2;
+  const int iters = (units + 255) / 256;
+  const int threads = std::min(256, ((units + iters - 1) / iters + 31) / 32 * 32);
+  DwArgs a{dev(in), dev(out), w, bias, stride, rate, pad, pre_relu ? 1 : 0, post_relu ? 1 : 0, TH, TW, ntx, RH, RW, clip};
+  auto kern = fast ? (RS == 5 ? depthwise3x3_tile_kernel<5, true> : depthwise3x3_tile_kernel<4, true>) : depthwise3x3_tile_kernel<4, false>;
+  if (smem > 48 * 1024) PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_before(st);
+  kern<<<dim3(ntx * nty, in.vchunks(), n_active), threads, smem, st>>>(a);
   const double frac = (double)n_active / in.N;
   return after_launch("depthwise3x3_kernel", st, 18.0 * total * 8, 4.0 * frac * ((double)in.pixels() + (double)out.pixels()) * in.C);
 }
