@@ -66,6 +66,33 @@ def test_corr_generic_path_matches_oracle(shape, cfg):
     assert rel_err(got, ref) < 2e-6
 
 
+REF_CASES = [((1, 196, 4, 4), (4, 1, 4, 1, 1)), ((1, 128, 8, 8), (4, 1, 4, 1, 1)), ((1, 96, 16, 16), (4, 1, 4, 1, 1)),
+             ((1, 64, 32, 32), (4, 1, 4, 1, 1)), ((1, 32, 64, 64), (4, 1, 4, 1, 1)), ((1, 32, 256, 256), (4, 1, 4, 1, 1)),
+             ((2, 33, 5, 35), (4, 1, 4, 1, 1)), ((1, 32, 112, 256), (4, 1, 4, 1, 1)),
+             ((1, 8, 12, 10), (3, 1, 3, 1, 1)), ((2, 5, 9, 9), (2, 3, 2, 1, 1)), ((1, 4, 16, 12), (4, 1, 4, 2, 2)),
+             ((1, 16, 20, 20), (20, 1, 20, 1, 2))]
+
+
+@pytest.mark.parametrize("shape,cfg", REF_CASES)
+def test_corr_matches_reference_cuda_kernel(shape, cfg):
+    """Second oracle: the reference's own corr_cuda_kernel.cu, compiled unchanged for sm_100a into oracle/_ref
+    (blob_rearrange x2 + CorrelateData + memsets as corr_cuda.c:52-78 drives them), on the same inputs -- pins
+    both the product kernel and the CPU restatement to outputs of the reference itself."""
+    from oracle import ref_corr
+    if not ref_corr.available():
+        pytest.skip("oracle/_ref/libcorr_reference.so not built (needs /root/reference at build time)")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(*shape, device="cuda", generator=g)
+    b = torch.randn(*shape, device="cuda", generator=g)
+    ref = ref_corr.corr_cuda_forward(a, b, *cfg, 1).cpu().numpy()
+    got = pwc.correlation_forward(a, b, *cfg, 1).cpu().numpy()
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 2e-6
+    if a.numel() <= 1 << 18:
+        cpu = O.correlation_forward(a.cpu().numpy(), b.cpu().numpy(), *cfg, 1)
+        assert rel_err(cpu, ref) < 2e-6
+
+
 def test_corr_properties_full_size():
     # size-independent properties at the bench resolution (level 2 of a 448x1024 pair)
     g = torch.Generator(device="cuda").manual_seed(0)
