@@ -1,22 +1,31 @@
 #!/usr/bin/env python
-"""Benchmark of the PReMVOS hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+"""Benchmark of the PReMVOS per-frame hot path on B200 (contract: task statement section 4 / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs B] [--boxes K]
 
-Workload (BASELINE.json configs[1]): PWC-Net full forward on synthetic Sintel-shaped 1024x436 frame
-pairs (network input 448x1024), random-init He-normal weights of the reference architecture.
-A step = one forward over a batch of B pairs per GPU.  Metric = frame-pairs/s, whole job.
+Workload = BASELINE.json's metric, "frame-pairs/sec (flow+proposal+refine) 1024x436": for every synthetic Sintel-shaped
+frame pair (t, t+1) of 1024x436 pixels
+    flow       PWC-Net full forward on the pair (448x1024 network input)                       BASELINE configs[1]
+    proposals  proposal network (ResNet-101 C4, 100 RoIs) on frame t+1 with BOTH weight sets    simple_run.sh:27-42
+               (568x1333 after CustomResize)
+    refine     refinement network (DeepLabv3+ / Xception-65, 385x385 crops) on 40 boxes of frame t+1 = the most the two
+               proposal passes can hand over (2 x RESULTS_PER_IM); the boxes are fixed synthetic ones because the detections
+               of random-init heads are data dependent -- the work per step stays constant
+random-init weights of the reference architectures.  A step = `--pairs` frame pairs per GPU through
+premvos_b200.pipeline.FramePipeline; the metric is whole-job frame pairs per second.
 
-  value    : device-resident inputs, K steps timed with CUDA events on the launching stream,
-             barrier + synchronize on both sides, max over ranks.
-  e2e      : the same through the host entry point (premvos_pwc_forward_host): pinned HOST input,
-             H2D copy + forward + D2H copy of the flow inside the timed region, every step.
-  roofline : dominant kernel of the step (by device time) from a per-launch CUDA-event pass over
-             one step (graphs bypassed so that each launch can be bracketed), algorithmic FLOPs or
-             bytes / measured time vs MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference : the CPU oracle restatement of the reference forward (the
-             reference's own CPU path cannot run: its CPU correlation is a stub and warp() hard-codes
-             .cuda()), all host threads, one pair per step.
+  value    : device-resident inputs, K steps timed with CUDA events on the launching stream, barrier + synchronize on
+             both sides, max over ranks.
+  e2e      : the same through FramePipeline.run_host: pinned HOST uint8 frames in, flow + detections + masks +
+             conf_scores out to pinned host memory, one synchronisation per step; copies inside the timed region.
+  stages   : each network alone, device resident (flow alone is BASELINE configs[1], proposals configs[2], refine configs[3]).
+  roofline : dominant kernel of the step (by device time) from a per-launch CUDA-event pass over one step run serially
+             on one stream (graphs bypassed so each launch can be bracketed): algorithmic FLOPs / measured time vs
+             MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the CPU oracle restatement of the reference forwards on all host threads, on a bounded
+             sample of the same unit (1 flow pair + 1 proposal pass + 2 refinement crops), scaled to the unit's
+             1 + 2 + 40 (the reference's own CPU path cannot run: its CPU correlation is a stub, warp() hard-codes .cuda(),
+             TensorFlow 1.8 / tensorpack are not installable).
 """
 import argparse
 import json
@@ -32,9 +41,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H_IN, W_IN = 436, 1024
-H_NET, W_NET = 448, 1024
-METRIC = "frame-pairs/sec (PWC-Net flow forward) 1024x436"
+METRIC = "frame-pairs/sec (flow+proposal+refine) 1024x436"
 UNIT = "frame-pairs/s"
+WORKLOAD = ("per frame pair 1024x436: PWC-Net full forward (448x1024 input) + proposal net x2 weight sets (ResNet-101 C4, "
+            "568x1333 input, 100 RoIs) + refinement net on 40 boxes (DeepLabv3+ Xception-65, 385x385 crops)")
+# algorithmic GFLOP per unit (2*MAC of every convolution of the reference graphs)
+GFLOP_FLOW, GFLOP_CROP = 168.2, 61.8
 
 
 def load_peaks():
@@ -44,6 +56,14 @@ def load_peaks():
         return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"],
                 "tensor_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback"}
+
+
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -80,107 +100,107 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_inputs(batch, sets):
-    """`sets` different device-resident input batches [batch,6,448,1024]; rotated so that consecutive
-    steps never read the same input (sets*batch*11 MB, sized > L2)."""
-    from premvos_b200 import synth
-    base = synth.synthetic_pwc_input(2, H_NET, W_NET, seed=1)
-    out = []
-    for s in range(sets):
-        x = np.empty((batch, 6, H_NET, W_NET), dtype=np.float32)
-        for b in range(batch):
-            k = s * batch + b
-            x[b] = np.roll(base[k % 2], shift=(7 * k, 13 * k), axis=(1, 2))
-        out.append(x)
-    return out
+def make_units(n_units, boxes_per_frame):
+    """`n_units` distinct synthetic units (frame pair, resized copies, boxes) as uint8 / float32 host arrays."""
+    from premvos_b200 import pipeline, synth
+    f1, f2 = synth.synthetic_frame_pair(H_IN, W_IN, seed=1)
+    units = []
+    for k in range(n_units):
+        a = np.roll(f1, shift=(7 * k, 13 * k), axis=(0, 1))
+        b = np.roll(f2, shift=(7 * k, 13 * k), axis=(0, 1))
+        pair, prop, frame = pipeline.prepare_unit(a, b)
+        boxes = synth.synthetic_boxes(boxes_per_frame, H_IN, W_IN, seed=100 + k)
+        units.append((pair, prop, frame, boxes))
+    return units
 
 
-def oracle_step_time(steps, warmup):
-    import torch
-    from oracle import pwc_oracle as O
-    from premvos_b200 import synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = {k: torch.from_numpy(v) for k, v in synth.pwc_synthetic_state_dict(0).items()}
-    x = torch.from_numpy(synth.synthetic_pwc_input(1, H_NET, W_NET, seed=1))
-    for _ in range(warmup):
-        O.pwc_forward(sd, x)
-    ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        O.pwc_forward(sd, x)
-        ts.append(time.perf_counter() - t0)
-    return float(np.mean(ts)), cores
-
-
-def measure_other_configs(steps=3):
-    """BASELINE configs C3 / C4 (parity-test cases, reported next to the headline for context): proposal_net on one
-    854x480 frame (749x1333 after CustomResize, ResNet-101, 100 RoIs) and refinement_net on 100 crops of 385x385,
-    both end to end through their host entry points (H2D of the frame, D2H of the results, every call)."""
+def oracle_unit_time(repeats, warmup, boxes_per_frame):
+    """Bounded CPU sample of one unit with the oracle: 1 PWC forward + 1 proposal-net forward + 2 refinement crops, all host
+    threads, scaled to the unit (1 flow + 2 proposal passes + boxes_per_frame crops).  -> (seconds per unit, cores, parts)"""
     import cv2
     import torch
-    from premvos_b200 import _lib, propnet, refnet, synth
-    out = {}
-    H, W = propnet.custom_resize_shape(480, 854)
-    net = propnet.ProposalNet().load_params(synth.propnet_synthetic_params(1))
-    img = cv2.resize(synth.synthetic_bgr_frame(480, 854, seed=2), (W, H)).astype(np.float32)
-    for _ in range(2):
-        net(img)
-    torch.cuda.synchronize()
-    l0 = _lib.kernel_launch_count()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        net(img)
-    dt = (time.perf_counter() - t0) / steps
-    out["proposal_net 1x854x480 frame (ResNet-101 C4, 100 RoIs)"] = {
-        "ms_per_frame": dt * 1e3, "frames_per_s": 1.0 / dt, "algorithmic_tflop_per_s": 0.508 / dt,
-        "launches_per_frame": (_lib.kernel_launch_count() - l0) // steps}
-    del net
-    rn = refnet.RefinementNet(max_batch=20).load_params(synth.refnet_synthetic_params(2))
-    frame = synth.synthetic_bgr_frame(480, 854, seed=3)
-    boxes = synth.synthetic_boxes(100, 480, 854, seed=3)
-    rn.refine(frame, boxes[:20])
-    torch.cuda.synchronize()
-    l0 = _lib.kernel_launch_count()
-    t0 = time.perf_counter()
-    for _ in range(max(1, steps - 1)):
-        rn.refine(frame, boxes)
-    dt = (time.perf_counter() - t0) / max(1, steps - 1)
-    out["refinement_net 100 crops 385x385 (DeepLabv3+ Xception-65)"] = {
-        "ms_per_100_crops": dt * 1e3, "crops_per_s": 100.0 / dt, "algorithmic_tflop_per_s": 6.18 / dt,
-        "launches_per_100_crops": (_lib.kernel_launch_count() - l0) // max(1, steps - 1)}
-    return out
+    from oracle import propnet_oracle as PO, pwc_oracle as O, refnet_oracle as RO
+    from premvos_b200 import pipeline, propnet, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Hn, Wn = pipeline.flow_input_shape(H_IN, W_IN)
+    Hp, Wp = propnet.custom_resize_shape(H_IN, W_IN)
+    sd = {k: torch.from_numpy(v) for k, v in synth.pwc_synthetic_state_dict(0).items()}
+    x = torch.from_numpy(synth.synthetic_pwc_input(1, Hn, Wn, seed=1))
+    PP = synth.propnet_synthetic_params(1)
+    img = cv2.resize(synth.synthetic_bgr_frame(H_IN, W_IN, seed=2), (Wp, Hp)).astype(np.float32)
+    RP = synth.refnet_synthetic_params(2)
+    frame = synth.synthetic_bgr_frame(H_IN, W_IN, seed=3)
+    boxes = synth.synthetic_boxes(2, H_IN, W_IN, seed=3)
+    image = (frame / 255).astype(np.float32)
+
+    def crops():
+        for b in boxes:
+            inputs, crop = RO.make_network_input(image, b, 385)
+            logits = RO.deeplab_logits(RP, inputs[None])[0]
+            RO.segmentation_output(logits, crop, H_IN, W_IN, 385)
+
+    parts = {"flow": [], "proposal_pass": [], "refine_crop": []}
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter(); O.pwc_forward(sd, x)
+        t1 = time.perf_counter(); PO.propnet_forward(PP, img)
+        t2 = time.perf_counter(); crops()
+        t3 = time.perf_counter()
+        if it >= warmup:
+            parts["flow"].append(t1 - t0); parts["proposal_pass"].append(t2 - t1); parts["refine_crop"].append((t3 - t2) / len(boxes))
+    parts = {k: float(np.mean(v)) for k, v in parts.items()}
+    sec = parts["flow"] + 2 * parts["proposal_pass"] + boxes_per_frame * parts["refine_crop"]
+    return sec, cores, parts
+
+
+def sample_text(repeats, parts, boxes_per_frame):
+    return ("oracle (torch CPU, all host threads) on a bounded sample of one unit: 1 PWC forward 448x1024 (%.2f s) + 1 proposal-net "
+            "forward 568x1333 (%.2f s) + 2 refinement crops 385x385 (%.2f s each), mean of %d repeat(s); unit time = flow + 2 x "
+            "proposal pass + %d x crop" % (parts["flow"], parts["proposal_pass"], parts["refine_crop"], repeats, boxes_per_frame))
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 40))
-    warm = max(0, min(args.warmup, 3))
-    sec, cores = oracle_step_time(steps, warm)
+    steps = max(1, min(args.steps, 3))
+    warm = max(0, min(args.warmup, 1))
+    sec, cores, parts = oracle_unit_time(steps, warm, args.boxes)
     val = 1.0 / sec
-    sample = "1 frame pair 448x1024 per step, %d timed steps" % steps
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PWC-Net full forward, 1024x436 synthetic Sintel-shaped pair (448x1024 net input)",
-                       "batch_per_step": 1, "note": "CPU oracle port of the reference forward on the host cores; the "
-                       "reference's own CPU path cannot run (corr.c is a stub, warp() hard-codes .cuda())"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "boxes_per_frame": args.boxes,
+                       "note": "CPU oracle port of the reference forwards on the host cores; the reference's own CPU path cannot "
+                               "run (corr.c is a stub, warp() hard-codes .cuda(), TF 1.8 / tensorpack not installable)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_text(steps, parts, args.boxes)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def time_stage(fn, iters, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU per step")
-    ap.add_argument("--fp32", action="store_true", help="fp32 SIMT convolutions instead of tensor cores")
+    ap.add_argument("--pairs", type=int, default=4, help="frame pairs per GPU per step")
+    ap.add_argument("--boxes", type=int, default=40, help="refinement boxes per frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other-configs", action="store_true", help="skip the proposal_net / refinement_net context timings")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-network context timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,7 +210,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from premvos_b200 import _lib, pwc, shard, synth
+    from premvos_b200 import _lib, pipeline, shard, synth
 
     assert torch.cuda.is_available(), "bench.py needs a GPU; the product has no CPU path"
     torch.cuda.set_device(local_rank)
@@ -200,26 +220,28 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     args.warmup = max(args.warmup, 3)
-    B = args.batch
+    B, K = args.pairs, args.boxes
 
     # weights: generated on rank 0, broadcast over NCCL (the path's only start-up collective)
-    sd = {k: torch.from_numpy(v) for k, v in synth.pwc_synthetic_state_dict(0).items()} if rank == 0 else {}
-    sd = shard.broadcast_state_dict(sd, src=0)
-    net = pwc.pwc_dc_net(None, tensor_cores=not args.fp32)
-    net.load_state_dict(sd)
-    net.cuda(local_rank).eval()
+    def weights(make):
+        sd = {k: torch.from_numpy(np.asarray(v)) for k, v in make().items()} if rank == 0 else {}
+        return shard.broadcast_state_dict(sd, src=0)
+    sd_flow = weights(lambda: synth.pwc_synthetic_state_dict(0))
+    P_gen = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(1)).items()}
+    P_spec = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(4)).items()}
+    P_ref = {k: v.numpy() for k, v in weights(lambda: synth.refnet_synthetic_params(2)).items()}
+    pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (H_IN, W_IN), pairs_per_step=B, boxes_per_frame=K)
 
-    sets = max(2, -(-300 // (B * 11)))          # > 2x the 126 MB L2 in total
-    host_inputs = make_inputs(B, sets)
-    dev_inputs = [torch.from_numpy(x).cuda() for x in host_inputs]
-    # end-to-end inputs: what the stage-1 driver has in hand after decoding + cv2.resize (script_pwc_multi.py:34-45) --
-    # uint8 RGB frames; BGR / 255 / planar run on the device (premvos_pwc_forward_host_u8)
-    def to_frames(x):
-        f = np.clip(np.rint(x * 255.0), 0, 255).astype(np.uint8)          # [B,6,H,W] BGR planes -> [B,2,H,W,3] RGB
-        f = f.reshape(x.shape[0], 2, 3, H_NET, W_NET)[:, :, ::-1]
-        return np.ascontiguousarray(np.transpose(f, (0, 1, 3, 4, 2)))
-    pinned = [torch.from_numpy(to_frames(x)).pin_memory() for x in host_inputs]
-    out_pinned = torch.empty((B, 2, H_NET // 4, W_NET // 4), dtype=torch.float32).pin_memory()
+    # `sets` different input batches, rotated so that consecutive steps never read the same input (> L2 in total)
+    per_set = pipe.h2d_bytes_per_step()
+    sets = max(2, -(-(2 * 126 << 20) // per_set))
+    units = make_units(sets * B, K)
+    host_sets, dev_sets = [], []
+    for s in range(sets):
+        u = units[s * B:(s + 1) * B]
+        hs = [torch.from_numpy(np.stack([x[i] for x in u])).pin_memory() for i in range(4)]
+        host_sets.append(hs)
+        dev_sets.append([t.cuda() for t in hs])
 
     def barrier():
         torch.cuda.synchronize()
@@ -236,7 +258,7 @@ def main():
 
     # ---- device-resident arm ----
     for i in range(args.warmup):
-        net(dev_inputs[i % sets])
+        pipe.run_device(*dev_sets[i % sets])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -245,88 +267,94 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        net(dev_inputs[i % sets])
+        pipe.run_device(*dev_sets[i % sets])
     e1.record()
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.kernel_launch_count() - launches0
     value = world * B * args.steps / (dev_ms * 1e-3)
 
-    # ---- end-to-end arm: host buffers in, host flow out, every step ----
+    # ---- end-to-end arm: pinned host buffers in, pinned host results out, every step ----
     for i in range(2):
-        net.forward_host_u8(pinned[i % sets].numpy(), out_pinned.numpy())
+        pipe.run_host(*host_sets[i % sets])
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        net.forward_host_u8(pinned[i % sets].numpy(), out_pinned.numpy())
+        pipe.run_host(*host_sets[i % sets])
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     e2e = world * B * args.steps / e2e_s
-    h2d = B * 2 * H_NET * W_NET * 3
-    d2h = B * 2 * (H_NET // 4) * (W_NET // 4) * 4
 
-    # ---- per-launch profile of one step (rank 0) -> roofline of the dominant kernel ----
+    # ---- per-launch profile of one step (rank 0), stages serial on one stream -> roofline of the dominant kernel ----
     roofline, kernels = None, None
     if rank == 0:
         peaks = load_peaks()
         _lib.profile_begin()
-        for i in range(3):
-            net(dev_inputs[i % sets])
+        pipe.run_device(*dev_sets[0], concurrent=False)
         prof = _lib.profile_end()
         total_ms = sum(v["ms"] for v in prof.values()) or 1.0
-        kernels = {k: {"launches_per_step": v["launches"] // 3, "ms_per_step": v["ms"] / 3,
-                       "share": v["ms"] / total_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / total_ms}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
         sec = top["ms"] * 1e-3
+        traffic = load_traffic(name)
         if "conv" in name and "small" not in name:
             ach = top["flops"] / sec / 1e12
             peak = peaks["tensor_sustained"]
             roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
-                        "avg_launch_us": top["ms"] * 1e3 / top["launches"], "launches_per_step": top["launches"] // 3,
-                        "algorithmic_gflop_per_step": top["flops"] / 3 / 1e9,
-                        "note": "achieved = algorithmic fp32 FLOPs / device time; every algorithmic FLOP is issued as 3 bf16 "
-                                "tensor-core FLOPs (split-bf16 x3 for 1e-3 fp32 parity), so tensor-pipe occupancy is 3x frac",
+                        "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + " bf16 sustained",
+                        "avg_launch_us": top["ms"] * 1e3 / top["launches"], "launches_per_step": top["launches"],
+                        "algorithmic_gflop_per_step": top["flops"] / 1e9, "serial_step_ms": total_ms,
+                        "note": "achieved = algorithmic fp32 FLOPs of all launches of this kernel in one step / their summed device "
+                                "time; every algorithmic FLOP is issued as 3 bf16 tensor-core FLOPs (split-bf16 x3 for 1e-3 fp32 "
+                                "parity), so tensor-pipe occupancy is 3x frac; traffic = mean DRAM bytes per launch (ncu)",
                         "bf16_tflops_issued": 3 * ach, "tensor_pipe_frac": 3 * ach / peak}
         else:
             ach = top["bytes"] / sec / 1e9
             peak = peaks["hbm"]
             roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + " copy",
-                        "avg_launch_us": top["ms"] * 1e3 / top["launches"], "launches_per_step": top["launches"] // 3}
+                        "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + " copy",
+                        "avg_launch_us": top["ms"] * 1e3 / top["launches"], "launches_per_step": top["launches"]}
+
+    # ---- each network alone, device resident (BASELINE configs[1..3]) ----
+    stages = None
+    if rank == 0 and not args.no_stages:
+        ff, pi, fr, bx = dev_sets[0]
+        o = pipe.out
+        t_flow = time_stage(lambda: pipe.flow_net.forward_u8(ff, out=o["flow"]), 20)
+        t_prop = time_stage(lambda: pipe.general.forward_device(pi[0]), 10)
+        t_ref = time_stage(lambda: pipe.refine.refine_device(fr[0], bx[0], masks=o["masks"][0], conf=o["conf"][0]), 5)
+        stages = {"flow": {"ms_per_pair": t_flow / B, "pairs_per_s": 1e3 * B / t_flow, "batch": B,
+                           "algorithmic_tflop_per_s": GFLOP_FLOW * B / t_flow},
+                  "proposal_pass": {"ms_per_frame": t_prop, "frames_per_s": 1e3 / t_prop, "input": [pipe.Hp, pipe.Wp]},
+                  "refine": {"ms_per_frame_of_%d_boxes" % K: t_ref, "crops_per_s": 1e3 * K / t_ref,
+                             "algorithmic_tflop_per_s": GFLOP_CROP * K / t_ref},
+                  "sum_serial_ms_per_pair": t_flow / B + 2 * t_prop + t_ref,
+                  "note": "each network alone on one stream, CUDA events; a unit = flow + 2 proposal passes + refine"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores = oracle_step_time(20, 1)
-        cpu_baseline = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "oracle PWC forward (torch CPU, all host threads), 1 frame pair 448x1024 per call, "
-                                  "mean of 20 calls after 1 warm-up (%.2f s each)" % sec}
+        sec, cores, parts = oracle_unit_time(1, 0, K)
+        cpu_baseline = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_text(1, parts, K)}
 
-    tc_layers = net.tensor_core_layers(B, H_NET, W_NET)
-    other = None
-    if rank == 0 and world == 1 and not args.no_other_configs:
-        try:
-            other = measure_other_configs()
-        except Exception as e:  # context only: never lose the headline line
-            other = {"error": repr(e)[:200]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None,
-                "dtype": "bf16x3 split-fp32 (fp32 accumulate)" if tc_layers else "f32",
-                "data": "synthetic",
-                "config": {"workload": "PWC-Net full forward, 1024x436 synthetic Sintel-shaped pair (448x1024 net input)",
-                           "batch_per_gpu_per_step": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                           "weights": "seeded He-normal (reference init), 9.37M params",
-                           "l2": "inputs rotate over %d device buffers (%d MB > 126 MB L2)" % (sets, sets * B * 11)},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "call": "premvos_pwc_forward_host_u8: pinned uint8 RGB frame pairs in (as decoded + resized by the "
-                                "stage-1 driver), fp32 flow out, synchronous per step"},
-                "gpu_launches": int(launches), "launches_per_forward": net.launches_per_forward(B, H_NET, W_NET),
-                "tensor_core_layers": tc_layers, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-                "other_configs": other}
+                "vs_baseline": None, "dtype": "bf16x3 split-fp32 (fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "global_pairs_per_step": B * world,
+                           "boxes_per_frame": K, "parallelism": "dp%d" % world,
+                           "weights": "seeded random init of the reference architectures (PWC-DC-Net 9.4M, 2 x ResNet-101 C4 "
+                                      "51.9M, Xception-65 DeepLabv3+ 40.8M params)",
+                           "l2": "inputs rotate over %d device input sets (%d MB > 126 MB L2); per-step activations are > 10 GB"
+                                 % (sets, sets * per_set >> 20)},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(),
+                        "d2h_bytes_per_step": pipe.d2h_bytes_per_step(),
+                        "call": "FramePipeline.run_host: pinned uint8 frames + boxes in (as decoded + cv2-resized by the stage "
+                                "drivers), flow + detections + per-box masks + conf_scores out to pinned host memory, synchronous per step"},
+                "gpu_launches": int(launches), "launches_per_step": pipe.launches_per_step(),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "stages": stages}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()

@@ -124,6 +124,9 @@ int premvos_pwc_forward_host(premvos_pwc_t* net, const float* x_host, float* flo
  * the BGR swap, /255 (float32(double(u)/255.0)), planar layout (:47-56) happen on the device.  Same result, bit for bit, as
  * premvos_pwc_forward_host on the float tensor the reference builds; a quarter of its host->device bytes. */
 int premvos_pwc_forward_host_u8(premvos_pwc_t* net, const unsigned char* frames_rgb_host, float* flow_host);
+/* The same with DEVICE pointers (frames uint8 RGB [batch, 2, height, width, 3], flow fp32 NCHW); enqueues on `stream`,
+ * does not synchronise.  One forward in flight per handle. */
+int premvos_pwc_forward_u8(premvos_pwc_t* net, const unsigned char* frames_rgb_dev, float* flow_dev, void* stream);
 /* Number of kernel launches one forward() performs (nodes of the captured graph). */
 int premvos_pwc_launches_per_forward(const premvos_pwc_t* net);
 /* Number of convolution layers of this handle that run on the tcgen05 tensor-core path (0 = pure
@@ -178,7 +181,8 @@ int premvos_nms_host(const float* boxes, const float* scores, int n, float iou_t
  * premvos_propnet_forward       : img is a DEVICE pointer; enqueues on `stream`, does not synchronise;
  *                                 fetch with premvos_propnet_read_results (synchronises `stream`).
  * premvos_propnet_forward_host  : img and all outputs are HOST pointers; copies, runs, synchronises.
- * Any output pointer except n_out may be NULL.
+ * Any output pointer except n_out may be NULL.  The whole forward is one CUDA graph captured at finalize
+ * (set_option("cuda_graph", 0) before finalize turns that off); one forward in flight per handle.
  * --------------------------------------------------------------------------------------------- */
 typedef struct premvos_propnet premvos_propnet_t;
 
@@ -187,9 +191,17 @@ int premvos_propnet_set_option(premvos_propnet_t* net, const char* key, int valu
 int premvos_propnet_set_param(premvos_propnet_t* net, const char* name, const float* host_data, int64_t numel);
 int premvos_propnet_finalize(premvos_propnet_t* net);
 int premvos_propnet_forward(premvos_propnet_t* net, const float* img_dev, void* stream);
+/* Same with the frame as the DEVICE uint8 BGR [H, W, 3] image eval.py:75-78 hands to pred_func (cv2.resize of a uint8
+ * frame stays uint8); the uint8 -> fp32 conversion is exact, so results are bit-identical to premvos_propnet_forward. */
+int premvos_propnet_forward_u8(premvos_propnet_t* net, const unsigned char* img_bgr_dev, void* stream);
 int premvos_propnet_read_results(premvos_propnet_t* net, void* stream, int* n_out, float* final_boxes, float* final_probs,
                                  int64_t* final_labels, float* final_posterior, int64_t* second_final_labels,
                                  float* second_final_posterior);
+/* Device-to-device hand-over of the last forward's results, enqueued on `stream` without synchronising: n_out_dev int[1],
+ * final_boxes_dev fp32 [20,4], final_probs_dev fp32 [20], second_final_posterior_dev fp32 [20, second_num_class] (rows
+ * >= *n_out_dev are unspecified; any pointer except n_out_dev may be NULL). */
+int premvos_propnet_copy_results(premvos_propnet_t* net, void* stream, int* n_out_dev, float* final_boxes_dev,
+                                 float* final_probs_dev, float* second_final_posterior_dev);
 int premvos_propnet_forward_host(premvos_propnet_t* net, const float* img_host, int* n_out, float* final_boxes,
                                  float* final_probs, int64_t* final_labels, float* final_posterior,
                                  int64_t* second_final_labels, float* second_final_posterior);
@@ -233,6 +245,13 @@ typedef struct premvos_refnet premvos_refnet_t;
 int premvos_refnet_create(premvos_refnet_t** out, int max_batch, int input_size, int middle_units);
 int premvos_refnet_set_param(premvos_refnet_t* net, const char* name, const float* host_data, int64_t numel);
 int premvos_refnet_finalize(premvos_refnet_t* net);
+/* forward: the same with every pointer a DEVICE pointer (frame uint8 RGB, boxes fp32 xywh, masks uint8 [num_boxes, height,
+ *   width], conf_scores fp32 [num_boxes], posteriors fp32 or NULL); enqueues on `stream`, never synchronises -- the entry
+ *   point of a resident pipeline (frames decoded once, proposals handed over on the device).  One forward in flight per
+ *   handle.  A full launch group (max_batch proposals) replays a CUDA graph captured at finalize. */
+int premvos_refnet_forward(premvos_refnet_t* net, const unsigned char* frame_rgb_dev, int height, int width,
+                           const float* boxes_xywh_dev, int num_boxes, unsigned char* masks_dev, float* conf_scores_dev,
+                           float* posteriors_dev, void* stream);
 int premvos_refnet_forward_host(premvos_refnet_t* net, const unsigned char* frame_rgb, int height, int width,
                                 const float* boxes_xywh, int num_boxes, unsigned char* masks_out, float* conf_scores_out,
                                 float* posteriors_out);

@@ -13,13 +13,15 @@ EXPORTS = [
     "premvos_profile_end",
     "premvos_corr_output_shape", "premvos_corr_forward", "premvos_conv2d_forward",
     "premvos_pwc_create", "premvos_pwc_set_param", "premvos_pwc_finalize", "premvos_pwc_forward",
-    "premvos_pwc_forward_host", "premvos_pwc_forward_host_u8", "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
+    "premvos_pwc_forward_host", "premvos_pwc_forward_host_u8", "premvos_pwc_forward_u8",
+    "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
     "premvos_pwc_get_tensor", "premvos_pwc_destroy", "premvos_pwc_tensor_core_layers",
     "premvos_propnet_create", "premvos_propnet_set_option", "premvos_propnet_set_param", "premvos_propnet_finalize",
-    "premvos_propnet_forward", "premvos_propnet_read_results", "premvos_propnet_forward_host",
+    "premvos_propnet_forward", "premvos_propnet_forward_u8", "premvos_propnet_read_results", "premvos_propnet_copy_results", "premvos_propnet_forward_host",
     "premvos_propnet_launches_per_forward", "premvos_propnet_get_tensor", "premvos_propnet_destroy",
     "premvos_topk_host", "premvos_nms_host",
-    "premvos_refnet_create", "premvos_refnet_set_param", "premvos_refnet_finalize", "premvos_refnet_forward_host",
+    "premvos_refnet_create", "premvos_refnet_set_param", "premvos_refnet_finalize", "premvos_refnet_forward",
+    "premvos_refnet_forward_host",
     "premvos_refnet_launches_per_forward", "premvos_refnet_get_tensor", "premvos_refnet_destroy",
 ]
 
@@ -57,6 +59,7 @@ def lib() -> ctypes.CDLL:
     L.premvos_pwc_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.premvos_pwc_forward_host.argtypes = [c_void_p, c_void_p, c_void_p]
     L.premvos_pwc_forward_host_u8.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.premvos_pwc_forward_u8.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.premvos_pwc_launches_per_forward.argtypes = [c_void_p]
     L.premvos_pwc_tensor_core_layers.argtypes = [c_void_p]
     L.premvos_pwc_set_option.argtypes = [c_void_p, c_char_p, c_int]
@@ -66,6 +69,7 @@ def lib() -> ctypes.CDLL:
     L.premvos_refnet_create.argtypes = [P(c_void_p), c_int, c_int, c_int]
     L.premvos_refnet_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
     L.premvos_refnet_finalize.argtypes = [c_void_p]
+    L.premvos_refnet_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.premvos_refnet_forward_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.premvos_refnet_launches_per_forward.argtypes = [c_void_p]
     L.premvos_refnet_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
@@ -78,7 +82,9 @@ def lib() -> ctypes.CDLL:
     L.premvos_propnet_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
     L.premvos_propnet_finalize.argtypes = [c_void_p]
     L.premvos_propnet_forward.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.premvos_propnet_forward_u8.argtypes = [c_void_p, c_void_p, c_void_p]
     L.premvos_propnet_read_results.argtypes = [c_void_p, c_void_p, P(c_int)] + [c_void_p] * 6
+    L.premvos_propnet_copy_results.argtypes = [c_void_p] * 6
     L.premvos_propnet_forward_host.argtypes = [c_void_p, c_void_p, P(c_int)] + [c_void_p] * 6
     L.premvos_propnet_launches_per_forward.argtypes = [c_void_p]
     L.premvos_propnet_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]

@@ -259,6 +259,7 @@ struct DetTailArgs {
   int* n_out; float* final_boxes; float* final_probs; int64_t* final_labels; float* final_posterior;
   int64_t* second_final_labels; float* second_final_posterior; int* final_box_index;
 };
+int det_u8_to_f32(const unsigned char* src, float* dst, long n, cudaStream_t st);
 int det_frcnn_tail(const DetTailArgs& a, cudaStream_t st);                                  // train.py:275-295
 
 // ---- refinement-network kernels, refine_ops.cu ------------------------------------------------------------
@@ -275,6 +276,8 @@ int gap_fc_relu(const CView& feat, const float* Wt /*[C][nout]*/, const float* b
 // logits fp32 channels-last [N,h,w,cs] -> per-proposal full-frame masks (0/1), optional posteriors, sum of (2p'-1) over the frame
 int refine_output(const TView& logits, const int* crops, int N, int S, int H, int W, unsigned char* mask, float* posterior,
                   double* conf_sum, cudaStream_t st);
+// conf_score[i] = (float)(conf_sum[i] / hw)  (refinement_net_functions.py:58-62: mean over the whole frame)
+int refine_conf_finish(const double* conf_sum, int N, long hw, float* conf_out, cudaStream_t st);
 
 // ---- layout / format conversion, layout.cu ---------------------------------------------------------
 // NCHW fp32 [N,C,H,W] -> channels-last view (fp32 or split)

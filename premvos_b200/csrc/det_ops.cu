@@ -59,6 +59,18 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict
   st_chunk(out.hi, out.lo, ((long)out.c0 * hw + p) * 8, f);
 }
 
+// uint8 frame -> the fp32 image tensor the graph is fed with (eval.py:75-78 hands pred_func the resized uint8 image)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, long n,
+                                                        int aligned) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (aligned && i + 4 <= n) {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(src + i);
+    *reinterpret_cast<float4*>(dst + i) = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+  } else {
+    for (long j = i; j < n && j < i + 4; j++) dst[j] = (float)src[j];
+  }
+}
+
 // ---- basemodel.py:81-82: pad (0,1) zeros, 3x3 stride-2 VALID max pooling -------------------------------
 __global__ void __launch_bounds__(256) maxpool_kernel(CV in, CV out) {
   const int nch = (in.C + 7) / 8;
@@ -524,6 +536,13 @@ int det_preprocess(const float* img_hwc, const CView& out, cudaStream_t st) {
   prof_before(st);
   preprocess_kernel<<<blocks_for(hw), 256, 0, st>>>(img_hwc, dev(out));
   return after_launch("preprocess_kernel", st, 0.0, (double)hw * (12.0 + 32.0));
+}
+
+int det_u8_to_f32(const unsigned char* src, float* dst, long n, cudaStream_t st) {
+  const int aligned = ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 15) == 0;
+  prof_before(st);
+  u8_to_f32_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(src, dst, n, aligned);
+  return after_launch("u8_to_f32_kernel", st, 0.0, 5.0 * n);
 }
 
 int det_maxpool3x3s2(const CView& in, const CView& out, cudaStream_t st) {

@@ -77,6 +77,9 @@ struct premvos_propnet {
   int64_t *final_labels = nullptr, *second_final_labels = nullptr;
   int* final_box_index = nullptr;
   int launches_per_forward = 0;
+  cudaGraph_t graph = nullptr;       // the whole forward (fixed shapes per handle, device-side counts)
+  cudaGraphExec_t exec = nullptr;
+  int graph_nodes = 0, opt_cuda_graph = 1;
 };
 
 namespace {
@@ -362,6 +365,16 @@ int run_network(premvos_propnet* n, cudaStream_t st) {
   return 0;
 }
 
+// img_dev already holds the frame
+int enqueue_network(premvos_propnet* n, cudaStream_t st) {
+  if (n->exec && !profiling_enabled()) {
+    PV_CUDA(cudaGraphLaunch(n->exec, st));
+    count_launch(n->graph_nodes);
+    return 0;
+  }
+  return run_network(n, st);
+}
+
 void free_layer(ConvLayer* L) {
   if (!L->used) return;
   free_conv_weights_umma(&L->w);
@@ -398,6 +411,7 @@ extern "C" int premvos_propnet_set_option(premvos_propnet_t* n, const char* key,
     build_shape_table(n);
     return 0;
   }
+  if (k == "cuda_graph") { n->opt_cuda_graph = value; return 0; }
   return fail(PREMVOS_ERR_INVALID_ARG, "premvos_propnet_set_option: unknown option '%s'", key);
 }
 
@@ -425,6 +439,19 @@ extern "C" int premvos_propnet_finalize(premvos_propnet_t* n) {
   PV_TRY(run_network(n, n->stream));  // warm-up: validates every launch configuration
   PV_CUDA(cudaStreamSynchronize(n->stream));
   n->launches_per_forward = (int)(g_launch_count.load() - before);
+  if (n->opt_cuda_graph) {
+    const int64_t b2 = g_launch_count.load();
+    PV_CUDA(cudaStreamBeginCapture(n->stream, cudaStreamCaptureModeThreadLocal));
+    int r = run_network(n, n->stream);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(n->stream, &g);
+    if (r != 0) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail((int)e, "premvos_propnet_finalize: graph capture failed: %s", cudaGetErrorString(e));
+    n->graph = g;
+    n->graph_nodes = (int)(g_launch_count.load() - b2);
+    g_launch_count.fetch_sub(n->graph_nodes);  // captured, not executed
+    PV_CUDA(cudaGraphInstantiate(&n->exec, n->graph, 0));
+  }
   n->finalized = true;
   return 0;
 }
@@ -434,7 +461,15 @@ extern "C" int premvos_propnet_forward(premvos_propnet_t* n, const float* img_de
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_forward: call premvos_propnet_finalize first");
   cudaStream_t st = (cudaStream_t)stream;
   PV_CUDA(cudaMemcpyAsync(n->img_dev, img_dev, (size_t)n->H * n->W * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return run_network(n, st);
+  return enqueue_network(n, st);
+}
+
+extern "C" int premvos_propnet_forward_u8(premvos_propnet_t* n, const unsigned char* img_bgr_dev, void* stream) {
+  PV_CHECK(n && img_bgr_dev, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_forward_u8: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_forward_u8: call premvos_propnet_finalize first");
+  cudaStream_t st = (cudaStream_t)stream;
+  PV_TRY(det_u8_to_f32(img_bgr_dev, n->img_dev, (long)n->H * n->W * 3, st));
+  return enqueue_network(n, st);
 }
 
 extern "C" int premvos_propnet_read_results(premvos_propnet_t* n, void* stream, int* n_out, float* final_boxes, float* final_probs,
@@ -460,13 +495,31 @@ extern "C" int premvos_propnet_read_results(premvos_propnet_t* n, void* stream, 
   return 0;
 }
 
+// Device-to-device hand-over of the last forward's results (fixed RESULTS_PER_IM rows + a device count): lets a resident
+// pipeline run the next frame on this handle, or feed the boxes to the refinement network, without a host round trip.
+extern "C" int premvos_propnet_copy_results(premvos_propnet_t* n, void* stream, int* n_out_dev, float* final_boxes_dev,
+                                            float* final_probs_dev, float* second_final_posterior_dev) {
+  PV_CHECK(n && n_out_dev, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_copy_results: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_copy_results: network not finalized");
+  cudaStream_t st = (cudaStream_t)stream;
+  PV_CUDA(cudaMemcpyAsync(n_out_dev, n->n_out, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (final_boxes_dev)
+    PV_CUDA(cudaMemcpyAsync(final_boxes_dev, n->final_boxes, (size_t)RESULTS_PER_IM * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (final_probs_dev)
+    PV_CUDA(cudaMemcpyAsync(final_probs_dev, n->final_probs, (size_t)RESULTS_PER_IM * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (second_final_posterior_dev && n->second_num_class > 0)
+    PV_CUDA(cudaMemcpyAsync(second_final_posterior_dev, n->second_final_posterior,
+                            (size_t)RESULTS_PER_IM * n->second_num_class * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 extern "C" int premvos_propnet_forward_host(premvos_propnet_t* n, const float* img_host, int* n_out, float* final_boxes, float* final_probs,
                                             int64_t* final_labels, float* final_posterior, int64_t* second_final_labels,
                                             float* second_final_posterior) {
   PV_CHECK(n && img_host && n_out, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_forward_host: null argument");
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_forward_host: call premvos_propnet_finalize first");
   PV_CUDA(cudaMemcpyAsync(n->img_dev, img_host, (size_t)n->H * n->W * 3 * sizeof(float), cudaMemcpyHostToDevice, n->stream));
-  PV_TRY(run_network(n, n->stream));
+  PV_TRY(enqueue_network(n, n->stream));
   return premvos_propnet_read_results(n, n->stream, n_out, final_boxes, final_probs, final_labels, final_posterior, second_final_labels,
                                       second_final_posterior);
 }
@@ -543,6 +596,8 @@ extern "C" void premvos_propnet_destroy(premvos_propnet_t* n) {
   free_layer(&n->conv0); free_layer(&n->rpn0); free_layer(&n->rpn_heads);
   for (auto* vec : {&n->backbone, &n->head})
     for (auto& b : *vec) { free_layer(&b->c1); free_layer(&b->c2); free_layer(&b->c3); free_layer(&b->sc); }
+  if (n->exec) cudaGraphExecDestroy(n->exec);
+  if (n->graph) cudaGraphDestroy(n->graph);
   if (n->stream) cudaStreamDestroy(n->stream);
   delete n;
 }

@@ -649,6 +649,15 @@ extern "C" int premvos_pwc_forward_host_u8(premvos_pwc_t* n, const unsigned char
   return 0;
 }
 
+// Same unit of work with the frames already on the device (a resident pipeline decodes / uploads each frame once).
+extern "C" int premvos_pwc_forward_u8(premvos_pwc_t* n, const unsigned char* frames_rgb_dev, float* flow_dev, void* stream) {
+  PV_CHECK(n && frames_rgb_dev && flow_dev, PREMVOS_ERR_INVALID_ARG, "premvos_pwc_forward_u8: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_pwc_forward_u8: call premvos_pwc_finalize first");
+  cudaStream_t st = (cudaStream_t)stream;
+  PV_TRY(frames_u8_to_x(frames_rgb_dev, n->x_in, n->B, n->H, n->W, st));
+  return enqueue_forward(n, n->x_in, flow_dev, st);
+}
+
 extern "C" int premvos_pwc_launches_per_forward(const premvos_pwc_t* n) { return n ? n->launches_per_forward : 0; }
 
 extern "C" int premvos_pwc_tensor_core_layers(const premvos_pwc_t* n) { return n ? n->tensor_core_layers : 0; }

@@ -290,6 +290,11 @@ __device__ __forceinline__ float fg_prob(float l0, float l1) {  // softmax(...)[
   return e1 / (e0 + e1);
 }
 
+__global__ void conf_finish_kernel(const double* __restrict__ sum, int N, double hw, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = (float)(sum[i] / hw);
+}
+
 __global__ void __launch_bounds__(256) refine_output_kernel(OutArgs a) {
   __shared__ double red[8];
   const int n = blockIdx.y;
@@ -473,6 +478,13 @@ int refine_output(const TView& logits, const int* crops, int N, int S, int H, in
   prof_before(st);
   refine_output_kernel<<<grid, 256, 0, st>>>(a);
   return after_launch("refine_output_kernel", st, 100.0 * N * H * W, (double)N * H * W * (posterior ? 5.0 : 1.0));
+}
+
+int refine_conf_finish(const double* conf_sum, int N, long hw, float* conf_out, cudaStream_t st) {
+  if (N == 0) return 0;
+  prof_before(st);
+  conf_finish_kernel<<<blocks_for(N), 256, 0, st>>>(conf_sum, N, (double)hw, conf_out);
+  return after_launch("conf_finish_kernel", st, 0.0, 12.0 * N);
 }
 
 }  // namespace premvos

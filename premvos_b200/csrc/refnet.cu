@@ -50,6 +50,11 @@ struct premvos_refnet {
   unsigned char* frame_dev = nullptr; size_t frame_cap = 0;
   unsigned char* mask_dev = nullptr; size_t mask_cap = 0;
   float* post_dev = nullptr; size_t post_cap = 0;
+  void* hboxes_dev = nullptr; size_t hboxes_cap = 0;   // forward_host staging: boxes / conf_scores of one frame
+  void* hconf_dev = nullptr; size_t hconf_cap = 0;
+  cudaGraph_t graph = nullptr;                          // the network body for a full launch group (na == NB)
+  cudaGraphExec_t exec = nullptr;
+  int graph_nodes = 0, opt_cuda_graph = 1;
   int launches_per_forward = 0;
 };
 
@@ -359,12 +364,56 @@ extern "C" int premvos_refnet_finalize(premvos_refnet_t* n) {
   const int64_t before = g_launch_count.load();
   PV_TRY(run_batch(n, n->NB, n->stream));  // warm-up on the zero-initialised input: validates every launch configuration
   PV_CUDA(cudaStreamSynchronize(n->stream));
-  n->launches_per_forward = (int)(g_launch_count.load() - before) + 2;
+  n->launches_per_forward = (int)(g_launch_count.load() - before) + 3;
+  if (n->opt_cuda_graph) {
+    const int64_t b2 = g_launch_count.load();
+    PV_CUDA(cudaStreamBeginCapture(n->stream, cudaStreamCaptureModeThreadLocal));
+    int r = run_batch(n, n->NB, n->stream);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(n->stream, &g);
+    if (r != 0) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail((int)e, "premvos_refnet_finalize: graph capture failed: %s", cudaGetErrorString(e));
+    n->graph = g;
+    n->graph_nodes = (int)(g_launch_count.load() - b2);
+    g_launch_count.fetch_sub(n->graph_nodes);  // captured, not executed
+    PV_CUDA(cudaGraphInstantiate(&n->exec, n->graph, 0));
+  }
   n->finalized = true;
   return 0;
 }
 
-// The batched equivalent of MergeTrack/refinement_net_functions.py:do_refinement's inner loop: one frame, n proposal boxes.
+// One frame, n proposal boxes, everything on the device and on `st`; no synchronisation.  The batched equivalent of
+// MergeTrack/refinement_net_functions.py:do_refinement's inner loop.
+static int enqueue_refine(premvos_refnet* n, const unsigned char* frame_dev, int height, int width, const float* boxes_dev, int num_boxes,
+                          unsigned char* masks_dev, float* conf_dev, float* post_dev, cudaStream_t st) {
+  const size_t hw = (size_t)height * width;
+  for (int b0 = 0; b0 < num_boxes; b0 += n->NB) {
+    const int na = std::min(n->NB, num_boxes - b0);
+    PV_TRY(refine_make_input(frame_dev, height, width, boxes_dev + (size_t)b0 * 4, na, n->S, n->input, n->crops, st));
+    if (na == n->NB && n->exec && !profiling_enabled()) {
+      PV_CUDA(cudaGraphLaunch(n->exec, st));
+      count_launch(n->graph_nodes);
+    } else {
+      PV_TRY(run_batch(n, na, st));
+    }
+    PV_TRY(refine_output(n->logits, n->crops, na, n->S, height, width, masks_dev + (size_t)b0 * hw,
+                         post_dev ? post_dev + (size_t)b0 * hw : nullptr, n->conf_sum, st));
+    PV_TRY(refine_conf_finish(n->conf_sum, na, (long)hw, conf_dev + b0, st));
+  }
+  return 0;
+}
+
+extern "C" int premvos_refnet_forward(premvos_refnet_t* n, const unsigned char* frame_rgb_dev, int height, int width,
+                                      const float* boxes_xywh_dev, int num_boxes, unsigned char* masks_dev, float* conf_scores_dev,
+                                      float* posteriors_dev, void* stream) {
+  PV_CHECK(n && frame_rgb_dev && (num_boxes == 0 || (boxes_xywh_dev && masks_dev && conf_scores_dev)), PREMVOS_ERR_INVALID_ARG,
+           "premvos_refnet_forward: null argument");
+  PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_refnet_forward: call premvos_refnet_finalize first");
+  PV_CHECK(height > 0 && width > 0 && num_boxes >= 0, PREMVOS_ERR_INVALID_ARG, "premvos_refnet_forward: bad sizes");
+  return enqueue_refine(n, frame_rgb_dev, height, width, boxes_xywh_dev, num_boxes, masks_dev, conf_scores_dev, posteriors_dev,
+                        (cudaStream_t)stream);
+}
+
 extern "C" int premvos_refnet_forward_host(premvos_refnet_t* n, const unsigned char* frame_rgb, int height, int width, const float* boxes_xywh,
                                            int num_boxes, unsigned char* masks_out, float* conf_scores_out, float* posteriors_out) {
   PV_CHECK(n && frame_rgb && (num_boxes == 0 || (boxes_xywh && masks_out && conf_scores_out)), PREMVOS_ERR_INVALID_ARG,
@@ -374,24 +423,28 @@ extern "C" int premvos_refnet_forward_host(premvos_refnet_t* n, const unsigned c
   if (num_boxes == 0) return 0;
   cudaStream_t st = n->stream;
   const size_t hw = (size_t)height * width;
+  // posteriors (4 B/pixel/proposal, a test / debugging output) are staged one launch group at a time; masks and
+  // conf_scores of all proposals stay on the device until the end: one synchronisation per frame
+  const int group = posteriors_out ? n->NB : num_boxes;
   PV_TRY(ensure((void**)&n->frame_dev, &n->frame_cap, hw * 3));
-  PV_TRY(ensure((void**)&n->mask_dev, &n->mask_cap, hw * n->NB));
-  if (posteriors_out) PV_TRY(ensure((void**)&n->post_dev, &n->post_cap, hw * n->NB * sizeof(float)));
+  PV_TRY(ensure((void**)&n->mask_dev, &n->mask_cap, hw * group));
+  PV_TRY(ensure((void**)&n->hboxes_dev, &n->hboxes_cap, (size_t)num_boxes * 4 * sizeof(float)));
+  PV_TRY(ensure((void**)&n->hconf_dev, &n->hconf_cap, (size_t)num_boxes * sizeof(float)));
+  if (posteriors_out) PV_TRY(ensure((void**)&n->post_dev, &n->post_cap, hw * group * sizeof(float)));
   PV_CUDA(cudaMemcpyAsync(n->frame_dev, frame_rgb, hw * 3, cudaMemcpyHostToDevice, st));
-  std::vector<double> sums(n->NB);
-  for (int b0 = 0; b0 < num_boxes; b0 += n->NB) {
-    const int na = std::min(n->NB, num_boxes - b0);
-    PV_CUDA(cudaMemcpyAsync(n->boxes_dev, boxes_xywh + (size_t)b0 * 4, (size_t)na * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-    PV_TRY(refine_make_input(n->frame_dev, height, width, n->boxes_dev, na, n->S, n->input, n->crops, st));
-    PV_TRY(run_batch(n, na, st));
-    PV_TRY(refine_output(n->logits, n->crops, na, n->S, height, width, n->mask_dev, posteriors_out ? n->post_dev : nullptr, n->conf_sum, st));
+  PV_CUDA(cudaMemcpyAsync(n->hboxes_dev, boxes_xywh, (size_t)num_boxes * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+  for (int b0 = 0; b0 < num_boxes; b0 += group) {
+    const int na = std::min(group, num_boxes - b0);
+    PV_TRY(enqueue_refine(n, n->frame_dev, height, width, (const float*)n->hboxes_dev + (size_t)b0 * 4, na, n->mask_dev,
+                          (float*)n->hconf_dev + b0, posteriors_out ? n->post_dev : nullptr, st));
     PV_CUDA(cudaMemcpyAsync(masks_out + (size_t)b0 * hw, n->mask_dev, hw * na, cudaMemcpyDeviceToHost, st));
-    if (posteriors_out)
+    if (posteriors_out) {
       PV_CUDA(cudaMemcpyAsync(posteriors_out + (size_t)b0 * hw, n->post_dev, hw * na * sizeof(float), cudaMemcpyDeviceToHost, st));
-    PV_CUDA(cudaMemcpyAsync(sums.data(), n->conf_sum, (size_t)na * sizeof(double), cudaMemcpyDeviceToHost, st));
-    PV_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < na; i++) conf_scores_out[b0 + i] = (float)(sums[i] / (double)hw);
+      PV_CUDA(cudaStreamSynchronize(st));
+    }
   }
+  PV_CUDA(cudaMemcpyAsync(conf_scores_out, n->hconf_dev, (size_t)num_boxes * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PV_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -444,6 +497,10 @@ extern "C" void premvos_refnet_destroy(premvos_refnet_t* n) {
   if (n->frame_dev) cudaFree(n->frame_dev);
   if (n->mask_dev) cudaFree(n->mask_dev);
   if (n->post_dev) cudaFree(n->post_dev);
+  if (n->hboxes_dev) cudaFree(n->hboxes_dev);
+  if (n->hconf_dev) cudaFree(n->hconf_dev);
+  if (n->exec) cudaGraphExecDestroy(n->exec);
+  if (n->graph) cudaGraphDestroy(n->graph);
   if (n->stream) cudaStreamDestroy(n->stream);
   delete n;
 }

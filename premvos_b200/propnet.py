@@ -108,6 +108,49 @@ class ProposalNet:
         return (boxes[:m].copy(), probs[:m].copy(), labels[:m].copy(), post[:m].copy(), slabels[:m].copy(),
                 spost[:m, :self.second_num_class].copy())
 
+    # -- resident-pipeline entry points (device tensors, no synchronisation until read_results) -----------
+    def forward_device(self, img):
+        """img: CUDA tensor [h,w,3] BGR, uint8 or float32 (0..255), already resized.  Enqueues the whole graph on the
+        current torch stream; fetch with read_results(h, w)."""
+        import torch
+        if not isinstance(img, torch.Tensor) or not img.is_cuda or img.dtype not in (torch.uint8, torch.float32):
+            raise TypeError("img must be a CUDA uint8 / float32 tensor (this build has no CPU path)")
+        if img.dim() != 3 or img.shape[2] != 3 or not img.is_contiguous():
+            raise ValueError("expected a contiguous [h,w,3] BGR image, got %s" % (tuple(img.shape),))
+        H, W = int(img.shape[0]), int(img.shape[1])
+        with torch.cuda.device(img.device):
+            h = self._handle(H, W)
+            st = torch.cuda.current_stream().cuda_stream
+            fn = _lib.lib().premvos_propnet_forward_u8 if img.dtype == torch.uint8 else _lib.lib().premvos_propnet_forward
+            _lib.check(fn(h, img.data_ptr(), st))
+
+    def copy_results_device(self, H, W, count, boxes, probs=None):
+        """Device-to-device copy of the last forward_device's results on the current torch stream (no synchronisation):
+        count CUDA int32 [1], boxes CUDA float32 [20,4], probs CUDA float32 [20]."""
+        import torch
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_propnet_copy_results(self._handle(H, W), st, count.data_ptr(), boxes.data_ptr(),
+                                                           None if probs is None else probs.data_ptr(), None))
+
+    def read_results(self, H, W):
+        """Synchronises the current torch stream and returns the six arrays of pred_func for the last forward_device."""
+        import torch
+        h = self._handle(H, W)
+        n = ctypes.c_int()
+        boxes = np.zeros((RESULTS_PER_IM, 4), np.float32)
+        probs = np.zeros((RESULTS_PER_IM,), np.float32)
+        labels = np.zeros((RESULTS_PER_IM,), np.int64)
+        post = np.zeros((RESULTS_PER_IM, self.num_class), np.float32)
+        slabels = np.zeros((RESULTS_PER_IM,), np.int64)
+        spost = np.zeros((RESULTS_PER_IM, max(self.second_num_class, 1)), np.float32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_propnet_read_results(h, st, ctypes.byref(n), vp(boxes), vp(probs), vp(labels), vp(post),
+                                                           vp(slabels), vp(spost)))
+        m = n.value
+        return (boxes[:m].copy(), probs[:m].copy(), labels[:m].copy(), post[:m].copy(), slabels[:m].copy(),
+                spost[:m, :self.second_num_class].copy())
+
     def get_tensor(self, name, H, W):
         L = _lib.lib()
         h = self._handle(H, W)

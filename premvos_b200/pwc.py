@@ -240,6 +240,24 @@ class PWCDCNet:
         _lib.check(_lib.lib().premvos_pwc_forward_host_u8(h, fa.ctypes.data_as(ctypes.c_void_p), oa.ctypes.data_as(ctypes.c_void_p)))
         return out
 
+    def forward_u8(self, frames: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """Device-resident variant of forward_host_u8: `frames` is a CUDA uint8 tensor [B,2,H,W,3] (RGB); enqueues on the
+        current stream and returns the CUDA flow tensor without synchronising."""
+        if not isinstance(frames, torch.Tensor) or not frames.is_cuda or frames.dtype != torch.uint8:
+            raise TypeError("frames must be a CUDA uint8 tensor (this build has no CPU path)")
+        if frames.dim() != 5 or frames.shape[1] != 2 or frames.shape[4] != 3 or not frames.is_contiguous():
+            raise ValueError("frames must be contiguous [B,2,H,W,3], got %s" % (tuple(frames.shape),))
+        B, _, H, W, _ = frames.shape
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (script_pwc_multi.py:38-45), got %dx%d" % (H, W))
+        with torch.cuda.device(frames.device):
+            h = self._handle(B, H, W)
+            if out is None:
+                out = torch.empty((B, 2, H // 4, W // 4), dtype=torch.float32, device=frames.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().premvos_pwc_forward_u8(h, frames.data_ptr(), out.data_ptr(), st))
+        return out
+
     def get_tensor(self, name: str, B, H, W) -> np.ndarray:
         """Test hook: intermediate of the last forward, NCHW (see include/premvos_b200.h)."""
         L = _lib.lib()

@@ -93,6 +93,28 @@ class RefinementNet:
         _lib.check(_lib.lib().premvos_refnet_forward_host(self._h(), vp(img), H, W, vp(boxes), n, vp(masks), vp(conf), vp(post)))
         return masks, conf, post
 
+    def refine_device(self, frame, boxes_xywh, masks=None, conf=None):
+        """Resident-pipeline entry point: `frame` CUDA uint8 RGB [H,W,3], `boxes_xywh` CUDA float32 [n,4]; enqueues on the
+        current torch stream, never synchronises.  -> (masks CUDA uint8 [n,H,W], conf_scores CUDA float32 [n])"""
+        import torch
+        if not (isinstance(frame, torch.Tensor) and frame.is_cuda and frame.dtype == torch.uint8 and frame.is_contiguous()):
+            raise TypeError("frame must be a contiguous CUDA uint8 tensor (this build has no CPU path)")
+        if frame.dim() != 3 or frame.shape[2] != 3:
+            raise ValueError("expected an RGB frame [H,W,3], got %s" % (tuple(frame.shape),))
+        if not (isinstance(boxes_xywh, torch.Tensor) and boxes_xywh.is_cuda and boxes_xywh.dtype == torch.float32
+                and boxes_xywh.is_contiguous() and boxes_xywh.dim() == 2 and boxes_xywh.shape[1] == 4):
+            raise TypeError("boxes_xywh must be a contiguous CUDA float32 tensor [n,4]")
+        n, H, W = int(boxes_xywh.shape[0]), int(frame.shape[0]), int(frame.shape[1])
+        with torch.cuda.device(frame.device):
+            if masks is None:
+                masks = torch.empty((n, H, W), dtype=torch.uint8, device=frame.device)
+            if conf is None:
+                conf = torch.empty((n,), dtype=torch.float32, device=frame.device)
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().premvos_refnet_forward(self._h(), frame.data_ptr(), H, W, boxes_xywh.data_ptr(), n,
+                                                         masks.data_ptr(), conf.data_ptr(), None, st))
+        return masks, conf
+
     def get_tensor(self, name):
         L = _lib.lib()
         n = ctypes.c_int64()

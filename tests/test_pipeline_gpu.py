@@ -1,0 +1,131 @@
+"""GPU tests of the resident pipeline (premvos_b200/pipeline.py) and of the device entry points it uses
+(premvos_pwc_forward_u8, premvos_propnet_forward_u8 + copy_results, premvos_refnet_forward): every stage must give the
+same bits as the host entry point of the same network, which the per-network tests hold against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from premvos_b200 import _lib, pipeline, propnet, pwc, refnet, synth
+
+pytestmark = pytest.mark.gpu
+
+NB = (1, 1, 1, 1)
+H, W = 100, 140
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _lib.lib()
+
+
+@pytest.fixture(scope="module")
+def parts():
+    sd = synth.pwc_synthetic_state_dict(3)
+    G = synth.propnet_synthetic_params(5, NB)
+    S = synth.propnet_synthetic_params(6, NB)
+    R = synth.refnet_synthetic_params(0, 0)
+    pipe = pipeline.FramePipeline({k: torch.from_numpy(v) for k, v in sd.items()}, G, S, R, (H, W), pairs_per_step=2,
+                                  boxes_per_frame=3, refine_batch=2, num_blocks=NB, middle_units=0, refine_input_size=129)
+    frames = [synth.synthetic_bgr_frame(H, W, seed=20 + i)[:, :, ::-1].copy() for i in range(4)]   # RGB uint8
+    return pipe, sd, G, S, R, frames
+
+
+def _stage_refs(sd, G, S, R, f0, f1, boxes):
+    """The same unit through the host entry points of the three networks."""
+    pair, prop, frame = pipeline.prepare_unit(f0, f1)
+    net = pwc.pwc_dc_net(None)
+    net.load_state_dict(sd)
+    net.cuda().eval()
+    flow = net.forward_host_u8(pair[None].copy())[0]
+    dets = [propnet.ProposalNet(NB).load_params(P)(prop) for P in (G, S)]
+    rn = refnet.RefinementNet(max_batch=2, input_size=129, middle_units=0).load_params(R)
+    masks, conf, _ = rn.refine(frame, boxes)
+    return flow, dets, masks, conf
+
+
+def test_device_entry_points_equal_host_entry_points(parts):
+    pipe, sd, G, S, R, frames = parts
+    boxes = synth.synthetic_boxes(3, H, W, seed=9, min_size=20, max_size=90)
+    flow, dets, masks, conf = _stage_refs(sd, G, S, R, frames[0], frames[1], boxes)
+    pair, prop, frame = pipeline.prepare_unit(frames[0], frames[1])
+    # proposal net: uint8 device image -> read_results
+    pn = propnet.ProposalNet(NB).load_params(G)
+    pn.forward_device(torch.from_numpy(prop).cuda())
+    got = pn.read_results(*prop.shape[:2])
+    for a, b in zip(got, dets[0]):
+        np.testing.assert_array_equal(a, b)
+    # refinement net: device frame + boxes (3 boxes with groups of 2: one graph replay + one partial group)
+    rn = refnet.RefinementNet(max_batch=2, input_size=129, middle_units=0).load_params(R)
+    m, c = rn.refine_device(torch.from_numpy(frame).cuda(), torch.from_numpy(boxes).cuda())
+    np.testing.assert_array_equal(m.cpu().numpy(), masks)
+    np.testing.assert_array_equal(c.cpu().numpy(), conf)
+    with pytest.raises(TypeError):
+        rn.refine_device(torch.from_numpy(frame), torch.from_numpy(boxes).cuda())
+    with pytest.raises(TypeError):
+        pn.forward_device(torch.from_numpy(prop))
+
+
+def test_pipeline_step_fixed_boxes_and_host_call(parts):
+    pipe, sd, G, S, R, frames = parts
+    units = [(frames[0], frames[1]), (frames[1], frames[2])]
+    prep = [pipeline.prepare_unit(a, b) for a, b in units]
+    boxes = np.stack([synth.synthetic_boxes(3, H, W, seed=30 + i, min_size=20, max_size=90) for i in range(2)])
+    ff = torch.from_numpy(np.stack([p[0] for p in prep]))
+    pi = torch.from_numpy(np.stack([p[1] for p in prep]))
+    fr = torch.from_numpy(np.stack([p[2] for p in prep]))
+    before = _lib.kernel_launch_count()
+    out = pipe.run_device(ff.cuda(), pi.cuda(), fr.cuda(), torch.from_numpy(boxes).cuda())
+    torch.cuda.synchronize()
+    assert _lib.kernel_launch_count() - before == pipe.launches_per_step()
+    out = {k: v.cpu().numpy().copy() for k, v in out.items()}
+    for b, (f0, f1) in enumerate(units):
+        flow, dets, masks, conf = _stage_refs(sd, G, S, R, f0, f1, boxes[b])
+        # a batch-2 PWC handle may plan another (deterministic) split-K factor than the batch-1 handle: equal within rounding
+        assert rel_err(out["flow"][b], flow) < 1e-4
+        for which in range(2):
+            n = len(dets[which][0])
+            assert out["det_count"][which, b] == n
+            np.testing.assert_array_equal(out["det_boxes"][which, b, :n], dets[which][0])
+            np.testing.assert_array_equal(out["det_probs"][which, b, :n], dets[which][1])
+        np.testing.assert_array_equal(out["masks"][b], masks)
+        np.testing.assert_array_equal(out["conf"][b], conf)
+    # the end-to-end call on pinned host buffers gives the same bits, twice (staging is reused)
+    for _ in range(2):
+        host = pipe.run_host(ff.pin_memory(), pi.pin_memory(), fr.pin_memory(), torch.from_numpy(boxes).pin_memory())
+        for k in out:
+            np.testing.assert_array_equal(host[k].numpy(), out[k])
+    with pytest.raises(ValueError):
+        pipe.run_device(ff.cuda()[:1], pi.cuda(), fr.cuda(), None)
+
+
+def test_pipeline_refines_detected_boxes_and_shards_a_video(parts):
+    pipe, sd, G, S, R, frames = parts
+    # one rank
+    whole = pipeline.run_video(pipe, frames)
+    assert sorted(whole) == [0, 1, 2]
+    # two ranks, run one after the other on this GPU: the union is the same result, unit by unit
+    merged = {}
+    for r in range(2):
+        part = pipeline.run_video(pipe, frames, rank=r, world=2)
+        assert sorted(part) == list(range(r, 3, 2))
+        merged.update(part)
+    for t in whole:
+        for k in whole[t]:
+            np.testing.assert_array_equal(np.asarray(merged[t][k]), np.asarray(whole[t][k]))
+    # the refined boxes are the combined detections of the two passes (stage 4)
+    for t in whole:
+        r = whole[t]
+        prop = pipeline.prepare_unit(frames[t], frames[t + 1])[1]
+        g = r["det_boxes"][0][:r["det_count"][0]]
+        s = r["det_boxes"][1][:r["det_count"][1]]
+        bx = pipeline.combine_proposals(g, s, (H, W), prop.shape[:2])
+        assert len(bx) == r["det_count"].sum()
+        bx = bx[:pipe.K]
+        assert r["num_boxes"] == len(bx)
+        if len(bx):
+            rn = refnet.RefinementNet(max_batch=2, input_size=129, middle_units=0).load_params(R)
+            masks, conf, _ = rn.refine(frames[t + 1], bx)
+            np.testing.assert_array_equal(r["masks"][:len(bx)], masks)
+            np.testing.assert_array_equal(r["conf"][:len(bx)], conf)

@@ -57,3 +57,29 @@ def test_two_rank_gloo_roundtrip():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == ("ok", 3.0)
+
+
+def test_combine_proposals_matches_the_json_round_trip():
+    """pipeline.combine_proposals == detect_one_image post-processing (eval.py:93-96) + convert_results_to_json
+    (train.py:399-408) + combine_general_and_specific.py:37 on the same boxes."""
+    import json
+    from premvos_b200 import pipeline, propnet
+    rng = np.random.default_rng(0)
+    H, W = 480, 854
+    Hp, Wp = propnet.custom_resize_shape(H, W)
+    assert (Hp, Wp) == (749, 1333) and pipeline.flow_input_shape(436, 1024) == (448, 1024) and pipeline.flow_input_shape(480, 854) == (512, 896)
+    sets = []
+    for n in (5, 0, 20):
+        x1 = rng.uniform(-20, Wp - 50, n); y1 = rng.uniform(-20, Hp - 50, n)
+        sets.append(np.stack([x1, y1, x1 + rng.uniform(5, 400, n), y1 + rng.uniform(5, 400, n)], 1).astype(np.float32).reshape(-1, 4))
+    for g, s in ((sets[0], sets[2]), (sets[1], sets[0]), (sets[1], sets[1])):
+        ref = []
+        for boxes in (g, s):
+            scale = (Hp * 1.0 / H + Wp * 1.0 / W) / 2
+            b = propnet.clip_boxes(boxes.copy() / scale, (H, W))
+            res = [propnet.SecondDetectionResult(bb, 0.9, 1, None, None, 1, None, None) for bb in b]
+            ref += json.loads(json.dumps(propnet.convert_results_to_json(res)))
+        got = pipeline.combine_proposals(g, s, (H, W), (Hp, Wp))
+        assert got.shape == (len(ref), 4) and got.dtype == np.float32
+        if ref:
+            np.testing.assert_array_equal(got, np.array([r["bbox"] for r in ref], dtype=np.float32))
