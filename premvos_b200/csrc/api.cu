@@ -31,6 +31,11 @@ static std::vector<LaunchRec> g_recs;
 static cudaEvent_t g_pending_e0 = nullptr;
 
 bool profiling_enabled() { return g_profiling; }
+// stable storage for dynamically built profile labels (per-layer breakdowns, PREMVOS_PROFILE_LAYERS=1)
+const char* prof_intern(const std::string& s) {
+  static std::map<std::string, int> pool;
+  return pool.emplace(s, 0).first->first.c_str();
+}
 void prof_before(cudaStream_t st) {
   if (!g_profiling) return;
   cudaEventCreate(&g_pending_e0);

@@ -42,6 +42,7 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 // with CUDA events on the launching stream and records the launch's algorithmic FLOPs / bytes.
 bool profiling_enabled();
 void prof_before(cudaStream_t st);
+const char* prof_intern(const std::string& s);
 void prof_after(const char* what, cudaStream_t st, double flops, double bytes);
 inline int after_launch(const char* what, cudaStream_t st = nullptr, double flops = 0.0, double bytes = 0.0) {
   count_launch();
@@ -205,7 +206,7 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
 // host_w: torch Conv2d layout [Cout][Cin][R][S].  cin_map (optional): physical channel (inside the input
 // view) of every reference input channel, cin_phys = physical channel count of that view.
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
-                           const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0);
+                           const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0, long m_hint = 0);
 void free_conv_weights_umma(ConvWeightsUmma* w);
 struct ConvPlanUmma;
 void free_conv_plan_umma(ConvPlanUmma* plan);

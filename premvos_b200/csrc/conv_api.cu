@@ -3,6 +3,8 @@
 // TMA + tcgen05 implicit GEMM).  Allocates its scratch per call -- not a hot-path function.
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace premvos;
@@ -50,13 +52,17 @@ extern "C" int premvos_conv2d_forward(const float* x_dev, const float* w_host, c
     o.res = res;
   }
   ConvWeightsUmma w;
-  PV_TRY(pack_conv_weights_umma(&w, w_host, bias_host, cout, cin, kh, kw));
+  PV_TRY(pack_conv_weights_umma(&w, w_host, bias_host, cout, cin, kh, kw, nullptr, 0, 0, (long)batch * Ho * Wo));
   ConvGeom g;
   g.stride = stride; g.dil = dilation; g.pad_t = pad_top; g.pad_l = pad_left; g.pad_b = pad_bottom; g.pad_r = pad_right;
   g.slope = slope;
   ConvPlanUmma plan;
   int r = plan_conv_umma(&plan, in, o, w, g);
   if (r == 0) r = launch_conv_umma(plan, st);
+  // tuning aid: PREMVOS_CONV_REPEAT=n launches the same convolution n more times back to back (idempotent), so that a
+  // profile shows the kernel without a different kernel before it
+  if (const char* rep = getenv("PREMVOS_CONV_REPEAT"))
+    for (int i = 0; i < atoi(rep) && r == 0; i++) r = launch_conv_umma(plan, st);
   if (r == 0) r = cp8_to_nchw(out, 0, out_dev, st);
   cudaError_t e = cudaStreamSynchronize(st);
   free_conv_weights_umma(&w);

@@ -118,6 +118,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the 64-bit descriptors given as {low word, constant high word}: the issuer advances only the low words
+// (start address >> 4 inside bits [0,14)) with 32-bit adds, so that one MMA costs the issuing thread a handful of
+// instructions.  (tools/ubench/mma_rate.cu: descriptors rebuilt with shifts/masks per MMA cap one issuing thread at
+// ~150 cycles per MMA; precomputed ones reach the tensor pipe's 64 / 128 cycles per 128xNx16 MMA.)
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on `bar` when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -154,7 +169,8 @@ struct UmmaConvArgs {
   int box_w, box_h;          // A box (pixels) as it lies in shared memory
   int KC, kblocks;           // 8-channel chunks per k-block (even); k-blocks
   int BN, Cout;
-  int dbg;                   // ablation switches (PREMVOS_DBG): 1 = producer skips the copies, 2 = issuer skips the MMAs
+  int dbg;                   // ablation switches (PREMVOS_DBG): 1 = producer skips the copies, 2 = issuer skips the MMAs,
+                             // 4 = epilogue only drains TMEM, 8 = one k-block per work item
   int NACC;                  // accumulator replicas (1..3): product p of {lo*hi, hi*lo, hi*hi} accumulates into replica p % NACC;
                              // independent accumulators let the tensor pipe overlap the otherwise serial MMA chain
   int TPS;                   // taps per weight stage (divides R*S): one bulk copy fetches TPS taps x {hi, lo}
@@ -183,9 +199,14 @@ struct UmmaConvArgs {
   int flat_hw;               // > 0: 1x1 stride-1 layer run over the FLATTENED pixel list of each plane (tiles of 128 consecutive
                              // pixels, no 2-D tile padding); value = real H*W, geometry fields describe an [ceil(HW/8)][8] image
   int nbuf;                  // TMEM accumulator buffers (2: the epilogue of item i overlaps the MMAs of item i+1)
+  int lockstep;              // 1x1 layers: A and weight rings advance together and share one barrier pair per k-block
+  int epi_warps;             // 4 or 8 epilogue warps (8: kernel instantiation with 384 threads, one CTA per SM)
 };
 
-__global__ void __launch_bounds__(UMMA_THREADS, 2)
+// EPI_WARPS = 4: 256 threads, up to two CTAs per SM.  EPI_WARPS = 8: 384 threads, one CTA per SM owning the whole TMEM (256-wide N
+// tiles); two warps share each TMEM lane quarter and split the accumulator columns.
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const UmmaConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -216,14 +237,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     w.tx0 = (tile % a.tiles_x) * (a.mt_horizontal ? 8 * a.MT : 8);
     w.kb_begin = a.ksplit > 1 ? w.z * a.kb_per : 0;
     w.kb_end = a.ksplit > 1 ? min(a.kblocks, w.kb_begin + a.kb_per) : a.kblocks;
+    if (a.dbg & 8) w.kb_end = w.kb_begin + 1;   // ablation: one k-block per item (wrong results)
     return w;
   };
 
   if (warp == 0 && lane == 0) {  // one-time setup
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
-    for (int s = 0; s < a.a_stages; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < a.a_stages && s < MAX_A_STAGES; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < a.w_stages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_addr_slot, a.tmem_cols);
@@ -241,6 +263,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int n_img = wk.n_img;
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)wk.ntile * a.kblocks + wk.kb_begin) * taps * 2 * a.w_plane;
     const int bx = wk.tx0 * a.stride - a.pad_l, by = wk.ty0 * a.stride - a.pad_t;
+    if (a.lockstep) {
+      // 1x1 layers: one ring, one barrier pair per k-block -- the A box and the weight block of a k-block share the stage
+      // index and the w_full / w_empty barriers (a tcgen05.commit per ring per k-block costs more than the k-block's MMAs)
+      for (int kb = wk.kb_begin; kb < wk.kb_end; kb++) {
+        mbar_wait(&w_empty[w_st], w_ph ^ 1u);
+        if (a.dbg & 1) {
+          if (elect_one()) mbar_arrive(&w_full[w_st]);
+        } else if (elect_one()) {
+          uint8_t* dst = a_smem + (size_t)w_st * 2 * a.a_plane;
+          mbar_arrive_expect_tx(&w_full[w_st], 2u * (uint32_t)a.a_box_bytes + w_bytes);
+          if (a.merged_x) {
+            tma_load_4d(&tmA_hi, &w_full[w_st], dst, bx * 8, by, kb * a.KC, n_img);
+            tma_load_4d(&tmA_lo, &w_full[w_st], dst + a.a_plane, bx * 8, by, kb * a.KC, n_img);
+          } else {
+            tma_load_5d(&tmA_hi, &w_full[w_st], dst, 0, bx, by, kb * a.KC, n_img);
+            tma_load_5d(&tmA_lo, &w_full[w_st], dst + a.a_plane, 0, bx, by, kb * a.KC, n_img);
+          }
+          bulk_load_1d(w_smem + (size_t)w_st * a.w_stage, wsrc, w_bytes, &w_full[w_st]);
+        }
+        __syncwarp();
+        wsrc += w_bytes;
+        if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
+      }
+      continue;
+    }
     for (int kb = wk.kb_begin; kb < wk.kb_end; kb++) {
       int tin = 0;  // tap index inside the current weight stage
       for (int r = 0; r < a.R; r++)
@@ -290,13 +337,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_lo32 = (a_lbo >> 4) << 16, w_lo32 = (w_lbo >> 4) << 16;
     const uint32_t a_base = smem_u32(a_smem), w_base = smem_u32(w_smem);
     const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = (uint32_t)a.w_stage;
-    const uint32_t a_kstep = 2u * a_lbo, w_kstep = 2u * w_lbo, a_mstep = a.mt_horizontal ? 128u : 16u * a_sbo;
+    const uint32_t a_kstep16 = (2u * a_lbo) >> 4, w_kstep16 = (2u * w_lbo) >> 4, a_mstep16 = (a.mt_horizontal ? 128u : 16u * a_sbo) >> 4;
+    const uint32_t a_plane16 = (uint32_t)a.a_plane >> 4, w_plane16 = (uint32_t)a.w_plane >> 4;
     const uint32_t tap_row = a.halo ? (uint32_t)(a.dil * a.box_w) * 16u : 0u, tap_col = a.halo ? (uint32_t)a.dil * 16u : 0u;
     uint32_t a_st = 0, a_ph = 0, w_st = 0, w_ph = 0, cur_a = 0, a_addr_stage = 0;
     uint32_t buf = 0, empty_ph = 0;   // bit b = phase of tmem_empty_bar[b]
     const int ksteps = a.KC / 2;
     const uint32_t rep_cols = (uint32_t)(a.MT * a.BN);
-    const uint32_t rep1 = a.NACC > 1 ? rep_cols : 0u, rep2 = a.NACC > 2 ? 2u * rep_cols : 0u;
     // One barrier handshake per weight stage (TPS taps): all of its MMAs are issued in one go, one commit
     // releases the stage.  (A per-tap handshake costs ~500 cycles of mbarrier/commit latency -- more than the
     // MMAs of one tap.)  Tap mode additionally waits for / releases one A stage per tap.
@@ -323,7 +370,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tc_fence_after();
         uint32_t w_addr_tap = w_base + w_st * w_stage_bytes;
         for (int t = 0; t < a.TPS; t++) {
-          if (!a.halo) {
+          if (a.lockstep) {
+            cur_a = w_st;
+            a_addr_stage = a_base + w_st * a_stage_bytes;
+          } else if (!a.halo) {
             mbar_wait(&a_full[a_st], a_ph);
             tc_fence_after();
             cur_a = a_st;
@@ -331,21 +381,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
           }
           if (elect_one()) {
-            uint32_t aa0 = a_addr_stage + tap_off, ww = w_addr_tap;
-            for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aa0 += a_kstep, ww += w_kstep) {
-              const uint64_t dWh = ((uint64_t)w_hi32 << 32) | (w_lo32 + ((ww & 0x3FFFFu) >> 4));
-              const uint64_t dWl = ((uint64_t)w_hi32 << 32) | (w_lo32 + (((ww + (uint32_t)a.w_plane) & 0x3FFFFu) >> 4));
-              uint32_t aa = aa0, d = tmem_acc;
-              for (int mt = 0; mt < a.MT; mt++, aa += a_mstep, d += (uint32_t)a.BN) {
-                const uint64_t dAh = ((uint64_t)a_hi32 << 32) | (a_lo32 + ((aa & 0x3FFFFu) >> 4));
-                const uint64_t dAl = ((uint64_t)a_hi32 << 32) | (a_lo32 + (((aa + (uint32_t)a.a_plane) & 0x3FFFFu) >> 4));
-                umma_bf16(d, dAl, dWh, idesc, accum);
-                umma_bf16(d + rep1, dAh, dWl, idesc, a.NACC > 1 ? accum : 1u);
-                umma_bf16(d + rep2, dAh, dWh, idesc, a.NACC > 2 ? accum : 1u);
+            // low descriptor words of the hi planes; the lo planes lie a_plane / w_plane bytes behind (all offsets are
+            // multiples of 16 bytes and shared-memory addresses are < 2^18, so plain adds never carry into the LBO field)
+            uint32_t aH = a_lo32 + ((a_addr_stage + tap_off) >> 4), wH = w_lo32 + (w_addr_tap >> 4);
+            for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aH += a_kstep16, wH += w_kstep16) {
+              const uint32_t wL = wH + w_plane16;
+              uint32_t ah = aH, d = tmem_acc;
+              for (int mt = 0; mt < a.MT; mt++, ah += a_mstep16, d += (uint32_t)a.BN) {
+                const uint32_t al = ah + a_plane16;
+                umma_bf16_lo(d, al, a_hi32, wH, w_hi32, idesc, accum);
+                umma_bf16_lo(d, ah, a_hi32, wL, w_hi32, idesc, 1u);
+                umma_bf16_lo(d, ah, a_hi32, wH, w_hi32, idesc, 1u);
               }
               accum = 1u;
             }
-            if (!a.halo) umma_commit(&a_empty[cur_a]);
+            if (!a.halo && !a.lockstep) umma_commit(&a_empty[cur_a]);
           }
           __syncwarp();
           w_addr_tap += 2u * (uint32_t)a.w_plane;
@@ -370,6 +420,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const long hw = a.flat_hw > 0 ? (long)a.flat_hw : (long)a.Ho * a.Wo;
     uint32_t buf = 0, full_ph = 0;    // bit b = phase of tmem_full_bar[b]
     const uint32_t buf_cols = (uint32_t)(a.MT * a.BN * a.NACC);
+    // accumulator columns of this warp: all of them, or one half when two warps share a lane quarter
+    const int col_part = (warp - 4) >> 2, col_span = EPI_WARPS == 8 ? a.BN / 2 : a.BN;
+    const int col_begin = col_part * col_span, col_end = col_begin + col_span;
     for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
     const Work wk = decode(t);
     const int n_img = wk.n_img, ty0 = wk.ty0, tx0 = wk.tx0, ntile = wk.ntile;
@@ -381,11 +434,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const int oy = ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
       const long pix = (long)oy * a.Wo + ox;
       const bool in_img = a.flat_hw > 0 ? pix < hw : (oy < a.Ho && ox < a.Wo);
-      for (int c0 = 0; c0 < a.BN; c0 += 16) {
+      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
         uint32_t v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * a.BN + c0);
-        const bool last_ld = (mt == a.MT - 1) && (c0 + 16 >= a.BN);
+        const bool last_ld = (mt == a.MT - 1) && (c0 + 16 >= col_end);
         tmem_ld16(taddr, v);
         // global loads of this group (bias, residual) are issued while the TMEM load is in flight
         const int co0 = ntile * a.BN + c0;
@@ -418,6 +471,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if (a.dbg & 4) continue;   // ablation: epilogue drains TMEM only
         if (a.ksplit > 1) {  // raw partial sums; bias / residual / activation happen in conv_finish_kernel
           if (in_img) {
             float* pp = a.partial + (long)wk.z * a.partial_stride + ((long)n_img * hw + pix) * a.cout_pad + co0;
@@ -606,7 +660,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
-                           const int* cin_map, int cin_phys, int kc_hint) {
+                           const int* cin_map, int cin_phys, int kc_hint, long m_hint) {
   out->R = R; out->S = S; out->Cin = Cin; out->Cout = Cout;
   const int phys = cin_map ? cin_phys : Cin;   // physical input channels (after the view's chunk padding)
   out->CinPhys = phys;
@@ -619,8 +673,16 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   PV_CHECK(kc >= 2 && (kc % 2) == 0 && kc <= 16, PREMVOS_ERR_INVALID_ARG, "pack_conv_weights_umma: KC=%d", kc);
   out->KC = kc;
   out->kblocks = (chunks + kc - 1) / kc;
+  // N tile: 128 columns, or 256 for 1x1 layers whose output (m_hint pixels) still fills the machine with 256 x 256 tiles: a
+  // 1x1 layer moves 9x more A bytes per MMA than a 3x3 layer in halo mode, so at 128 x 128 it is bound by the L2 -> shared
+  // memory fill and by the per-k-block barrier round trip; 256 x 256 halves the bytes and quarters the handshakes per FLOP
   int bn = round_up(Cout, 16);
-  if (bn > 128) bn = 128;
+  int bn_cap = 128;
+  if (R * S == 1 && Cout >= 256 && m_hint > 0 && (m_hint / 256) * ((Cout + 255) / 256) >= 120) bn_cap = 256;
+  bn_cap = env_int("PREMVOS_BN", bn_cap);
+  if (bn_cap != 256 || R * S != 1) bn_cap = std::min(bn_cap, 128);
+  if (bn > bn_cap) bn = bn_cap;
+  if (bn > 128 && kc_hint == 0 && env_int("PREMVOS_KC", 0) == 0) { kc = std::min(4, round_up(chunks, 2)); out->KC = kc; out->kblocks = (chunks + kc - 1) / kc; }
   out->BN = bn;
   out->ntiles = (Cout + bn - 1) / bn;
   const int KP = out->kblocks * kc * 8;
@@ -707,7 +769,9 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const long tiles_v = (long)((geoW + 7) / 8) * ((geoH + 31) / 32), tiles_h = (long)((geoW + 15) / 16) * ((geoH + 15) / 16);
   const bool horiz = tiles_h < tiles_v;
   const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
-  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && taps > 1) ? 2 : 1;   // 1x1 layers measured best with one sub-tile
+  int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && taps > 1) ? 2 : 1;   // 1x1 layers measured best with one sub-tile at BN = 128
+  const bool wide = w.BN > 128;                                           // 256-wide N tile: one CTA per SM owns the whole TMEM
+  if (wide) mt_pref = 1;   // measured (tools/conv_sweep2.py): 256 x 256 single-buffered tiles lose to 128 x 256 double-buffered ones
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
   const int tps_env = env_int("PREMVOS_TPS", 0);
@@ -754,7 +818,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.tiles_x = (geoW + tile_w - 1) / tile_w;
   a.tiles_y = (geoH + tile_h - 1) / tile_h;
   // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
-  int budget = (a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
+  int budget = (!wide && a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
   if (env_int("PREMVOS_BUDGET_KB", 0) > 0) budget = env_int("PREMVOS_BUDGET_KB", 0) * 1024;
   if (a.halo && budget > 120 * 1024) a.a_stages = 3;
   while (a.w_stages < MAX_W_STAGES && a.w_stages * a.TPS < 3 * taps &&
@@ -762,6 +826,14 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     a.w_stages++;
   while (!a.halo && a.a_stages < MAX_A_STAGES && a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 2 * a.a_plane + 1024 <= budget)
     a.a_stages++;
+  // 1x1 layers: one ring for A and weights (see the kernel), as deep as the budget allows
+  a.lockstep = (!a.halo && taps == 1 && env_int("PREMVOS_LOCKSTEP", 1) != 0) ? 1 : 0;
+  if (a.lockstep) {
+    int st = (budget - 1024) / (2 * a.a_plane + a.w_stage);
+    st = std::max(2, std::min(st, MAX_W_STAGES));
+    st = std::min(st, std::max(2, a.kblocks + 1));
+    a.a_stages = a.w_stages = st;
+  }
   plan->smem_bytes = a.a_stages * 2 * a.a_plane + a.w_stages * a.w_stage + 128 /*align slack*/ + 512 /*barriers*/;
   PV_CHECK(plan->smem_bytes <= SMEM_LIMIT, PREMVOS_ERR_UNSUPPORTED, "conv_umma: %d bytes of shared memory needed", plan->smem_bytes);
   a.w = w.w; a.bias = w.bias; a.slope = g.slope;
@@ -770,7 +842,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.cp_cout = cp_cout; a.f32_first = f32_first; a.f32_linear = out.f32_linear ? 1 : 0; a.f32_accum = out.f32_accumulate ? 1 : 0;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
   a.dbg = env_int("PREMVOS_DBG", 0);
-  a.NACC = env_int("PREMVOS_NACC", 1);
+  a.NACC = 1;   // accumulator replicas were an experiment (no gain: the dependent-MMA chain is not the limiter)
   PV_CHECK(a.NACC >= 1 && a.NACC <= 3 && a.NACC * a.MT * w.BN <= 512, PREMVOS_ERR_INVALID_ARG, "conv_umma: NACC=%d does not fit TMEM", a.NACC);
   uint32_t cols = 32;
   while ((int)cols < a.NACC * a.MT * w.BN) cols <<= 1;
@@ -800,13 +872,14 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.ntiles = w.ntiles; a.n_images = in.N;
   a.total_work = plan->grid_x * plan->grid_y * a.ksplit;
   // two CTAs per SM when shared memory and TMEM allow it; a second accumulator buffer when TMEM allows that too
-  const int cps = (plan->smem_bytes <= 112 * 1024 && a.NACC * a.MT * w.BN <= 256) ? 2 : 1;
+  const int cps = (!wide && plan->smem_bytes <= 112 * 1024 && a.NACC * a.MT * w.BN <= 256) ? 2 : 1;
   a.nbuf = (2 * a.NACC * a.MT * w.BN <= (cps == 2 ? 256 : 512)) ? 2 : 1;
   a.nbuf = env_int("PREMVOS_NBUF", a.nbuf);
   cols = 32;
   while ((int)cols < a.nbuf * a.NACC * a.MT * w.BN) cols <<= 1;
   a.tmem_cols = cols;
   plan->ctas_per_sm = cps;
+  a.epi_warps = (wide && w.BN % 32 == 0 && env_int("PREMVOS_EPI8", 1) != 0) ? 8 : 4;
 
   // input tensor maps over the view's chunk planes: [N][chunks][H][W][8]
   const int vchunks = (in.C + 7) / 8;
@@ -844,7 +917,11 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
 int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   static bool attr_set = false;
   if (!attr_set) {
-    PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    // experiment: one shared-memory carve-out for every kernel of the process, so that alternating small kernels and
+    // 110-224 KB convolution kernels never reconfigure the SMs
+    if (env_int("PREMVOS_PREFER_SHARED", 0)) PV_CUDA(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
+    PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   // persistent CTAs: at most ctas_per_sm per SM, each walks the work items b, b + grid, ...  A smaller active batch
@@ -863,10 +940,23 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   }
   const int grid = std::min(a.total_work, num_sms * plan.ctas_per_sm);
   prof_before(st);
-  conv_umma_kernel<<<grid, UMMA_THREADS, plan.smem_bytes, st>>>(
-      *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
+  if (a.epi_warps == 8)
+    conv_umma_kernel<8><<<grid, 128 + 32 * 8, plan.smem_bytes, st>>>(
+        *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
+  else
+    conv_umma_kernel<4><<<grid, UMMA_THREADS, plan.smem_bytes, st>>>(
+        *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
   const double frac = (double)a.n_images / plan.N;
-  PV_TRY(after_launch("conv_umma_kernel", st, plan.flops * frac, plan.bytes * frac));
+  const char* label = "conv_umma_kernel";
+  static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
+  if (per_layer && profiling_enabled()) {   // per-layer breakdown for tools/profile_nets.py
+    char buf[256];
+    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d]", a.n_images,
+             a.flat_hw > 0 ? a.flat_hw : a.Ho, a.flat_hw > 0 ? 1 : a.Wo, a.kblocks * a.KC * 8, a.Cout, a.R, a.stride, a.dil, a.MT, a.BN,
+             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep);
+    label = prof_intern(buf);
+  }
+  PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));
   if (plan.grid_z > 1) {
     const int na = (active_n >= 0 && active_n < plan.N) ? active_n : plan.N;
     const long total = (long)na * a.Ho * a.Wo * ((a.Cout + 7) / 8);

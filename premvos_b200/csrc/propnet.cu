@@ -162,7 +162,8 @@ int make_conv(premvos_propnet* n, ConvLayer* L, const std::string& scope, bool b
       for (int i = 0; i < cin; i++)
         for (int o = 0; o < cout; o++)
           w[(((size_t)o * cin + i) * kh + y) * kw + x] = W[(((size_t)y * kw + x) * cin + i) * cout + o] * scale[o];
-  PV_TRY(pack_conv_weights_umma(&L->w, w.data(), b.data(), cout, cin, kh, kw, cin_map, cin_phys));
+  const long m_out = out.cp.hi ? (long)out.cp.N * out.cp.H * out.cp.W : (long)out.f32.N * out.f32.H * out.f32.W;
+  PV_TRY(pack_conv_weights_umma(&L->w, w.data(), b.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out));
   PV_TRY(plan_conv_umma(&L->plan, in, out, L->w, g));
   L->used = true;
   return 0;

@@ -45,6 +45,10 @@ CASES = [
     (1, 2048, 9, 9, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, True),     # tiny grid 1x1 with residual through the split-K path
     (3, 728, 25, 25, 728, 1, 1, 1, (0, 0, 0, 0), 1.0, True),    # Xception middle flow: flattened 1x1, 625 px (not a multiple of 8)
     (2, 1024, 46, 83, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, False),  # ResNet group2 conv1: flattened, 3818 px
+    (20, 728, 25, 25, 728, 1, 1, 1, (0, 0, 0, 0), 1.0, True),   # bench-size Xception middle flow: 256 x 256 tiles (BN 256, MT 2,
+                                                                #   8 epilogue warps, lockstep ring), N tail 216, residual
+    (6, 264, 97, 97, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, False),   # wide tile, one N tile, K = 33 chunks (k-block tail), ragged M tail
+    (16, 128, 49, 49, 1024, 1, 1, 1, (0, 0, 0, 0), 0.0, False), # wide tile, 4 N tiles, KC from a 128-channel input
 ]
 
 
