@@ -39,7 +39,7 @@ namespace {
 
 constexpr int UMMA_THREADS = 256;
 constexpr int MAX_A_STAGES = 4, MAX_W_STAGES = 8;
-constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_LIMIT = 226 * 1024;   // dynamic part; 1 KB of the 227 KB stays for static shared memory (debug timestamps)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,6 +159,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// PREMVOS_DBG & 32: per-launch CTA timing statistics (ns, %globaltimer): [0] min start, [1] max end, [2] sum of CTA durations,
+// [3] max CTA duration, [4] min CTA duration, [5] CTAs
+__device__ unsigned long long g_dbg_cta[8];
+__device__ unsigned long long g_dbg_rec[512][6];   // per CTA: smid, start, end, issuer first MMA, issuer last commit, epilogue end
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct UmmaConvArgs {
   int tiles_x, tiles_y, MT;  // tiles per image; MT accumulators (16 rows x 8 cols each) per CTA ...
   int mt_horizontal;         // ... side by side in x (1) or stacked in y (0), whichever pads the image less
@@ -199,6 +209,11 @@ struct UmmaConvArgs {
   int flat_hw;               // > 0: 1x1 stride-1 layer run over the FLATTENED pixel list of each plane (tiles of 128 consecutive
                              // pixels, no 2-D tile padding); value = real H*W, geometry fields describe an [ceil(HW/8)][8] image
   int nbuf;                  // TMEM accumulator buffers (2: the epilogue of item i overlaps the MMAs of item i+1)
+  // tail split: when the item count is a little more than a whole number of waves, the last `tail_items` items are split along K
+  // into `tail_split` sub-items each (work indices >= main_work), which store raw fp32 partial sums [z][tail item][row][BN] into
+  // `partial`; conv_finish_tail_kernel adds them in a fixed order and applies the epilogue.  Without it those few items cost a
+  // whole extra wave (e.g. 300 items on 148 CTAs: 3 waves instead of 2.03).
+  int tail_items, tail_split, tail_kb_per, main_work;
   int lockstep;              // 1x1 layers: A and weight rings advance together and share one barrier pair per k-block
   int epi_warps;             // 4 or 8 epilogue warps (8: kernel instantiation with 384 threads, one CTA per SM)
 };
@@ -222,12 +237,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ long long dbg_ts[5][24];   // PREMVOS_DBG & 32: per-k-block timestamps of CTA 0 (tuning aid)
+  int dbg_i = 0, dbg_j = 0;
+  const bool dbg_on = (a.dbg & 32) && blockIdx.x == 0;
+  const unsigned long long dbg_t0 = (a.dbg & 32) ? globaltimer_ns() : 0ull;
+  __shared__ unsigned long long dbg_ev[4];
+  if ((a.dbg & 32) && threadIdx.x < 4) dbg_ev[threadIdx.x] = 0;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int taps = a.R * a.S;
   // decode of a work item (once per item, the only integer divisions in the kernel)
-  struct Work { int n_img, ty0, tx0, ntile, z, kb_begin, kb_end; };
+  struct Work { int n_img, ty0, tx0, ntile, z, kb_begin, kb_end, tail_slot; };
   auto decode = [&](int t) {
     Work w;
+    w.tail_slot = -1;
+    int tz = 0;
+    if (a.tail_items > 0 && t >= a.main_work) {   // K-split sub-item of one of the last items
+      const int u = t - a.main_work;
+      w.tail_slot = u / a.tail_split;
+      tz = u - w.tail_slot * a.tail_split;
+      t = a.main_work + w.tail_slot;
+    }
     const int tile = t % tiles_per_img;
     int r = t / tiles_per_img;
     w.n_img = r % a.n_images; r /= a.n_images;
@@ -237,6 +266,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     w.tx0 = (tile % a.tiles_x) * (a.mt_horizontal ? 8 * a.MT : 8);
     w.kb_begin = a.ksplit > 1 ? w.z * a.kb_per : 0;
     w.kb_end = a.ksplit > 1 ? min(a.kblocks, w.kb_begin + a.kb_per) : a.kblocks;
+    if (w.tail_slot >= 0) { w.z = tz; w.kb_begin = tz * a.tail_kb_per; w.kb_end = min(a.kblocks, w.kb_begin + a.tail_kb_per); }
     if (a.dbg & 8) w.kb_end = w.kb_begin + 1;   // ablation: one k-block per item (wrong results)
     return w;
   };
@@ -268,6 +298,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       // index and the w_full / w_empty barriers (a tcgen05.commit per ring per k-block costs more than the k-block's MMAs)
       for (int kb = wk.kb_begin; kb < wk.kb_end; kb++) {
         mbar_wait(&w_empty[w_st], w_ph ^ 1u);
+        if (dbg_on && lane == 0 && dbg_j < 24) dbg_ts[3][dbg_j] = clock64();
         if (a.dbg & 1) {
           if (elect_one()) mbar_arrive(&w_full[w_st]);
         } else if (elect_one()) {
@@ -283,6 +314,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           bulk_load_1d(w_smem + (size_t)w_st * a.w_stage, wsrc, w_bytes, &w_full[w_st]);
         }
         __syncwarp();
+        if (dbg_on && lane == 0 && dbg_j < 24) dbg_ts[4][dbg_j++] = clock64();
         wsrc += w_bytes;
         if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
       }
@@ -369,46 +401,69 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         mbar_wait(&w_full[w_st], w_ph);
         tc_fence_after();
         uint32_t w_addr_tap = w_base + w_st * w_stage_bytes;
-        for (int t = 0; t < a.TPS; t++) {
-          if (a.lockstep) {
-            cur_a = w_st;
-            a_addr_stage = a_base + w_st * a_stage_bytes;
-          } else if (!a.halo) {
+        if (a.halo || a.lockstep) {
+          // One elected region per weight stage: every MMA of its TPS taps and the commits that release the stage.  The
+          // tensor pipe queues very few MMAs per CTA (tools/ubench + PREMVOS_DBG ablations: MMA time adds to the issuer's
+          // control time instead of overlapping it), so every instruction between two UTCHMMAs of consecutive stages is
+          // idle tensor time: no second elect, no __syncwarp, tap bookkeeping only in the elected lane (always the same one).
+          if (a.lockstep) { cur_a = w_st; a_addr_stage = a_base + w_st * a_stage_bytes; }
+          if (elect_one()) {
+            if ((a.dbg & 32) && dbg_ev[0] == 0) dbg_ev[0] = globaltimer_ns();
+            if (dbg_on && dbg_i < 24) dbg_ts[0][dbg_i] = clock64();
+            for (int t = 0; t < a.TPS; t++) {
+              uint32_t aH = a_lo32 + ((a_addr_stage + tap_off) >> 4), wH = w_lo32 + (w_addr_tap >> 4);
+              for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aH += a_kstep16, wH += w_kstep16) {
+                const uint32_t wL = wH + w_plane16;
+                uint32_t ah = aH, d = tmem_acc;
+                for (int mt = 0; mt < a.MT; mt++, ah += a_mstep16, d += (uint32_t)a.BN) {
+                  const uint32_t al = ah + a_plane16;
+                  umma_bf16_lo(d, al, a_hi32, wH, w_hi32, idesc, accum);
+                  umma_bf16_lo(d, ah, a_hi32, wL, w_hi32, idesc, 1u);
+                  umma_bf16_lo(d, ah, a_hi32, wH, w_hi32, idesc, 1u);
+                }
+                accum = 1u;
+              }
+              w_addr_tap += 2u * (uint32_t)a.w_plane;
+              if (++s == a.S) { s = 0; r++; row_off += tap_row; tap_off = row_off; } else { tap_off += tap_col; }
+            }
+            if (dbg_on && dbg_i < 24) dbg_ts[1][dbg_i] = clock64();
+            umma_commit(&w_empty[w_st]);                                   // frees the weight slot (and the A box in lockstep mode)
+            if (a.halo && wg == wgroups - 1) umma_commit(&a_empty[cur_a]);  // ... and the halo box after the last tap
+            if (dbg_on && dbg_i < 24) dbg_ts[2][dbg_i++] = clock64();
+          }
+          accum = 1u;   // lanes that were not elected: keep the (unused) copy consistent
+        } else {
+          // tap mode: one A box per tap, waited for by the whole warp
+          for (int t = 0; t < a.TPS; t++) {
             mbar_wait(&a_full[a_st], a_ph);
             tc_fence_after();
             cur_a = a_st;
             a_addr_stage = a_base + a_st * a_stage_bytes;
             if (++a_st == (uint32_t)a.a_stages) { a_st = 0; a_ph ^= 1u; }
-          }
-          if (elect_one()) {
-            // low descriptor words of the hi planes; the lo planes lie a_plane / w_plane bytes behind (all offsets are
-            // multiples of 16 bytes and shared-memory addresses are < 2^18, so plain adds never carry into the LBO field)
-            uint32_t aH = a_lo32 + ((a_addr_stage + tap_off) >> 4), wH = w_lo32 + (w_addr_tap >> 4);
-            for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aH += a_kstep16, wH += w_kstep16) {
-              const uint32_t wL = wH + w_plane16;
-              uint32_t ah = aH, d = tmem_acc;
-              for (int mt = 0; mt < a.MT; mt++, ah += a_mstep16, d += (uint32_t)a.BN) {
-                const uint32_t al = ah + a_plane16;
-                umma_bf16_lo(d, al, a_hi32, wH, w_hi32, idesc, accum);
-                umma_bf16_lo(d, ah, a_hi32, wL, w_hi32, idesc, 1u);
-                umma_bf16_lo(d, ah, a_hi32, wH, w_hi32, idesc, 1u);
+            if (elect_one()) {
+              uint32_t aH = a_lo32 + (a_addr_stage >> 4), wH = w_lo32 + (w_addr_tap >> 4);
+              for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aH += a_kstep16, wH += w_kstep16) {
+                const uint32_t wL = wH + w_plane16;
+                uint32_t ah = aH, d = tmem_acc;
+                for (int mt = 0; mt < a.MT; mt++, ah += a_mstep16, d += (uint32_t)a.BN) {
+                  const uint32_t al = ah + a_plane16;
+                  umma_bf16_lo(d, al, a_hi32, wH, w_hi32, idesc, accum);
+                  umma_bf16_lo(d, ah, a_hi32, wL, w_hi32, idesc, 1u);
+                  umma_bf16_lo(d, ah, a_hi32, wH, w_hi32, idesc, 1u);
+                }
+                accum = 1u;
               }
-              accum = 1u;
+              umma_commit(&a_empty[cur_a]);
+              if (t == a.TPS - 1) umma_commit(&w_empty[w_st]);
             }
-            if (!a.halo && !a.lockstep) umma_commit(&a_empty[cur_a]);
+            accum = 1u;
+            w_addr_tap += 2u * (uint32_t)a.w_plane;
           }
-          __syncwarp();
-          w_addr_tap += 2u * (uint32_t)a.w_plane;
-          if (++s == a.S) { s = 0; r++; row_off += tap_row; tap_off = row_off; } else { tap_off += tap_col; }
         }
-        if (elect_one()) {
-          umma_commit(&w_empty[w_st]);                                   // frees the weight slot once read
-          if (a.halo && wg == wgroups - 1) umma_commit(&a_empty[cur_a]);  // ... and the halo box after the last tap
-        }
-        __syncwarp();
         if (++w_st == (uint32_t)a.w_stages) { w_st = 0; w_ph ^= 1u; }
       }
     }
+    if ((a.dbg & 32) && lane == 0) dbg_ev[1] = globaltimer_ns();
     if (elect_one()) umma_commit(&tmem_full_bar[buf]);  // accumulators of this item complete
     __syncwarp();
     if (a.nbuf > 1) buf ^= 1u;
@@ -442,7 +497,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tmem_ld16(taddr, v);
         // global loads of this group (bias, residual) are issued while the TMEM load is in flight
         const int co0 = ntile * a.BN + c0;
-        const bool live = in_img && co0 < a.Cout && a.ksplit == 1;
+        const bool live = in_img && co0 < a.Cout && a.ksplit == 1 && wk.tail_slot < 0;
         float4 bv[4];
         uint4 rres[4];
         if (live) {
@@ -472,6 +527,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
         if (a.dbg & 4) continue;   // ablation: epilogue drains TMEM only
+        if (wk.tail_slot >= 0) {  // tail sub-item: raw partial sums of this tile, [z][tail item][MT*128 rows][BN]
+          float* pp = a.partial + (((long)(wk.z * a.tail_items + wk.tail_slot) * a.MT + mt) * 128 + m) * a.BN + c0;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            reinterpret_cast<float4*>(pp)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          continue;
+        }
         if (a.ksplit > 1) {  // raw partial sums; bias / residual / activation happen in conv_finish_kernel
           if (in_img) {
             float* pp = a.partial + (long)wk.z * a.partial_stride + ((long)n_img * hw + pix) * a.cout_pad + co0;
@@ -543,33 +606,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
     if (a.nbuf > 1) buf ^= 1u;
+    if ((a.dbg & 32) && warp == 4 && lane == 0) dbg_ev[2] = globaltimer_ns();
     }  // work loop
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+  if ((a.dbg & 32) && threadIdx.x == 0) {
+    const unsigned long long t1 = globaltimer_ns(), d = t1 - dbg_t0;
+    atomicMin(&g_dbg_cta[0], dbg_t0); atomicMax(&g_dbg_cta[1], t1); atomicAdd(&g_dbg_cta[2], d);
+    atomicMax(&g_dbg_cta[3], d); atomicMin(&g_dbg_cta[4], d); atomicAdd(&g_dbg_cta[5], 1ull);
+    if (blockIdx.x < 512) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* rr = g_dbg_rec[blockIdx.x];
+      rr[0] = smid; rr[1] = dbg_t0; rr[2] = t1; rr[3] = dbg_ev[0]; rr[4] = dbg_ev[1]; rr[5] = dbg_ev[2];
+    }
+  }
+  if (dbg_on && threadIdx.x == 32 && (a.dbg & 64)) {
+    for (int i = 1; i < dbg_i; i++)
+      printf("kb %2d: issuer wait->start %6lld  issue %6lld  commit %5lld | producer empty-wait %6lld issue %5lld (start-to-start %6lld)\n", i,
+             dbg_ts[0][i] - dbg_ts[2][i - 1], dbg_ts[1][i] - dbg_ts[0][i], dbg_ts[2][i] - dbg_ts[1][i],
+             dbg_ts[3][i] - dbg_ts[4][i - 1], dbg_ts[4][i] - dbg_ts[3][i], dbg_ts[0][i] - dbg_ts[0][i - 1]);
+  }
 }
 
-// Sums the split-K partials in split order and applies the same epilogue as the fused path (bias, residual, LeakyReLU/ReLU,
-// CP8 split store and/or fp32 channels-last store).  One thread per (pixel, 8-channel chunk).
-__global__ void __launch_bounds__(256) conv_finish_kernel(const UmmaConvArgs a, int n_active) {
+// Shared tail of the split-K finish kernels: bias, residual, fp32 outputs, activation, CP8 split store for one (pixel, 8-channel
+// chunk).  pg = global pixel index (n_img * hw + pix), c8 = 8-channel chunk of the output.
+__device__ __forceinline__ void finish_store(const UmmaConvArgs& a, int n_img, long pix, long pg, int c8, float (&f)[8]) {
   const long hw = a.flat_hw > 0 ? (long)a.flat_hw : (long)a.Ho * a.Wo;
-  const int cchunks = (a.Cout + 7) / 8;
-  const long total = (long)n_active * hw * cchunks;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const long pg = idx % ((long)n_active * hw);   // pixel fastest -> coalesced CP8 stores
-  const int c8 = (int)(idx / ((long)n_active * hw));
-  const int n_img = (int)(pg / hw);
-  const long pix = pg - (long)n_img * hw;
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) f[j] = 0.f;
-  for (int z = 0; z < a.ksplit; z++) {
-    const float* pp = a.partial + (long)z * a.partial_stride + pg * a.cout_pad + c8 * 8;
-    const float4 p0 = reinterpret_cast<const float4*>(pp)[0], p1 = reinterpret_cast<const float4*>(pp)[1];
-    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
-  }
 #pragma unroll
   for (int j = 0; j < 8; j++) f[j] += __ldg(a.bias + c8 * 8 + j);
   if (a.res_hi) {
@@ -611,6 +676,65 @@ __global__ void __launch_bounds__(256) conv_finish_kernel(const UmmaConvArgs a, 
     for (int j = 0; j < 8; j++)
       if (c8 * 8 + j >= a.f32_first && c8 * 8 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
   }
+}
+
+// Sums the split-K partials in split order and applies the same epilogue as the fused path (bias, residual, LeakyReLU/ReLU,
+// CP8 split store and/or fp32 channels-last store).  One thread per (pixel, 8-channel chunk).
+__global__ void __launch_bounds__(256) conv_finish_kernel(const UmmaConvArgs a, int n_active) {
+  const long hw = a.flat_hw > 0 ? (long)a.flat_hw : (long)a.Ho * a.Wo;
+  const int cchunks = (a.Cout + 7) / 8;
+  const long total = (long)n_active * hw * cchunks;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long pg = idx % ((long)n_active * hw);   // pixel fastest -> coalesced CP8 stores
+  const int c8 = (int)(idx / ((long)n_active * hw));
+  const int n_img = (int)(pg / hw);
+  const long pix = pg - (long)n_img * hw;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = 0.f;
+  for (int z = 0; z < a.ksplit; z++) {
+    const float* pp = a.partial + (long)z * a.partial_stride + pg * a.cout_pad + c8 * 8;
+    const float4 p0 = reinterpret_cast<const float4*>(pp)[0], p1 = reinterpret_cast<const float4*>(pp)[1];
+    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+  }
+  finish_store(a, n_img, pix, pg, c8, f);
+}
+
+// Finishes the K-split tail items of a launch (see UmmaConvArgs::tail_items): one thread per (tail item, tile row, 8-channel chunk
+// of the item's N tile); partial sums are added in split order (deterministic).
+__global__ void __launch_bounds__(256) conv_finish_tail_kernel(const UmmaConvArgs a) {
+  const int rows = a.MT * 128, cch = a.BN / 8;
+  const long total = (long)a.tail_items * rows * cch;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int row = (int)(idx % rows);            // row fastest -> coalesced CP8 stores
+  const int cc = (int)((idx / rows) % cch);
+  const int slot = (int)(idx / ((long)rows * cch));
+  // decode the item exactly as the convolution kernel does
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int t = a.main_work + slot;
+  const int tile = t % tiles_per_img;
+  int r = t / tiles_per_img;
+  const int n_img = r % a.n_images; r /= a.n_images;
+  const int ntile = r % a.ntiles;
+  const int ty0 = (tile / a.tiles_x) * (a.mt_horizontal ? 16 : 16 * a.MT), tx0 = (tile % a.tiles_x) * (a.mt_horizontal ? 8 * a.MT : 8);
+  const int mt = row >> 7, m = row & 127;
+  const int oy = ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
+  const long hw = a.flat_hw > 0 ? (long)a.flat_hw : (long)a.Ho * a.Wo;
+  const long pix = (long)oy * a.Wo + ox;
+  const bool in_img = a.flat_hw > 0 ? pix < hw : (oy < a.Ho && ox < a.Wo);
+  const int c8 = (ntile * a.BN) / 8 + cc;       // global 8-channel chunk
+  if (!in_img || c8 * 8 >= a.Cout) return;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = 0.f;
+  for (int z = 0; z < a.tail_split; z++) {
+    const float* pp = a.partial + ((long)(z * a.tail_items + slot) * rows + row) * a.BN + cc * 8;
+    const float4 p0 = reinterpret_cast<const float4*>(pp)[0], p1 = reinterpret_cast<const float4*>(pp)[1];
+    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+  }
+  finish_store(a, n_img, pix, (long)n_img * hw + pix, c8, f);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -879,6 +1003,28 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   while ((int)cols < a.nbuf * a.NACC * a.MT * w.BN) cols <<= 1;
   a.tmem_cols = cols;
   plan->ctas_per_sm = cps;
+  // tail split (see UmmaConvArgs): only for un-split layers with at least one full wave and a small remainder
+  a.tail_items = 0; a.tail_split = 1; a.tail_kb_per = a.kblocks; a.main_work = a.total_work;
+  if (a.ksplit == 1 && env_int("PREMVOS_TAIL", 1) != 0) {
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
+    const int slots = num_sms * cps, rem = a.total_work % slots;
+    if (a.total_work > slots && rem > 0 && rem * 3 <= slots && a.kblocks >= 4) {
+      int split = std::min(slots / rem, a.kblocks / 2);
+      split = std::min(split, env_int("PREMVOS_TAIL_SPLIT", 16));
+      if (split >= 2) {
+        a.tail_kb_per = (a.kblocks + split - 1) / split;
+        a.tail_split = (a.kblocks + a.tail_kb_per - 1) / a.tail_kb_per;
+        a.tail_items = rem;
+        a.main_work = a.total_work - rem;
+        const size_t elems = (size_t)a.tail_split * rem * a.MT * 128 * w.BN;
+        PV_CUDA(cudaMalloc((void**)&a.partial, elems * sizeof(float)));
+        PV_CUDA(cudaMemset(a.partial, 0, elems * sizeof(float)));
+        plan->scratch = a.partial;
+        a.total_work = a.main_work + rem * a.tail_split;
+      }
+    }
+  }
   a.epi_warps = (wide && w.BN % 32 == 0 && env_int("PREMVOS_EPI8", 1) != 0) ? 8 : 4;
 
   // input tensor maps over the view's chunk planes: [N][chunks][H][W][8]
@@ -927,9 +1073,11 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   // persistent CTAs: at most ctas_per_sm per SM, each walks the work items b, b + grid, ...  A smaller active batch
   // just shortens the list (the image index is a digit of the work index).
   UmmaConvArgs a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
-  if (active_n >= 0 && active_n < plan.N) {
-    a.total_work = a.total_work / plan.N * active_n;
+  if (active_n >= 0 && active_n < plan.N) {   // a smaller active batch: plain item list, no tail split
+    const int items = a.tail_items > 0 ? a.main_work + a.tail_items : a.total_work;
+    a.total_work = items / plan.N * active_n;
     a.n_images = active_n;
+    a.tail_items = 0; a.main_work = a.total_work;
   }
   if (a.total_work == 0) return 0;
   static int num_sms = 0;
@@ -939,6 +1087,10 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
     PV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = std::min(a.total_work, num_sms * plan.ctas_per_sm);
+  if (a.dbg & 32) {
+    const unsigned long long init[8] = {~0ull, 0, 0, 0, ~0ull, 0, 0, 0};
+    PV_CUDA(cudaMemcpyToSymbol(g_dbg_cta, init, sizeof(init)));
+  }
   prof_before(st);
   if (a.epi_warps == 8)
     conv_umma_kernel<8><<<grid, 128 + 32 * 8, plan.smem_bytes, st>>>(
@@ -951,12 +1103,37 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
   if (per_layer && profiling_enabled()) {   // per-layer breakdown for tools/profile_nets.py
     char buf[256];
-    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d]", a.n_images,
+    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d_tail%dx%d]", a.n_images,
              a.flat_hw > 0 ? a.flat_hw : a.Ho, a.flat_hw > 0 ? 1 : a.Wo, a.kblocks * a.KC * 8, a.Cout, a.R, a.stride, a.dil, a.MT, a.BN,
-             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep);
+             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep, a.tail_items, a.tail_split);
     label = prof_intern(buf);
   }
   PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));
+  if (a.dbg & 32) {
+    unsigned long long r[8];
+    PV_CUDA(cudaStreamSynchronize(st));
+    PV_CUDA(cudaMemcpyFromSymbol(r, g_dbg_cta, sizeof(r)));
+    fprintf(stderr, "conv_umma dbg: %llu CTAs, first start -> last end %.2f us, CTA duration min %.2f avg %.2f max %.2f us\n", r[5],
+            (r[1] - r[0]) * 1e-3, r[4] * 1e-3, r[5] ? r[2] * 1e-3 / r[5] : 0.0, r[3] * 1e-3);
+    if (a.dbg & 128) {
+      static unsigned long long rec[512][6];
+      PV_CUDA(cudaMemcpyFromSymbol(rec, g_dbg_rec, sizeof(rec)));
+      std::vector<int> order;
+      for (int i = 0; i < grid && i < 512; i++) order.push_back(i);
+      std::sort(order.begin(), order.end(), [&](int x, int y) { return rec[x][2] - rec[x][1] > rec[y][2] - rec[y][1]; });
+      for (size_t k = 0; k < order.size(); k += (k < 12 ? 1 : 16)) {
+        const unsigned long long* q = rec[order[k]];
+        fprintf(stderr, "  cta %3d sm %3llu: start +%6.2f  first MMA +%6.2f  last item MMAs issued +%6.2f  epilogue done +%6.2f  end +%6.2f us\n", order[k], q[0],
+                (q[1] - r[0]) * 1e-3, (q[3] - q[1]) * 1e-3, (q[4] - q[1]) * 1e-3, (q[5] - q[1]) * 1e-3, (q[2] - q[1]) * 1e-3);
+      }
+    }
+  }
+  if (a.tail_items > 0) {
+    const long total = (long)a.tail_items * a.MT * 128 * (a.BN / 8);
+    prof_before(st);
+    conv_finish_tail_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    PV_TRY(after_launch("conv_finish_kernel", st, 0.0, (double)total * 32.0 * (a.tail_split + 1)));
+  }
   if (plan.grid_z > 1) {
     const int na = (active_n >= 0 && active_n < plan.N) ? active_n : plan.N;
     const long total = (long)na * a.Ho * a.Wo * ((a.Cout + 7) / 8);

@@ -49,6 +49,9 @@ CASES = [
                                                                 #   8 epilogue warps, lockstep ring), N tail 216, residual
     (6, 264, 97, 97, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, False),   # wide tile, one N tile, K = 33 chunks (k-block tail), ragged M tail
     (16, 128, 49, 49, 1024, 1, 1, 1, (0, 0, 0, 0), 0.0, False), # wide tile, 4 N tiles, KC from a 128-channel input
+    (1, 64, 480, 160, 128, 3, 1, 1, (1, 1, 1, 1), 0.1, True),   # 300 items on 296 CTA slots: the last 4 are K-split (tail split),
+                                                                #   halo mode, residual through conv_finish_tail_kernel
+    (2, 96, 240, 168, 72, 3, 1, 2, (2, 2, 2, 2), 0.0, False),   # tail split with ragged tiles / N tail, dilation 2
 ]
 
 

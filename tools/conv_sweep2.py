@@ -18,7 +18,7 @@ SHAPES = {
     "xc_e2": (20, 256, 97, 97, 256, 1, 1, 1),
     "xc_e1": (20, 128, 193, 193, 128, 1, 1, 1),
 }
-KEYS = ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_BUDGET_KB", "PREMVOS_KSPLIT", "PREMVOS_BN", "PREMVOS_DBG", "PREMVOS_NBUF", "PREMVOS_FLAT", "PREMVOS_CONV_REPEAT", "PREMVOS_LOCKSTEP", "PREMVOS_EPI8")
+KEYS = ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_BUDGET_KB", "PREMVOS_KSPLIT", "PREMVOS_BN", "PREMVOS_DBG", "PREMVOS_NBUF", "PREMVOS_FLAT", "PREMVOS_CONV_REPEAT", "PREMVOS_LOCKSTEP", "PREMVOS_EPI8", "PREMVOS_TAIL", "PREMVOS_TAIL_SPLIT")
 
 
 def run(name, env):

@@ -22,14 +22,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) { return (1u << 
 __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return ((uint64_t)((sbo >> 4) | (1u << 14)) << 32) | (((lbo >> 4) << 16) + ((addr & 0x3FFFFu) >> 4));
 }
-__global__ void __launch_bounds__(128) k(int n, int BN, int a_sbo, int a_lbo, int b_lbo, int ncols, int nacc, int a_span, int b_span, int mode, long long* out) {
+__global__ void __launch_bounds__(384) k(int n, int BN, int a_sbo, int a_lbo, int b_lbo, int ncols, int nacc, int a_span, int b_span, int mode, int pollers, int sleep_ns, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, never;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (a_span + b_span) / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&never, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -68,6 +68,10 @@ __global__ void __launch_bounds__(128) k(int n, int BN, int a_sbo, int a_lbo, in
     while (!mbar_try_wait(&bar, 0)) {}
     long long t1 = clock64();
     if (blockIdx.x == 0) out[0] = t1 - t0;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&never)) : "memory");
+  } else if (warp >= 2 && warp < 2 + pollers) {
+    // like the epilogue warps of conv_umma.cu during the main loop: all 32 lanes poll a barrier in shared memory
+    while (!mbar_try_wait(&never, 0)) { if (sleep_ns) __nanosleep(sleep_ns); }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -90,12 +94,15 @@ int main() {
   };
   for (auto& c : cfgs) {
     // B descriptor SBO is fixed at 128 in the kernel; for the K-adjacent B variant use sbo 256 via a_sbo trick is not possible -> note
-    for (int mode = 0; mode < 2; mode++) {
-      for (int rep = 0; rep < 2; rep++) k<<<c.ctas, 128, c.a_span + c.b_span + 256>>>(n, c.BN, c.a_sbo, c.a_lbo, c.b_lbo, c.ncols, c.nacc, c.a_span, c.b_span, mode, d);
-      cudaError_t e = cudaDeviceSynchronize();
-      long long cyc = 0; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
-      printf("%s %s : %6.1f cycles/MMA (ideal %d)  %s\n", c.name, mode ? "precomputed" : "rebuilt    ", (double)cyc / n, c.BN / 2, cudaGetErrorString(e));
-    }
+    for (int pollers : {0, 4, 8})
+      for (int sleep_ns : {0, 200}) {
+        if (pollers == 0 && sleep_ns) continue;
+        const int mode = 1;
+        for (int rep = 0; rep < 2; rep++) k<<<c.ctas, 384, c.a_span + c.b_span + 256>>>(n, c.BN, c.a_sbo, c.a_lbo, c.b_lbo, c.ncols, c.nacc, c.a_span, c.b_span, mode, pollers, sleep_ns, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long cyc = 0; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+        printf("%s pollers=%d sleep=%3dns : %6.1f cycles/MMA (ideal %d)  %s\n", c.name, pollers, sleep_ns, (double)cyc / n, c.BN / 2, cudaGetErrorString(e));
+      }
   }
   return 0;
 }
