@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4, help="frame pairs per GPU per step")
     ap.add_argument("--boxes", type=int, default=40, help="refinement boxes per frame")
+    ap.add_argument("--refine-batch", type=int, default=0, help="refinement crops per launch group (0 = all boxes of a frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-network context timings")
     args = ap.parse_args()
@@ -230,7 +231,7 @@ def main():
     P_gen = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(1)).items()}
     P_spec = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(4)).items()}
     P_ref = {k: v.numpy() for k, v in weights(lambda: synth.refnet_synthetic_params(2)).items()}
-    pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (H_IN, W_IN), pairs_per_step=B, boxes_per_frame=K)
+    pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (H_IN, W_IN), pairs_per_step=B, boxes_per_frame=K, refine_batch=args.refine_batch or None)
 
     # `sets` different input batches, rotated so that consecutive steps never read the same input (> L2 in total)
     per_set = pipe.h2d_bytes_per_step()
@@ -344,7 +345,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3 split-fp32 (fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "global_pairs_per_step": B * world,
-                           "boxes_per_frame": K, "parallelism": "dp%d" % world,
+                           "boxes_per_frame": K, "refine_batch": args.refine_batch or K, "parallelism": "dp%d" % world,
                            "weights": "seeded random init of the reference architectures (PWC-DC-Net 9.4M, 2 x ResNet-101 C4 "
                                       "51.9M, Xception-65 DeepLabv3+ 40.8M params)",
                            "l2": "inputs rotate over %d device input sets (%d MB > 126 MB L2); per-step activations are > 10 GB"

@@ -64,6 +64,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (the issuer looks at the NEXT stage's barrier before it issues the current stage's MMAs)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug must become a trap (launch error), never a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -406,6 +418,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           // tensor pipe queues very few MMAs per CTA (tools/ubench + PREMVOS_DBG ablations: MMA time adds to the issuer's
           // control time instead of overlapping it), so every instruction between two UTCHMMAs of consecutive stages is
           // idle tensor time: no second elect, no __syncwarp, tap bookkeeping only in the elected lane (always the same one).
+          // (Tried and dropped: one elected lane running the whole K loop with a non-blocking probe of the next stage's
+          // barrier -- 416 instead of 512 control cycles per k-block, but lane-private ring state costs R2UR moves in front of
+          // every UTCHMMA: +70 issue cycles, slower for halo layers.  In-kernel timestamps, PREMVOS_DBG=96: a 1x1 k-block at
+          // 128x256 takes ~1050 cycles = 46 B/clk of L2 -> shared-memory fill, i.e. these layers sit at the fill cap.)
           if (a.lockstep) { cur_a = w_st; a_addr_stage = a_base + w_st * a_stage_bytes; }
           if (elect_one()) {
             if ((a.dbg & 32) && dbg_ev[0] == 0) dbg_ev[0] = globaltimer_ns();
@@ -1009,7 +1025,9 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     int num_sms = 148;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
     const int slots = num_sms * cps, rem = a.total_work % slots;
-    if (a.total_work > slots && rem > 0 && rem * 3 <= slots && a.kblocks >= 4) {
+    // ideal tensor-pipe cycles of one item; the extra finish launch (~5 us) only pays off when a wave is long
+    const long item_cycles = (long)a.kblocks * taps * (w.KC / 2) * a.MT * 3 * (w.BN / 2);
+    if (a.total_work > slots && rem > 0 && rem * 3 <= slots && a.kblocks >= 4 && item_cycles >= env_int("PREMVOS_TAIL_MIN_CYCLES", 12000)) {
       int split = std::min(slots / rem, a.kblocks / 2);
       split = std::min(split, env_int("PREMVOS_TAIL_SPLIT", 16));
       if (split >= 2) {
