@@ -14,9 +14,9 @@ frame pair (t, t+1) of 1024x436 pixels
 random-init weights of the reference architectures.  A step = `--pairs` frame pairs per GPU through
 premvos_b200.pipeline.FramePipeline; the metric is whole-job frame pairs per second.
 
-  value    : device-resident inputs, K steps timed with CUDA events on the launching stream, barrier + synchronize on
+  value    : device-resident ORIGINAL frames (the stage drivers' cv2.resize calls run on the device), K steps timed with CUDA events on the launching stream, barrier + synchronize on
              both sides, max over ranks.
-  e2e      : the same through FramePipeline.run_host: pinned HOST uint8 frames in, flow + detections + masks +
+  e2e      : the same through FramePipeline.run_frames_host: pinned HOST uint8 frames t, t+1 in, flow + detections + masks +
              conf_scores out to pinned host memory, one synchronisation per step; copies inside the timed region.
   stages   : each network alone, device resident (flow alone is BASELINE configs[1], proposals configs[2], refine configs[3]).
   roofline : dominant kernel of the step (by device time) from a per-launch CUDA-event pass over one step run serially
@@ -101,16 +101,15 @@ class ClockSampler(threading.Thread):
 
 
 def make_units(n_units, boxes_per_frame):
-    """`n_units` distinct synthetic units (frame pair, resized copies, boxes) as uint8 / float32 host arrays."""
-    from premvos_b200 import pipeline, synth
+    """`n_units` distinct synthetic units: (frame t, frame t+1) uint8 RGB [436,1024,3] as a decoder hands them over, and the
+    boxes of frame t+1 (float32 [K,4] xywh)."""
+    from premvos_b200 import synth
     f1, f2 = synth.synthetic_frame_pair(H_IN, W_IN, seed=1)
     units = []
     for k in range(n_units):
-        a = np.roll(f1, shift=(7 * k, 13 * k), axis=(0, 1))
-        b = np.roll(f2, shift=(7 * k, 13 * k), axis=(0, 1))
-        pair, prop, frame = pipeline.prepare_unit(a, b)
-        boxes = synth.synthetic_boxes(boxes_per_frame, H_IN, W_IN, seed=100 + k)
-        units.append((pair, prop, frame, boxes))
+        a = np.ascontiguousarray(np.roll(f1, shift=(7 * k, 13 * k), axis=(0, 1)))
+        b = np.ascontiguousarray(np.roll(f2, shift=(7 * k, 13 * k), axis=(0, 1)))
+        units.append((a, b, synth.synthetic_boxes(boxes_per_frame, H_IN, W_IN, seed=100 + k)))
     return units
 
 
@@ -234,13 +233,13 @@ def main():
     pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (H_IN, W_IN), pairs_per_step=B, boxes_per_frame=K, refine_batch=args.refine_batch or None)
 
     # `sets` different input batches, rotated so that consecutive steps never read the same input (> L2 in total)
-    per_set = pipe.h2d_bytes_per_step()
+    per_set = pipe.h2d_bytes_per_step(original_frames=True)
     sets = max(2, -(-(2 * 126 << 20) // per_set))
     units = make_units(sets * B, K)
     host_sets, dev_sets = [], []
     for s in range(sets):
         u = units[s * B:(s + 1) * B]
-        hs = [torch.from_numpy(np.stack([x[i] for x in u])).pin_memory() for i in range(4)]
+        hs = [torch.from_numpy(np.stack([x[i] for x in u])).pin_memory() for i in range(3)]
         host_sets.append(hs)
         dev_sets.append([t.cuda() for t in hs])
 
@@ -259,7 +258,7 @@ def main():
 
     # ---- device-resident arm ----
     for i in range(args.warmup):
-        pipe.run_device(*dev_sets[i % sets])
+        pipe.run_frames_device(*dev_sets[i % sets])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -268,7 +267,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        pipe.run_device(*dev_sets[i % sets])
+        pipe.run_frames_device(*dev_sets[i % sets])
     e1.record()
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -277,11 +276,11 @@ def main():
 
     # ---- end-to-end arm: pinned host buffers in, pinned host results out, every step ----
     for i in range(2):
-        pipe.run_host(*host_sets[i % sets])
+        pipe.run_frames_host(*host_sets[i % sets])
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        pipe.run_host(*host_sets[i % sets])
+        pipe.run_frames_host(*host_sets[i % sets])
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
@@ -292,7 +291,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         _lib.profile_begin()
-        pipe.run_device(*dev_sets[0], concurrent=False)
+        pipe.run_frames_device(*dev_sets[0], concurrent=False)
         prof = _lib.profile_end()
         total_ms = sum(v["ms"] for v in prof.values()) or 1.0
         kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / total_ms}
@@ -321,7 +320,8 @@ def main():
     # ---- each network alone, device resident (BASELINE configs[1..3]) ----
     stages = None
     if rank == 0 and not args.no_stages:
-        ff, pi, fr, bx = dev_sets[0]
+        fr, bx = dev_sets[0][1], dev_sets[0][2]
+        ff, pi = pipe.prepare_device(dev_sets[0][0], fr)
         o = pipe.out
         t_flow = time_stage(lambda: pipe.flow_net.forward_u8(ff, out=o["flow"]), 20)
         t_prop = time_stage(lambda: pipe.general.forward_device(pi[0]), 10)
@@ -350,11 +350,12 @@ def main():
                                       "51.9M, Xception-65 DeepLabv3+ 40.8M params)",
                            "l2": "inputs rotate over %d device input sets (%d MB > 126 MB L2); per-step activations are > 10 GB"
                                  % (sets, sets * per_set >> 20)},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(original_frames=True),
                         "d2h_bytes_per_step": pipe.d2h_bytes_per_step(),
-                        "call": "FramePipeline.run_host: pinned uint8 frames + boxes in (as decoded + cv2-resized by the stage "
-                                "drivers), flow + detections + per-box masks + conf_scores out to pinned host memory, synchronous per step"},
-                "gpu_launches": int(launches), "launches_per_step": pipe.launches_per_step(),
+                        "call": "FramePipeline.run_frames_host: pinned uint8 frames t, t+1 + boxes in (as a decoder hands them over; the stage "
+                                "drivers' cv2.resize calls run on the device, bit-exact), flow + detections + per-box masks + conf_scores "
+                                "out to pinned host memory, synchronous per step"},
+                "gpu_launches": int(launches), "launches_per_step": pipe.launches_per_step_from_frames(),
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "stages": stages}
         print(json.dumps(line), flush=True)
     if distributed:

@@ -96,6 +96,20 @@ int premvos_conv2d_forward(const float* x, const float* w, const float* bias, co
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for uint8 images, on the device, BIT-EXACT with OpenCV
+ * (8-bit linear resize is integer arithmetic on 11-bit fixed-point coefficients, modules/imgproc/src/resize.cpp).
+ * Replaces the host-side resizes of the reference's stage drivers: script_pwc_multi.py:38-45 (frames -> multiples of 64) and
+ * proposal_net eval.py:75-78 / common.py:35-62 (CustomResize -> cv2.resize).
+ * src_dev  uint8 [batch, src_h, src_w, channels] (device), dst_dev uint8 [batch, dst_h, dst_w, channels] (device);
+ * channels 1 or 3; reverse_channels != 0 writes the channels in reverse order (RGB frame -> resized BGR image: resize acts per
+ * channel).  Enqueues on `stream`, does not synchronise.  The coefficient tables of a geometry are built on the first call with
+ * it (one small device allocation, cached for the life of the process).  An exact 2x down-scale in both directions (which
+ * OpenCV turns into INTER_AREA) returns PREMVOS_ERR_UNSUPPORTED.
+ * --------------------------------------------------------------------------------------------- */
+int premvos_resize_linear_u8(const unsigned char* src_dev, int batch, int src_h, int src_w, unsigned char* dst_dev, int dst_h,
+                             int dst_w, int channels, int reverse_channels, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * PWC-DC-Net forward (optical flow).
  *
  * Life cycle: create(batch,H,W) -> set_param(name, host fp32 data) for each of the 128 state_dict

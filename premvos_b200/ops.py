@@ -65,3 +65,24 @@ def non_max_suppression(boxes: np.ndarray, scores: np.ndarray, max_output_size: 
                                            float(iou_threshold), int(max_output_size), out.ctypes.data_as(ctypes.c_void_p),
                                            ctypes.byref(n)))
     return out[:n.value].copy()
+
+
+def resize_linear_u8(img: torch.Tensor, dst_h: int, dst_w: int, reverse_channels: bool = False, out: torch.Tensor = None) -> torch.Tensor:
+    """cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR), bit-exact, on the device (premvos_resize_linear_u8).
+    img: CUDA uint8 [H,W,C] or [B,H,W,C] with C in (1, 3).  Enqueues on the current stream."""
+    if not isinstance(img, torch.Tensor) or not img.is_cuda or img.dtype != torch.uint8 or not img.is_contiguous():
+        raise TypeError("img must be a contiguous CUDA uint8 tensor (premvos_b200 has no CPU path)")
+    if img.dim() not in (3, 4):
+        raise ValueError("expected [H,W,C] or [B,H,W,C], got %s" % (tuple(img.shape),))
+    B = 1 if img.dim() == 3 else int(img.shape[0])
+    H, W, C = (int(v) for v in img.shape[-3:])
+    shape = (dst_h, dst_w, C) if img.dim() == 3 else (B, dst_h, dst_w, C)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=img.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CUDA uint8 tensor of shape %s" % (shape,))
+    with torch.cuda.device(img.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_resize_linear_u8(img.data_ptr(), B, H, W, out.data_ptr(), int(dst_h), int(dst_w), C,
+                                                       1 if reverse_channels else 0, st))
+    return out

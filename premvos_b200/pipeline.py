@@ -20,6 +20,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import ops as _ops
 from . import propnet as _propnet
 from . import pwc as _pwc
 from . import refnet as _refnet
@@ -73,6 +74,8 @@ class FramePipeline:
             "conf": torch.zeros((B, K), dtype=torch.float32, device=d),
         }
         self._stage = None   # device + pinned staging of run_host, allocated on first use
+        self._resized = None
+        self._frames_prev_dev = None
 
     # ---- sizes ---------------------------------------------------------------------------------------------
     def input_shapes(self):
@@ -87,6 +90,10 @@ class FramePipeline:
         per_group = int(_lib.lib().premvos_refnet_launches_per_forward(self.refine._h()))
         return (self.flow_net.launches_per_forward(self.B, self.Hn, self.Wn) + 1
                 + self.B * (2 * (self.general.launches_per_forward(self.Hp, self.Wp) + 1) + groups * per_group))
+
+    def launches_per_step_from_frames(self, num_boxes=None):
+        resize = 1 + (0 if (self.Hn, self.Wn) == (self.H, self.W) else 2 * self.B)
+        return self.launches_per_step(num_boxes) + resize
 
     # ---- device-resident step ------------------------------------------------------------------------------
     def run_device(self, flow_frames, prop_images, frames, boxes=None, concurrent=True):
@@ -143,6 +150,53 @@ class FramePipeline:
                 cur.wait_stream(s)
         return result
 
+    # ---- the same step from the ORIGINAL frames: the stage drivers' cv2.resize calls run on the device -------------
+    def prepare_device(self, frames_prev, frames_cur):
+        """frames_prev, frames_cur: CUDA uint8 RGB [B,H,W,3] (frames t and t+1 of every unit).  Builds the two resized
+        inputs on the device with the bit-exact cv2.resize kernel (premvos_resize_linear_u8): both frames at multiples of 64
+        for the flow network (script_pwc_multi.py:38-45) and the CustomResize'd BGR frame t+1 for the proposal passes
+        (eval.py:75-78).  -> (flow_frames [B,2,Hn,Wn,3], prop_images [B,Hp,Wp,3]), overwritten by the next call."""
+        B = self.B
+        if tuple(frames_prev.shape) != (B, self.H, self.W, 3) or tuple(frames_cur.shape) != (B, self.H, self.W, 3):
+            raise ValueError("frames must be [B,H,W,3] = %s" % ((B, self.H, self.W, 3),))
+        if self._resized is None:
+            self._resized = (torch.empty((B, 2, self.Hn, self.Wn, 3), dtype=torch.uint8, device=self.dev),
+                             torch.empty((B, self.Hp, self.Wp, 3), dtype=torch.uint8, device=self.dev))
+        ff, pi = self._resized
+        for b in range(B):
+            if (self.Hn, self.Wn) == (self.H, self.W):
+                ff[b, 0].copy_(frames_prev[b]); ff[b, 1].copy_(frames_cur[b])
+            else:
+                _ops.resize_linear_u8(frames_prev[b], self.Hn, self.Wn, out=ff[b, 0])
+                _ops.resize_linear_u8(frames_cur[b], self.Hn, self.Wn, out=ff[b, 1])
+        _ops.resize_linear_u8(frames_cur, self.Hp, self.Wp, reverse_channels=True, out=pi)
+        return ff, pi
+
+    def run_frames_device(self, frames_prev, frames_cur, boxes=None, concurrent=True):
+        """run_device on the original frames (CUDA uint8 RGB [B,H,W,3] each): resizes on the device, then the step."""
+        ff, pi = self.prepare_device(frames_prev, frames_cur)
+        return self.run_device(ff, pi, frames_cur, boxes, concurrent=concurrent)
+
+    def run_frames_host(self, frames_prev, frames_cur, boxes=None):
+        """End-to-end step from pinned HOST frames (uint8 RGB [B,H,W,3] each, what a decoder hands over): one upload per
+        frame, everything else on the device; results in pinned host buffers, one synchronisation."""
+        dev, host = self._staging()
+        if self._frames_prev_dev is None:
+            self._frames_prev_dev = torch.empty((self.B, self.H, self.W, 3), dtype=torch.uint8, device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        self._frames_prev_dev.copy_(frames_prev, non_blocking=True)
+        dev["frames"].copy_(frames_cur, non_blocking=True)
+        if boxes is not None:
+            dev["boxes"].copy_(boxes, non_blocking=True)
+        res = self.run_frames_device(self._frames_prev_dev, dev["frames"], dev["boxes"] if boxes is not None else None)
+        for k, v in self.out.items():
+            host[k].copy_(v, non_blocking=True)
+        cur.synchronize()
+        out = dict(host)
+        if "num_boxes" in res:
+            out["num_boxes"] = res["num_boxes"]
+        return out
+
     def combined_boxes_xywh(self, general_x1y1x2y2, specific_x1y1x2y2):
         return combine_proposals(general_x1y1x2y2, specific_x1y1x2y2, (self.H, self.W), (self.Hp, self.Wp))
 
@@ -174,9 +228,12 @@ class FramePipeline:
             out["num_boxes"] = res["num_boxes"]
         return out
 
-    def h2d_bytes_per_step(self, with_boxes=True):
+    def h2d_bytes_per_step(self, with_boxes=True, original_frames=False):
         shp = self.input_shapes()
-        n = sum(int(np.prod(shp[k])) for k in ("flow_frames", "prop_images", "frames"))
+        if original_frames:   # run_frames_host: frames t and t+1 of every unit
+            n = 2 * int(np.prod(shp["frames"]))
+        else:                 # run_host: the two resized inputs + frame t+1
+            n = sum(int(np.prod(shp[k])) for k in ("flow_frames", "prop_images", "frames"))
         return n + (int(np.prod(shp["boxes"])) * 4 if with_boxes else 0)
 
     def d2h_bytes_per_step(self):

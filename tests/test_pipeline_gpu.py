@@ -129,3 +129,60 @@ def test_pipeline_refines_detected_boxes_and_shards_a_video(parts):
             masks, conf, _ = rn.refine(frames[t + 1], bx)
             np.testing.assert_array_equal(r["masks"][:len(bx)], masks)
             np.testing.assert_array_equal(r["conf"][:len(bx)], conf)
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", [(436, 1024, 448, 1024), (436, 1024, 568, 1333), (480, 854, 512, 896), (480, 854, 749, 1333),
+                                         (100, 140, 800, 1120), (37, 53, 64, 64), (64, 64, 37, 53), (5, 7, 64, 128)])
+def test_device_resize_is_bit_exact_with_cv2(sh, sw, dh, dw):
+    from oracle import cv_resize_oracle as RZ   # pinned against cv2 itself in tests/test_oracle_resize.py
+    from premvos_b200 import ops
+
+    class cv2:   # the checker: the restatement (cv2 may be absent on a GPU box)
+        INTER_LINEAR = 1
+        resize = staticmethod(lambda im, size, interpolation=1: RZ.resize_linear_u8(im, size[1], size[0]))
+    rng = np.random.default_rng(sh + dw)
+    img = rng.integers(0, 256, (2, sh, sw, 3), dtype=np.uint8)
+    got = ops.resize_linear_u8(torch.from_numpy(img).cuda(), dh, dw).cpu().numpy()
+    for b in range(2):
+        np.testing.assert_array_equal(got[b], cv2.resize(img[b], (dw, dh), interpolation=cv2.INTER_LINEAR))
+    # RGB -> resized BGR in one pass (the proposal stage's input), and a single-channel image
+    rev = ops.resize_linear_u8(torch.from_numpy(img[0]).cuda(), dh, dw, reverse_channels=True).cpu().numpy()
+    np.testing.assert_array_equal(rev, cv2.resize(np.ascontiguousarray(img[0][:, :, ::-1]), (dw, dh)))
+    g1 = ops.resize_linear_u8(torch.from_numpy(np.ascontiguousarray(img[0][:, :, :1])).cuda(), dh, dw).cpu().numpy()
+    np.testing.assert_array_equal(g1[:, :, 0], cv2.resize(img[0][:, :, 0], (dw, dh)))
+
+
+def test_device_resize_errors():
+    from premvos_b200 import ops
+    x = torch.zeros((8, 8, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.PremvosError):
+        ops.resize_linear_u8(x, 4, 4)            # exact 2x down-scale = INTER_AREA in OpenCV
+    with pytest.raises(TypeError):
+        ops.resize_linear_u8(x.cpu(), 16, 16)
+    with pytest.raises(_lib.PremvosError):
+        ops.resize_linear_u8(torch.zeros((8, 8, 2), dtype=torch.uint8, device="cuda"), 16, 16)
+
+
+def test_pipeline_from_original_frames_equals_host_prepared_inputs(parts):
+    pipe, sd, G, S, R, frames = parts
+    units = [(frames[0], frames[1]), (frames[2], frames[3])]
+    prep = [pipeline.prepare_unit(a, b) for a, b in units]
+    boxes = torch.from_numpy(np.stack([synth.synthetic_boxes(3, H, W, seed=40 + i, min_size=20, max_size=90) for i in range(2)]))
+    ff = torch.from_numpy(np.stack([p[0] for p in prep])).cuda()
+    pi = torch.from_numpy(np.stack([p[1] for p in prep])).cuda()
+    fr = torch.from_numpy(np.stack([p[2] for p in prep])).cuda()
+    want = {k: v.cpu().numpy().copy() for k, v in pipe.run_device(ff, pi, fr, boxes.cuda()).items()}
+    prev = torch.from_numpy(np.stack([u[0] for u in units]))
+    cur = torch.from_numpy(np.stack([u[1] for u in units]))
+    f2, p2 = pipe.prepare_device(prev.cuda(), cur.cuda())
+    np.testing.assert_array_equal(f2.cpu().numpy(), ff.cpu().numpy())       # device resize == cv2.resize, bit for bit
+    np.testing.assert_array_equal(p2.cpu().numpy(), pi.cpu().numpy())
+    before = _lib.kernel_launch_count()
+    got = pipe.run_frames_device(prev.cuda(), cur.cuda(), boxes.cuda())
+    torch.cuda.synchronize()
+    assert _lib.kernel_launch_count() - before == pipe.launches_per_step_from_frames()
+    for k in want:
+        np.testing.assert_array_equal(got[k].cpu().numpy(), want[k])
+    host = pipe.run_frames_host(prev.pin_memory(), cur.pin_memory(), boxes.pin_memory())
+    for k in want:
+        np.testing.assert_array_equal(host[k].numpy(), want[k])

@@ -22,11 +22,12 @@ else:
     pipe = pipeline.FramePipeline(sd, synth.propnet_synthetic_params(1), synth.propnet_synthetic_params(4),
                                   synth.refnet_synthetic_params(2), (H, W), pairs_per_step=4, boxes_per_frame=40)
     units = bench.make_units(4, 40)
-    dev = [torch.from_numpy(np.stack([u[i] for u in units])).cuda() for i in range(4)]
+    dev = [torch.from_numpy(np.stack([u[i] for u in units])).cuda() for i in range(3)]
     if what == "flow":
-        run = lambda: pipe.flow_net.forward_u8(dev[0], out=pipe.out["flow"])
+        ff, _ = pipe.prepare_device(dev[0], dev[1])
+        run = lambda: pipe.flow_net.forward_u8(ff, out=pipe.out["flow"])
     else:
-        run = lambda: pipe.run_device(*dev, concurrent=False)
+        run = lambda: pipe.run_frames_device(*dev, concurrent=False)
 for _ in range(2):
     run()
 torch.cuda.synchronize()
