@@ -110,6 +110,31 @@ int premvos_resize_linear_u8(const unsigned char* src_dev, int batch, int src_h,
                              int dst_w, int channels, int reverse_channels, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * MergeTrack's live mask propagation, on the device.
+ *
+ * premvos_warp_masks_u8 replaces MergeTrack/merge_functions.py:209-217 `warp_flow(img, flow, binarize)` for all masks of a
+ * frame at once (the loop of warp_proposals, :226) and the `toBbox` of :231:
+ *     map = (x, y) - flow;  res = cv2.remap(mask, map, None, cv2.INTER_LINEAR);  if binarize: res = (res == 1)
+ * BIT-EXACT with OpenCV's 8-bit remap (map quantised to 1/32 pixel, 15-bit bilinear table, constant border 0).
+ *   masks_dev uint8 [n, height, width] (device), flow_dev float32 [height, width, 2] (device, (u, v) interleaved = the
+ *   layout of a .flo file / of premvos_flow_postprocess), out_dev uint8 [n, height, width] (device, != masks_dev),
+ *   bbox_dev float32 [n, 4] (device, 16-byte aligned, may be NULL): the tight box [x, y, w, h] of every warped mask's
+ *   non-zero pixels, zeros for an empty one (pycocotools rleToBbox) -- the `bbox` do_refinement reads
+ *   (MergeTrack/refinement_net_functions.py:44), so premvos_refnet_forward can consume it without a host round trip.
+ * Enqueues on `stream` (1 launch, 3 with bbox_dev), never synchronises, allocates nothing.  n == 0 is a no-op.
+ *
+ * premvos_flow_postprocess replaces optical_flow_net-PWC-Net/script_pwc_multi.py:59-68 for a batch: flow2 float32
+ * [batch, 2, net_h/4, net_w/4] (what premvos_pwc_forward writes) -> x20 -> cv2.resize of u and v to (width, height)
+ * (float32 INTER_LINEAR) -> u *= width/net_w, v *= height/net_h -> out float32 [batch, height, width, 2] (the payload of a
+ * .flo file, what MergeTrack's get_flow returns).  Same coordinate arithmetic as OpenCV; products and sums are rounded
+ * to float32 one by one.  Enqueues on `stream`; the coefficient tables of a geometry are cached on the first call.
+ * --------------------------------------------------------------------------------------------- */
+int premvos_warp_masks_u8(const unsigned char* masks_dev, int n, int height, int width, const float* flow_dev,
+                          unsigned char* out_dev, float* bbox_dev, int binarize, void* stream);
+int premvos_flow_postprocess(const float* flow2_dev, int batch, int net_h, int net_w, float* out_dev, int height, int width,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * PWC-DC-Net forward (optical flow).
  *
  * Life cycle: create(batch,H,W) -> set_param(name, host fp32 data) for each of the 128 state_dict

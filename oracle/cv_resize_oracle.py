@@ -57,3 +57,31 @@ def resize_linear_u8(src, dst_h, dst_w):
     out = (((b0[:, None, None].astype(np.int64) * (r0 >> 4)) >> 16) + ((b1[:, None, None].astype(np.int64) * (r1 >> 4)) >> 16) + 2) >> 2
     out = np.clip(out, 0, 255).astype(np.uint8)
     return out[:, :, 0] if squeeze else out
+
+
+def resize_linear_f32(src, dst_h, dst_w):
+    """cv2.resize(src float32 [H, W], (dst_w, dst_h), INTER_LINEAR): same coordinates as the 8-bit path, float coefficients
+    (1 - f, f), horizontal pass then vertical pass, every product / sum rounded to float32 (OpenCV's SIMD rows may fuse a
+    multiply-add: pinned against cv2 to 1e-6 relative, not bit-exact).  Used by script_pwc_multi.py:64-65 on the flow."""
+    src = np.asarray(src, dtype=np.float32)
+    sh, sw = src.shape
+    sx, _, _ = linear_coefficients(dst_w, sw, True)
+    sy, _, _ = linear_coefficients(dst_h, sh, False)
+
+    def frac(dst_n, src_n, clamp):
+        scale = 1.0 / (float(dst_n) / src_n)
+        f = ((np.arange(dst_n, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f)
+        f = (f - s.astype(np.float32)).astype(np.float32)
+        if clamp:
+            f[(s < 0) | (s >= src_n - 1)] = 0
+        return f
+
+    fx, fy = frac(dst_w, sw, True), frac(dst_h, sh, False)
+    sx1 = np.minimum(sx + 1, sw - 1)
+    sy0, sy1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    one = np.float32(1.0)
+    rows = (src[:, sx] * (one - fx)[None, :]).astype(np.float32) + (src[:, sx1] * fx[None, :]).astype(np.float32)
+    rows = rows.astype(np.float32)
+    out = (rows[sy0] * (one - fy)[:, None]).astype(np.float32) + (rows[sy1] * fy[:, None]).astype(np.float32)
+    return out.astype(np.float32)

@@ -294,3 +294,19 @@ def synthetic_boxes(n, h, w, seed=3, min_size=40, max_size=300):
     x0 = rng.uniform(0, w - bw)
     y0 = rng.uniform(0, h - bh)
     return np.round(np.stack([x0, y0, bw, bh], 1), 1).astype(np.float32)
+
+
+def synthetic_masks(n, h, w, seed=4):
+    """`n` object masks uint8 [n,h,w] (0/1): unions of ellipses, the shape of MergeTrack's selected proposals; the last mask
+    of a set of 3 or more is empty (an object that left the frame)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[:h, :w]
+    masks = np.zeros((n, h, w), np.uint8)
+    for i in range(n):
+        if n >= 3 and i == n - 1:
+            break
+        for _ in range(3):
+            cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+            ry, rx = rng.uniform(0.05, 0.3) * h, rng.uniform(0.05, 0.3) * w
+            masks[i] |= ((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) < 1).astype(np.uint8)
+    return masks
