@@ -324,11 +324,13 @@ def main():
         ff, pi = pipe.prepare_device(dev_sets[0][0], fr)
         o = pipe.out
         t_flow = time_stage(lambda: pipe.flow_net.forward_u8(ff, out=o["flow"]), 20)
-        t_prop = time_stage(lambda: pipe.general.forward_device(pi[0]), 10)
+        t_prop = time_stage(lambda: pipe.general.forward_device(pi if B > 1 else pi[0]), 10) / B     # as the pipeline runs it: B frames per forward
+        t_prop1 = time_stage(lambda: pipe.general.forward_device(pi[0]), 10)                        # BASELINE configs[2]: one frame per forward
         t_ref = time_stage(lambda: pipe.refine.refine_device(fr[0], bx[0], masks=o["masks"][0], conf=o["conf"][0]), 5)
         stages = {"flow": {"ms_per_pair": t_flow / B, "pairs_per_s": 1e3 * B / t_flow, "batch": B,
                            "algorithmic_tflop_per_s": GFLOP_FLOW * B / t_flow},
-                  "proposal_pass": {"ms_per_frame": t_prop, "frames_per_s": 1e3 / t_prop, "input": [pipe.Hp, pipe.Wp]},
+                  "proposal_pass": {"ms_per_frame": t_prop, "frames_per_s": 1e3 / t_prop, "input": [pipe.Hp, pipe.Wp], "batch": B,
+                                    "ms_per_frame_batch1": t_prop1},
                   "refine": {"ms_per_frame_of_%d_boxes" % K: t_ref, "crops_per_s": 1e3 * K / t_ref,
                              "algorithmic_tflop_per_s": GFLOP_CROP * K / t_ref},
                   "sum_serial_ms_per_pair": t_flow / B + 2 * t_prop + t_ref,

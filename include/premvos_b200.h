@@ -202,6 +202,10 @@ int premvos_nms_host(const float* boxes, const float* scores, int n, float iou_t
  *
  * Life cycle: create(H, W of the ALREADY RESIZED image, num_class = 2, second_num_class = 81)
  *   [-> set_option("num_blocks0".."num_blocks3", count): ResNet depth, default 3,4,23,3 (config.py:61)]
+ *   [-> set_option("batch", B), 1..16, default 1: B frames per forward.  The reference runs one frame per session.run
+ *       (eval.py:61-110); a resident pipeline hands over several frames at once so that every convolution launch covers all of
+ *       them (batch-1 ResNet layers have 23..184 work items for 148 SMs).  img is then [B, H, W, 3], copy_results hands over B
+ *       images, read_results_image reads one; per-image results equal the batch-1 results up to fp32 summation order.]
  *   -> set_param(name, host fp32, numel) for every tensorpack variable, names and layouts as in a
  *      tensorpack checkpoint: "conv0/W" (HWIO), "conv0/bn/gamma|beta|mean/EMA|variance/EMA",
  *      "group{0..3}/block{i}/{conv1,conv2,conv3,convshortcut}/...", "rpn/conv0/{W,b}", "rpn/class/{W,b}",
@@ -219,7 +223,7 @@ int premvos_nms_host(const float* boxes, const float* scores, int n, float iou_t
  *
  * premvos_propnet_forward       : img is a DEVICE pointer; enqueues on `stream`, does not synchronise;
  *                                 fetch with premvos_propnet_read_results (synchronises `stream`).
- * premvos_propnet_forward_host  : img and all outputs are HOST pointers; copies, runs, synchronises.
+ * premvos_propnet_forward_host  : img and all outputs are HOST pointers; copies, runs, synchronises (batch 1 only).
  * Any output pointer except n_out may be NULL.  The whole forward is one CUDA graph captured at finalize
  * (set_option("cuda_graph", 0) before finalize turns that off); one forward in flight per handle.
  * --------------------------------------------------------------------------------------------- */
@@ -236,9 +240,13 @@ int premvos_propnet_forward_u8(premvos_propnet_t* net, const unsigned char* img_
 int premvos_propnet_read_results(premvos_propnet_t* net, void* stream, int* n_out, float* final_boxes, float* final_probs,
                                  int64_t* final_labels, float* final_posterior, int64_t* second_final_labels,
                                  float* second_final_posterior);
-/* Device-to-device hand-over of the last forward's results, enqueued on `stream` without synchronising: n_out_dev int[1],
- * final_boxes_dev fp32 [20,4], final_probs_dev fp32 [20], second_final_posterior_dev fp32 [20, second_num_class] (rows
- * >= *n_out_dev are unspecified; any pointer except n_out_dev may be NULL). */
+/* read_results for image `image` (0 .. batch-1) of the last forward of a batched handle; read_results reads image 0. */
+int premvos_propnet_read_results_image(premvos_propnet_t* net, void* stream, int image, int* n_out, float* final_boxes,
+                                       float* final_probs, int64_t* final_labels, float* final_posterior,
+                                       int64_t* second_final_labels, float* second_final_posterior);
+/* Device-to-device hand-over of the last forward's results, enqueued on `stream` without synchronising: n_out_dev int[B],
+ * final_boxes_dev fp32 [B,20,4], final_probs_dev fp32 [B,20], second_final_posterior_dev fp32 [B,20,second_num_class] with
+ * B = the handle's batch (rows >= n_out_dev[b] are unspecified; any pointer except n_out_dev may be NULL). */
 int premvos_propnet_copy_results(premvos_propnet_t* net, void* stream, int* n_out_dev, float* final_boxes_dev,
                                  float* final_probs_dev, float* second_final_posterior_dev);
 int premvos_propnet_forward_host(premvos_propnet_t* net, const float* img_host, int* n_out, float* final_boxes,
@@ -249,7 +257,8 @@ int premvos_propnet_launches_per_forward(const premvos_propnet_t* net);
  * converted to fp32).  Names: "conv0", "pool0", "block<i>", "featuremap", "rpn_hidden", "rpn_out" ([fh,fw,80]:
  * 15 logits + 60 deltas), "rpn_scores", "rpn_decoded_boxes", "topk_indices", "nms_keep", "proposal_boxes",
  * "proposal_scores", "roi_resized", "feature_fastrcnn", "pooled", "head_logits", "fastrcnn_all_probs",
- * "fastrcnn_all_boxes", "final_box_index", "cell_anchors".  Pass host_out = NULL to query *numel. */
+ * "fastrcnn_all_boxes", "final_box_index", "cell_anchors".  Pass host_out = NULL to query *numel.  On a batched handle
+ * activations hold all images ([B,C,H,W]); "<name>@<b>" selects image b for the per-image detection tensors (default 0). */
 int premvos_propnet_get_tensor(premvos_propnet_t* net, const char* name, float* host_out, int64_t* numel);
 void premvos_propnet_destroy(premvos_propnet_t* net);
 

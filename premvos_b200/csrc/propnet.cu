@@ -27,6 +27,8 @@ namespace {
 
 const int NUM_ANCHOR = 15, ANCHOR_STRIDE = 16, MAX_SIZE = 1333;
 const int PRE_NMS_TOPK = 1000, POST_NMS_TOPK = 100, RESULTS_PER_IM = 20;
+// per-image strides of the detection buffers
+const int S_TOPK = 1024, S_KEEP = 128, S_MASK = 1024 * 32;
 const float RPN_NMS_THRESH = 0.7f, FRCNN_NMS_THRESH = 0.5f, SCORE_THRESH = 0.5f, BN_EPS = 1e-5f;
 
 struct ConvLayer {
@@ -47,13 +49,15 @@ struct Bottleneck {
 struct premvos_propnet {
   int H = 0, W = 0, num_class = 2, second_num_class = 81;
   int blocks[4] = {3, 4, 23, 3};
+  int batch = 1;             // frames per forward (option "batch"): one launch group for all of them
   bool finalized = false;
   std::map<std::string, std::vector<float>> params;
   std::map<std::string, std::vector<int64_t>> shapes;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;
 
-  float* img_dev = nullptr;  // [H][W][3] fp32 BGR 0..255
+  float* img_dev = nullptr;  // [batch][H][W][3] fp32 BGR 0..255
+  // every per-image buffer below holds `batch` consecutive copies (strides: the S_* constants)
   CView img, c0, pool;
   ConvLayer conv0;
   std::vector<std::unique_ptr<Bottleneck>> backbone, head;
@@ -233,13 +237,13 @@ void make_cell_anchors(float* out /*[15][4]*/) {
 }
 
 int build_network(premvos_propnet* n) {
-  const int H = n->H, W = n->W;
-  PV_TRY(dev_alloc(n, &n->img_dev, (size_t)H * W * 3));
-  PV_TRY(alloc_cview(n, &n->img, 1, 8, H, W));
+  const int H = n->H, W = n->W, NB = n->batch;
+  PV_TRY(dev_alloc(n, &n->img_dev, (size_t)NB * H * W * 3));
+  PV_TRY(alloc_cview(n, &n->img, NB, 8, H, W));
   n->img.C = 8;
   // conv0: pad (2,3) + 7x7 stride 2 VALID + BN + ReLU (basemodel.py:79-80)
   const int H0 = (H + 5 - 7) / 2 + 1, W0 = (W + 5 - 7) / 2 + 1;
-  PV_TRY(alloc_cview(n, &n->c0, 1, 64, H0, W0));
+  PV_TRY(alloc_cview(n, &n->c0, NB, 64, H0, W0));
   {
     ConvGeom g; g.stride = 2; g.pad_t = g.pad_l = 2; g.pad_b = g.pad_r = 3; g.slope = 0.f;
     ConvOut o; o.cp = n->c0;
@@ -247,7 +251,7 @@ int build_network(premvos_propnet* n) {
     PV_TRY(make_conv(n, &n->conv0, "conv0", true, n->img, o, g, map3, 8));
   }
   const int H1 = (H0 + 1 - 3) / 2 + 1, W1 = (W0 + 1 - 3) / 2 + 1;
-  PV_TRY(alloc_cview(n, &n->pool, 1, 64, H1, W1));
+  PV_TRY(alloc_cview(n, &n->pool, NB, 64, H1, W1));
   CView cur = n->pool;
   const int chs[4] = {64, 128, 256, 512};
   for (int g = 0; g < 3; g++)
@@ -264,7 +268,7 @@ int build_network(premvos_propnet* n) {
            H / ANCHOR_STRIDE, W / ANCHOR_STRIDE);
   n->n_anchor_total = n->fh * n->fw * NUM_ANCHOR;
   // RPN head (model.py:31-51)
-  PV_TRY(alloc_cview(n, &n->rpn_hidden, 1, 1024, n->fh, n->fw));
+  PV_TRY(alloc_cview(n, &n->rpn_hidden, NB, 1024, n->fh, n->fw));
   {
     ConvGeom g = ConvGeom::same3x3(1, 0.f);
     ConvOut o; o.cp = n->rpn_hidden;
@@ -280,8 +284,8 @@ int build_network(premvos_propnet* n) {
     }
     for (int o = 0; o < 15; o++) b[o] = n->params["rpn/class/b"][o];
     for (int o = 0; o < 60; o++) b[15 + o] = n->params["rpn/box/b"][o];
-    n->rpn_out.N = 1; n->rpn_out.H = n->fh; n->rpn_out.W = n->fw; n->rpn_out.cs = 80; n->rpn_out.coff = 0; n->rpn_out.C = 75;
-    PV_TRY(dev_alloc(n, &n->rpn_out.p, (size_t)n->fh * n->fw * 80));
+    n->rpn_out.N = NB; n->rpn_out.H = n->fh; n->rpn_out.W = n->fw; n->rpn_out.cs = 80; n->rpn_out.coff = 0; n->rpn_out.C = 75;
+    PV_TRY(dev_alloc(n, &n->rpn_out.p, (size_t)NB * n->fh * n->fw * 80));
     PV_TRY(pack_conv_weights_umma(&n->rpn_heads.w, w.data(), b.data(), 75, 1024, 1, 1));
     ConvOut o; o.f32 = n->rpn_out;
     ConvGeom g;
@@ -292,15 +296,16 @@ int build_network(premvos_propnet* n) {
   make_cell_anchors(ca);
   PV_TRY(dev_alloc(n, &n->cell_anchors, 60));
   PV_CUDA(cudaMemcpy(n->cell_anchors, ca, sizeof(ca), cudaMemcpyHostToDevice));
-  PV_TRY(dev_alloc(n, &n->d_scores, (size_t)n->n_anchor_total));
-  PV_TRY(dev_alloc(n, &n->d_boxes, (size_t)n->n_anchor_total * 4));
-  PV_TRY(dev_alloc(n, &n->topk_idx, 1024)); PV_TRY(dev_alloc(n, &n->topk_score, 1024)); PV_TRY(dev_alloc(n, &n->topk_count, 1));
-  PV_TRY(dev_alloc(n, &n->valid_boxes, 1024 * 4)); PV_TRY(dev_alloc(n, &n->valid_scores, 1024));
-  PV_TRY(dev_alloc(n, &n->valid_src, 1024)); PV_TRY(dev_alloc(n, &n->valid_count, 1));
-  PV_TRY(dev_alloc(n, &n->nms_mask, 1024 * 32)); PV_TRY(dev_alloc(n, &n->keep, 128)); PV_TRY(dev_alloc(n, &n->keep_count, 1));
-  PV_TRY(dev_alloc(n, &n->prop_boxes, 128 * 4)); PV_TRY(dev_alloc(n, &n->prop_scores, 128));
-  // RoIAlign + conv5 head on a fixed batch of POST_NMS_TOPK RoIs
-  PV_TRY(alloc_cview(n, &n->roi, POST_NMS_TOPK, 1024, 14, 14));
+  const size_t nb = (size_t)NB;
+  PV_TRY(dev_alloc(n, &n->d_scores, nb * n->n_anchor_total));
+  PV_TRY(dev_alloc(n, &n->d_boxes, nb * n->n_anchor_total * 4));
+  PV_TRY(dev_alloc(n, &n->topk_idx, nb * S_TOPK)); PV_TRY(dev_alloc(n, &n->topk_score, nb * S_TOPK)); PV_TRY(dev_alloc(n, &n->topk_count, nb));
+  PV_TRY(dev_alloc(n, &n->valid_boxes, nb * S_TOPK * 4)); PV_TRY(dev_alloc(n, &n->valid_scores, nb * S_TOPK));
+  PV_TRY(dev_alloc(n, &n->valid_src, nb * S_TOPK)); PV_TRY(dev_alloc(n, &n->valid_count, nb));
+  PV_TRY(dev_alloc(n, &n->nms_mask, nb * S_MASK)); PV_TRY(dev_alloc(n, &n->keep, nb * S_KEEP)); PV_TRY(dev_alloc(n, &n->keep_count, nb));
+  PV_TRY(dev_alloc(n, &n->prop_boxes, nb * S_KEEP * 4)); PV_TRY(dev_alloc(n, &n->prop_scores, nb * S_KEEP));
+  // RoIAlign + conv5 head on a fixed batch of POST_NMS_TOPK RoIs per image
+  PV_TRY(alloc_cview(n, &n->roi, NB * POST_NMS_TOPK, 1024, 14, 14));
   cur = n->roi;
   for (int b = 0; b < n->blocks[3]; b++) {
     n->head.emplace_back(new Bottleneck());
@@ -322,47 +327,61 @@ int build_network(premvos_propnet* n) {
   PV_TRY(dev_alloc(n, &n->fc_w, fw.size())); PV_TRY(dev_alloc(n, &n->fc_b, fb.size()));
   PV_CUDA(cudaMemcpy(n->fc_w, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice));
   PV_CUDA(cudaMemcpy(n->fc_b, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice));
-  PV_TRY(dev_alloc(n, &n->fc_out, (size_t)POST_NMS_TOPK * n->nfc));
-  PV_TRY(dev_alloc(n, &n->pooled, (size_t)POST_NMS_TOPK * 2048));
-  PV_TRY(dev_alloc(n, &n->all_probs, 128 * 2)); PV_TRY(dev_alloc(n, &n->all_boxes, 128 * 4));
-  PV_TRY(dev_alloc(n, &n->second_probs, (size_t)128 * (nsec > 0 ? nsec : 1)));
-  PV_TRY(dev_alloc(n, &n->n_out, 1));
-  PV_TRY(dev_alloc(n, &n->final_boxes, RESULTS_PER_IM * 4)); PV_TRY(dev_alloc(n, &n->final_probs, RESULTS_PER_IM));
-  PV_TRY(dev_alloc(n, &n->final_labels, RESULTS_PER_IM)); PV_TRY(dev_alloc(n, &n->final_posterior, RESULTS_PER_IM * 2));
-  PV_TRY(dev_alloc(n, &n->second_final_labels, RESULTS_PER_IM));
-  PV_TRY(dev_alloc(n, &n->second_final_posterior, (size_t)RESULTS_PER_IM * (nsec > 0 ? nsec : 1)));
-  PV_TRY(dev_alloc(n, &n->final_box_index, RESULTS_PER_IM));
+  PV_TRY(dev_alloc(n, &n->fc_out, nb * POST_NMS_TOPK * n->nfc));
+  PV_TRY(dev_alloc(n, &n->pooled, nb * POST_NMS_TOPK * 2048));
+  PV_TRY(dev_alloc(n, &n->all_probs, nb * S_KEEP * 2)); PV_TRY(dev_alloc(n, &n->all_boxes, nb * S_KEEP * 4));
+  PV_TRY(dev_alloc(n, &n->second_probs, nb * S_KEEP * (nsec > 0 ? nsec : 1)));
+  PV_TRY(dev_alloc(n, &n->n_out, nb));
+  PV_TRY(dev_alloc(n, &n->final_boxes, nb * RESULTS_PER_IM * 4)); PV_TRY(dev_alloc(n, &n->final_probs, nb * RESULTS_PER_IM));
+  PV_TRY(dev_alloc(n, &n->final_labels, nb * RESULTS_PER_IM)); PV_TRY(dev_alloc(n, &n->final_posterior, nb * RESULTS_PER_IM * 2));
+  PV_TRY(dev_alloc(n, &n->second_final_labels, nb * RESULTS_PER_IM));
+  PV_TRY(dev_alloc(n, &n->second_final_posterior, nb * RESULTS_PER_IM * (nsec > 0 ? nsec : 1)));
+  PV_TRY(dev_alloc(n, &n->final_box_index, nb * RESULTS_PER_IM));
   return 0;
 }
 
 int run_network(premvos_propnet* n, cudaStream_t st) {
-  PV_TRY(det_preprocess(n->img_dev, n->img, st));
+  const int NB = n->batch, nsec = n->second_num_class > 0 ? n->second_num_class : 1;
+  for (int b = 0; b < NB; b++) PV_TRY(det_preprocess(n->img_dev + (size_t)b * n->H * n->W * 3, n->img.batch_range(b, 1), st));
+  // backbone + RPN head: every frame of the batch in the same launches
   PV_TRY(launch_conv_umma(n->conv0.plan, st));
   PV_TRY(det_maxpool3x3s2(n->c0, n->pool, st));
   for (auto& b : n->backbone) PV_TRY(run_bottleneck(b.get(), st));
   PV_TRY(launch_conv_umma(n->rpn0.plan, st));
   PV_TRY(launch_conv_umma(n->rpn_heads.plan, st));
-  PV_TRY(det_rpn_decode(n->rpn_out.p, n->rpn_out.cs, n->fh, n->fw, NUM_ANCHOR, n->cell_anchors, (float)ANCHOR_STRIDE,
-                        logf((float)MAX_SIZE / 16.0f), n->d_scores, n->d_boxes, st));
-  // generate_rpn_proposals (model.py:170-217)
-  PV_TRY(det_topk(n->d_scores, n->n_anchor_total, PRE_NMS_TOPK, n->topk_idx, n->topk_score, n->topk_count, st));
-  PV_TRY(det_gather_clip_valid(n->d_boxes, n->topk_idx, n->topk_score, n->topk_count, (float)n->H, (float)n->W, 0.f, n->valid_boxes,
-                               n->valid_scores, n->valid_src, n->valid_count, st));
-  PV_TRY(det_nms(n->valid_boxes, n->valid_count, RPN_NMS_THRESH, POST_NMS_TOPK, n->nms_mask, n->keep, n->keep_count, st));
-  PV_TRY(det_gather_proposals(n->valid_boxes, n->valid_scores, n->keep, n->keep_count, POST_NMS_TOPK, n->prop_boxes, n->prop_scores, st));
-  // RoIAlign on the /16 grid (train.py:159), conv5 head, pooled features -> heads
-  PV_TRY(det_roi_align(n->featuremap, n->prop_boxes, 1.0f / ANCHOR_STRIDE, 14, n->roi, st));
+  for (int b = 0; b < NB; b++) {
+    const size_t na = (size_t)n->n_anchor_total;
+    float *scores = n->d_scores + b * na, *boxes = n->d_boxes + b * na * 4;
+    PV_TRY(det_rpn_decode(n->rpn_out.p + (size_t)b * n->fh * n->fw * n->rpn_out.cs, n->rpn_out.cs, n->fh, n->fw, NUM_ANCHOR, n->cell_anchors,
+                          (float)ANCHOR_STRIDE, logf((float)MAX_SIZE / 16.0f), scores, boxes, st));
+    // generate_rpn_proposals (model.py:170-217)
+    PV_TRY(det_topk(scores, n->n_anchor_total, PRE_NMS_TOPK, n->topk_idx + b * S_TOPK, n->topk_score + b * S_TOPK, n->topk_count + b, st));
+    PV_TRY(det_gather_clip_valid(boxes, n->topk_idx + b * S_TOPK, n->topk_score + b * S_TOPK, n->topk_count + b, (float)n->H, (float)n->W, 0.f,
+                                 n->valid_boxes + b * S_TOPK * 4, n->valid_scores + b * S_TOPK, n->valid_src + b * S_TOPK, n->valid_count + b, st));
+    PV_TRY(det_nms(n->valid_boxes + b * S_TOPK * 4, n->valid_count + b, RPN_NMS_THRESH, POST_NMS_TOPK, n->nms_mask + (size_t)b * S_MASK,
+                   n->keep + b * S_KEEP, n->keep_count + b, st));
+    PV_TRY(det_gather_proposals(n->valid_boxes + b * S_TOPK * 4, n->valid_scores + b * S_TOPK, n->keep + b * S_KEEP, n->keep_count + b,
+                                POST_NMS_TOPK, n->prop_boxes + b * S_KEEP * 4, n->prop_scores + b * S_KEEP, st));
+    // RoIAlign on the /16 grid (train.py:159)
+    PV_TRY(det_roi_align(n->featuremap.batch_range(b, 1), n->prop_boxes + b * S_KEEP * 4, 1.0f / ANCHOR_STRIDE, 14,
+                         n->roi.batch_range(b * POST_NMS_TOPK, POST_NMS_TOPK), st));
+  }
+  // conv5 head on the RoIs of all frames, pooled features -> heads
   for (auto& b : n->head) PV_TRY(run_bottleneck(b.get(), st));
   PV_TRY(det_gap_fc(n->head.back()->out, n->fc_w, n->fc_b, n->nfc, n->pooled, n->fc_out, st));
-  DetTailArgs t;
-  t.logits = n->fc_out; t.nfc = n->nfc; t.nsecond = n->second_num_class; t.prop_boxes = n->prop_boxes; t.prop_count = n->keep_count;
-  t.img_h = (float)n->H; t.img_w = (float)n->W; t.clip = logf((float)MAX_SIZE / 16.0f); t.score_thresh = SCORE_THRESH;
-  t.nms_thresh = FRCNN_NMS_THRESH; t.max_rois = POST_NMS_TOPK; t.results_per_im = RESULTS_PER_IM;
-  t.all_probs = n->all_probs; t.all_boxes = n->all_boxes; t.second_probs = n->second_probs;
-  t.n_out = n->n_out; t.final_boxes = n->final_boxes; t.final_probs = n->final_probs; t.final_labels = n->final_labels;
-  t.final_posterior = n->final_posterior; t.second_final_labels = n->second_final_labels;
-  t.second_final_posterior = n->second_final_posterior; t.final_box_index = n->final_box_index;
-  PV_TRY(det_frcnn_tail(t, st));
+  for (int b = 0; b < NB; b++) {
+    DetTailArgs t;
+    t.logits = n->fc_out + (size_t)b * POST_NMS_TOPK * n->nfc; t.nfc = n->nfc; t.nsecond = n->second_num_class;
+    t.prop_boxes = n->prop_boxes + b * S_KEEP * 4; t.prop_count = n->keep_count + b;
+    t.img_h = (float)n->H; t.img_w = (float)n->W; t.clip = logf((float)MAX_SIZE / 16.0f); t.score_thresh = SCORE_THRESH;
+    t.nms_thresh = FRCNN_NMS_THRESH; t.max_rois = POST_NMS_TOPK; t.results_per_im = RESULTS_PER_IM;
+    t.all_probs = n->all_probs + b * S_KEEP * 2; t.all_boxes = n->all_boxes + b * S_KEEP * 4; t.second_probs = n->second_probs + (size_t)b * S_KEEP * nsec;
+    t.n_out = n->n_out + b; t.final_boxes = n->final_boxes + b * RESULTS_PER_IM * 4; t.final_probs = n->final_probs + b * RESULTS_PER_IM;
+    t.final_labels = n->final_labels + b * RESULTS_PER_IM; t.final_posterior = n->final_posterior + b * RESULTS_PER_IM * 2;
+    t.second_final_labels = n->second_final_labels + b * RESULTS_PER_IM;
+    t.second_final_posterior = n->second_final_posterior + (size_t)b * RESULTS_PER_IM * nsec; t.final_box_index = n->final_box_index + b * RESULTS_PER_IM;
+    PV_TRY(det_frcnn_tail(t, st));
+  }
   return 0;
 }
 
@@ -413,6 +432,11 @@ extern "C" int premvos_propnet_set_option(premvos_propnet_t* n, const char* key,
     return 0;
   }
   if (k == "cuda_graph") { n->opt_cuda_graph = value; return 0; }
+  if (k == "batch") {
+    PV_CHECK(value >= 1 && value <= 16, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_set_option: batch in [1,16]");
+    n->batch = value;
+    return 0;
+  }
   return fail(PREMVOS_ERR_INVALID_ARG, "premvos_propnet_set_option: unknown option '%s'", key);
 }
 
@@ -461,7 +485,7 @@ extern "C" int premvos_propnet_forward(premvos_propnet_t* n, const float* img_de
   PV_CHECK(n && img_dev, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_forward: null argument");
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_forward: call premvos_propnet_finalize first");
   cudaStream_t st = (cudaStream_t)stream;
-  PV_CUDA(cudaMemcpyAsync(n->img_dev, img_dev, (size_t)n->H * n->W * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PV_CUDA(cudaMemcpyAsync(n->img_dev, img_dev, (size_t)n->batch * n->H * n->W * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return enqueue_network(n, st);
 }
 
@@ -469,31 +493,42 @@ extern "C" int premvos_propnet_forward_u8(premvos_propnet_t* n, const unsigned c
   PV_CHECK(n && img_bgr_dev, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_forward_u8: null argument");
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_forward_u8: call premvos_propnet_finalize first");
   cudaStream_t st = (cudaStream_t)stream;
-  PV_TRY(det_u8_to_f32(img_bgr_dev, n->img_dev, (long)n->H * n->W * 3, st));
+  PV_TRY(det_u8_to_f32(img_bgr_dev, n->img_dev, (long)n->batch * n->H * n->W * 3, st));
   return enqueue_network(n, st);
+}
+
+extern "C" int premvos_propnet_read_results_image(premvos_propnet_t* n, void* stream, int image, int* n_out, float* final_boxes,
+                                                  float* final_probs, int64_t* final_labels, float* final_posterior,
+                                                  int64_t* second_final_labels, float* second_final_posterior) {
+  PV_CHECK(n && n_out, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_results: null argument");
+  PV_CHECK(image >= 0 && image < n->batch, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_results: image %d outside the batch of %d", image,
+           n->batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t o = (size_t)image * RESULTS_PER_IM;
+  PV_CUDA(cudaMemcpyAsync(n_out, n->n_out + image, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PV_CUDA(cudaStreamSynchronize(st));
+  const int m = *n_out;
+  PV_CHECK(m >= 0 && m <= RESULTS_PER_IM, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_results: corrupt result count %d", m);
+  if (m == 0) return 0;
+  if (final_boxes) PV_CUDA(cudaMemcpyAsync(final_boxes, n->final_boxes + o * 4, (size_t)m * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_probs) PV_CUDA(cudaMemcpyAsync(final_probs, n->final_probs + o, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_labels) PV_CUDA(cudaMemcpyAsync(final_labels, n->final_labels + o, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (final_posterior)
+    PV_CUDA(cudaMemcpyAsync(final_posterior, n->final_posterior + o * 2, (size_t)m * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (second_final_labels)
+    PV_CUDA(cudaMemcpyAsync(second_final_labels, n->second_final_labels + o, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (second_final_posterior && n->second_num_class > 0)
+    PV_CUDA(cudaMemcpyAsync(second_final_posterior, n->second_final_posterior + o * n->second_num_class,
+                            (size_t)m * n->second_num_class * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PV_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 extern "C" int premvos_propnet_read_results(premvos_propnet_t* n, void* stream, int* n_out, float* final_boxes, float* final_probs,
                                             int64_t* final_labels, float* final_posterior, int64_t* second_final_labels,
                                             float* second_final_posterior) {
-  PV_CHECK(n && n_out, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_results: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  PV_CUDA(cudaMemcpyAsync(n_out, n->n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PV_CUDA(cudaStreamSynchronize(st));
-  const int m = *n_out;
-  PV_CHECK(m >= 0 && m <= RESULTS_PER_IM, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_results: corrupt result count %d", m);
-  if (m == 0) return 0;
-  if (final_boxes) PV_CUDA(cudaMemcpyAsync(final_boxes, n->final_boxes, (size_t)m * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (final_probs) PV_CUDA(cudaMemcpyAsync(final_probs, n->final_probs, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (final_labels) PV_CUDA(cudaMemcpyAsync(final_labels, n->final_labels, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  if (final_posterior) PV_CUDA(cudaMemcpyAsync(final_posterior, n->final_posterior, (size_t)m * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (second_final_labels)
-    PV_CUDA(cudaMemcpyAsync(second_final_labels, n->second_final_labels, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  if (second_final_posterior && n->second_num_class > 0)
-    PV_CUDA(cudaMemcpyAsync(second_final_posterior, n->second_final_posterior, (size_t)m * n->second_num_class * sizeof(float),
-                            cudaMemcpyDeviceToHost, st));
-  PV_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return premvos_propnet_read_results_image(n, stream, 0, n_out, final_boxes, final_probs, final_labels, final_posterior,
+                                            second_final_labels, second_final_posterior);
 }
 
 // Device-to-device hand-over of the last forward's results (fixed RESULTS_PER_IM rows + a device count): lets a resident
@@ -503,14 +538,15 @@ extern "C" int premvos_propnet_copy_results(premvos_propnet_t* n, void* stream, 
   PV_CHECK(n && n_out_dev, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_copy_results: null argument");
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_copy_results: network not finalized");
   cudaStream_t st = (cudaStream_t)stream;
-  PV_CUDA(cudaMemcpyAsync(n_out_dev, n->n_out, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  const size_t nb = (size_t)n->batch;   // `batch` images: [batch] counts, [batch][RESULTS_PER_IM] rows
+  PV_CUDA(cudaMemcpyAsync(n_out_dev, n->n_out, nb * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (final_boxes_dev)
-    PV_CUDA(cudaMemcpyAsync(final_boxes_dev, n->final_boxes, (size_t)RESULTS_PER_IM * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PV_CUDA(cudaMemcpyAsync(final_boxes_dev, n->final_boxes, nb * RESULTS_PER_IM * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (final_probs_dev)
-    PV_CUDA(cudaMemcpyAsync(final_probs_dev, n->final_probs, (size_t)RESULTS_PER_IM * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PV_CUDA(cudaMemcpyAsync(final_probs_dev, n->final_probs, nb * RESULTS_PER_IM * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (second_final_posterior_dev && n->second_num_class > 0)
     PV_CUDA(cudaMemcpyAsync(second_final_posterior_dev, n->second_final_posterior,
-                            (size_t)RESULTS_PER_IM * n->second_num_class * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                            nb * RESULTS_PER_IM * n->second_num_class * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -519,7 +555,9 @@ extern "C" int premvos_propnet_forward_host(premvos_propnet_t* n, const float* i
                                             float* second_final_posterior) {
   PV_CHECK(n && img_host && n_out, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_forward_host: null argument");
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_forward_host: call premvos_propnet_finalize first");
-  PV_CUDA(cudaMemcpyAsync(n->img_dev, img_host, (size_t)n->H * n->W * 3 * sizeof(float), cudaMemcpyHostToDevice, n->stream));
+  PV_CHECK(n->batch == 1, PREMVOS_ERR_UNSUPPORTED,
+           "premvos_propnet_forward_host: one image per call; a batched handle is driven with premvos_propnet_forward[_u8] + read_results_image");
+  PV_CUDA(cudaMemcpyAsync(n->img_dev, img_host, (size_t)n->batch * n->H * n->W * 3 * sizeof(float), cudaMemcpyHostToDevice, n->stream));
   PV_TRY(enqueue_network(n, n->stream));
   return premvos_propnet_read_results(n, n->stream, n_out, final_boxes, final_probs, final_labels, final_posterior, second_final_labels,
                                       second_final_posterior);
@@ -533,12 +571,16 @@ extern "C" int premvos_propnet_get_tensor(premvos_propnet_t* n, const char* name
   PV_CHECK(n->finalized, PREMVOS_ERR_NOT_READY, "premvos_propnet_get_tensor: network not finalized");
   PV_CUDA(cudaDeviceSynchronize());
   std::string k(name);
+  int img = 0;   // "<tensor>@<b>": the per-image tensor of image b of the batch (default image 0); activations hold all images
+  const size_t at = k.find('@');
+  if (at != std::string::npos) { img = atoi(k.c_str() + at + 1); k = k.substr(0, at); }
+  PV_CHECK(img >= 0 && img < n->batch, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_get_tensor: image %d outside the batch of %d", img, n->batch);
   CView cv; bool is_cv = false;
   const float* fptr = nullptr; const int* iptr = nullptr; int64_t cnt = 0;
   int h_topk = 0, h_valid = 0, h_keep = 0;
-  PV_CUDA(cudaMemcpy(&h_topk, n->topk_count, 4, cudaMemcpyDeviceToHost));
-  PV_CUDA(cudaMemcpy(&h_valid, n->valid_count, 4, cudaMemcpyDeviceToHost));
-  PV_CUDA(cudaMemcpy(&h_keep, n->keep_count, 4, cudaMemcpyDeviceToHost));
+  PV_CUDA(cudaMemcpy(&h_topk, n->topk_count + img, 4, cudaMemcpyDeviceToHost));
+  PV_CUDA(cudaMemcpy(&h_valid, n->valid_count + img, 4, cudaMemcpyDeviceToHost));
+  PV_CUDA(cudaMemcpy(&h_keep, n->keep_count + img, 4, cudaMemcpyDeviceToHost));
   if (k == "featuremap") { cv = n->featuremap; is_cv = true; }
   else if (k == "conv0") { cv = n->c0; is_cv = true; }
   else if (k == "pool0") { cv = n->pool; is_cv = true; }
@@ -551,18 +593,18 @@ extern "C" int premvos_propnet_get_tensor(premvos_propnet_t* n, const char* name
   else if (k == "roi_resized") { cv = n->roi; is_cv = true; }
   else if (k == "feature_fastrcnn") { cv = n->head.back()->out; is_cv = true; }
   else if (k == "cell_anchors") { fptr = n->cell_anchors; cnt = 60; }
-  else if (k == "rpn_out") { fptr = n->rpn_out.p; cnt = (int64_t)n->fh * n->fw * 80; }
-  else if (k == "rpn_scores") { fptr = n->d_scores; cnt = n->n_anchor_total; }
-  else if (k == "rpn_decoded_boxes") { fptr = n->d_boxes; cnt = (int64_t)n->n_anchor_total * 4; }
-  else if (k == "topk_indices") { iptr = n->valid_src; cnt = h_valid; }
-  else if (k == "nms_keep") { iptr = n->keep; cnt = h_keep; }
-  else if (k == "proposal_boxes") { fptr = n->prop_boxes; cnt = (int64_t)h_keep * 4; }
-  else if (k == "proposal_scores") { fptr = n->prop_scores; cnt = h_keep; }
-  else if (k == "head_logits") { fptr = n->fc_out; cnt = (int64_t)POST_NMS_TOPK * n->nfc; }
-  else if (k == "pooled") { fptr = n->pooled; cnt = (int64_t)POST_NMS_TOPK * 2048; }
-  else if (k == "fastrcnn_all_probs") { fptr = n->all_probs; cnt = (int64_t)h_keep * 2; }
-  else if (k == "fastrcnn_all_boxes") { fptr = n->all_boxes; cnt = (int64_t)h_keep * 4; }
-  else if (k == "final_box_index") { int m = 0; PV_CUDA(cudaMemcpy(&m, n->n_out, 4, cudaMemcpyDeviceToHost)); iptr = n->final_box_index; cnt = m; }
+  else if (k == "rpn_out") { fptr = n->rpn_out.p + (size_t)img * n->fh * n->fw * 80; cnt = (int64_t)n->fh * n->fw * 80; }
+  else if (k == "rpn_scores") { fptr = n->d_scores + (size_t)img * n->n_anchor_total; cnt = n->n_anchor_total; }
+  else if (k == "rpn_decoded_boxes") { fptr = n->d_boxes + (size_t)img * n->n_anchor_total * 4; cnt = (int64_t)n->n_anchor_total * 4; }
+  else if (k == "topk_indices") { iptr = n->valid_src + img * S_TOPK; cnt = h_valid; }
+  else if (k == "nms_keep") { iptr = n->keep + img * S_KEEP; cnt = h_keep; }
+  else if (k == "proposal_boxes") { fptr = n->prop_boxes + img * S_KEEP * 4; cnt = (int64_t)h_keep * 4; }
+  else if (k == "proposal_scores") { fptr = n->prop_scores + img * S_KEEP; cnt = h_keep; }
+  else if (k == "head_logits") { fptr = n->fc_out + (size_t)img * POST_NMS_TOPK * n->nfc; cnt = (int64_t)POST_NMS_TOPK * n->nfc; }
+  else if (k == "pooled") { fptr = n->pooled + (size_t)img * POST_NMS_TOPK * 2048; cnt = (int64_t)POST_NMS_TOPK * 2048; }
+  else if (k == "fastrcnn_all_probs") { fptr = n->all_probs + img * S_KEEP * 2; cnt = (int64_t)h_keep * 2; }
+  else if (k == "fastrcnn_all_boxes") { fptr = n->all_boxes + img * S_KEEP * 4; cnt = (int64_t)h_keep * 4; }
+  else if (k == "final_box_index") { int m = 0; PV_CUDA(cudaMemcpy(&m, n->n_out + img, 4, cudaMemcpyDeviceToHost)); iptr = n->final_box_index + img * RESULTS_PER_IM; cnt = m; }
   else return fail(PREMVOS_ERR_INVALID_ARG, "premvos_propnet_get_tensor: unknown tensor '%s'", name);
   (void)h_topk;
   if (is_cv) {

@@ -60,8 +60,9 @@ class FramePipeline:
                                             middle_units=middle_units).load_params(refine_params)
         # build every handle now (weight packing, buffer allocation, graph capture)
         self.flow_net._handle(self.B, self.Hn, self.Wn)
-        self.general._handle(self.Hp, self.Wp)
-        self.specific._handle(self.Hp, self.Wp)
+        # the B frames of a step go through each proposal network as ONE batched forward (every conv launch covers all of them)
+        self.general._handle(self.Hp, self.Wp, self.B)
+        self.specific._handle(self.Hp, self.Wp, self.B)
         self.refine._h()
         self.streams = [torch.cuda.Stream(self.dev) for _ in range(4)]
         B, K, d = self.B, self.K, self.dev
@@ -89,7 +90,7 @@ class FramePipeline:
         from . import _lib
         per_group = int(_lib.lib().premvos_refnet_launches_per_forward(self.refine._h()))
         return (self.flow_net.launches_per_forward(self.B, self.Hn, self.Wn) + 1
-                + self.B * (2 * (self.general.launches_per_forward(self.Hp, self.Wp) + 1) + groups * per_group))
+                + 2 * (self.general.launches_per_forward(self.Hp, self.Wp, self.B) + 1) + self.B * groups * per_group)
 
     def launches_per_step_from_frames(self, num_boxes=None):
         resize = 1 + (0 if (self.Hn, self.Wn) == (self.H, self.W) else 2 * self.B)
@@ -119,10 +120,8 @@ class FramePipeline:
             self.flow_net.forward_u8(flow_frames, out=o["flow"])
         for which, (net, s) in enumerate(((self.general, s_gen), (self.specific, s_spec))):
             with torch.cuda.stream(s):
-                for b in range(B):
-                    net.forward_device(prop_images[b])
-                    net.copy_results_device(self.Hp, self.Wp, o["det_count"][which, b:b + 1], o["det_boxes"][which, b],
-                                            o["det_probs"][which, b])
+                net.forward_device(prop_images if B > 1 else prop_images[0])
+                net.copy_results_device(self.Hp, self.Wp, o["det_count"][which], o["det_boxes"][which], o["det_probs"][which], batch=B)
         result = dict(o)
         if boxes is not None:
             if tuple(boxes.shape) != (B, self.K, 4):

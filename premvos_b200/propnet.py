@@ -62,8 +62,9 @@ class ProposalNet:
         except Exception:
             pass
 
-    def _handle(self, H, W):
-        key = (H, W)
+    def _handle(self, H, W, batch=1):
+        """Device handle for resized images of H x W, `batch` frames per forward (premvos_propnet_set_option "batch")."""
+        key = (H, W) if batch == 1 else (H, W, int(batch))
         if key in self._handles:
             return self._handles[key]
         if not self._params:
@@ -74,6 +75,8 @@ class ProposalNet:
         try:
             for g, nb in enumerate(self.num_blocks):
                 _lib.check(L.premvos_propnet_set_option(h, b"num_blocks%d" % g, int(nb)))
+            if batch != 1:
+                _lib.check(L.premvos_propnet_set_option(h, b"batch", int(batch)))
             for k, v in self._params.items():
                 _lib.check(L.premvos_propnet_set_param(h, k.encode(), v.ctypes.data_as(ctypes.c_void_p), v.size))
             _lib.check(L.premvos_propnet_finalize(h))
@@ -83,8 +86,8 @@ class ProposalNet:
         self._handles[key] = h
         return h
 
-    def launches_per_forward(self, H, W):
-        return int(_lib.lib().premvos_propnet_launches_per_forward(self._handle(H, W)))
+    def launches_per_forward(self, H, W, batch=1):
+        return int(_lib.lib().premvos_propnet_launches_per_forward(self._handle(H, W, batch)))
 
     # -- pred_func -----------------------------------------------------------------------------------
     def __call__(self, img):
@@ -110,32 +113,39 @@ class ProposalNet:
 
     # -- resident-pipeline entry points (device tensors, no synchronisation until read_results) -----------
     def forward_device(self, img):
-        """img: CUDA tensor [h,w,3] BGR, uint8 or float32 (0..255), already resized.  Enqueues the whole graph on the
-        current torch stream; fetch with read_results(h, w)."""
+        """img: CUDA tensor [h,w,3] BGR, uint8 or float32 (0..255), already resized -- or [B,h,w,3]: B frames in one launch
+        group (a batched handle).  Enqueues the whole graph on the current torch stream; fetch with read_results(h, w[, B, b])
+        or copy_results_device."""
         import torch
         if not isinstance(img, torch.Tensor) or not img.is_cuda or img.dtype not in (torch.uint8, torch.float32):
             raise TypeError("img must be a CUDA uint8 / float32 tensor (this build has no CPU path)")
-        if img.dim() != 3 or img.shape[2] != 3 or not img.is_contiguous():
-            raise ValueError("expected a contiguous [h,w,3] BGR image, got %s" % (tuple(img.shape),))
-        H, W = int(img.shape[0]), int(img.shape[1])
+        if img.dim() not in (3, 4) or img.shape[-1] != 3 or not img.is_contiguous():
+            raise ValueError("expected a contiguous [h,w,3] or [B,h,w,3] BGR image, got %s" % (tuple(img.shape),))
+        H, W = int(img.shape[-3]), int(img.shape[-2])
+        batch = 1 if img.dim() == 3 else int(img.shape[0])
         with torch.cuda.device(img.device):
-            h = self._handle(H, W)
+            h = self._handle(H, W, batch)
             st = torch.cuda.current_stream().cuda_stream
             fn = _lib.lib().premvos_propnet_forward_u8 if img.dtype == torch.uint8 else _lib.lib().premvos_propnet_forward
             _lib.check(fn(h, img.data_ptr(), st))
 
-    def copy_results_device(self, H, W, count, boxes, probs=None):
+    def copy_results_device(self, H, W, count, boxes, probs=None, batch=1):
         """Device-to-device copy of the last forward_device's results on the current torch stream (no synchronisation):
-        count CUDA int32 [1], boxes CUDA float32 [20,4], probs CUDA float32 [20]."""
+        count CUDA int32 [B], boxes CUDA float32 [B,20,4], probs CUDA float32 [B,20] (contiguous; B = batch, may be squeezed
+        for batch 1)."""
         import torch
+        for t, numel in ((count, batch), (boxes, batch * RESULTS_PER_IM * 4), (probs, batch * RESULTS_PER_IM)):
+            if t is not None and (not t.is_cuda or not t.is_contiguous() or t.numel() != numel):
+                raise ValueError("copy_results_device: outputs must be contiguous CUDA tensors for %d image(s)" % batch)
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(_lib.lib().premvos_propnet_copy_results(self._handle(H, W), st, count.data_ptr(), boxes.data_ptr(),
+        _lib.check(_lib.lib().premvos_propnet_copy_results(self._handle(H, W, batch), st, count.data_ptr(), boxes.data_ptr(),
                                                            None if probs is None else probs.data_ptr(), None))
 
-    def read_results(self, H, W):
-        """Synchronises the current torch stream and returns the six arrays of pred_func for the last forward_device."""
+    def read_results(self, H, W, batch=1, image=0):
+        """Synchronises the current torch stream and returns the six arrays of pred_func for the last forward_device
+        (image `image` of a batched forward)."""
         import torch
-        h = self._handle(H, W)
+        h = self._handle(H, W, batch)
         n = ctypes.c_int()
         boxes = np.zeros((RESULTS_PER_IM, 4), np.float32)
         probs = np.zeros((RESULTS_PER_IM,), np.float32)
@@ -145,15 +155,15 @@ class ProposalNet:
         spost = np.zeros((RESULTS_PER_IM, max(self.second_num_class, 1)), np.float32)
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(_lib.lib().premvos_propnet_read_results(h, st, ctypes.byref(n), vp(boxes), vp(probs), vp(labels), vp(post),
-                                                           vp(slabels), vp(spost)))
+        _lib.check(_lib.lib().premvos_propnet_read_results_image(h, st, int(image), ctypes.byref(n), vp(boxes), vp(probs), vp(labels),
+                                                                 vp(post), vp(slabels), vp(spost)))
         m = n.value
         return (boxes[:m].copy(), probs[:m].copy(), labels[:m].copy(), post[:m].copy(), slabels[:m].copy(),
                 spost[:m, :self.second_num_class].copy())
 
-    def get_tensor(self, name, H, W):
+    def get_tensor(self, name, H, W, batch=1):
         L = _lib.lib()
-        h = self._handle(H, W)
+        h = self._handle(H, W, batch)
         n = ctypes.c_int64()
         _lib.check(L.premvos_propnet_get_tensor(h, name.encode(), None, ctypes.byref(n)))
         buf = np.empty(n.value, dtype=np.float32)

@@ -87,8 +87,9 @@ def test_pipeline_step_fixed_boxes_and_host_call(parts):
         for which in range(2):
             n = len(dets[which][0])
             assert out["det_count"][which, b] == n
-            np.testing.assert_array_equal(out["det_boxes"][which, b, :n], dets[which][0])
-            np.testing.assert_array_equal(out["det_probs"][which, b, :n], dets[which][1])
+            # the pipeline runs the B frames as one batched forward: equal to the batch-1 results up to fp32 summation order
+            np.testing.assert_allclose(out["det_boxes"][which, b, :n], dets[which][0], rtol=1e-4, atol=1e-3)
+            np.testing.assert_allclose(out["det_probs"][which, b, :n], dets[which][1], rtol=1e-4, atol=1e-5)
         np.testing.assert_array_equal(out["masks"][b], masks)
         np.testing.assert_array_equal(out["conf"][b], conf)
     # the end-to-end call on pinned host buffers gives the same bits, twice (staging is reused)

@@ -143,6 +143,49 @@ def test_propnet_second_seed_and_determinism():
     assert abs(got[0].shape[0] - ref[0].shape[0]) <= 1
 
 
+def test_batched_forward_equals_single_image_forwards():
+    # set_option("batch", 3): three frames through every launch at once; per image the same results as a batch-1 forward
+    # up to fp32 summation order (another split-K plan), the same index tensors, and the oracle's feature map
+    import torch
+    nb = (1, 2, 2, 1)
+    H, W, B = 160, 224, 3
+    P = synth.propnet_synthetic_params(5, nb)
+    net = propnet.ProposalNet(nb).load_params(P)
+    imgs = np.stack([synth.synthetic_bgr_frame(H, W, seed=6 + i) for i in range(B)])          # uint8 BGR
+    singles, fms, idx = [], [], []
+    for i in range(B):
+        net.forward_device(torch.from_numpy(imgs[i]).cuda())
+        singles.append(net.read_results(H, W))
+        fms.append(net.get_tensor("featuremap", H, W).copy())
+        idx.append({k: net.get_tensor(k, H, W).copy() for k in ("topk_indices", "nms_keep", "proposal_boxes", "head_logits")})
+    per_forward = net.launches_per_forward(H, W, B)      # builds the batched handle (warm-up + graph capture) first
+    before = _lib.kernel_launch_count()
+    net.forward_device(torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    assert _lib.kernel_launch_count() - before == per_forward + 1      # + the uint8 -> fp32 conversion
+    fm = net.get_tensor("featuremap", H, W, B).reshape(B, -1)
+    _, inter = O.propnet_forward(P, imgs[1].astype(np.float32), list(nb), True)
+    assert rel_err(fm[1], inter["featuremap"].numpy().reshape(-1)) < TOL
+    counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    boxes = torch.zeros((B, 20, 4), device="cuda")
+    probs = torch.zeros((B, 20), device="cuda")
+    net.copy_results_device(H, W, counts, boxes, probs, batch=B)
+    for i in range(B):
+        assert rel_err(fm[i], fms[i]) < 1e-4
+        for k in ("topk_indices", "nms_keep"):
+            np.testing.assert_array_equal(net.get_tensor("%s@%d" % (k, i), H, W, B), idx[i][k])
+        for k in ("proposal_boxes", "head_logits"):
+            assert rel_err(net.get_tensor("%s@%d" % (k, i), H, W, B), idx[i][k]) < 1e-4
+        got = net.read_results(H, W, B, i)
+        assert len(got[0]) == len(singles[i][0]) == int(counts[i])
+        for a, b in zip(got, singles[i]):
+            np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-3)
+        np.testing.assert_array_equal(boxes[i, :len(got[0])].cpu().numpy(), got[0])
+        np.testing.assert_array_equal(probs[i, :len(got[0])].cpu().numpy(), got[1])
+    with pytest.raises(_lib.PremvosError):
+        net.get_tensor("nms_keep@3", H, W, B)
+
+
 def test_detect_one_image_end_to_end():
     nb = (1, 1, 1, 1)
     P = synth.propnet_synthetic_params(10, nb)
