@@ -252,6 +252,19 @@ int premvos_propnet_copy_results(premvos_propnet_t* net, void* stream, int* n_ou
 int premvos_propnet_forward_host(premvos_propnet_t* net, const float* img_host, int* n_out, float* final_boxes,
                                  float* final_probs, int64_t* final_labels, float* final_posterior,
                                  int64_t* second_final_labels, float* second_final_posterior);
+/* Mask R-CNN mask head (proposal_net/model.py:495-509, train.py:297-309; config.MODE_MASK -- inactive under simple_run.sh's
+ * `--forward`).  set_option("mode_mask", 1) before the first set_param adds the variables
+ * "maskrcnn/deconv/{W [2,2,256,2048], b [256]}" and "maskrcnn/conv/{W [1,1,256,1], b [1]}"; every forward then also runs
+ * RoIAlign on the final boxes -> conv5 group -> Deconv2D 2x2 stride 2 + ReLU (one tcgen05 GEMM to the 4 x 256 phase channels) ->
+ * 1x1 conv + sigmoid.  read_masks copies the first min(max_rows, 20) masks of image `image` (the `final_masks` output,
+ * fp32 [rows, 14, 14], row i belongs to final_boxes[i]) to the host and synchronises `stream`. */
+int premvos_propnet_read_masks(premvos_propnet_t* net, void* stream, int image, float* final_masks, int max_rows);
+/* eval.py:35-58 `fill_full_mask(box, mask, shape)` for the n boxes of an image, on the device (host pointers, synchronous):
+ * out[i] uint8 [height, width] = (cv2.resize(masks[i] (mask_size x mask_size fp32), (w, h)) > 0.5) pasted at the box's integer
+ * rectangle x0 = int(x1 + 0.5) .. int(x2 - 0.5), zero elsewhere; boxes fp32 [n,4] x1y1x2y2 already clipped to the image.
+ * OpenCV's float32 INTER_LINEAR arithmetic (INTER_AREA's 2x2 mean for an exact 2x down-scale, as cv2.resize substitutes). */
+int premvos_fill_full_masks_host(const float* masks_host, const float* boxes_host, int n, int mask_size, int height, int width,
+                                 unsigned char* out_host);
 int premvos_propnet_launches_per_forward(const premvos_propnet_t* net);
 /* Test hook: intermediates of the LAST forward as fp32 (CP8 activations are returned NCHW; index tensors are
  * converted to fp32).  Names: "conv0", "pool0", "block<i>", "featuremap", "rpn_hidden", "rpn_out" ([fh,fw,80]:

@@ -63,6 +63,12 @@ SECOND_NUM_CLASS = 81    # --second_head
 # ---------------------------------------------------------------------------------------------
 # parameters (tensorpack variable names)
 # ---------------------------------------------------------------------------------------------
+def maskrcnn_param_shapes(num_class=NUM_CLASS):
+    """model.py:495-509 (tensorpack Deconv2D 'deconv': W [kh, kw, out, in]; Conv2D 'conv': W HWIO)."""
+    return OrderedDict([("maskrcnn/deconv/W", (2, 2, 256, 2048)), ("maskrcnn/deconv/b", (256,)),
+                        ("maskrcnn/conv/W", (1, 1, 256, num_class - 1)), ("maskrcnn/conv/b", (num_class - 1,))])
+
+
 def propnet_param_shapes(num_blocks=RESNET_NUM_BLOCK, num_class=NUM_CLASS, second_num_class=SECOND_NUM_CLASS):
     t = OrderedDict()
 
@@ -133,16 +139,16 @@ SecondDetectionResult = namedtuple(
 
 
 def detect_one_image(img, model_func, size=SHORT_EDGE_SIZE, max_size=MAX_SIZE):
-    """eval.py:61-110 with USE_SECOND_HEAD, no masks, no feature extraction."""
+    """eval.py:61-110 with USE_SECOND_HEAD, no feature extraction; masks (a seventh model output) are pasted by fill_full_mask."""
     import cv2
     orig_shape = img.shape[:2]
     newh, neww = custom_resize_shape(orig_shape[0], orig_shape[1], size, max_size)
     resized_img = cv2.resize(img, (neww, newh), interpolation=cv2.INTER_LINEAR)
     scale = (resized_img.shape[0] * 1.0 / img.shape[0] + resized_img.shape[1] * 1.0 / img.shape[1]) / 2
-    boxes, probs, labels, posteriors, second_labels, second_posteriors = model_func(resized_img)
+    boxes, probs, labels, posteriors, second_labels, second_posteriors, *masks = model_func(resized_img)
     boxes = boxes / scale
     boxes = clip_boxes_np(boxes, orig_shape)
-    masks = [None] * len(boxes)
+    masks = [fill_full_mask(b, m, orig_shape) for b, m in zip(boxes, masks[0])] if masks else [None] * len(boxes)
     features = [None for _ in range(labels.size)]
     return [SecondDetectionResult(*args) for args in
             zip(boxes, probs, labels, posteriors, masks, second_labels, second_posteriors, features)]
@@ -491,6 +497,52 @@ def propnet_forward(P, img_hwc, num_blocks=RESNET_NUM_BLOCK, return_intermediate
     out = (final_boxes.astype(np.float32), final_probs, final_labels, final_posterior.astype(np.float32),
            second_final_labels, second_final_posterior.astype(np.float32))
     inter["pred_indices"] = pred
+    if "maskrcnn/deconv/W" in P:      # config.MODE_MASK: `final_masks` is the seventh output (train.py:52-62, 297-309)
+        out = out + (final_masks(P, fm, out[0], final_labels, num_blocks),)
     if return_intermediates:
         return out, inter
     return out
+
+
+# ---- Mask R-CNN mask head (MODE_MASK, inactive under simple_run.sh's --forward) --------------------------
+def maskrcnn_head(P, feature):
+    """model.py:495-509: Deconv2D(256, 2, stride 2) + ReLU, Conv2D(num_class - 1, 1).  feature [N,2048,7,7] -> [N,#cat,14,14].
+    tf conv2d_transpose: out[2y+dy, 2x+dx, co] += in[y, x, ci] * W[dy, dx, co, ci]  (== torch conv_transpose2d, weight [ci,co,dy,dx])."""
+    wt = torch.as_tensor(P["maskrcnn/deconv/W"]).permute(3, 2, 0, 1).contiguous()
+    l = F.relu(F.conv_transpose2d(feature, wt, torch.as_tensor(P["maskrcnn/deconv/b"]), stride=2))
+    w2 = torch.as_tensor(P["maskrcnn/conv/W"]).permute(3, 2, 0, 1).contiguous()
+    return F.conv2d(l, w2, torch.as_tensor(P["maskrcnn/conv/b"]))
+
+
+def final_masks(P, featuremap, final_boxes, final_labels, num_blocks=RESNET_NUM_BLOCK):
+    """train.py:297-309: RoIAlign on the FINAL boxes, conv5 again, mask head, logits of each box's own category, sigmoid.
+    -> float32 [n, 14, 14]."""
+    n = len(final_boxes)
+    if n == 0:
+        return np.zeros((0, 14, 14), np.float32)
+    roi = roi_align(featuremap, torch.as_tensor(np.asarray(final_boxes, np.float32)) * np.float32(1.0 / ANCHOR_STRIDE), 14)
+    logits = maskrcnn_head(P, resnet_conv5(P, roi, num_blocks[-1]))
+    idx = torch.as_tensor(np.asarray(final_labels, np.int64) - 1)
+    return torch.sigmoid(logits[torch.arange(n), idx]).numpy().astype(np.float32)
+
+
+def fill_full_mask(box, mask, shape):
+    """eval.py:35-58: paste the MxM mask into its box on a zero canvas of `shape` = (h, w); cv2.resize (float32 INTER_LINEAR;
+    INTER_AREA for an exact 2x down-scale, as OpenCV substitutes) restated by oracle/cv_resize_oracle.py, threshold 0.5."""
+    from oracle import cv_resize_oracle as RZ
+    box = np.asarray(box, np.float32)
+    x0, y0 = (int(v) for v in box[:2] + np.float32(0.5))
+    x1, y1 = (int(v) for v in box[2:] - np.float32(0.5))
+    x1, y1 = max(x0, x1), max(y0, y1)
+    w, h = x1 + 1 - x0, y1 + 1 - y0
+    m = np.asarray(mask, np.float32)
+    M = m.shape[0]
+    if (w, h) == (M, M):
+        r = m
+    elif M == 2 * w and M == 2 * h:
+        r = ((m[0::2, 0::2] + m[0::2, 1::2] + m[1::2, 0::2] + m[1::2, 1::2]) * np.float32(0.25)).astype(np.float32)
+    else:
+        r = RZ.resize_linear_f32(m, h, w)
+    ret = np.zeros(shape, np.uint8)
+    ret[y0:y1 + 1, x0:x1 + 1] = (r > 0.5).astype(np.uint8)
+    return ret

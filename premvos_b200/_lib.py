@@ -19,7 +19,7 @@ EXPORTS = [
     "premvos_pwc_get_tensor", "premvos_pwc_destroy", "premvos_pwc_tensor_core_layers",
     "premvos_propnet_create", "premvos_propnet_set_option", "premvos_propnet_set_param", "premvos_propnet_finalize",
     "premvos_propnet_forward", "premvos_propnet_forward_u8", "premvos_propnet_read_results", "premvos_propnet_read_results_image", "premvos_propnet_copy_results", "premvos_propnet_forward_host",
-    "premvos_propnet_launches_per_forward", "premvos_propnet_get_tensor", "premvos_propnet_destroy",
+    "premvos_propnet_read_masks", "premvos_fill_full_masks_host", "premvos_propnet_launches_per_forward", "premvos_propnet_get_tensor", "premvos_propnet_destroy",
     "premvos_topk_host", "premvos_nms_host",
     "premvos_refnet_create", "premvos_refnet_set_param", "premvos_refnet_finalize", "premvos_refnet_forward",
     "premvos_refnet_forward_host",
@@ -91,6 +91,8 @@ def lib() -> ctypes.CDLL:
     L.premvos_propnet_read_results_image.argtypes = [c_void_p, c_void_p, c_int, P(c_int)] + [c_void_p] * 6
     L.premvos_propnet_copy_results.argtypes = [c_void_p] * 6
     L.premvos_propnet_forward_host.argtypes = [c_void_p, c_void_p, P(c_int)] + [c_void_p] * 6
+    L.premvos_propnet_read_masks.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int]
+    L.premvos_fill_full_masks_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.premvos_propnet_launches_per_forward.argtypes = [c_void_p]
     L.premvos_propnet_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
     L.premvos_propnet_destroy.argtypes = [c_void_p]

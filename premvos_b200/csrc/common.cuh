@@ -251,6 +251,10 @@ int det_gather_proposals(const float* boxes, const float* scores, const int* kee
                          float* out_boxes, float* out_scores, cudaStream_t st);
 int det_roi_align(const CView& fm, const float* rois, float spatial_scale, int out_size, const CView& out, cudaStream_t st);
 int det_gap_fc(const CView& feat, const float* Wt, const float* bias, int nout, float* pooled_out, float* out, cudaStream_t st);
+// mask head tail: d = ReLU(deconv 2x2 s2) as CP8 [N, 4*256, 7, 7] (phase-major channels) -> sigmoid(1x1 conv) fp32 [N,14,14]
+int det_mask_head(const CView& d, const float* w /*[256]*/, const float* b /*[1]*/, float* masks, cudaStream_t st);   // model.py:495-509
+// eval.py:35-58 for n boxes: masks fp32 [n,M,M], boxes fp32 [n,4] x1y1x2y2 (clipped to the image) -> uint8 [n,H,W]
+int det_fill_full_masks(const float* masks, const float* boxes, int n, int M, int H, int W, unsigned char* out, cudaStream_t st);
 struct DetTailArgs {
   const float* logits; int nfc, nsecond;
   const float* prop_boxes; const int* prop_count;

@@ -337,6 +337,80 @@ __global__ void __launch_bounds__(128) gather_proposals_kernel(const float* __re
   out_scores[t] = s;
 }
 
+// ---- Mask R-CNN mask head tail (model.py:495-509, train.py:297-309) ------------------------------------------------------
+// d = ReLU(Deconv2D 2x2 stride 2) kept in its GEMM form: CP8 [N, 4*256, 7, 7] with channel (dy*2+dx)*256 + co (a 2x2 stride-2
+// transposed convolution has no overlap: out[2y+dy, 2x+dx, co] = in[y, x, :] . W[dy, dx, co, :]).  The 1x1 convolution to the
+// single class-agnostic category acts per output pixel, so it is applied per phase here, followed by the sigmoid:
+// masks[n, 2y+dy, 2x+dx] = sigmoid(b + sum_co d[n, (dy*2+dx)*256 + co, y, x] * w[co]).  One warp per output pixel.
+__global__ void __launch_bounds__(256) mask_head_kernel(CV d, const float* __restrict__ w /*[256]*/, const float* __restrict__ b,
+                                                        float* __restrict__ masks /*[N][2H][2W]*/) {
+  const int lane = threadIdx.x & 31;
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int OH = 2 * d.H, OW = 2 * d.W;
+  const long total = (long)d.N * OH * OW;
+  if (wid >= total) return;
+  const int ox = (int)(wid % OW), oy = (int)((wid / OW) % OH), n = (int)(wid / ((long)OW * OH));
+  const int phase = (oy & 1) * 2 + (ox & 1);
+  const F8 v = ld_chunk(d.hi, d.lo, cv_elem(d, n, phase * 32 + lane, oy >> 1, ox >> 1));   // 32 chunks = 256 channels per phase
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc = fmaf(v.v[j], __ldg(w + lane * 8 + j), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) masks[wid] = 1.f / (1.f + expf(-(acc + __ldg(b))));
+}
+
+// ---- fill_full_mask (eval.py:35-58) for all boxes of an image ---------------------------------------------------------------
+// canvas[n, y, x] = (cv2.resize(mask[n] (MxM float32), (w, h)) > 0.5) inside the box's integer rectangle, 0 outside.
+// OpenCV's float32 INTER_LINEAR arithmetic (coordinates (float)((d + 0.5) * scale - 0.5) with a double scale, x clamps the
+// fraction, y clips the row indices; products and sums rounded one by one), INTER_AREA's 2x2 mean for an exact 2x down-scale,
+// a plain copy for w = h = M.  One thread per canvas pixel: warp-level bilinear taps of a 784-byte mask that stays in L1.
+__device__ __forceinline__ void cv_axis(int d, int dst_n, int src_n, bool clamp_fraction, int* s0, int* s1, float* f) {
+  const double scale = 1.0 / ((double)dst_n / (double)src_n);
+  float fx = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);   // no FMA contraction: the host rounds the product first
+  int s = (int)floorf(fx);
+  fx -= (float)s;
+  if (clamp_fraction) {
+    if (s < 0) { s = 0; fx = 0.f; }
+    if (s >= src_n - 1) { s = src_n - 1; fx = 0.f; }
+    *s0 = s; *s1 = min(s + 1, src_n - 1);
+  } else {
+    *s0 = max(0, min(src_n - 1, s)); *s1 = max(0, min(src_n - 1, s + 1));
+  }
+  *f = fx;
+}
+
+__global__ void __launch_bounds__(256) fill_full_mask_kernel(const float* __restrict__ masks, const float* __restrict__ boxes, int M, int H, int W,
+                                                             unsigned char* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= W) return;
+  const float4 b = reinterpret_cast<const float4*>(boxes)[n];
+  const int x0 = (int)__fadd_rn(b.x, 0.5f), y0 = (int)__fadd_rn(b.y, 0.5f);      // int() truncates
+  const int x1 = max(x0, (int)__fsub_rn(b.z, 0.5f)), y1 = max(y0, (int)__fsub_rn(b.w, 0.5f));
+  unsigned char v = 0;
+  if (x >= x0 && x <= x1 && y >= y0 && y <= y1) {
+    const int w = x1 + 1 - x0, h = y1 + 1 - y0, dx = x - x0, dy = y - y0;
+    const float* m = masks + (long)n * M * M;
+    float r;
+    if (w == M && h == M) {
+      r = __ldg(m + dy * M + dx);
+    } else if (M == 2 * w && M == 2 * h) {
+      const float* p = m + (2 * dy) * M + 2 * dx;
+      r = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__ldg(p), __ldg(p + 1)), __ldg(p + M)), __ldg(p + M + 1)), 0.25f);
+    } else {
+      int sx0, sx1, sy0, sy1; float fx, fy;
+      cv_axis(dx, w, M, true, &sx0, &sx1, &fx);
+      cv_axis(dy, h, M, false, &sy0, &sy1, &fy);
+      const float a0 = __fsub_rn(1.f, fx), b0 = __fsub_rn(1.f, fy);
+      const float r0 = __fadd_rn(__fmul_rn(__ldg(m + sy0 * M + sx0), a0), __fmul_rn(__ldg(m + sy0 * M + sx1), fx));
+      const float r1 = __fadd_rn(__fmul_rn(__ldg(m + sy1 * M + sx0), a0), __fmul_rn(__ldg(m + sy1 * M + sx1), fx));
+      r = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, fy));
+    }
+    v = r > 0.5f ? 1 : 0;
+  }
+  out[((long)n * H + y) * W + x] = v;
+}
+
 // ---- RoIAlign (model.py:301-374) ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) roi_align_kernel(CV fm, const float* __restrict__ rois /*[N][4] x1y1x2y2 image coords*/,
                                                         float spatial_scale, int out_size, CV out) {
@@ -606,6 +680,21 @@ int det_gap_fc(const CView& feat, const float* Wt, const float* bias, int nout, 
   prof_before(st);
   gap_fc_kernel<<<feat.N, 256, round_up(feat.C, 8) * sizeof(float), st>>>(dev(feat), Wt, bias, nout, pooled_out, out);
   return after_launch("gap_fc_kernel", st, 2.0 * feat.N * feat.C * nout, 4.0 * ((double)feat.pixels() * feat.C + (double)feat.C * nout));
+}
+
+int det_mask_head(const CView& d, const float* w, const float* b, float* masks, cudaStream_t st) {
+  PV_CHECK(d.C == 1024, PREMVOS_ERR_INVALID_ARG, "det_mask_head: expected the 4 x 256 phase channels of the 2x2 deconvolution");
+  const long total = (long)d.N * 4 * d.H * d.W;
+  prof_before(st);
+  mask_head_kernel<<<blocks_for(total * 32), 256, 0, st>>>(dev(d), w, b, masks);
+  return after_launch("mask_head_kernel", st, 2.0 * total * 256, 4.0 * ((double)d.pixels() * d.C + total));
+}
+
+int det_fill_full_masks(const float* masks, const float* boxes, int n, int M, int H, int W, unsigned char* out, cudaStream_t st) {
+  if (n == 0) return 0;
+  prof_before(st);
+  fill_full_mask_kernel<<<dim3((W + 255) / 256, H, n), 256, 0, st>>>(masks, boxes, M, H, W, out);
+  return after_launch("fill_full_mask_kernel", st, 0.0, (double)n * ((double)H * W + 4.0 * M * M));
 }
 
 int det_frcnn_tail(const DetTailArgs& h, cudaStream_t st) {

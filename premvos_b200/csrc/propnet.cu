@@ -49,6 +49,7 @@ struct Bottleneck {
 struct premvos_propnet {
   int H = 0, W = 0, num_class = 2, second_num_class = 81;
   int blocks[4] = {3, 4, 23, 3};
+  int mode_mask = 0;         // option "mode_mask": also run the Mask R-CNN mask head on the final boxes (config.MODE_MASK)
   int batch = 1;             // frames per forward (option "batch"): one launch group for all of them
   bool finalized = false;
   std::map<std::string, std::vector<float>> params;
@@ -80,6 +81,11 @@ struct premvos_propnet {
   float *final_boxes = nullptr, *final_probs = nullptr, *final_posterior = nullptr, *second_final_posterior = nullptr;
   int64_t *final_labels = nullptr, *second_final_labels = nullptr;
   int* final_box_index = nullptr;
+  // mask head (mode_mask): RoIAlign on the final boxes -> conv5 again -> deconv (as a 1x1 GEMM to 4 x 256 phases) -> 1x1 + sigmoid
+  CView roi_m, deconv_out;
+  std::vector<std::unique_ptr<Bottleneck>> head_m;
+  ConvLayer deconv;
+  float *mask_w = nullptr, *mask_b = nullptr, *final_masks = nullptr;   // final_masks [batch][RESULTS_PER_IM][14][14]
   int launches_per_forward = 0;
   cudaGraph_t graph = nullptr;       // the whole forward (fixed shapes per handle, device-side counts)
   cudaGraphExec_t exec = nullptr;
@@ -124,6 +130,12 @@ void build_shape_table(premvos_propnet* n) {
   if (n->second_num_class > 0) {
     n->shapes["secondclassification/class/W"] = {2048, n->second_num_class};
     n->shapes["secondclassification/class/b"] = {n->second_num_class};
+  }
+  if (n->mode_mask) {   // model.py:495-509: tensorpack Deconv2D W [kh, kw, out, in], Conv2D W HWIO
+    n->shapes["maskrcnn/deconv/W"] = {2, 2, 256, 2048};
+    n->shapes["maskrcnn/deconv/b"] = {256};
+    n->shapes["maskrcnn/conv/W"] = {1, 1, 256, n->num_class - 1};
+    n->shapes["maskrcnn/conv/b"] = {n->num_class - 1};
   }
 }
 
@@ -337,6 +349,36 @@ int build_network(premvos_propnet* n) {
   PV_TRY(dev_alloc(n, &n->second_final_labels, nb * RESULTS_PER_IM));
   PV_TRY(dev_alloc(n, &n->second_final_posterior, nb * RESULTS_PER_IM * (nsec > 0 ? nsec : 1)));
   PV_TRY(dev_alloc(n, &n->final_box_index, nb * RESULTS_PER_IM));
+  if (n->mode_mask) {
+    // train.py:297-309: a second RoIAlign on the (<= 20) final boxes of every image and the conv5 group again (same weights)
+    PV_TRY(alloc_cview(n, &n->roi_m, NB * RESULTS_PER_IM, 1024, 14, 14));
+    cur = n->roi_m;
+    for (int b = 0; b < n->blocks[3]; b++) {
+      n->head_m.emplace_back(new Bottleneck());
+      PV_TRY(make_bottleneck(n, n->head_m.back().get(), "group3/block" + std::to_string(b), cur, 512, b == 0 ? 2 : 1));
+      cur = n->head_m.back()->out;
+    }
+    // Deconv2D(256, 2, stride 2) + ReLU as ONE 1x1 GEMM with 4 x 256 outputs: channel (dy*2+dx)*256 + co
+    const std::vector<float>&dw = n->params["maskrcnn/deconv/W"], &db = n->params["maskrcnn/deconv/b"];
+    std::vector<float> w((size_t)1024 * 2048), b(1024);
+    for (int ph = 0; ph < 4; ph++)
+      for (int co = 0; co < 256; co++) {
+        b[ph * 256 + co] = db[co];
+        for (int ci = 0; ci < 2048; ci++) w[(size_t)(ph * 256 + co) * 2048 + ci] = dw[((size_t)ph * 256 + co) * 2048 + ci];
+      }
+    PV_TRY(alloc_cview(n, &n->deconv_out, NB * RESULTS_PER_IM, 1024, cur.H, cur.W));
+    PV_TRY(pack_conv_weights_umma(&n->deconv.w, w.data(), b.data(), 1024, 2048, 1, 1, nullptr, 0, 0,
+                                  (long)n->deconv_out.N * cur.H * cur.W));
+    ConvGeom g; g.slope = 0.f;
+    ConvOut o; o.cp = n->deconv_out;
+    PV_TRY(plan_conv_umma(&n->deconv.plan, cur, o, n->deconv.w, g));
+    n->deconv.used = true;
+    PV_CHECK(n->num_class == 2, PREMVOS_ERR_UNSUPPORTED, "mask head: class-agnostic only");
+    PV_TRY(dev_alloc(n, &n->mask_w, 256)); PV_TRY(dev_alloc(n, &n->mask_b, 1));
+    PV_CUDA(cudaMemcpy(n->mask_w, n->params["maskrcnn/conv/W"].data(), 256 * 4, cudaMemcpyHostToDevice));
+    PV_CUDA(cudaMemcpy(n->mask_b, n->params["maskrcnn/conv/b"].data(), 4, cudaMemcpyHostToDevice));
+    PV_TRY(dev_alloc(n, &n->final_masks, nb * RESULTS_PER_IM * 4 * cur.H * cur.W));
+  }
   return 0;
 }
 
@@ -381,6 +423,15 @@ int run_network(premvos_propnet* n, cudaStream_t st) {
     t.second_final_labels = n->second_final_labels + b * RESULTS_PER_IM;
     t.second_final_posterior = n->second_final_posterior + (size_t)b * RESULTS_PER_IM * nsec; t.final_box_index = n->final_box_index + b * RESULTS_PER_IM;
     PV_TRY(det_frcnn_tail(t, st));
+  }
+  if (n->mode_mask) {
+    // rows >= n_out of final_boxes hold older / zero boxes: their masks are computed and never read
+    for (int b = 0; b < NB; b++)
+      PV_TRY(det_roi_align(n->featuremap.batch_range(b, 1), n->final_boxes + b * RESULTS_PER_IM * 4, 1.0f / ANCHOR_STRIDE, 14,
+                           n->roi_m.batch_range(b * RESULTS_PER_IM, RESULTS_PER_IM), st));
+    for (auto& b : n->head_m) PV_TRY(run_bottleneck(b.get(), st));
+    PV_TRY(launch_conv_umma(n->deconv.plan, st));
+    PV_TRY(det_mask_head(n->deconv_out, n->mask_w, n->mask_b, n->final_masks, st));
   }
   return 0;
 }
@@ -432,6 +483,13 @@ extern "C" int premvos_propnet_set_option(premvos_propnet_t* n, const char* key,
     return 0;
   }
   if (k == "cuda_graph") { n->opt_cuda_graph = value; return 0; }
+  if (k == "mode_mask") {
+    PV_CHECK(n->params.empty(), PREMVOS_ERR_NOT_READY, "premvos_propnet_set_option: set mode_mask before loading parameters");
+    n->mode_mask = value ? 1 : 0;
+    n->shapes.clear();
+    build_shape_table(n);
+    return 0;
+  }
   if (k == "batch") {
     PV_CHECK(value >= 1 && value <= 16, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_set_option: batch in [1,16]");
     n->batch = value;
@@ -563,6 +621,40 @@ extern "C" int premvos_propnet_forward_host(premvos_propnet_t* n, const float* i
                                       second_final_posterior);
 }
 
+extern "C" int premvos_propnet_read_masks(premvos_propnet_t* n, void* stream, int image, float* final_masks, int max_rows) {
+  PV_CHECK(n && final_masks, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_masks: null argument");
+  PV_CHECK(n->finalized && n->mode_mask, PREMVOS_ERR_NOT_READY, "premvos_propnet_read_masks: the handle was not built with option mode_mask");
+  PV_CHECK(image >= 0 && image < n->batch && max_rows >= 0, PREMVOS_ERR_INVALID_ARG, "premvos_propnet_read_masks: image %d / rows %d", image, max_rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = max_rows < RESULTS_PER_IM ? max_rows : RESULTS_PER_IM;
+  if (rows)
+    PV_CUDA(cudaMemcpyAsync(final_masks, n->final_masks + (size_t)image * RESULTS_PER_IM * 196, (size_t)rows * 196 * sizeof(float),
+                            cudaMemcpyDeviceToHost, st));
+  PV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// eval.py:35-58 for the n boxes of an image (single-op entry point; host pointers, synchronous)
+extern "C" int premvos_fill_full_masks_host(const float* masks_host, const float* boxes_host, int n, int mask_size, int height, int width,
+                                            unsigned char* out_host) {
+  PV_CHECK(n >= 0 && mask_size >= 2 && mask_size % 2 == 0 && height > 0 && width > 0 && height <= 65535 && n <= 65535, PREMVOS_ERR_INVALID_ARG,
+           "premvos_fill_full_masks_host: bad sizes");
+  if (n == 0) return 0;
+  PV_CHECK(masks_host && boxes_host && out_host, PREMVOS_ERR_INVALID_ARG, "premvos_fill_full_masks_host: null argument");
+  float *d_m = nullptr, *d_b = nullptr; unsigned char* d_o = nullptr;
+  const size_t mb = (size_t)n * mask_size * mask_size * 4, ob = (size_t)n * height * width;
+  PV_CUDA(cudaMalloc((void**)&d_m, mb)); PV_CUDA(cudaMalloc((void**)&d_b, (size_t)n * 16)); PV_CUDA(cudaMalloc((void**)&d_o, ob));
+  PV_CUDA(cudaMemcpy(d_m, masks_host, mb, cudaMemcpyHostToDevice));
+  PV_CUDA(cudaMemcpy(d_b, boxes_host, (size_t)n * 16, cudaMemcpyHostToDevice));
+  int r = det_fill_full_masks(d_m, d_b, n, mask_size, height, width, d_o, nullptr);
+  if (r == 0) {
+    cudaError_t e = cudaMemcpy(out_host, d_o, ob, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) r = fail((int)e, "premvos_fill_full_masks_host: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_m); cudaFree(d_b); cudaFree(d_o);
+  return r;
+}
+
 extern "C" int premvos_propnet_launches_per_forward(const premvos_propnet_t* n) { return n ? n->launches_per_forward : 0; }
 
 // Test hook: intermediates of the LAST forward as fp32 (integer tensors converted), see include/premvos_b200.h.
@@ -593,6 +685,10 @@ extern "C" int premvos_propnet_get_tensor(premvos_propnet_t* n, const char* name
   else if (k == "roi_resized") { cv = n->roi; is_cv = true; }
   else if (k == "feature_fastrcnn") { cv = n->head.back()->out; is_cv = true; }
   else if (k == "cell_anchors") { fptr = n->cell_anchors; cnt = 60; }
+  else if (k == "final_masks" && n->mode_mask) {
+    int m = 0; PV_CUDA(cudaMemcpy(&m, n->n_out + img, 4, cudaMemcpyDeviceToHost));
+    fptr = n->final_masks + (size_t)img * RESULTS_PER_IM * 196; cnt = (int64_t)m * 196;
+  }
   else if (k == "rpn_out") { fptr = n->rpn_out.p + (size_t)img * n->fh * n->fw * 80; cnt = (int64_t)n->fh * n->fw * 80; }
   else if (k == "rpn_scores") { fptr = n->d_scores + (size_t)img * n->n_anchor_total; cnt = n->n_anchor_total; }
   else if (k == "rpn_decoded_boxes") { fptr = n->d_boxes + (size_t)img * n->n_anchor_total * 4; cnt = (int64_t)n->n_anchor_total * 4; }
@@ -636,8 +732,8 @@ extern "C" void premvos_propnet_destroy(premvos_propnet_t* n) {
   if (!n) return;
   cudaDeviceSynchronize();
   for (void* p : n->allocs) cudaFree(p);
-  free_layer(&n->conv0); free_layer(&n->rpn0); free_layer(&n->rpn_heads);
-  for (auto* vec : {&n->backbone, &n->head})
+  free_layer(&n->conv0); free_layer(&n->rpn0); free_layer(&n->rpn_heads); free_layer(&n->deconv);
+  for (auto* vec : {&n->backbone, &n->head, &n->head_m})
     for (auto& b : *vec) { free_layer(&b->c1); free_layer(&b->c2); free_layer(&b->c3); free_layer(&b->sc); }
   if (n->exec) cudaGraphExecDestroy(n->exec);
   if (n->graph) cudaGraphDestroy(n->graph);

@@ -30,11 +30,14 @@ class ProposalNet:
     """The `--forward --agnostic --second_head` graph.  `load_params(dict)` takes tensorpack variable names
     (as `get_model_loader(path)` would restore them); device handles are created per resized-image shape."""
 
-    def __init__(self, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81):
+    def __init__(self, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81, mode_mask=False):
+        """mode_mask=True (config.MODE_MASK): the graph also has the Mask R-CNN mask head (model.py:495-509) and pred_func
+        returns `final_masks` [n,14,14] as a seventh output (train.py:52-62)."""
         self.num_blocks = tuple(num_blocks)
         self.num_class = num_class
         self.second_num_class = second_num_class
-        self._shapes = propnet_param_shapes(self.num_blocks, num_class, second_num_class)
+        self.mode_mask = bool(mode_mask)
+        self._shapes = propnet_param_shapes(self.num_blocks, num_class, second_num_class, self.mode_mask)
         self._params = OrderedDict()
         self._handles = {}
 
@@ -75,6 +78,8 @@ class ProposalNet:
         try:
             for g, nb in enumerate(self.num_blocks):
                 _lib.check(L.premvos_propnet_set_option(h, b"num_blocks%d" % g, int(nb)))
+            if self.mode_mask:
+                _lib.check(L.premvos_propnet_set_option(h, b"mode_mask", 1))
             if batch != 1:
                 _lib.check(L.premvos_propnet_set_option(h, b"batch", int(batch)))
             for k, v in self._params.items():
@@ -108,8 +113,18 @@ class ProposalNet:
         _lib.check(_lib.lib().premvos_propnet_forward_host(h, vp(img), ctypes.byref(n), vp(boxes), vp(probs), vp(labels),
                                                            vp(post), vp(slabels), vp(spost)))
         m = n.value
-        return (boxes[:m].copy(), probs[:m].copy(), labels[:m].copy(), post[:m].copy(), slabels[:m].copy(),
-                spost[:m, :self.second_num_class].copy())
+        out = (boxes[:m].copy(), probs[:m].copy(), labels[:m].copy(), post[:m].copy(), slabels[:m].copy(),
+               spost[:m, :self.second_num_class].copy())
+        return out + (self.read_masks(H, W, m),) if self.mode_mask else out
+
+    def read_masks(self, H, W, rows, batch=1, image=0):
+        """`final_masks` of the last forward: float32 [rows,14,14] (sigmoid outputs, row i belongs to final_boxes[i])."""
+        import torch
+        masks = np.zeros((int(rows), 14, 14), np.float32)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_propnet_read_masks(self._handle(H, W, batch), st, int(image),
+                                                         masks.ctypes.data_as(ctypes.c_void_p), int(rows)))
+        return masks
 
     # -- resident-pipeline entry points (device tensors, no synchronisation until read_results) -----------
     def forward_device(self, img):
@@ -197,17 +212,40 @@ def clip_boxes(boxes, shape):
     return boxes.reshape(orig_shape)
 
 
+def fill_full_masks(boxes, masks, shape):
+    """eval.py:35-58 for all boxes of an image, on the device: boxes [n,4] x1y1x2y2 (original-image coordinates, clipped),
+    masks float32 [n,M,M] -> uint8 [n,h,w] (premvos_fill_full_masks_host)."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+    masks = np.ascontiguousarray(masks, dtype=np.float32)
+    n = boxes.shape[0]
+    if masks.ndim != 3 or masks.shape[0] != n or masks.shape[1] != masks.shape[2]:
+        raise ValueError("masks must be [n,M,M] with n = len(boxes), got %s" % (masks.shape,))
+    out = np.zeros((n, int(shape[0]), int(shape[1])), np.uint8)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.lib().premvos_fill_full_masks_host(vp(masks), vp(boxes), n, int(masks.shape[1]), int(shape[0]), int(shape[1]), vp(out)))
+    return out
+
+
+def fill_full_mask(box, mask, shape):
+    """eval.py:35-58 (one box)."""
+    return fill_full_masks(np.asarray(box)[None], np.asarray(mask)[None], shape)[0]
+
+
 def detect_one_image(img, model_func, size=SHORT_EDGE_SIZE, max_size=MAX_SIZE):
-    """eval.py:61-110 for USE_SECOND_HEAD without masks / feature extraction."""
+    """eval.py:61-110 for USE_SECOND_HEAD without feature extraction; with a seventh `final_masks` output (MODE_MASK) every
+    result carries its full-image binary mask (fill_full_mask)."""
     import cv2
     orig_shape = img.shape[:2]
     newh, neww = custom_resize_shape(orig_shape[0], orig_shape[1], size, max_size)
     resized_img = cv2.resize(img, (neww, newh), interpolation=cv2.INTER_LINEAR)
     scale = (resized_img.shape[0] * 1.0 / img.shape[0] + resized_img.shape[1] * 1.0 / img.shape[1]) / 2
-    boxes, probs, labels, posteriors, second_labels, second_posteriors = model_func(resized_img)
+    boxes, probs, labels, posteriors, second_labels, second_posteriors, *masks = model_func(resized_img)
     boxes = boxes / scale
     boxes = clip_boxes(boxes, orig_shape)
-    masks = [None] * len(boxes)
+    if masks:
+        masks = list(fill_full_masks(boxes, masks[0], orig_shape)) if len(boxes) else []
+    else:
+        masks = [None] * len(boxes)
     features = [None for _ in range(labels.size)]
     return [SecondDetectionResult(*args) for args in
             zip(boxes, probs, labels, posteriors, masks, second_labels, second_posteriors, features)]

@@ -124,7 +124,7 @@ def synthetic_pwc_input(batch: int, h_: int, w_: int, seed: int = 1) -> np.ndarr
 
 
 # ---- proposal network (tensorpack variable names, proposal_net/basemodel.py + model.py) -----------------
-def propnet_param_shapes(num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81):
+def propnet_param_shapes(num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81, mode_mask=False):
     t = OrderedDict()
 
     def conv_bn(scope, k, cin, cout):
@@ -156,7 +156,24 @@ def propnet_param_shapes(num_blocks=(3, 4, 23, 3), num_class=2, second_num_class
     if second_num_class:
         t["secondclassification/class/W"] = (2048, second_num_class)
         t["secondclassification/class/b"] = (second_num_class,)
+    if mode_mask:   # model.py:495-509
+        t["maskrcnn/deconv/W"] = (2, 2, 256, 2048)
+        t["maskrcnn/deconv/b"] = (256,)
+        t["maskrcnn/conv/W"] = (1, 1, 256, num_class - 1)
+        t["maskrcnn/conv/b"] = (num_class - 1,)
     return t
+
+
+def maskrcnn_synthetic_params(seed=0, num_class=2):
+    """Seeded weights of the Mask R-CNN mask head (proposal_net/model.py:495-509): 'maskrcnn/deconv/{W [2,2,256,2048], b}',
+    'maskrcnn/conv/{W [1,1,256,num_class-1], b}'; the 1x1 layer is wide enough that sigmoid outputs spread over (0,1)."""
+    rng = np.random.default_rng(seed + 7777)
+    P = OrderedDict()
+    P["maskrcnn/deconv/W"] = (rng.standard_normal((2, 2, 256, 2048)) * np.sqrt(2.0 / 2048)).astype(np.float32)
+    P["maskrcnn/deconv/b"] = (rng.standard_normal((256,)) * 0.05).astype(np.float32)
+    P["maskrcnn/conv/W"] = (rng.standard_normal((1, 1, 256, num_class - 1)) * (4.0 / np.sqrt(256))).astype(np.float32)
+    P["maskrcnn/conv/b"] = (rng.standard_normal((num_class - 1,)) * 0.05).astype(np.float32)
+    return P
 
 
 def propnet_synthetic_params(seed=0, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81):

@@ -1,6 +1,7 @@
 """CPU checks that pin the proposal-network oracle to what the reference itself states, plus hand-derived cases
 for the TensorFlow kernels it restates (the reference ships no golden vectors for this network)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import propnet_oracle as O
@@ -93,3 +94,34 @@ def test_forward_contract_small_net():
                              size=96, max_size=128)
     js = O.convert_results_to_json(res)
     assert all(set(r) == {"bbox", "score"} and len(r["bbox"]) == 4 for r in js)
+
+
+def test_mask_head_oracle_shapes_and_fill_full_mask():
+    # model.py:495-509 / train.py:297-309 / eval.py:35-58 restatements: shapes, the deconvolution's phase structure, the paste
+    import torch
+    from premvos_b200 import synth
+    P = synth.maskrcnn_synthetic_params(0)
+    assert {k: v.shape for k, v in P.items()} == dict(O.maskrcnn_param_shapes())
+    feat = torch.randn(3, 2048, 7, 7, generator=torch.Generator().manual_seed(0))
+    logits = O.maskrcnn_head(P, feat)
+    assert tuple(logits.shape) == (3, 1, 14, 14)
+    # out[2y+dy, 2x+dx] depends only on in[y, x] and W[dy, dx]
+    d = torch.relu(torch.einsum("nchw,oc->nohw", feat, torch.as_tensor(P["maskrcnn/deconv/W"][1, 0])) +
+                   torch.as_tensor(P["maskrcnn/deconv/b"])[None, :, None, None])
+    want = torch.einsum("nohw,o->nhw", d, torch.as_tensor(P["maskrcnn/conv/W"][0, 0, :, 0])) + float(P["maskrcnn/conv/b"][0])
+    assert torch.allclose(logits[:, 0, 1::2, 0::2], want, rtol=1e-4, atol=1e-4)
+    # fill_full_mask: integer rectangle int(x0 + .5) .. int(x1 - .5), identity when the box is 14 x 14, 2x2 mean when it is 7 x 7
+    m = np.random.default_rng(1).uniform(0, 1, (14, 14)).astype(np.float32)
+    full = O.fill_full_mask(np.array([3.2, 5.4, 17.4, 19.3], np.float32), m, (30, 40))
+    assert full.shape == (30, 40) and full[:5].sum() == 0 and full[:, :3].sum() == 0
+    np.testing.assert_array_equal(full[5:19, 3:17], (m > 0.5).astype(np.uint8))
+    half = O.fill_full_mask(np.array([0, 0, 7, 7], np.float32), m, (10, 10))
+    np.testing.assert_array_equal(half[:7, :7], (m.reshape(7, 2, 7, 2).mean(axis=(1, 3)) > 0.5).astype(np.uint8))
+    cv2 = pytest.importorskip("cv2")
+    for box in ([1.0, 2.0, 30.7, 22.2], [0.0, 0.0, 3.4, 25.0], [10.2, 10.1, 10.9, 10.4]):
+        b = np.array(box, np.float32)
+        x0, y0 = list(map(int, b[:2] + 0.5)); x1, y1 = list(map(int, b[2:] - 0.5))
+        x1, y1 = max(x0, x1), max(y0, y1)
+        ref = np.zeros((30, 40), np.uint8)
+        ref[y0:y1 + 1, x0:x1 + 1] = (cv2.resize(m, (x1 + 1 - x0, y1 + 1 - y0)) > 0.5).astype(np.uint8)
+        np.testing.assert_array_equal(O.fill_full_mask(b, m, (30, 40)), ref)
