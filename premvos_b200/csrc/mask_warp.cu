@@ -10,8 +10,8 @@
 //                             arithmetic as OpenCV (float coefficient tables built on the host).
 //
 // HBM-bound byte work: the map is computed once per pixel and reused for every mask; each thread owns 4 consecutive pixels
-// (two 16-byte flow loads, one 4-byte store per mask), the per-mask bounding boxes are reduced with redux.sync + one atomic
-// per warp that holds a set pixel.
+// (two 16-byte flow loads, one 4-byte store per mask), the per-mask bounding boxes are reduced with redux.sync + atomics
+// only from warps whose pixels still extend the box (a plain load first: dense masks otherwise serialise on 4 addresses).
 #include <limits.h>
 #include <math.h>
 
@@ -139,10 +139,13 @@ __global__ void __launch_bounds__(256) warp_masks_kernel(const unsigned char* __
         const int wxmin = __reduce_min_sync(0xffffffffu, xmin), wymin = __reduce_min_sync(0xffffffffu, ymin);
         const int wymax = __reduce_max_sync(0xffffffffu, ymax);
         if ((threadIdx.x & 31) == 0) {
-          atomicMin(bbox + 4 * i + 0, wxmin);
-          atomicMin(bbox + 4 * i + 1, wymin);
-          atomicMax(bbox + 4 * i + 2, wxmax);
-          atomicMax(bbox + 4 * i + 3, wymax);
+          // look before the atomic: once a few warps have reported, the box already covers most others (a stale read only
+          // costs a redundant atomic, never a missed one: the values move monotonically)
+          volatile int* bb = bbox + 4 * i;
+          if (wxmin < bb[0]) atomicMin(bbox + 4 * i + 0, wxmin);
+          if (wymin < bb[1]) atomicMin(bbox + 4 * i + 1, wymin);
+          if (wxmax > bb[2]) atomicMax(bbox + 4 * i + 2, wxmax);
+          if (wymax > bb[3]) atomicMax(bbox + 4 * i + 3, wymax);
         }
       }
     }
