@@ -121,7 +121,8 @@ int premvos_resize_linear_u8(const unsigned char* src_dev, int batch, int src_h,
  *   bbox_dev float32 [n, 4] (device, 16-byte aligned, may be NULL): the tight box [x, y, w, h] of every warped mask's
  *   non-zero pixels, zeros for an empty one (pycocotools rleToBbox) -- the `bbox` do_refinement reads
  *   (MergeTrack/refinement_net_functions.py:44), so premvos_refnet_forward can consume it without a host round trip.
- * Enqueues on `stream` (1 launch, 3 with bbox_dev), never synchronises, allocates nothing.  n == 0 is a no-op.
+ * Enqueues on `stream` (1 launch, 3 with bbox_dev), never synchronises, allocates nothing.  n == 0 is a no-op; with bbox_dev
+ * n <= 3072 (the per-CTA boxes live in shared memory).
  *
  * premvos_flow_postprocess replaces optical_flow_net-PWC-Net/script_pwc_multi.py:59-68 for a batch: flow2 float32
  * [batch, 2, net_h/4, net_w/4] (what premvos_pwc_forward writes) -> x20 -> cv2.resize of u and v to (width, height)

@@ -10,8 +10,10 @@
 //                             arithmetic as OpenCV (float coefficient tables built on the host).
 //
 // HBM-bound byte work: the map is computed once per pixel and reused for every mask; each thread owns 4 consecutive pixels
-// (two 16-byte flow loads, one 4-byte store per mask), the per-mask bounding boxes are reduced with redux.sync + atomics
-// only from warps whose pixels still extend the box (a plain load first: dense masks otherwise serialise on 4 addresses).
+// (two 16-byte flow loads, one 4-byte store per mask), the per-mask bounding boxes are reduced with redux.sync per warp,
+// shared-memory atomics per CTA and one set of global atomics per CTA and mask it touches.  Measured (tools/bench_aux.py, 40
+// masks of 1080p, smooth flow): 0.73 TB/s of algorithmic bytes -- the kernel is ISSUE-bound (~88 SASS instructions per pixel
+// and mask: predicated byte gathers with 64-bit address arithmetic); batching the tap loads of 4 masks did not help (0.59).
 #include <limits.h>
 #include <math.h>
 
@@ -82,6 +84,11 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) warp_masks_kernel(const unsigned char* __restrict__ masks, int n, int H, int W,
                                                         const float* __restrict__ flow, unsigned char* __restrict__ out,
                                                         int* __restrict__ bbox, int binarize) {
+  extern __shared__ int cta_box[];   // [n][xmin, ymin, xmax, ymax] of this CTA's pixels (only with bbox)
+  if (bbox) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<int4*>(cta_box)[i] = make_int4(INT_MAX, INT_MAX, -1, -1);
+    __syncthreads();
+  }
   const long HW = (long)H * W;
   const long p0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * PX;
   Tap tap[PX];
@@ -135,18 +142,26 @@ __global__ void __launch_bounds__(256) warp_masks_kernel(const unsigned char* __
     }
     if (bbox) {
       const int wxmax = __reduce_max_sync(0xffffffffu, xmax);
-      if (wxmax >= 0) {   // the warp holds a set pixel of mask i
+      if (wxmax >= 0) {   // the warp holds a set pixel of mask i: fold its extent into the CTA's box (shared-memory atomics)
         const int wxmin = __reduce_min_sync(0xffffffffu, xmin), wymin = __reduce_min_sync(0xffffffffu, ymin);
         const int wymax = __reduce_max_sync(0xffffffffu, ymax);
         if ((threadIdx.x & 31) == 0) {
-          // look before the atomic: once a few warps have reported, the box already covers most others (a stale read only
-          // costs a redundant atomic, never a missed one: the values move monotonically)
-          volatile int* bb = bbox + 4 * i;
-          if (wxmin < bb[0]) atomicMin(bbox + 4 * i + 0, wxmin);
-          if (wymin < bb[1]) atomicMin(bbox + 4 * i + 1, wymin);
-          if (wxmax > bb[2]) atomicMax(bbox + 4 * i + 2, wxmax);
-          if (wymax > bb[3]) atomicMax(bbox + 4 * i + 3, wymax);
+          atomicMin(&cta_box[4 * i + 0], wxmin);
+          atomicMin(&cta_box[4 * i + 1], wymin);
+          atomicMax(&cta_box[4 * i + 2], wxmax);
+          atomicMax(&cta_box[4 * i + 3], wymax);
         }
+      }
+    }
+  }
+  if (bbox) {   // one set of global atomics per CTA and mask it touches (dense masks otherwise serialise on 4 addresses per mask)
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (cta_box[4 * i + 2] >= 0) {
+        atomicMin(bbox + 4 * i + 0, cta_box[4 * i + 0]);
+        atomicMin(bbox + 4 * i + 1, cta_box[4 * i + 1]);
+        atomicMax(bbox + 4 * i + 2, cta_box[4 * i + 2]);
+        atomicMax(bbox + 4 * i + 3, cta_box[4 * i + 3]);
       }
     }
   }
@@ -256,10 +271,12 @@ extern "C" int premvos_warp_masks_u8(const unsigned char* masks_dev, int n, int 
   const unsigned blocks = (unsigned)((HW + 256 * PX - 1) / (256 * PX));
   const bool vec = HW % PX == 0 && (reinterpret_cast<uintptr_t>(out_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(flow_dev) & 15) == 0;
   prof_before(st);
+  const size_t smem = bb ? (size_t)n * 16 : 0;
+  PV_CHECK(smem <= 48 * 1024, PREMVOS_ERR_UNSUPPORTED, "premvos_warp_masks_u8: at most 3072 masks per call with boxes");
   if (vec)
-    warp_masks_kernel<true><<<blocks, 256, 0, st>>>(masks_dev, n, height, width, flow_dev, out_dev, bb, binarize);
+    warp_masks_kernel<true><<<blocks, 256, smem, st>>>(masks_dev, n, height, width, flow_dev, out_dev, bb, binarize);
   else
-    warp_masks_kernel<false><<<blocks, 256, 0, st>>>(masks_dev, n, height, width, flow_dev, out_dev, bb, binarize);
+    warp_masks_kernel<false><<<blocks, 256, smem, st>>>(masks_dev, n, height, width, flow_dev, out_dev, bb, binarize);
   // algorithmic bytes: the flow once, every mask read once and written once
   PV_TRY(after_launch("warp_masks_kernel", st, 0.0, (double)HW * (8.0 + 2.0 * n)));
   if (bb) {
