@@ -12,8 +12,9 @@
 // HBM-bound byte work: the map is computed once per pixel and reused for every mask; each thread owns 4 consecutive pixels
 // (two 16-byte flow loads, one 4-byte store per mask), the per-mask bounding boxes are reduced with redux.sync per warp,
 // shared-memory atomics per CTA and one set of global atomics per CTA and mask it touches.  Measured (tools/bench_aux.py, 40
-// masks of 1080p, smooth flow): 0.73 TB/s of algorithmic bytes -- the kernel is ISSUE-bound (~88 SASS instructions per pixel
-// and mask: predicated byte gathers with 64-bit address arithmetic); batching the tap loads of 4 masks did not help (0.59).
+// masks of 1080p, smooth flow): the kernel is ISSUE-bound, not latency-bound (batching the tap loads of 4 masks did not help) --
+// hence weights and validity are computed once per pixel, and threads whose taps are all inside the image take a branch-free
+// path (4 byte loads, 4 IMADs per pixel and mask).
 #include <limits.h>
 #include <math.h>
 
@@ -27,8 +28,10 @@
 namespace premvos {
 namespace {
 
-struct Tap {   // quantised source position of one destination pixel
-  int ix, iy, ax, ay;
+struct Tap {   // quantised source position and fixed-point weights of one destination pixel, the same for every mask of the frame
+  int off;                  // iy * W + ix: element offset of the top-left tap inside a mask (0 when no tap is inside)
+  int valid;                // bit 0..3: tap (iy,ix), (iy,ix+1), (iy+1,ix), (iy+1,ix+1) lies inside the image
+  int w00, w01, w10, w11;   // 15-bit bilinear weights
 };
 
 __device__ __forceinline__ int cv_round_x32(float coord) {
@@ -38,29 +41,37 @@ __device__ __forceinline__ int cv_round_x32(float coord) {
   return __float2int_rn(p);
 }
 
-__device__ __forceinline__ Tap make_tap(float fx, float fy, int x, int y) {
+__device__ __forceinline__ Tap make_tap(float fx, float fy, int x, int y, int H, int W) {
   const int sx = cv_round_x32(__fadd_rn(-fx, (float)x)), sy = cv_round_x32(__fadd_rn(-fy, (float)y));
+  const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));
+  const int ax = sx & 31, ay = sy & 31;
   Tap t;
-  t.ix = max(-32768, min(32767, sx >> 5));
-  t.iy = max(-32768, min(32767, sy >> 5));
-  t.ax = sx & 31;
-  t.ay = sy & 31;
+  t.w00 = min((32 - ay) * (32 - ax) * 32, 32767);   // saturate_cast<short>(1.0 * 32768)
+  t.w01 = (32 - ay) * ax * 32;
+  t.w10 = ay * (32 - ax) * 32;
+  t.w11 = ay * ax * 32;
+  const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+  const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+  t.valid = (y0 && x0 ? 1 : 0) | (y0 && x1 ? 2 : 0) | (y1 && x0 ? 4 : 0) | (y1 && x1 ? 8 : 0);
+  t.off = t.valid ? iy * W + ix : 0;   // a valid tap means -1 <= iy < H, -1 <= ix < W: fits an int for H, W <= 32767
   return t;
 }
 
-__device__ __forceinline__ int remap_pixel(const unsigned char* __restrict__ m, int H, int W, const Tap& t) {
-  const int w00 = min((32 - t.ay) * (32 - t.ax) * 32, 32767), w01 = (32 - t.ay) * t.ax * 32;
-  const int w10 = t.ay * (32 - t.ax) * 32, w11 = t.ay * t.ax * 32;
-  const bool y0 = (unsigned)t.iy < (unsigned)H, y1 = (unsigned)(t.iy + 1) < (unsigned)H;
-  const bool x0 = (unsigned)t.ix < (unsigned)W, x1 = (unsigned)(t.ix + 1) < (unsigned)W;
-  const unsigned char* r0 = m + (long)t.iy * W + t.ix;
+// one pixel of one mask.  INTERIOR: all four taps are inside the image (the common case, decided once per thread for all masks)
+template <bool INTERIOR>
+__device__ __forceinline__ int remap_pixel(const unsigned char* __restrict__ m, int W, const Tap& t) {
+  const unsigned char* r0 = m + t.off;
   const unsigned char* r1 = r0 + W;
-  int acc = 0;
-  if (y0 && x0) acc += w00 * (int)__ldg(r0);
-  if (y0 && x1) acc += w01 * (int)__ldg(r0 + 1);
-  if (y1 && x0) acc += w10 * (int)__ldg(r1);
-  if (y1 && x1) acc += w11 * (int)__ldg(r1 + 1);
-  return min(255, (acc + 16384) >> 15);
+  int acc = 16384;
+  if (INTERIOR) {
+    acc += t.w00 * (int)__ldg(r0) + t.w01 * (int)__ldg(r0 + 1) + t.w10 * (int)__ldg(r1) + t.w11 * (int)__ldg(r1 + 1);
+  } else {   // taps outside read the constant border 0
+    if (t.valid & 1) acc += t.w00 * (int)__ldg(r0);
+    if (t.valid & 2) acc += t.w01 * (int)__ldg(r0 + 1);
+    if (t.valid & 4) acc += t.w10 * (int)__ldg(r1);
+    if (t.valid & 8) acc += t.w11 * (int)__ldg(r1 + 1);
+  }
+  return min(255, acc >> 15);
 }
 
 __global__ void bbox_init_kernel(int* __restrict__ bbox, int n, int H, int W) {
@@ -116,20 +127,45 @@ __global__ void __launch_bounds__(256) warp_masks_kernel(const unsigned char* __
       if (px[k] == W) { px[k] = 0; py[k]++; }
     }
 #pragma unroll
-    for (int k = 0; k < PX; k++) tap[k] = make_tap(f[2 * k], f[2 * k + 1], px[k], py[k]);
+    for (int k = 0; k < PX; k++) tap[k] = make_tap(f[2 * k], f[2 * k + 1], px[k], py[k], H, W);
   }
+  // interior threads (every tap of every pixel inside the image, all pixels real) take the branch-free path for all masks
+  bool interior = active && (VEC || p0 + PX <= HW);
+#pragma unroll
+  for (int k = 0; k < PX; k++) interior = interior && tap[k].valid == 15;
+  const bool one_row = active && py[0] == py[PX - 1];
   for (int i = 0; i < n; i++) {
     int xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
     if (active) {
       const unsigned char* m = masks + i * HW;
       unsigned char v[PX];
+      unsigned set = 0;
+      if (interior) {
 #pragma unroll
-      for (int k = 0; k < PX; k++) {
-        const int r = remap_pixel(m, H, W, tap[k]);
-        v[k] = (unsigned char)(binarize ? (r == 1) : r);
-        if (v[k] && (VEC || p0 + k < HW)) {
-          xmin = min(xmin, px[k]); xmax = max(xmax, px[k]);
-          ymin = min(ymin, py[k]); ymax = max(ymax, py[k]);
+        for (int k = 0; k < PX; k++) {
+          const int r = remap_pixel<true>(m, W, tap[k]);
+          v[k] = (unsigned char)(binarize ? (r == 1) : r);
+          set |= (v[k] ? 1u : 0u) << k;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PX; k++) {
+          const int r = remap_pixel<false>(m, W, tap[k]);
+          v[k] = (unsigned char)(binarize ? (r == 1) : r);
+          set |= ((v[k] && (VEC || p0 + k < HW)) ? 1u : 0u) << k;
+        }
+      }
+      if (set) {
+        if (one_row) {   // consecutive pixels of one row: the first / last set pixel bound x
+          xmin = px[0] + __ffs(set) - 1; xmax = px[0] + 31 - __clz(set);
+          ymin = ymax = py[0];
+        } else {
+#pragma unroll
+          for (int k = 0; k < PX; k++)
+            if (set >> k & 1u) {
+              xmin = min(xmin, px[k]); xmax = max(xmax, px[k]);
+              ymin = min(ymin, py[k]); ymax = max(ymax, py[k]);
+            }
         }
       }
       if (VEC) {
