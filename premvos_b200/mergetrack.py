@@ -149,3 +149,78 @@ class LivePropagator:
         warped, bbox = warp_masks_device(masks_t, flow)
         masks, conf = self.refine_net.refine_device(frame_t1, bbox)
         return {"flow": flow, "warped": warped, "bbox": bbox, "masks": masks, "conf": conf}
+
+
+# ---- on-disk formats of stage 7 (host side) -------------------------------------------------------------
+def pascal_colormap():
+    """The 256-entry PASCAL VOC palette as uint8 [256,3] -- what `(np.array(pascal_colormap) * 255).round()` gives for the
+    table at merge_functions.py:250-506 (bit-interleaved class index: bit 3j+c of the index is bit 7-j of channel c)."""
+    cm = np.zeros((256, 3), np.uint8)
+    for i in range(256):
+        c = i
+        for j in range(8):
+            for ch in range(3):
+                cm[i, ch] |= ((c >> ch) & 1) << (7 - j)
+            c >>= 3
+    return cm
+
+
+def save_with_pascal_colormap(filename, arr):
+    """merge_functions.py:508-514: an indexed PNG whose pixel values are the object ids and whose palette is the VOC colormap
+    (PIL's `quantize(palette=...)` of a single-band image copies the data as is and attaches the palette)."""
+    from PIL import Image
+    im = Image.fromarray(np.squeeze(np.asarray(arr).astype("uint8")))     # single band "L"; putpalette turns it into "P"
+    im.putpalette(pascal_colormap().reshape(-1).tolist())
+    im.save(filename)
+
+
+def save_pngs(proposals, output_fn, empty=False):
+    """merge_functions.py:516-525: one indexed PNG per frame, pixel = id of the proposal that covers it (later ones win)."""
+    import os
+    png = np.zeros_like(np.asarray(proposals[0]["mask"]))
+    if not empty:
+        for prop in proposals:
+            png[np.asarray(prop["mask"]).astype("bool")] = prop["id"]
+    output_fol = os.path.dirname(output_fn)
+    if output_fol and not os.path.exists(output_fol):
+        os.makedirs(output_fol)
+    save_with_pascal_colormap(output_fn, png)
+
+
+def to_bbox_host(mask):
+    """pycocotools toBbox of a binary mask on the host: [x, y, w, h] float64, zeros when empty."""
+    m = np.asarray(mask) != 0
+    if not m.any():
+        return np.zeros(4, np.float64)
+    ys, xs = np.flatnonzero(m.any(axis=1)), np.flatnonzero(m.any(axis=0))
+    return np.array([xs[0], ys[0], xs[-1] - xs[0] + 1, ys[-1] - ys[0] + 1], np.float64)
+
+
+def read_ann(ann_fn):
+    """merge_functions.py:14-25: first-frame annotation PNG (or an id array) -> one template proposal per object id."""
+    if isinstance(ann_fn, np.ndarray):
+        ann = ann_fn
+    else:
+        from PIL import Image
+        ann = np.array(Image.open(ann_fn))
+    new_proposals = []
+    for id_ in [i for i in np.unique(ann) if i != 0]:
+        ann_mask = (ann == id_).astype(np.uint8)
+        new_proposals.append({"id": id_, "bbox": to_bbox_host(ann_mask), "segmentation": rle_encode(ann_mask), "conf_score": "1.0",
+                              "score": 1.0})
+    return new_proposals
+
+
+def read_props(prop_fn):
+    """merge_functions.py:27-36: proposals JSON of a frame; a missing / unreadable file is an empty list; proposals without a
+    ReID vector get an all-inf one."""
+    import json
+    try:
+        with open(prop_fn, "r") as f:
+            proposals = json.load(f)
+        for prop in proposals:
+            if "ReID" not in prop.keys():
+                prop["ReID"] = np.inf * np.ones((128))
+    except Exception:
+        proposals = []
+    return proposals
