@@ -5,9 +5,10 @@ The reference restores its weights with three mechanisms:
   * proposal net:   tensorpack `get_model_loader(path)` (proposal_net/train.py:653-657): a `.npz` / `.npy` dict of
                     variables (DictRestore) or a TensorFlow checkpoint (SaverRestore)
   * refinement net: `tf.train.Saver.restore` of a TensorFlow checkpoint (refinement_net/core/Engine.py)
-TensorFlow checkpoints (`.index` + `.data-*` tensor bundles) are not parsed here -- convert them once where TensorFlow is
-installed (`np.savez(out, **{v.name: sess.run(v) for v in tf.global_variables()})`); this module reads the resulting
-`.npz` / `.npy` dictionaries, which is also tensorpack's own exchange format (`tensorpack/scripts/dump-model-params.py`).
+This module reads `.npz` / `.npy` variable dictionaries (tensorpack's own exchange format,
+`tensorpack/scripts/dump-model-params.py`) and, through premvos_b200/tf_checkpoint.py, TensorFlow checkpoints themselves
+(`<prefix>.index` + `<prefix>.data-*`; that reader restates the bundle format without TensorFlow and is unpinned -- when in
+doubt convert once where TensorFlow is installed: `np.savez(out, **{v.name: sess.run(v) for v in tf.global_variables()})`).
 
 What a dictionary from either tool looks like and what is done with it:
   * names may carry the `:0` tensor suffix and a tower / scope prefix (`tower0/`, `tower-pred-0/`)       -> stripped
@@ -17,6 +18,7 @@ What a dictionary from either tool looks like and what is done with it:
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -29,7 +31,11 @@ _PREFIXES = ("tower-pred-0/", "tower0/", "tower_0/", "InferenceTower/")
 
 
 def _read_dict(path):
-    if str(path).endswith(".npy"):
+    path = str(path)
+    if os.path.exists(path + ".index"):   # a TensorFlow checkpoint prefix
+        from . import tf_checkpoint
+        return tf_checkpoint.read_checkpoint(path)
+    if path.endswith(".npy"):
         d = np.load(path, allow_pickle=True, encoding="latin1").item()
     else:
         with np.load(path) as z:
@@ -69,9 +75,18 @@ def _select(d, shapes, what):
     return out
 
 
+def select_proposal_net_variables(d, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81, mode_mask=False):
+    """{name: array} as read from any source -> the dict ProposalNet.load_params takes."""
+    return _select(d, propnet_param_shapes(num_blocks, num_class, second_num_class, mode_mask), "proposal_net")
+
+
+def select_refinement_net_variables(d, middle_units=16, n_classes=2):
+    return _select(d, refnet_param_shapes(middle_units, n_classes), "refinement_net")
+
+
 def load_proposal_net_variables(path, num_blocks=(3, 4, 23, 3), num_class=2, second_num_class=81, mode_mask=False):
-    """`.npz` / `.npy` dictionary of tensorpack variables -> the dict ProposalNet.load_params takes (float32, exact shapes;
-    unrelated variables ignored)."""
+    """`.npz` / `.npy` dictionary of tensorpack variables, or a TensorFlow checkpoint prefix -> the dict
+    ProposalNet.load_params takes (float32, exact shapes; unrelated variables ignored)."""
     return _select(_read_dict(path), propnet_param_shapes(num_blocks, num_class, second_num_class, mode_mask), "proposal_net")
 
 
