@@ -63,6 +63,21 @@ def normalise_variable_names(d):
 
 def _select(d, shapes, what):
     d = normalise_variable_names(d)
+    # an unknown enclosing scope (e.g. the network's layer name in refinement_net's graph): accept `<scope>/<name>` when it is
+    # the only variable that ends with the wanted name
+    tails = None
+    for k in shapes:
+        if k in d:
+            continue
+        if tails is None:
+            tails = {}
+            for full in d:
+                parts = full.split("/")
+                for i in range(1, len(parts)):
+                    tails.setdefault("/".join(parts[i:]), []).append(full)
+        cands = tails.get(k, [])
+        if len(cands) == 1:
+            d[k] = d[cands[0]]
     missing = [k for k in shapes if k not in d]
     if missing:
         raise KeyError("%s: %d variable(s) missing, e.g. %s" % (what, len(missing), missing[:5]))

@@ -45,3 +45,16 @@ def test_errors_and_npy(tmp_path):
         weights.load_refinement_net_variables(tmp_path / "missing.npz", middle_units=0)
     with pytest.raises(ValueError):
         weights.normalise_variable_names({"a:0": np.zeros(1), "tower0/a": np.zeros(1)})
+
+
+def test_unknown_enclosing_scope_is_stripped(tmp_path):
+    R = synth.refnet_synthetic_params(1, 0)
+    weights.save_variables(tmp_path / "scoped.npz", {"deeplab_layer/" + k + ":0": v for k, v in R.items()})
+    got = weights.load_refinement_net_variables(tmp_path / "scoped.npz", middle_units=0)
+    assert all(np.array_equal(got[k], R[k]) for k in R)
+    # ambiguous tails are not guessed
+    amb = {"a/" + k: v for k, v in R.items()}
+    amb.update({"b/" + k: v for k, v in R.items()})
+    weights.save_variables(tmp_path / "amb.npz", amb)
+    with pytest.raises(KeyError):
+        weights.load_refinement_net_variables(tmp_path / "amb.npz", middle_units=0)
