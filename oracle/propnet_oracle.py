@@ -26,9 +26,13 @@ behaviour (TensorFlow 1.8, tensorpack @6fdde15 per proposal_net/README:9):
                                    lerp of floor/ceil neighbours.
   tensorpack BatchNorm ........... inference form (x - mean) * gamma / sqrt(var + 1e-5) + beta.
 
-PARITY UNPINNED for this network: the reference ships no golden vectors for it and TensorFlow /
-tensorpack cannot be imported here; the only reference-held known answer on this path is the anchor
-table in utils/generate_anchors.py:20-38, which tests/test_oracle_propnet.py checks.
+PARITY UNPINNED for the network's TensorFlow graph: the reference ships no golden vectors for it and
+TensorFlow / tensorpack cannot be imported here.  Pinned pieces: the anchor table in
+utils/generate_anchors.py:20-38 (tests/test_oracle_propnet.py), and -- against vectors produced by the
+REFERENCE'S OWN functions executed from their source in the build container
+(tests/golden/make_reference_function_goldens.py, tests/test_reference_function_goldens.py) --
+clip_boxes and CustomResize (common.py), fill_full_mask (eval.py) bit-exactly, and the NMS IoU against
+utils/np_box_ops.py to 1e-6.
 """
 from __future__ import annotations
 

@@ -24,8 +24,11 @@ Third-party arithmetic that is not vendored is restated from its published behav
   pycocotools RLE (maskApi.c rleEncode + rleToString): column-major runs starting with a zero-run, LEB128-like
       string with differences against the run two positions earlier.
 
-PARITY UNPINNED for this network: the reference ships no golden vectors for it and TensorFlow cannot be imported
-here; the restated resize kernels are pinned by hand-derived cases in tests/test_oracle_refnet.py.
+PARITY UNPINNED for the network's TensorFlow graph: the reference ships no golden vectors for it and TensorFlow cannot be
+imported here; the restated resize kernels are pinned by hand-derived cases in tests/test_oracle_refnet.py.  Pinned against
+vectors produced by the reference's own numpy functions executed from their source in the build container
+(tests/golden/make_reference_function_goldens.py): encode_bbox_as_mask_np (BoundingBox.py:15-19) and normalize / the ImageNet
+constants (Normalization.py), bit-exactly.
 """
 from __future__ import annotations
 
@@ -157,6 +160,21 @@ def crop_box(bbox_y0x0y1x1, h, w):
     return max(y0 - MARGIN, 0), max(x0 - MARGIN, 0), min(y1 + MARGIN, h), min(x1 + MARGIN, w)
 
 
+def encode_bbox_as_mask_np(bbox_y0x0y1x1, shape):
+    """datasets/util/BoundingBox.py:15-19: 1 inside round(bbox) (numpy rounding: half to even), uint8 [H,W,1]."""
+    encoded = np.zeros(tuple(shape[:2]) + (1,), np.uint8)
+    y0, x0, y1, x1 = np.round(bbox_y0x0y1x1).astype(np.int64)
+    encoded[y0:y1, x0:x1] = 1
+    return encoded
+
+
+def normalize(img, img_mean=None, img_std=None):
+    """datasets/util/Normalization.py:9-21 on a numpy image [..., 3]."""
+    img_mean = IMAGENET_RGB_MEAN if img_mean is None else img_mean
+    img_std = IMAGENET_RGB_STD if img_std is None else img_std
+    return ((np.asarray(img, np.float32) - img_mean) / img_std).astype(np.float32)
+
+
 def make_network_input(image, bbox_xywh, size=INPUT_SIZE):
     """image: float32 [H,W,3] RGB in 0..1 (already /255, FewShotFeedSegmentationDataset.py:37); bbox: x,y,w,h.
     Returns (inputs [385,385,4] float32 = what the `inputs` placeholder path feeds the network, crop box)."""
@@ -164,9 +182,7 @@ def make_network_input(image, bbox_xywh, size=INPUT_SIZE):
     H, W = image.shape[:2]
     x0, y0, bw, bh = [np.float32(v) for v in bbox_xywh]
     bbox = np.array([y0, x0, y0 + bh, x0 + bw], dtype=np.float32)      # FewShotFeedSegmentationDataset.py:40-43
-    guidance = np.zeros((H, W, 1), np.uint8)                            # BoundingBox.py:15-19
-    gy0, gx0, gy1, gx1 = np.round(bbox).astype(np.int64)
-    guidance[gy0:gy1, gx0:gx1] = 1
+    guidance = encode_bbox_as_mask_np(bbox, (H, W))
     cy0, cx0, cy1, cx1 = crop_box(bbox, H, W)
     img_c = torch.from_numpy(image[cy0:cy1, cx0:cx1]).permute(2, 0, 1)
     g_c = torch.from_numpy(guidance[cy0:cy1, cx0:cx1].astype(np.float32)).permute(2, 0, 1)
