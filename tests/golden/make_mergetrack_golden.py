@@ -1,5 +1,6 @@
-"""Generates tests/golden/mergetrack_golden.npz with OpenCV itself (cv2.remap / cv2.resize as the reference calls them in
-MergeTrack/merge_functions.py:209-217 and optical_flow_net-PWC-Net/script_pwc_multi.py:59-68), run in the build container.
+"""Generates tests/golden/mergetrack_golden.npz with the reference's own warp_flow (MergeTrack/merge_functions.py:209-217,
+source exec'd unmodified) and with OpenCV itself for the flow post-processing (cv2.resize as
+optical_flow_net-PWC-Net/script_pwc_multi.py:59-68 calls it), run in the build container.
 IPP is switched off for the float resize so that the vectors are those of OpenCV's own published code path.
 
     python tests/golden/make_mergetrack_golden.py
@@ -15,19 +16,15 @@ sys.path.insert(0, ROOT)
 from premvos_b200 import synth  # noqa: E402
 
 
-def reference_warp_flow(img, flow, binarize=True):
-    # MergeTrack/merge_functions.py:209-217, verbatim semantics (on a copy: the reference negates `flow` in place)
-    h, w = flow.shape[:2]
-    flow = -flow
-    flow[:, :, 0] += np.arange(w)
-    flow[:, :, 1] += np.arange(h)[:, np.newaxis]
-    res = cv2.remap(img, flow, None, cv2.INTER_LINEAR)
-    if binarize:
-        res = np.equal(res, 1).astype(np.uint8)
-    return res
+def _reference_warp_flow():
+    """MergeTrack/merge_functions.py:209-217 itself: the function's unmodified source, exec'd from where it lies."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from make_reference_function_goldens import extract
+    return extract("/root/reference/code/MergeTrack/merge_functions.py", ["warp_flow"])["warp_flow"]
 
 
 def main():
+    reference_warp_flow = _reference_warp_flow()
     H, W = 60, 84
     masks = synth.synthetic_masks(3, H, W, seed=11)
     rng = np.random.default_rng(12)

@@ -11,6 +11,7 @@ Functions executed:
   proposal_net/utils/np_box_ops.py  iou (whole module: pure numpy)
   MergeTrack/merge_functions.py     warp_flow, get_flow
   optical_flow_net-PWC-Net/script_pwc_multi.py   writeFlowFile
+  proposal_net/data.py              get_all_anchors (with the reference's config.py and utils/generate_anchors.py)
   refinement_net/datasets/util/BoundingBox.py    encode_bbox_as_mask_np (numpy namespace with the removed alias np.int = int)
   refinement_net/datasets/util/Normalization.py  normalize, unnormalize (whole module: pure numpy)
 """
@@ -110,6 +111,34 @@ def main():
         def __getattr__(self, name):
             return getattr(np, name)
 
+    # ---- proposal_net/data.py get_all_anchors with the reference's own config.py and generate_anchors.py ----
+    os.environ.setdefault("USER", "premvos")          # config.py reads it at import time
+    spec = importlib.util.spec_from_file_location("ref_config", os.path.join(REF, "proposal_net/config.py"))
+    ref_config = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_config)
+    spec = importlib.util.spec_from_file_location("ref_generate_anchors", os.path.join(REF, "proposal_net/utils/generate_anchors.py"))
+    ga = importlib.util.module_from_spec(spec)
+    ga.np = None
+    spec.loader.exec_module(ga)
+
+    class NpCompat0:   # numpy 2 dropped the aliases np.float / np.int the reference uses; everything else is numpy itself
+        float = float
+        int = int
+
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+    ga.np = NpCompat0()
+    dat = extract(os.path.join(REF, "proposal_net/data.py"), ["get_all_anchors"],
+                  {"np": NpCompat0(), "config": ref_config, "memoized": lambda f: f, "generate_anchors": ga.generate_anchors})
+    field = dat["get_all_anchors"]()
+    import hashlib
+    out["anchors_shape"] = np.array(field.shape)
+    out["anchors_sha1"] = np.frombuffer(hashlib.sha1(np.ascontiguousarray(field).tobytes()).digest(), dtype=np.uint8)
+    out["anchors_cell00"], out["anchors_cell57"] = field[0, 0], field[5, 7]
+    out["config_consts"] = np.array([ref_config.ANCHOR_STRIDE, ref_config.MAX_SIZE, ref_config.SHORT_EDGE_SIZE, ref_config.TEST_PRE_NMS_TOPK,
+                                     ref_config.TEST_POST_NMS_TOPK, ref_config.RESULTS_PER_IM], np.int64)
+    out["config_thresh"] = np.array([ref_config.RPN_PROPOSAL_NMS_THRESH, ref_config.FASTRCNN_NMS_THRESH, ref_config.RESULT_SCORE_THRESH], np.float64)
     bb = extract(os.path.join(REF, "refinement_net/datasets/util/BoundingBox.py"), ["encode_bbox_as_mask_np"], {"np": NpCompat()})
     gboxes = np.array([[3.5, 4.5, 20.5, 30.49], [0.2, 0.7, 9.5, 11.5], [10, 12, 10.4, 40], [2.5, 2.5, 3.5, 3.5], [-0.4, 0.0, 47.6, 69.9]], np.float32)
     out["guid_boxes"] = gboxes

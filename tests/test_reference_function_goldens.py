@@ -65,3 +65,16 @@ def test_guidance_mask_and_normalisation_equal_reference_functions():
     np.testing.assert_array_equal(RO.IMAGENET_RGB_STD, G["norm_std"])
     np.testing.assert_array_equal(RO.normalize(G["norm_in"]), G["norm_out"])
     assert np.abs(G["norm_back"] - G["norm_in"]).max() < 1e-6
+
+
+def test_anchor_field_and_config_constants_equal_the_reference():
+    import hashlib
+    field = PO.get_all_anchors()
+    assert tuple(G["anchors_shape"]) == field.shape == (83, 83, 15, 4) and field.dtype == np.float32
+    assert hashlib.sha1(np.ascontiguousarray(field).tobytes()).digest() == G["anchors_sha1"].tobytes()
+    np.testing.assert_array_equal(field[0, 0], G["anchors_cell00"])
+    np.testing.assert_array_equal(field[5, 7], G["anchors_cell57"])
+    # config.py constants the oracle (and the CUDA library) hard-code
+    want = [PO.ANCHOR_STRIDE, PO.MAX_SIZE, PO.SHORT_EDGE_SIZE, PO.TEST_PRE_NMS_TOPK, PO.TEST_POST_NMS_TOPK, PO.RESULTS_PER_IM]
+    assert list(G["config_consts"]) == want
+    assert list(G["config_thresh"]) == [PO.RPN_PROPOSAL_NMS_THRESH, PO.FASTRCNN_NMS_THRESH, PO.RESULT_SCORE_THRESH]
