@@ -54,6 +54,25 @@ def test_argument_errors(L):
         _lib.check(L.premvos_pwc_forward(None, None, None, None))
 
 
+def test_argument_errors_of_the_byte_work_entry_points(L):
+    # argument checks come before any CUDA call: they must answer on a machine without a GPU
+    assert L.premvos_resize_linear_u8(None, 1, 8, 8, None, 16, 16, 3, 0, None) == -1
+    assert L.premvos_warp_masks_u8(None, 2, 8, 8, None, None, None, 1, None) == -1
+    assert L.premvos_warp_masks_u8(None, 0, 8, 8, None, None, None, 1, None) == 0        # no masks: a no-op
+    assert L.premvos_warp_masks_u8(None, -1, 8, 8, None, None, None, 1, None) == -1
+    assert L.premvos_flow_postprocess(None, 1, 64, 64, None, 60, 60, None) == -1
+    assert L.premvos_fill_full_masks_host(None, None, 0, 14, 32, 32, None) == 0           # no boxes: a no-op
+    assert L.premvos_fill_full_masks_host(None, None, 2, 14, 32, 32, None) == -1
+    assert L.premvos_fill_full_masks_host(None, None, 0, 13, 32, 32, None) == -1          # odd mask size
+    h = ctypes.c_void_p()
+    assert L.premvos_propnet_create(ctypes.byref(h), 128, 160, 2, 81) in (0, -6)          # -6: no device visible here
+    if h.value:
+        assert L.premvos_propnet_set_option(h, b"batch", 0) == -1 and L.premvos_propnet_set_option(h, b"batch", 17) == -1
+        assert L.premvos_propnet_set_option(h, b"batch", 4) == 0 and L.premvos_propnet_set_option(h, b"mode_mask", 1) == 0
+        assert L.premvos_propnet_set_option(h, b"no_such_option", 1) == -1
+        L.premvos_propnet_destroy(h)
+
+
 def test_corr_shapes_match_oracle_shape_math(L):
     from oracle import pwc_oracle as O
     oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
