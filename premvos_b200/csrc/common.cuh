@@ -178,6 +178,7 @@ struct ConvWeightsUmma {
   __nv_bfloat16* w = nullptr;  // device, packed shared-memory images [ntile][kblock][tap][hi|lo][KC][BN][8]
   float* bias = nullptr;       // device [ntiles*BN]
   int R = 3, S = 3, Cin = 0, CinPhys = 0, Cout = 0, KC = 2, kblocks = 0, BN = 0, ntiles = 0;
+  int pair = 0;  // packed for conv_pair_kernel (cta_group::2): [ntile][kblock][CTA rank][hi|lo][KC][128][8]
 };
 struct ConvGeom {
   int stride = 1, dil = 1;
@@ -198,6 +199,7 @@ struct ConvOut {
 struct ConvPlanUmma {  // everything one launch needs; built once per layer at finalize time
   alignas(64) unsigned char map_a_hi[128];
   alignas(64) unsigned char map_a_lo[128];
+  alignas(64) unsigned char map_w[128];   // CTA-pair kernel: packed weights as 128-byte rows
   alignas(16) unsigned char args[320];
   int grid_x = 0, grid_y = 0, grid_z = 1, smem_bytes = 0, halo = 0, MT = 0, N = 0, ctas_per_sm = 1;
   void* scratch = nullptr;   // split-K partial sums (owned by the plan, see free_conv_plan_umma)
@@ -206,7 +208,7 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
 // host_w: torch Conv2d layout [Cout][Cin][R][S].  cin_map (optional): physical channel (inside the input
 // view) of every reference input channel, cin_phys = physical channel count of that view.
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
-                           const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0, long m_hint = 0);
+                           const int* cin_map = nullptr, int cin_phys = 0, int kc_hint = 0, long m_hint = 0, bool allow_pair = false);
 void free_conv_weights_umma(ConvWeightsUmma* w);
 struct ConvPlanUmma;
 void free_conv_plan_umma(ConvPlanUmma* plan);

@@ -52,7 +52,8 @@ extern "C" int premvos_conv2d_forward(const float* x_dev, const float* w_host, c
     o.res = res;
   }
   ConvWeightsUmma w;
-  PV_TRY(pack_conv_weights_umma(&w, w_host, bias_host, cout, cin, kh, kw, nullptr, 0, 0, (long)batch * Ho * Wo));
+  const bool flat = kh == 1 && kw == 1 && stride == 1 && pad_top == 0 && pad_left == 0 && pad_bottom == 0 && pad_right == 0;
+  PV_TRY(pack_conv_weights_umma(&w, w_host, bias_host, cout, cin, kh, kw, nullptr, 0, 0, (long)batch * Ho * Wo, flat));
   ConvGeom g;
   g.stride = stride; g.dil = dilation; g.pad_t = pad_top; g.pad_l = pad_left; g.pad_b = pad_bottom; g.pad_r = pad_right;
   g.slope = slope;

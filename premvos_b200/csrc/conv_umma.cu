@@ -160,6 +160,65 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---- CTA-pair (cta_group::2) variants: a cluster of two CTAs on the two SMs of a TPC runs ONE 256 x N MMA per instruction ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// executed by every thread of both CTAs (convergent warps)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA box into THIS CTA's shared memory, bytes credited to the barrier at `mbar_cluster_addr` (the pair leader's)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t mbar_cluster_addr, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t mbar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows of each CTA] * B[N/2 rows of each CTA]^T; issued by one thread of the leader CTA
+__device__ __forceinline__ void umma_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one arrival on the barrier at this shared-memory offset in BOTH CTAs once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // Un-swizzled ("interleaved") K-major operand descriptor: core matrix = 8 rows x 16 B, rows 16 B apart.
 //   bits [0,14) start>>4 | [16,30) LBO>>4 (byte distance between the two 8-element K halves of one MMA)
 //   | [32,46) SBO>>4 (byte distance between 8-row groups along M/N) | [46,48) version = 1 (sm_100)
@@ -228,6 +287,7 @@ struct UmmaConvArgs {
   int tail_items, tail_split, tail_kb_per, main_work;
   int lockstep;              // 1x1 layers: A and weight rings advance together and share one barrier pair per k-block
   int epi_warps;             // 4 or 8 epilogue warps (8: kernel instantiation with 384 threads, one CTA per SM)
+  int pair;                  // 1: conv_pair_kernel (cta_group::2, 256 pixels x 256 output channels per CTA pair); see there
 };
 
 // EPI_WARPS = 4: 256 threads, up to two CTAs per SM.  EPI_WARPS = 8: 384 threads, one CTA per SM owning the whole TMEM (256-wide N
@@ -753,6 +813,276 @@ __global__ void __launch_bounds__(256) conv_finish_tail_kernel(const UmmaConvArg
   finish_store(a, n_img, pix, (long)n_img * hw + pix, c8, f);
 }
 
+
+// ---- CTA-pair kernel for 1x1 / stride-1 layers -------------------------------------------------------------------------
+// A 1x1 layer moves 9x more A bytes per MMA than a 3x3 layer in halo mode; at 128 x 256 tiles one SM has to ingest 62.5 B/clk of
+// operands to keep its tensor pipe busy, the L2 delivers ~43-46.  A CTA PAIR (cluster of 2 = the two SMs of a TPC) computes a
+// 256 pixel x 256 channel tile with tcgen05.mma.cta_group::2: each CTA loads ITS 128 pixels of A and ITS 128 of the 256 weight
+// rows, the MMA reads both shared memories and writes 128 accumulator rows into each CTA's tensor memory -- 41.7 B/clk per SM and
+// still 256 TMEM columns per buffer, so the epilogue of item i overlaps the MMAs of item i+1 (tools/ubench/pair_mma.cu: the
+// un-swizzled CP8 layouts are valid split operands, 128 cycles per 256 x 256 x 16 MMA = the tensor pipe's rate).
+//
+// Protocol (the one CUTLASS's 2-SM kernels use): both CTAs run a producer warp; every TMA (.cta_group::2) credits its bytes to the
+// LEADER's full barrier, which the leader's producer arms with the bytes of both CTAs; the leader's issuer waits on it, issues the
+// MMAs for the pair and commits (multicast) to the empty barrier of BOTH CTAs and, per item, to both tmem_full barriers; the
+// epilogue warps of both CTAs arrive on the leader's tmem_empty barrier (the peer's over the cluster).
+// Work item = (pixel-tile pair, 256-wide channel tile); CTA r of a pair owns pixel tile 2*mp + r of the list (image, tile), which
+// may lie in another image than its peer's or beyond the end (zero rows, nothing stored).  Items are ordered channel-tile-minor:
+// pairs running at the same time share their A tiles through the L2.  Tail items are split along K exactly as in conv_umma_kernel.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmW, const UmmaConvArgs a) {
+  constexpr int EPI_WARPS = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = a_smem + (size_t)a.w_stages * 2 * a.a_plane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + (size_t)a.w_stages * a.w_stage);
+  uint64_t* full = bars;                      // [MAX_W_STAGES]  (used in the leader CTA)
+  uint64_t* empty = bars + MAX_W_STAGES;      // [MAX_W_STAGES]  (each CTA waits on its own copy)
+  uint64_t* tmem_full_bar = empty + MAX_W_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]  (used in the leader CTA, 2 * EPI_WARPS arrivals)
+  uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_per_img = a.tiles_y;
+  struct Work { int ntile, mp, z, kb_begin, kb_end, tail_slot; };
+  auto decode = [&](int t) {
+    Work w;
+    w.tail_slot = -1; w.z = 0; w.kb_begin = 0; w.kb_end = a.kblocks;
+    if (a.tail_items > 0 && t >= a.main_work) {
+      const int u = t - a.main_work;
+      w.tail_slot = u / a.tail_split;
+      w.z = u - w.tail_slot * a.tail_split;
+      t = a.main_work + w.tail_slot;
+      w.kb_begin = w.z * a.tail_kb_per;
+      w.kb_end = min(a.kblocks, w.kb_begin + a.tail_kb_per);
+    }
+    w.mp = t / a.ntiles;
+    w.ntile = t - w.mp * a.ntiles;
+    return w;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW);
+    for (int s = 0; s < a.w_stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_addr_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything can signal them
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_addr_slot, 0);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    uint32_t st = 0, ph = 0;
+    const uint32_t half_bytes = 2u * (uint32_t)a.a_box_bytes + 2u * (uint32_t)a.w_plane;   // what ONE CTA loads per k-block
+    const int w_rows = (2 * a.w_plane) >> 7;                                             // 128-byte rows of one CTA's weight block
+    for (int t = pair_id; t < a.total_work; t += n_pairs) {
+      const Work wk = decode(t);
+      const int mtile = 2 * wk.mp + (int)rank;
+      const int n_img = mtile / tiles_per_img, ty0 = (mtile - n_img * tiles_per_img) * 16;
+      int wrow = ((wk.ntile * a.kblocks + wk.kb_begin) * 2 + (int)rank) * w_rows;
+      for (int kb = wk.kb_begin; kb < wk.kb_end; kb++, wrow += 2 * w_rows) {
+        mbar_wait(&empty[st], ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = mapa_u32(smem_u32(&full[st]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[st], 2u * half_bytes);
+          uint8_t* dst = a_smem + (size_t)st * 2 * a.a_plane;
+          tma_load_4d_pair(&tmA_hi, fb, dst, 0, ty0, kb * a.KC, n_img);
+          tma_load_4d_pair(&tmA_lo, fb, dst + a.a_plane, 0, ty0, kb * a.KC, n_img);
+          tma_load_2d_pair(&tmW, fb, w_smem + (size_t)st * a.w_stage, 0, wrow);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)a.w_stages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    const uint32_t idesc = make_idesc_bf16(256, a.BN);
+    const uint32_t lbo = 128u * 16u;   // both operands: [k chunk][128 rows][8 ch], SBO = 128 B
+    const uint32_t hi32 = (128u >> 4) | (1u << 14), lo32 = (lbo >> 4) << 16;
+    const uint32_t a_base = smem_u32(a_smem) & 0x3FFFFu, w_base = smem_u32(w_smem) & 0x3FFFFu;
+    const uint32_t a_stage_bytes = 2u * (uint32_t)a.a_plane, w_stage_bytes = (uint32_t)a.w_stage;
+    const uint32_t kstep16 = (2u * lbo) >> 4, a_plane16 = (uint32_t)a.a_plane >> 4, w_plane16 = (uint32_t)a.w_plane >> 4;
+    const int ksteps = a.KC / 2;
+    uint32_t st = 0, ph = 0, buf = 0, empty_ph = 0;
+    for (int t = pair_id; t < a.total_work; t += n_pairs) {
+      const Work wk = decode(t);
+      mbar_wait(&tmem_empty_bar[buf], ((empty_ph >> buf) & 1u) ^ 1u);
+      empty_ph ^= 1u << buf;
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * 256u;
+      uint32_t accum = 0;
+      for (int kb = wk.kb_begin; kb < wk.kb_end; kb++) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          uint32_t aH = lo32 + ((a_base + st * a_stage_bytes) >> 4), wH = lo32 + ((w_base + st * w_stage_bytes) >> 4);
+          for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aH += kstep16, wH += kstep16) {
+            umma_pair_lo(tmem_acc, aH + a_plane16, hi32, wH, hi32, idesc, accum);
+            umma_pair_lo(tmem_acc, aH, hi32, wH + w_plane16, hi32, idesc, 1u);
+            umma_pair_lo(tmem_acc, aH, hi32, wH, hi32, idesc, 1u);
+            accum = 1u;
+          }
+          umma_commit_pair(&empty[st]);
+        }
+        accum = 1u;
+        if (++st == (uint32_t)a.w_stages) { st = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit_pair(&tmem_full_bar[buf]);
+      __syncwarp();
+      buf ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): 128 accumulator rows x BN columns of this CTA =====
+    const int q = warp & 3, m = q * 32 + lane;
+    const long hw = (long)a.flat_hw;
+    const uint32_t te_leader = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);   // [buf] at +8 bytes
+    uint32_t buf = 0, full_ph = 0;
+    const int col_part = (warp - 4) >> 2, col_span = a.BN / 2;
+    const int col_begin = col_part * col_span, col_end = col_begin + col_span;
+    for (int t = pair_id; t < a.total_work; t += n_pairs) {
+      const Work wk = decode(t);
+      const int mtile = 2 * wk.mp + (int)rank;
+      const int n_img = mtile / tiles_per_img;
+      const long pix = (long)(mtile - n_img * tiles_per_img) * 128 + m;
+      const bool in_img = n_img < a.n_images && pix < hw;
+      mbar_wait(&tmem_full_bar[buf], (full_ph >> buf) & 1u);
+      full_ph ^= 1u << buf;
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tmem_acc + (uint32_t)c0, v);
+        const int co0 = wk.ntile * a.BN + c0;
+        const bool live = in_img && co0 < a.Cout && wk.tail_slot < 0;
+        float4 bv[4];
+        uint4 rres[4];
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + co0) + j);
+          if (a.res_hi) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              if (co0 + 8 * h >= a.Cout) continue;
+              const long ri = (((long)n_img * a.res_chunks + a.res_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+              rres[2 * h] = *reinterpret_cast<const uint4*>(a.res_hi + ri);
+              rres[2 * h + 1] = *reinterpret_cast<const uint4*>(a.res_lo + ri);
+            }
+          }
+        }
+        tmem_ld_wait();
+        if (c0 + 16 >= col_end) {   // this warp's columns are all in registers: hand the buffer back to the issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(te_leader + buf * 8u);
+        }
+        if (a.dbg & 4) continue;
+        if (wk.tail_slot >= 0) {   // raw partial sums [z][tail item][rank][128 rows][BN]
+          float* pp = a.partial + ((((long)(wk.z * a.tail_items + wk.tail_slot) * 2 + rank) * 128 + m) * a.BN + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            reinterpret_cast<float4*>(pp)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          continue;
+        }
+        if (!live) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          f[4 * j] = __uint_as_float(v[4 * j]) + bv[j].x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv[j].y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv[j].z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+        }
+        if (a.res_hi) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (co0 + 8 * h >= a.Cout) continue;
+            const uint4 rh = rres[2 * h], rl = rres[2 * h + 1];
+            const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              f[8 * h + 2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+              f[8 * h + 2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+            }
+          }
+        }
+        if (a.out_f32 && a.f32_linear) {
+          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (co0 + j >= a.f32_first && co0 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+        if (a.out_hi) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (co0 + 8 * h >= a.cp_cout) continue;
+            uint32_t hw4[4], lw4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float x0 = f[8 * h + 2 * j], x1 = f[8 * h + 2 * j + 1];
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+              hw4[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lw4[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            const long oi = (((long)n_img * a.out_chunks + a.out_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+            *reinterpret_cast<uint4*>(a.out_hi + oi) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+            *reinterpret_cast<uint4*>(a.out_lo + oi) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+          }
+        }
+        if (a.out_f32 && !a.f32_linear) {
+          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (co0 + j >= a.f32_first && co0 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+        }
+      }
+      buf ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody frees TMEM / exits while the peer's MMAs, TMA credits or barrier arrivals may still be in flight
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// Finishes the K-split tail items of a pair launch: one thread per (tail item, CTA rank, accumulator row, 8-channel chunk).
+__global__ void __launch_bounds__(256) conv_pair_finish_tail_kernel(const UmmaConvArgs a) {
+  const int cch = a.BN / 8;
+  const long total = (long)a.tail_items * 2 * 128 * cch;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int m = (int)(idx % 128);                // row fastest -> coalesced CP8 stores
+  const int cc = (int)((idx / 128) % cch);
+  const int rank = (int)((idx / (128L * cch)) % 2);
+  const int slot = (int)(idx / (256L * cch));
+  const int t = a.main_work + slot;
+  const int mp = t / a.ntiles, ntile = t - mp * a.ntiles;
+  const int mtile = 2 * mp + rank, n_img = mtile / a.tiles_y;
+  const long hw = (long)a.flat_hw, pix = (long)(mtile - n_img * a.tiles_y) * 128 + m;
+  const int c8 = (ntile * a.BN) / 8 + cc;
+  if (n_img >= a.n_images || pix >= hw || c8 * 8 >= a.Cout) return;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = 0.f;
+  for (int z = 0; z < a.tail_split; z++) {
+    const float* pp = a.partial + ((((long)(z * a.tail_items + slot) * 2 + rank) * 128 + m) * a.BN + cc * 8);
+    const float4 p0 = reinterpret_cast<const float4*>(pp)[0], p1 = reinterpret_cast<const float4*>(pp)[1];
+    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+  }
+  finish_store(a, n_img, pix, (long)n_img * hw + pix, c8, f);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -800,7 +1130,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const float* host_b, int Cout, int Cin, int R, int S,
-                           const int* cin_map, int cin_phys, int kc_hint, long m_hint) {
+                           const int* cin_map, int cin_phys, int kc_hint, long m_hint, bool allow_pair) {
   out->R = R; out->S = S; out->Cin = Cin; out->Cout = Cout;
   const int phys = cin_map ? cin_phys : Cin;   // physical input channels (after the view's chunk padding)
   out->CinPhys = phys;
@@ -825,6 +1155,10 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   if (bn > 128 && kc_hint == 0 && env_int("PREMVOS_KC", 0) == 0) { kc = std::min(4, round_up(chunks, 2)); out->KC = kc; out->kblocks = (chunks + kc - 1) / kc; }
   out->BN = bn;
   out->ntiles = (Cout + bn - 1) / bn;
+  // CTA-pair kernel (conv_pair_kernel): 256-wide layers the caller declares flat (1x1, stride 1, no padding) whose item list fills
+  // the 74 pairs at least once; the weight image is then split into the two 128-row halves the two CTAs of a pair load
+  out->pair = (allow_pair && bn == 256 && kc == 4 && env_int("PREMVOS_PAIR", 1) != 0 &&
+               ((m_hint + 255) / 256) * out->ntiles >= env_int("PREMVOS_PAIR_MIN_ITEMS", 74)) ? 1 : 0;
   const int KP = out->kblocks * kc * 8;
   const int taps = R * S;
   const size_t plane_elems = (size_t)kc * bn * 8;   // one (tap, k-block) operand image of one plane
@@ -840,8 +1174,14 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
       const int kb = pc / (kc * 8), kcc = (pc / 8) % kc, e = pc & 7;
       for (int t = 0; t < taps; t++) {
         // [ntile][kblock][tap][plane][KC][BN][8]
-        const size_t base = ((((size_t)nt * out->kblocks + kb) * taps + t) * 2) * plane_elems + ((size_t)kcc * bn + row) * 8 + e;
-        split_bf16(host_w[((size_t)co * Cin + ci) * taps + t], &w[base], &w[base + plane_elems]);
+        size_t base = ((((size_t)nt * out->kblocks + kb) * taps + t) * 2) * plane_elems + ((size_t)kcc * bn + row) * 8 + e;
+        size_t lo_off = plane_elems;
+        if (out->pair) {   // [ntile][kblock][CTA rank][plane][KC][128][8]
+          const size_t half = plane_elems / 2;
+          base = ((((size_t)nt * out->kblocks + kb) * 2 + row / 128) * 2) * half + ((size_t)kcc * 128 + row % 128) * 8 + e;
+          lo_off = half;
+        }
+        split_bf16(host_w[((size_t)co * Cin + ci) * taps + t], &w[base], &w[base + lo_off]);
       }
     }
   }
@@ -860,6 +1200,91 @@ void free_conv_plan_umma(ConvPlanUmma* plan) {
 void free_conv_weights_umma(ConvWeightsUmma* w) {
   cudaFree(w->w); cudaFree(w->bias);
   w->w = nullptr; w->bias = nullptr;
+}
+
+
+// Plan of a CTA-pair launch (conv_pair_kernel): flattened 128-pixel tiles per image, pairs of tiles x 256-wide channel tiles.
+static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g, bool flat,
+                          int real_hw, int cp_cout, int f32_first) {
+  PV_CHECK(flat && w.BN == 256 && w.KC == 4, PREMVOS_ERR_INVALID_ARG,
+           "conv_umma: weights were packed for the CTA-pair kernel, which needs a 1x1 / stride-1 / unpadded layer (BN %d KC %d)", w.BN, w.KC);
+  UmmaConvArgs& a = *reinterpret_cast<UmmaConvArgs*>(plan->args);
+  const int geoH = (real_hw + 7) / 8;
+  a.pair = 1;
+  a.MT = 1; a.mt_horizontal = 0; a.halo = 0; a.merged_x = 1; a.lockstep = 1; a.NACC = 1; a.TPS = 1; a.nbuf = 2; a.epi_warps = 8;
+  a.tiles_x = 1; a.tiles_y = (real_hw + 127) / 128;
+  a.box_w = 8; a.box_h = 16;
+  a.a_box_bytes = w.KC * 128 * 16;
+  a.a_plane = a.a_box_bytes;
+  a.w_plane = w.KC * 128 * 16;       // ONE CTA's half of a (hi or lo) weight plane
+  a.w_stage = 2 * a.w_plane;
+  const int stage_bytes = 2 * a.a_plane + a.w_stage;
+  int st = (SMEM_LIMIT - 1024) / stage_bytes;
+  st = std::max(2, std::min(st, MAX_W_STAGES));
+  st = env_int("PREMVOS_PAIR_STAGES", st);
+  PV_CHECK(st >= 2 && st <= MAX_W_STAGES, PREMVOS_ERR_INVALID_ARG, "conv_umma: PREMVOS_PAIR_STAGES=%d", st);
+  a.a_stages = a.w_stages = st;
+  plan->smem_bytes = st * stage_bytes + 128 + 512;
+  PV_CHECK(plan->smem_bytes <= SMEM_LIMIT, PREMVOS_ERR_UNSUPPORTED, "conv_umma: %d bytes of shared memory needed", plan->smem_bytes);
+  a.w = w.w; a.bias = w.bias; a.slope = g.slope;
+  a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
+  a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
+  a.cp_cout = cp_cout; a.f32_first = f32_first; a.f32_linear = out.f32_linear ? 1 : 0; a.f32_accum = out.f32_accumulate ? 1 : 0;
+  a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
+  a.dbg = env_int("PREMVOS_DBG", 0);
+  a.tmem_cols = 512;
+  a.ksplit = 1; a.kb_per = a.kblocks; a.cout_pad = w.ntiles * w.BN; a.partial = nullptr; a.partial_stride = 0;
+  a.ntiles = w.ntiles; a.n_images = in.N;
+  const int mtiles = in.N * a.tiles_y;
+  a.total_work = ((mtiles + 1) / 2) * w.ntiles;
+  plan->grid_x = a.total_work; plan->grid_y = 1; plan->grid_z = 1; plan->ctas_per_sm = 1;
+  // tail split as in plan_conv_umma: slots = CTA pairs
+  a.tail_items = 0; a.tail_split = 1; a.tail_kb_per = a.kblocks; a.main_work = a.total_work;
+  if (env_int("PREMVOS_TAIL", 1) != 0) {
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
+    const int slots = num_sms / 2, rem = a.total_work % slots;
+    if (a.total_work > slots && rem > 0 && rem * 3 <= slots && a.kblocks >= 4) {
+      int split = std::min(slots / rem, a.kblocks / 2);
+      split = std::min(split, env_int("PREMVOS_TAIL_SPLIT", 16));
+      if (split >= 2) {
+        a.tail_kb_per = (a.kblocks + split - 1) / split;
+        a.tail_split = (a.kblocks + a.tail_kb_per - 1) / a.tail_kb_per;
+        a.tail_items = rem;
+        a.main_work = a.total_work - rem;
+        const size_t elems = (size_t)a.tail_split * rem * 2 * 128 * w.BN;
+        PV_CUDA(cudaMalloc((void**)&a.partial, elems * sizeof(float)));
+        PV_CUDA(cudaMemset(a.partial, 0, elems * sizeof(float)));
+        plan->scratch = a.partial;
+        a.total_work = a.main_work + rem * a.tail_split;
+      }
+    }
+  }
+  // tensor maps: activations [N][chunks][ceil(HW/8)][64], weights [rows][64] (128-byte rows of the packed image)
+  const int vchunks = (in.C + 7) / 8;
+  const size_t plane_bytes = (size_t)in.H * in.W * 16;
+  __nv_bfloat16* bases[2] = {in.hi + (size_t)in.c0 * in.H * in.W * 8, in.lo + (size_t)in.c0 * in.H * in.W * 8};
+  CUtensorMap* maps[2] = {(CUtensorMap*)plan->map_a_hi, (CUtensorMap*)plan->map_a_lo};
+  for (int k = 0; k < 2; k++) {
+    cuuint64_t dims[4] = {64, (cuuint64_t)geoH, (cuuint64_t)vchunks, (cuuint64_t)in.N};
+    cuuint64_t strides[3] = {128, plane_bytes, plane_bytes * in.chunks};
+    cuuint32_t box[4] = {64, 16, (cuuint32_t)w.KC, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    PV_TRY(encode_map(maps[k], bases[k], 4, dims, strides, box, estr));
+  }
+  {
+    const cuuint64_t rows = (cuuint64_t)w.ntiles * w.kblocks * 2 * (2 * a.w_plane / 128);
+    cuuint64_t dims[4] = {64, rows, 1, 1};
+    cuuint64_t strides[3] = {128, 0, 0};
+    cuuint32_t box[4] = {64, (cuuint32_t)(2 * a.w_plane / 128), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    PV_TRY(encode_map((CUtensorMap*)plan->map_w, w.w, 2, dims, strides, box, estr));
+  }
+  const double opx = (double)in.N * real_hw;
+  plan->flops = 2.0 * opx * (double)w.Cout * w.Cin;
+  plan->bytes = 4.0 * ((double)in.N * in.H * in.W * w.Cin + opx * w.Cout + (double)w.Cin * w.Cout);
+  plan->halo = 0; plan->MT = 1; plan->N = in.N;
+  return 0;
 }
 
 // Plans one convolution launch: tensor maps of the input view are encoded here (host only, no device work).
@@ -904,6 +1329,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
   a.merged_x = (g.stride == 1) ? 1 : 0;
   a.w_plane = w.KC * w.BN * 16;
+  if (w.pair) return plan_conv_pair(plan, in, out, w, g, flat, real_hw, cp_cout, f32_first);
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
   // two sub-tiles per CTA either stacked (32 x 8 pixels) or side by side (16 x 16): take the one that pads less
   const long tiles_v = (long)((geoW + 7) / 8) * ((geoH + 31) / 32), tiles_h = (long)((geoW + 15) / 16) * ((geoH + 15) / 16);
@@ -1078,6 +1504,45 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   return 0;
 }
 
+
+static int launch_conv_pair(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
+  UmmaConvArgs a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
+  if (active_n >= 0 && active_n < plan.N) {   // a smaller active batch: plain item list, no tail split
+    a.n_images = active_n;
+    a.total_work = ((active_n * a.tiles_y + 1) / 2) * a.ntiles;
+    a.tail_items = 0; a.main_work = a.total_work;
+  }
+  if (a.total_work == 0) return 0;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PV_CUDA(cudaGetDevice(&dev));
+    PV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int pairs = std::min(a.total_work, num_sms / 2);
+  prof_before(st);
+  conv_pair_kernel<<<2 * pairs, 384, plan.smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(plan.map_a_hi),
+                                                           *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo),
+                                                           *reinterpret_cast<const CUtensorMap*>(plan.map_w), a);
+  const double frac = (double)a.n_images / plan.N;
+  const char* label = "conv_umma_kernel";   // one roofline entry for the tensor-core convolution, whichever instantiation ran
+  static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
+  if (per_layer && profiling_enabled()) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "conv_pair[n%d_%dx1_cin%d_cout%d|BN%d_KC%d_st%d_items%d_tail%dx%d]", a.n_images, a.flat_hw, a.kblocks * a.KC * 8,
+             a.Cout, a.BN, a.KC, a.w_stages, a.total_work, a.tail_items, a.tail_split);
+    label = prof_intern(buf);
+  }
+  PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));
+  if (a.tail_items > 0) {
+    const long total = (long)a.tail_items * 2 * 128 * (a.BN / 8);
+    prof_before(st);
+    conv_pair_finish_tail_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    PV_TRY(after_launch("conv_finish_kernel", st, 0.0, (double)total * 32.0 * (a.tail_split + 1)));
+  }
+  return 0;
+}
+
 int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1086,11 +1551,13 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
     if (env_int("PREMVOS_PREFER_SHARED", 0)) PV_CUDA(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
     PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     PV_CUDA(cudaFuncSetAttribute(conv_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    PV_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   // persistent CTAs: at most ctas_per_sm per SM, each walks the work items b, b + grid, ...  A smaller active batch
   // just shortens the list (the image index is a digit of the work index).
   UmmaConvArgs a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
+  if (a.pair) return launch_conv_pair(plan, st, active_n);
   if (active_n >= 0 && active_n < plan.N) {   // a smaller active batch: plain item list, no tail split
     const int items = a.tail_items > 0 ? a.main_work + a.tail_items : a.total_work;
     a.total_work = items / plan.N * active_n;

@@ -151,7 +151,8 @@ int add_conv(premvos_refnet* n, const std::string& scope, bool bn, float eps, co
   ConvWeightsUmma* cw = n->conv_weights.back().get();
   ConvPlanUmma* pl = n->conv_plans.back().get();
   const long m_out = out.cp.hi ? (long)out.cp.N * out.cp.H * out.cp.W : (long)out.f32.N * out.f32.H * out.f32.W;
-  PV_TRY(pack_conv_weights_umma(cw, w.data(), shift.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out));
+  const bool flat = kh == 1 && kw == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0;
+  PV_TRY(pack_conv_weights_umma(cw, w.data(), shift.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out, flat));
   PV_TRY(plan_conv_umma(pl, in, out, *cw, g));
   n->steps.push_back([pl](cudaStream_t st, int na) { return launch_conv_umma(*pl, st, na); });
   return 0;

@@ -17,8 +17,24 @@ SHAPES = {
     "xc_mid": (20, 728, 25, 25, 728, 1, 1, 1),
     "xc_e2": (20, 256, 97, 97, 256, 1, 1, 1),
     "xc_e1": (20, 128, 193, 193, 128, 1, 1, 1),
+    # the benchmarked launch group: 40 crops
+    "xc40_mid": (40, 728, 25, 25, 728, 1, 1, 1),
+    "xc40_x1": (40, 728, 25, 25, 1024, 1, 1, 1),
+    "xc40_x2": (40, 1024, 25, 25, 1536, 1, 1, 1),
+    "xc40_x3": (40, 1536, 25, 25, 2048, 1, 1, 1),
+    "xc40_aspp": (40, 2048, 25, 25, 256, 1, 1, 1),
+    "xc40_e2": (40, 256, 97, 97, 256, 1, 1, 1),
+    "xc40_dec": (40, 304, 97, 97, 256, 1, 1, 1),
+    "xc40_e3": (40, 728, 49, 49, 728, 1, 1, 1),
+    # proposal network, batch 4 (568 x 1333 -> C4 35 x 83)
+    "p4_c3": (4, 256, 35, 83, 1024, 1, 1, 1),
+    "p4_c1": (4, 1024, 35, 83, 256, 1, 1, 1),
+    "p4_g1c3": (4, 128, 71, 166, 512, 1, 1, 1),
+    "p4_g0c3": (4, 64, 142, 333, 256, 1, 1, 1),
+    "h4_c3": (400, 512, 7, 7, 2048, 1, 1, 1),
+    "h4_c1": (400, 2048, 7, 7, 512, 1, 1, 1),
 }
-KEYS = ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_BUDGET_KB", "PREMVOS_KSPLIT", "PREMVOS_BN", "PREMVOS_DBG", "PREMVOS_NBUF", "PREMVOS_FLAT", "PREMVOS_CONV_REPEAT", "PREMVOS_LOCKSTEP", "PREMVOS_EPI8", "PREMVOS_TAIL", "PREMVOS_TAIL_SPLIT")
+KEYS = ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_BUDGET_KB", "PREMVOS_KSPLIT", "PREMVOS_BN", "PREMVOS_DBG", "PREMVOS_NBUF", "PREMVOS_FLAT", "PREMVOS_CONV_REPEAT", "PREMVOS_LOCKSTEP", "PREMVOS_EPI8", "PREMVOS_TAIL", "PREMVOS_TAIL_SPLIT", "PREMVOS_PAIR", "PREMVOS_PAIR_STAGES", "PREMVOS_PAIR_MIN_ITEMS")
 
 
 def run(name, env):
