@@ -22,10 +22,14 @@ premvos_b200.pipeline.FramePipeline; the metric is whole-job frame pairs per sec
   roofline : dominant kernel of the step (by device time) from a per-launch CUDA-event pass over one step run serially
              on one stream (graphs bypassed so each launch can be bracketed): algorithmic FLOPs / measured time vs
              MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference : the CPU oracle restatement of the reference forwards on all host threads, on a bounded
-             sample of the same unit (1 flow pair + 1 proposal pass + 2 refinement crops), scaled to the unit's
-             1 + 2 + 40 (the reference's own CPU path cannot run: its CPU correlation is a stub, warp() hard-codes .cuda(),
-             TensorFlow 1.8 / tensorpack are not installable).
+  cpu_baseline / --impl reference : the CPU oracle restatement of the reference forwards on all host threads.  A step of the
+             reference arm is ONE full unit actually executed (1 flow pair + 2 proposal passes + all `--boxes` refinement crops,
+             one at a time as the reference iterates) -- the bounded sample of the product arm's 4-unit step; --steps / --warmup
+             are honoured as given.  (The reference's own CPU path cannot run: its CPU correlation is a stub, warp() hard-codes
+             .cuda(), TensorFlow 1.8 / tensorpack are not installable.)
+  library_baseline : the oracle graphs on the GPU through torch / cuDNN in fp32 and TF32 (baseline/library_baseline.py) -- what a
+             plain library implementation of the same arithmetic does on this GPU; context, not the product path.
+  c1_correlation : BASELINE configs[0] on the device: the cost-volume kernel alone, GB/s of algorithmic bytes vs the HBM peak.
 """
 import argparse
 import json
@@ -59,10 +63,12 @@ def load_peaks():
 
 
 def load_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_ncu_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of the benchmarked step
+    (profiles/r02_ncu_traffic.json, else round 1's), or None."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p)).get(kernel)
     return None
 
 
@@ -113,9 +119,9 @@ def make_units(n_units, boxes_per_frame):
     return units
 
 
-def oracle_unit_time(repeats, warmup, boxes_per_frame):
-    """Bounded CPU sample of one unit with the oracle: 1 PWC forward + 1 proposal-net forward + 2 refinement crops, all host
-    threads, scaled to the unit (1 flow + 2 proposal passes + boxes_per_frame crops).  -> (seconds per unit, cores, parts)"""
+def oracle_unit_times(repeats, warmup, boxes_per_frame):
+    """`repeats` timed FULL units with the CPU oracle on all host threads, one at a time as the reference iterates: 1 PWC forward +
+    2 proposal-net forwards (general, specific) + `boxes_per_frame` refinement crops.  -> (seconds of every timed unit, cores, parts)"""
     import cv2
     import torch
     from oracle import propnet_oracle as PO, pwc_oracle as O, refnet_oracle as RO
@@ -126,11 +132,11 @@ def oracle_unit_time(repeats, warmup, boxes_per_frame):
     Hp, Wp = propnet.custom_resize_shape(H_IN, W_IN)
     sd = {k: torch.from_numpy(v) for k, v in synth.pwc_synthetic_state_dict(0).items()}
     x = torch.from_numpy(synth.synthetic_pwc_input(1, Hn, Wn, seed=1))
-    PP = synth.propnet_synthetic_params(1)
+    PPs = [synth.propnet_synthetic_params(1), synth.propnet_synthetic_params(4)]
     img = cv2.resize(synth.synthetic_bgr_frame(H_IN, W_IN, seed=2), (Wp, Hp)).astype(np.float32)
     RP = synth.refnet_synthetic_params(2)
     frame = synth.synthetic_bgr_frame(H_IN, W_IN, seed=3)
-    boxes = synth.synthetic_boxes(2, H_IN, W_IN, seed=3)
+    boxes = synth.synthetic_boxes(boxes_per_frame, H_IN, W_IN, seed=3)
     image = (frame / 255).astype(np.float32)
 
     def crops():
@@ -139,41 +145,90 @@ def oracle_unit_time(repeats, warmup, boxes_per_frame):
             logits = RO.deeplab_logits(RP, inputs[None])[0]
             RO.segmentation_output(logits, crop, H_IN, W_IN, 385)
 
-    parts = {"flow": [], "proposal_pass": [], "refine_crop": []}
+    units, parts = [], {"flow": [], "proposal_pass": [], "refine_crop": []}
     for it in range(warmup + repeats):
         t0 = time.perf_counter(); O.pwc_forward(sd, x)
-        t1 = time.perf_counter(); PO.propnet_forward(PP, img)
+        t1 = time.perf_counter(); PO.propnet_forward(PPs[0], img); PO.propnet_forward(PPs[1], img)
         t2 = time.perf_counter(); crops()
         t3 = time.perf_counter()
         if it >= warmup:
-            parts["flow"].append(t1 - t0); parts["proposal_pass"].append(t2 - t1); parts["refine_crop"].append((t3 - t2) / len(boxes))
-    parts = {k: float(np.mean(v)) for k, v in parts.items()}
-    sec = parts["flow"] + 2 * parts["proposal_pass"] + boxes_per_frame * parts["refine_crop"]
-    return sec, cores, parts
+            units.append(t3 - t0)
+            parts["flow"].append(t1 - t0); parts["proposal_pass"].append((t2 - t1) / 2); parts["refine_crop"].append((t3 - t2) / len(boxes))
+    return units, cores, {k: float(np.mean(v)) for k, v in parts.items()}
 
 
 def sample_text(repeats, parts, boxes_per_frame):
-    return ("oracle (torch CPU, all host threads) on a bounded sample of one unit: 1 PWC forward 448x1024 (%.2f s) + 1 proposal-net "
-            "forward 568x1333 (%.2f s) + 2 refinement crops 385x385 (%.2f s each), mean of %d repeat(s); unit time = flow + 2 x "
-            "proposal pass + %d x crop" % (parts["flow"], parts["proposal_pass"], parts["refine_crop"], repeats, boxes_per_frame))
+    return ("oracle (torch CPU, all host threads), %d full unit(s) executed: 1 PWC forward 448x1024 (%.2f s) + 2 proposal-net forwards "
+            "568x1333 (%.2f s each) + %d refinement crops 385x385 one at a time (%.3f s each); nothing extrapolated"
+            % (repeats, parts["flow"], parts["proposal_pass"], boxes_per_frame, parts["refine_crop"]))
+
+
+def bench_config(B, K, world, refine_batch, l2_note):
+    return {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "global_pairs_per_step": B * world, "boxes_per_frame": K,
+            "refine_batch": refine_batch or K, "parallelism": "dp%d" % world,
+            "weights": "seeded random init of the reference architectures (PWC-DC-Net 9.4M, 2 x ResNet-101 C4 51.9M, Xception-65 "
+                       "DeepLabv3+ 40.8M params)",
+            "l2": l2_note}
+
+
+def l2_note(B, K):
+    per_set = B * (2 * H_IN * W_IN * 3 + K * 16)
+    sets = max(2, -(-(2 * 126 << 20) // per_set))
+    return sets, per_set, ("inputs rotate over %d device input sets (%d MB > 126 MB L2); per-step activations are > 10 GB"
+                           % (sets, sets * per_set >> 20))
 
 
 def run_reference(args, rank):
+    """The reference arm: K timed steps after W warm-up steps, a step = one full unit on the host cores (see the module docstring)."""
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = max(0, min(args.warmup, 1))
-    sec, cores, parts = oracle_unit_time(steps, warm, args.boxes)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    units, cores, parts = oracle_unit_times(steps, warm, args.boxes)
+    sec = float(np.mean(units))
     val = 1.0 / sec
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "boxes_per_frame": args.boxes,
-                       "note": "CPU oracle port of the reference forwards on the host cores; the reference's own CPU path cannot "
-                               "run (corr.c is a stub, warp() hard-codes .cuda(), TF 1.8 / tensorpack not installable)"},
+            "config": bench_config(args.pairs, args.boxes, max(1, args.gpus), args.refine_batch, l2_note(args.pairs, args.boxes)[2]),
+            "reference_note": "CPU oracle port of the reference forwards on the host cores; a step of this arm is one unit (one frame "
+                              "pair) of the product arm's %d-pair step; the reference's own CPU path cannot run (corr.c is a stub, "
+                              "warp() hard-codes .cuda(), TF 1.8 / tensorpack not installable)" % args.pairs,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_text(steps, parts, args.boxes)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def c1_correlation(peak_gbs):
+    """BASELINE configs[0] on the device: the cost-volume operator alone (pad 4, md 4) on the stress shape [1,32,256,256], on PWC
+    level 2 of the benchmarked step [4,32,112,256] and on the 256x256 pyramid; CUDA events, inputs rotated over > L2 of buffers."""
+    import torch
+    from premvos_b200 import pwc
+    corr = pwc.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    out = {}
+    for name, shapes in (("stress_1x32x256x256", [(1, 32, 256, 256)]), ("pwc_level2_4x32x112x256", [(4, 32, 112, 256)]),
+                         ("pyramid_256x256", [(1, 196, 4, 4), (1, 128, 8, 8), (1, 96, 16, 16), (1, 64, 32, 32), (1, 32, 64, 64)])):
+        nbytes = sum(4 * (2 * c + 81) * h * w * b for b, c, h, w in shapes)
+        sets = max(2, min(64, (2 * 126 << 20) // max(nbytes, 1) + 1))
+        bufs = [[(torch.randn(s, device="cuda"), torch.randn(s, device="cuda")) for s in shapes] for _ in range(sets)]
+        def run(i):
+            for a, b in bufs[i % sets]:
+                corr(a, b)
+        for i in range(3):
+            run(i)
+        torch.cuda.synchronize()
+        iters = 50
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / iters
+        out[name] = {"us": us, "algorithmic_bytes": nbytes, "gbs": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peak_gbs,
+                     "launches": len(shapes)}
+    out["note"] = ("premvos_corr_forward through pwc.Correlation (includes the operator's output allocation); bytes = 4*(2C+81)*H*W per "
+                   "image (SURVEY 8d C1); the pyramid is launch-latency bound (5 launches of <= 0.7 MB)")
+    return out
 
 
 def time_stage(fn, iters, warm=2):
@@ -201,6 +256,7 @@ def main():
     ap.add_argument("--refine-batch", type=int, default=0, help="refinement crops per launch group (0 = all boxes of a frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-network context timings")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch / cuDNN context timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -233,8 +289,7 @@ def main():
     pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (H_IN, W_IN), pairs_per_step=B, boxes_per_frame=K, refine_batch=args.refine_batch or None)
 
     # `sets` different input batches, rotated so that consecutive steps never read the same input (> L2 in total)
-    per_set = pipe.h2d_bytes_per_step(original_frames=True)
-    sets = max(2, -(-(2 * 126 << 20) // per_set))
+    sets, per_set, l2_text = l2_note(B, K)
     units = make_units(sets * B, K)
     host_sets, dev_sets = [], []
     for s in range(sets):
@@ -336,29 +391,40 @@ def main():
                   "sum_serial_ms_per_pair": t_flow / B + 2 * t_prop + t_ref,
                   "note": "each network alone on one stream, CUDA events; a unit = flow + 2 proposal passes + refine"}
 
+    h2d_bytes, d2h_bytes = pipe.h2d_bytes_per_step(original_frames=True), pipe.d2h_bytes_per_step()
+    launches_per_step = pipe.launches_per_step_from_frames()
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores, parts = oracle_unit_time(1, 0, K)
-        cpu_baseline = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_text(1, parts, K)}
+        units_s, cores, parts = oracle_unit_times(1, 0, K)
+        cpu_baseline = {"value": 1.0 / units_s[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_text(1, parts, K)}
+
+    # ---- context: the same arithmetic through torch / cuDNN on this GPU, and BASELINE configs[0] (rank 0, N=1 only) ----
+    library_baseline, c1 = None, None
+    if rank == 0 and world == 1:
+        c1 = c1_correlation(load_peaks()["hbm"])
+        if not args.no_library_baseline:
+            del pipe
+            torch.cuda.empty_cache()
+            try:
+                from baseline import library_baseline as LB
+                library_baseline = LB.run(pairs=B, boxes=K)
+            except Exception as e:   # context only: never fail the bench line over it
+                library_baseline = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3 split-fp32 (fp32 accumulate)", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "global_pairs_per_step": B * world,
-                           "boxes_per_frame": K, "refine_batch": args.refine_batch or K, "parallelism": "dp%d" % world,
-                           "weights": "seeded random init of the reference architectures (PWC-DC-Net 9.4M, 2 x ResNet-101 C4 "
-                                      "51.9M, Xception-65 DeepLabv3+ 40.8M params)",
-                           "l2": "inputs rotate over %d device input sets (%d MB > 126 MB L2); per-step activations are > 10 GB"
-                                 % (sets, sets * per_set >> 20)},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step(original_frames=True),
-                        "d2h_bytes_per_step": pipe.d2h_bytes_per_step(),
+                "config": bench_config(B, K, world, args.refine_batch, l2_text),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "call": "FramePipeline.run_frames_host: pinned uint8 frames t, t+1 + boxes in (as a decoder hands them over; the stage "
                                 "drivers' cv2.resize calls run on the device, bit-exact), flow + detections + per-box masks + conf_scores "
                                 "out to pinned host memory, synchronous per step"},
-                "gpu_launches": int(launches), "launches_per_step": pipe.launches_per_step_from_frames(),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "stages": stages}
+                "gpu_launches": int(launches), "launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "library_baseline": library_baseline,
+                "c1_correlation": c1, "kernels": kernels, "stages": stages}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()

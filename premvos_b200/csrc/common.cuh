@@ -212,7 +212,17 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
 void free_conv_weights_umma(ConvWeightsUmma* w);
 struct ConvPlanUmma;
 void free_conv_plan_umma(ConvPlanUmma* plan);
-int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g);
+// Scratch of the CTA-pair kernel's stream-K schedule (partial sums + flags).  One per network / stream: the layers of a network
+// run one after the other and share it; launches that may run CONCURRENTLY must not (ws == nullptr: the plan owns a private one).
+struct ConvWorkspace {
+  void* base = nullptr;
+  float* partial = nullptr;
+  unsigned* flags = nullptr;
+};
+int conv_workspace_reserve(ConvWorkspace* ws);
+void conv_workspace_free(ConvWorkspace* ws);
+int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g,
+                   ConvWorkspace* ws = nullptr);
 // active_n >= 0: process only the first active_n images of the planned batch
 int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n = -1);
 

@@ -161,6 +161,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // ---- CTA-pair (cta_group::2) variants: a cluster of two CTAs on the two SMs of a TPC runs ONE 256 x N MMA per instruction ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -179,6 +187,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same without the cluster-scope release (which costs a MEMBAR.ALL.GPU per arrival): what is handed over here is tensor memory,
+// ordered by tcgen05.fence::before_thread_sync on this side and ::after_thread_sync on the waiting side, not generic memory.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA box into THIS CTA's shared memory, bytes credited to the barrier at `mbar_cluster_addr` (the pair leader's)
 __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t mbar_cluster_addr, void* dst, int c0, int c1, int c2, int c3) {
@@ -288,6 +301,8 @@ struct UmmaConvArgs {
   int lockstep;              // 1x1 layers: A and weight rings advance together and share one barrier pair per k-block
   int epi_warps;             // 4 or 8 epilogue warps (8: kernel instantiation with 384 threads, one CTA per SM)
   int pair;                  // 1: conv_pair_kernel (cta_group::2, 256 pixels x 256 output channels per CTA pair); see there
+  int stream_k_all;          // pair kernel: 1 = no round-robin phase, all items are cut into equal k-block ranges (tuning switch)
+  unsigned* sk_flags;        // pair kernel, stream-K: [pairs][2 ranks][8 epilogue warps] flags; `partial` = [pairs][2][128][256] fp32
 };
 
 // EPI_WARPS = 4: 256 threads, up to two CTAs per SM.  EPI_WARPS = 8: 384 threads, one CTA per SM owning the whole TMEM (256-wide N
@@ -848,23 +863,49 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int tiles_per_img = a.tiles_y;
-  struct Work { int ntile, mp, z, kb_begin, kb_end, tail_slot; };
-  auto decode = [&](int t) {
-    Work w;
-    w.tail_slot = -1; w.z = 0; w.kb_begin = 0; w.kb_end = a.kblocks;
-    if (a.tail_items > 0 && t >= a.main_work) {
-      const int u = t - a.main_work;
-      w.tail_slot = u / a.tail_split;
-      w.z = u - w.tail_slot * a.tail_split;
-      t = a.main_work + w.tail_slot;
-      w.kb_begin = w.z * a.tail_kb_per;
-      w.kb_end = min(a.kblocks, w.kb_begin + a.tail_kb_per);
+  // Schedule.  Phase 1: all but the last full round of items go round-robin, item t to pair t % P, so that the pairs running at the
+  // same time work on neighbouring items = share their A tiles (same pixel tiles) and weight tiles in the L2 (an all-stream-K order
+  // measured 10 % slower on the big layers: 74 pairs reading 74 different tiles).  Phase 2 ("stream-K" over the last round plus the
+  // remainder, P <= items < 2P, or over everything when there are fewer items than pairs): the (item, k-block) units of those
+  // items, item-major, are cut into P equal contiguous ranges, pair p takes range p as fragments (item, [kb_begin, kb_end)); a
+  // range is at least half an item long (the host picks P), so an item is finished from at most two partial sums.  A fragment that does not start at k-block 0 is a CONTRIBUTOR: it is the first
+  // fragment of its pair's range, stores raw fp32 partial sums into workspace slot `pair` and raises one flag per epilogue warp.
+  // The fragment that starts at k-block 0 but ends early is the FINISHER: it is the last fragment of its pair's range, waits for the
+  // flags of the following pair(s), adds their partial sums in pair order (deterministic) and runs the epilogue.  A pair runs its
+  // contributor before anything it could wait for, and only ever waits for pairs with a higher index.
+  const int K = a.kblocks;
+  const int rounds = a.total_work / n_pairs;
+  const int n_main = a.stream_k_all ? 0 : (a.total_work % n_pairs == 0 ? a.total_work : max(0, rounds - 1) * n_pairs);
+  const long U = (long)(a.total_work - n_main) * K;
+  auto range_begin = [&](int p) { return U * p / n_pairs; };
+  const long u_end = range_begin(pair_id + 1);
+  struct Work { int ntile, mp, item, kb_begin, kb_end; };
+  struct Cursor { int t; long u; };
+  auto next_fragment = [&](Cursor& c, Work& w) {
+    if (c.t < n_main) {
+      w.item = c.t; w.kb_begin = 0; w.kb_end = K;
+      c.t += n_pairs;
+    } else if (c.u < u_end) {
+      const int ri = (int)(c.u / K);
+      w.item = n_main + ri;
+      w.kb_begin = (int)(c.u - (long)ri * K);
+      w.kb_end = (int)min((long)K, (long)w.kb_begin + (u_end - c.u));
+      c.u += w.kb_end - w.kb_begin;
+    } else {
+      return false;
     }
-    w.mp = t / a.ntiles;
-    w.ntile = t - w.mp * a.ntiles;
-    return w;
+    w.mp = w.item / a.ntiles;
+    w.ntile = w.item - w.mp * a.ntiles;
+    return true;
   };
-
+  const Cursor cursor0{pair_id, range_begin(pair_id)};
+  const bool dbg_on = (a.dbg & 64) && (blockIdx.x == 0 || blockIdx.x == 41);
+  __shared__ long long dbg_frag[16][4];
+  int dbg_nf = 0;
+  const long long dbg_c0 = clock64();
+  const unsigned long long dbg_t0 = (a.dbg & 32) ? globaltimer_ns() : 0ull;
+  __shared__ unsigned long long dbg_ev[4];
+  if ((a.dbg & 32) && threadIdx.x < 4) dbg_ev[threadIdx.x] = 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmW);
     for (int s = 0; s < a.w_stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -883,8 +924,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint32_t st = 0, ph = 0;
     const uint32_t half_bytes = 2u * (uint32_t)a.a_box_bytes + 2u * (uint32_t)a.w_plane;   // what ONE CTA loads per k-block
     const int w_rows = (2 * a.w_plane) >> 7;                                             // 128-byte rows of one CTA's weight block
-    for (int t = pair_id; t < a.total_work; t += n_pairs) {
-      const Work wk = decode(t);
+    Cursor cur = cursor0;
+    Work wk;
+    while (next_fragment(cur, wk)) {
       const int mtile = 2 * wk.mp + (int)rank;
       const int n_img = mtile / tiles_per_img, ty0 = (mtile - n_img * tiles_per_img) * 16;
       int wrow = ((wk.ntile * a.kblocks + wk.kb_begin) * 2 + (int)rank) * w_rows;
@@ -912,8 +954,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t kstep16 = (2u * lbo) >> 4, a_plane16 = (uint32_t)a.a_plane >> 4, w_plane16 = (uint32_t)a.w_plane >> 4;
     const int ksteps = a.KC / 2;
     uint32_t st = 0, ph = 0, buf = 0, empty_ph = 0;
-    for (int t = pair_id; t < a.total_work; t += n_pairs) {
-      const Work wk = decode(t);
+    Cursor cur = cursor0;
+    Work wk;
+    while (next_fragment(cur, wk)) {
       mbar_wait(&tmem_empty_bar[buf], ((empty_ph >> buf) & 1u) ^ 1u);
       empty_ph ^= 1u << buf;
       tc_fence_after();
@@ -923,6 +966,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         mbar_wait(&full[st], ph);
         tc_fence_after();
         if (elect_one()) {
+          if ((a.dbg & 32) && dbg_ev[0] == 0) dbg_ev[0] = globaltimer_ns();
           uint32_t aH = lo32 + ((a_base + st * a_stage_bytes) >> 4), wH = lo32 + ((w_base + st * w_stage_bytes) >> 4);
           for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ks++, aH += kstep16, wH += kstep16) {
             umma_pair_lo(tmem_acc, aH + a_plane16, hi32, wH, hi32, idesc, accum);
@@ -937,6 +981,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
       if (elect_one()) umma_commit_pair(&tmem_full_bar[buf]);
       __syncwarp();
+      if ((a.dbg & 32) && lane == 0) dbg_ev[1] = globaltimer_ns();
       buf ^= 1u;
     }
   } else if (warp >= 4) {
@@ -947,64 +992,94 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     uint32_t buf = 0, full_ph = 0;
     const int col_part = (warp - 4) >> 2, col_span = a.BN / 2;
     const int col_begin = col_part * col_span, col_end = col_begin + col_span;
-    for (int t = pair_id; t < a.total_work; t += n_pairs) {
-      const Work wk = decode(t);
+    const int ew = warp - 4;   // epilogue warp 0..7 of this CTA
+    Cursor cur = cursor0;
+    Work wk;
+    while (next_fragment(cur, wk)) {
       const int mtile = 2 * wk.mp + (int)rank;
       const int n_img = mtile / tiles_per_img;
       const long pix = (long)(mtile - n_img * tiles_per_img) * 128 + m;
       const bool in_img = n_img < a.n_images && pix < hw;
+      const bool contributor = wk.kb_begin > 0;
+      // finisher: the pairs after this one whose range starts inside this item hold the rest of its k-blocks
+      int nq = 0;
+      if (!contributor && wk.kb_end < K) {
+        const long item_end = (long)(wk.item - n_main + 1) * K;
+        while (pair_id + 1 + nq < n_pairs && range_begin(pair_id + 1 + nq) < item_end) nq++;
+      }
+      long long dbg_f0 = 0, dbg_f1 = 0;
+      if (dbg_on && warp == 4 && lane == 0) dbg_f0 = clock64();
       mbar_wait(&tmem_full_bar[buf], (full_ph >> buf) & 1u);
       full_ph ^= 1u << buf;
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tmem_acc + (uint32_t)c0, v);
-        const int co0 = wk.ntile * a.BN + c0;
-        const bool live = in_img && co0 < a.Cout && wk.tail_slot < 0;
-        float4 bv[4];
-        uint4 rres[4];
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + co0) + j);
-          if (a.res_hi) {
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              if (co0 + 8 * h >= a.Cout) continue;
-              const long ri = (((long)n_img * a.res_chunks + a.res_c0 + (co0 >> 3) + h) * hw + pix) * 8;
-              rres[2 * h] = *reinterpret_cast<const uint4*>(a.res_hi + ri);
-              rres[2 * h + 1] = *reinterpret_cast<const uint4*>(a.res_lo + ri);
+      if (nq > 0) {   // the partial sums this warp will add were written by the same (rank, warp) of the contributing pairs
+        if (lane == 0) {
+          for (int j = 0; j < nq; j++) {
+            unsigned* flag = a.sk_flags + ((pair_id + 1 + j) * 2 + (int)rank) * 8 + ew;
+            uint32_t spins = 0;
+            while (ld_acquire_u32(flag) == 0u) {
+              if (++spins > (1u << 24)) __trap();
+              __nanosleep(64);
             }
+            *flag = 0u;   // self-cleaning: the next launch (stream order) finds it lowered
           }
         }
-        tmem_ld_wait();
-        if (c0 + 16 >= col_end) {   // this warp's columns are all in registers: hand the buffer back to the issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(te_leader + buf * 8u);
-        }
-        if (a.dbg & 4) continue;
-        if (wk.tail_slot >= 0) {   // raw partial sums [z][tail item][rank][128 rows][BN]
-          float* pp = a.partial + ((((long)(wk.z * a.tail_items + wk.tail_slot) * 2 + rank) * 128 + m) * a.BN + c0);
+        __syncwarp();
+      }
+      if (dbg_on && warp == 4 && lane == 0) dbg_f1 = clock64();
+      const uint32_t tmem_acc = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+      // Column loop, 16 accumulator columns (= two 8-channel chunks) per step.  The TMEM load of step g+1 is in flight while step g
+      // is processed (two register sets), addresses are running pointers (one 64-bit multiply per item, not per store), the hi/lo
+      // split converts two values per instruction (F2FP.PACK_AB; the scalar F2F conversions run at a quarter of that rate).
+      const long row = ((long)n_img * hw + pix);                          // pixel index inside its plane stack
+      const long chunk_stride = hw * 8;                                     // elements between two chunk planes
+      const int cg0 = (wk.ntile * a.BN + col_begin) >> 3;                   // first 8-channel chunk of this warp
+      __nv_bfloat16* ohi = a.out_hi + ((((long)n_img * a.out_chunks + a.out_c0 + cg0) * hw + pix) << 3);
+      __nv_bfloat16* olo = a.out_lo + (ohi - a.out_hi);
+      const __nv_bfloat16* rhi = a.res_hi ? a.res_hi + ((((long)n_img * a.res_chunks + a.res_c0 + cg0) * hw + pix) << 3) : nullptr;
+      const __nv_bfloat16* rlo = a.res_hi ? a.res_lo + (rhi - a.res_hi) : nullptr;
+      const float* bias = a.bias + wk.ntile * a.BN + col_begin;
+      // partial sums: [pair slot][rank][column / 4 (64)][row (128)] float4 -- a warp's 32 rows of one float4 column are contiguous
+      float4* ppart = reinterpret_cast<float4*>(a.partial) + (((long)pair_id * 2 + rank) * 64 + (col_begin >> 2)) * 128 + m;
+      (void)row;
+      uint32_t va[16], vb[16];
+      __syncwarp();
+      tmem_ld16(tmem_acc + (uint32_t)col_begin, va);
+      auto process = [&](uint32_t (&v)[16], int c0) {
+        const int co0 = wk.ntile * a.BN + c0, g = (c0 - col_begin) >> 4;
+        if (contributor) {   // raw partial sums into this pair's workspace slot, [pair][rank][128 rows][256]
+          float4* pp = ppart + (g << 2) * 128;
 #pragma unroll
           for (int j = 0; j < 4; j++)
-            reinterpret_cast<float4*>(pp)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          continue;
+            __stcg(pp + j * 128, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3])));
+          return;
         }
-        if (!live) continue;
+        if (!in_img || co0 >= a.Cout) return;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          f[4 * j] = __uint_as_float(v[4 * j]) + bv[j].x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv[j].y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv[j].z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
+        for (int jq = 0; jq < nq; jq++) {   // finisher: partial sums of the following pairs, in pair order (deterministic)
+          const float4* pp = reinterpret_cast<const float4*>(a.partial) + (((long)(pair_id + 1 + jq) * 2 + rank) * 64 + (c0 >> 2)) * 128 + m;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 t4 = __ldcg(pp + i * 128);
+            f[4 * i] += t4.x; f[4 * i + 1] += t4.y; f[4 * i + 2] += t4.z; f[4 * i + 3] += t4.w;
+          }
         }
-        if (a.res_hi) {
+        const float4* bp = reinterpret_cast<const float4*>(bias + (g << 4));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float4 b4 = __ldg(bp + j);
+          f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+        }
+        const bool second = co0 + 8 < a.Cout;   // the second chunk of this step exists
+        if (rhi) {
 #pragma unroll
           for (int h = 0; h < 2; h++) {
-            if (co0 + 8 * h >= a.Cout) continue;
-            const uint4 rh = rres[2 * h], rl = rres[2 * h + 1];
+            if (h == 1 && !second) break;
+            const uint4 rh = *reinterpret_cast<const uint4*>(rhi + (2 * g + h) * chunk_stride);
+            const uint4 rl = *reinterpret_cast<const uint4*>(rlo + (2 * g + h) * chunk_stride);
             const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -1013,74 +1088,80 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
           }
         }
-        if (a.out_f32 && a.f32_linear) {
-          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
+        if (a.slope != 1.f) {   // LeakyReLU / ReLU: max(f, slope * f) for 0 <= slope < 1
 #pragma unroll
-          for (int j = 0; j < 16; j++)
-            if (co0 + j >= a.f32_first && co0 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+          for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], f[j] * a.slope);
         }
 #pragma unroll
-        for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
-        if (a.out_hi) {
+        for (int h = 0; h < 2; h++) {
+          if (h == 1 && (!second || co0 + 8 >= a.cp_cout)) break;
+          uint32_t hw4[4], lw4[4];
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            if (co0 + 8 * h >= a.cp_cout) continue;
-            uint32_t hw4[4], lw4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const float x0 = f[8 * h + 2 * j], x1 = f[8 * h + 2 * j + 1];
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-              hw4[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lw4[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
-            const long oi = (((long)n_img * a.out_chunks + a.out_c0 + (co0 >> 3) + h) * hw + pix) * 8;
-            *reinterpret_cast<uint4*>(a.out_hi + oi) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
-            *reinterpret_cast<uint4*>(a.out_lo + oi) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+          for (int j = 0; j < 4; j++) {
+            const float x0 = f[8 * h + 2 * j], x1 = f[8 * h + 2 * j + 1];
+            const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+            const uint32_t hwd = *reinterpret_cast<const uint32_t*>(&hp);
+            const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - __uint_as_float(hwd << 16), x1 - __uint_as_float(hwd & 0xffff0000u));
+            hw4[j] = hwd; lw4[j] = *reinterpret_cast<const uint32_t*>(&lp);
           }
+          *reinterpret_cast<uint4*>(ohi + (2 * g + h) * chunk_stride) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+          *reinterpret_cast<uint4*>(olo + (2 * g + h) * chunk_stride) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
         }
-        if (a.out_f32 && !a.f32_linear) {
-          float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
-#pragma unroll
-          for (int j = 0; j < 16; j++)
-            if (co0 + j >= a.f32_first && co0 + j < a.Cout) pf[j] = a.f32_accum ? pf[j] + f[j] : f[j];
+      };
+      for (int c0 = col_begin; c0 < col_end; c0 += 32) {
+        tmem_ld_wait();                                                    // va (columns c0 ..) has landed
+        __syncwarp();
+        if (c0 + 16 < col_end) tmem_ld16(tmem_acc + (uint32_t)(c0 + 16), vb);
+        else {   // every column of this warp is in registers: hand the accumulator buffer back to the issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(te_leader + buf * 8u);
         }
+        if (!(a.dbg & 4)) process(va, c0);
+        if (c0 + 16 >= col_end) break;
+        tmem_ld_wait();
+        __syncwarp();
+        if (c0 + 32 < col_end) tmem_ld16(tmem_acc + (uint32_t)(c0 + 32), va);
+        else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(te_leader + buf * 8u);
+        }
+        if (!(a.dbg & 4)) process(vb, c0 + 16);
+      }
+      if (contributor) {   // this warp's share of the partial sums is written: publish it
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(a.sk_flags + (pair_id * 2 + (int)rank) * 8 + ew, 1u);
       }
       buf ^= 1u;
+      if ((a.dbg & 32) && lane == 0) dbg_ev[2] = max(dbg_ev[2], globaltimer_ns());
+      if (dbg_on && warp == 4 && lane == 0 && dbg_nf < 16) {
+        dbg_frag[dbg_nf][0] = dbg_f0 - dbg_c0; dbg_frag[dbg_nf][1] = dbg_f1 - dbg_c0; dbg_frag[dbg_nf][2] = clock64() - dbg_c0;
+        dbg_frag[dbg_nf][3] = wk.item * 1000 + wk.kb_begin * 10 + (contributor ? 1 : 0) + (nq ? 2 : 0);
+        dbg_nf++;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // nobody frees TMEM / exits while the peer's MMAs, TMA credits or barrier arrivals may still be in flight
   if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
-}
-
-// Finishes the K-split tail items of a pair launch: one thread per (tail item, CTA rank, accumulator row, 8-channel chunk).
-__global__ void __launch_bounds__(256) conv_pair_finish_tail_kernel(const UmmaConvArgs a) {
-  const int cch = a.BN / 8;
-  const long total = (long)a.tail_items * 2 * 128 * cch;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int m = (int)(idx % 128);                // row fastest -> coalesced CP8 stores
-  const int cc = (int)((idx / 128) % cch);
-  const int rank = (int)((idx / (128L * cch)) % 2);
-  const int slot = (int)(idx / (256L * cch));
-  const int t = a.main_work + slot;
-  const int mp = t / a.ntiles, ntile = t - mp * a.ntiles;
-  const int mtile = 2 * mp + rank, n_img = mtile / a.tiles_y;
-  const long hw = (long)a.flat_hw, pix = (long)(mtile - n_img * a.tiles_y) * 128 + m;
-  const int c8 = (ntile * a.BN) / 8 + cc;
-  if (n_img >= a.n_images || pix >= hw || c8 * 8 >= a.Cout) return;
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) f[j] = 0.f;
-  for (int z = 0; z < a.tail_split; z++) {
-    const float* pp = a.partial + ((((long)(z * a.tail_items + slot) * 2 + rank) * 128 + m) * a.BN + cc * 8);
-    const float4 p0 = reinterpret_cast<const float4*>(pp)[0], p1 = reinterpret_cast<const float4*>(pp)[1];
-    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+  if ((a.dbg & 32) && threadIdx.x == 0) {
+    const unsigned long long t1 = globaltimer_ns(), d = t1 - dbg_t0;
+    atomicMin(&g_dbg_cta[0], dbg_t0); atomicMax(&g_dbg_cta[1], t1); atomicAdd(&g_dbg_cta[2], d);
+    atomicMax(&g_dbg_cta[3], d); atomicMin(&g_dbg_cta[4], d); atomicAdd(&g_dbg_cta[5], 1ull);
+    if (blockIdx.x < 512) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* rr = g_dbg_rec[blockIdx.x];
+      rr[0] = smid; rr[1] = dbg_t0; rr[2] = t1; rr[3] = dbg_ev[0]; rr[4] = dbg_ev[1]; rr[5] = dbg_ev[2];
+    }
   }
-  finish_store(a, n_img, pix, (long)n_img * hw + pix, c8, f);
+  if (dbg_on && warp == 4 && lane == 0)
+    for (int i = 0; i < dbg_nf; i++)
+      printf("cta %d fragment %d (item*1000 + kb_begin*10 + contributor + 2*finisher = %lld): accumulator wait from %lld, flags done %lld, epilogue done %lld cycles\n",
+             (int)blockIdx.x, i, dbg_frag[i][3], dbg_frag[i][0], dbg_frag[i][1], dbg_frag[i][2]);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -1149,16 +1230,23 @@ int pack_conv_weights_umma(ConvWeightsUmma* out, const float* host_w, const floa
   int bn = round_up(Cout, 16);
   int bn_cap = 128;
   if (R * S == 1 && Cout >= 256 && m_hint > 0 && (m_hint / 256) * ((Cout + 255) / 256) >= 120) bn_cap = 256;
+  // CTA-pair kernel (conv_pair_kernel, cta_group::2, stream-K): layers the caller declares flat (1x1, stride 1, no padding) with at
+  // least 256 output channels and enough (item, k-block) units to give every one of the 74 pairs a few
+  bool pair = false;
+  if (allow_pair && R * S == 1 && Cout >= 256 && m_hint > 0 && kc_hint == 0 && env_int("PREMVOS_PAIR", 1) != 0 && env_int("PREMVOS_KC", 0) == 0 &&
+      env_int("PREMVOS_BN", 0) == 0) {
+    const int kc4 = std::min(4, round_up(chunks, 2));
+    const long units = ((m_hint + 255) / 256) * ((Cout + 255) / 256) * ((chunks + kc4 - 1) / kc4);
+    pair = kc4 == 4 && units >= env_int("PREMVOS_PAIR_MIN_UNITS", 296);
+  }
+  if (pair) bn_cap = 256;
   bn_cap = env_int("PREMVOS_BN", bn_cap);
   if (bn_cap != 256 || R * S != 1) bn_cap = std::min(bn_cap, 128);
   if (bn > bn_cap) bn = bn_cap;
   if (bn > 128 && kc_hint == 0 && env_int("PREMVOS_KC", 0) == 0) { kc = std::min(4, round_up(chunks, 2)); out->KC = kc; out->kblocks = (chunks + kc - 1) / kc; }
   out->BN = bn;
   out->ntiles = (Cout + bn - 1) / bn;
-  // CTA-pair kernel (conv_pair_kernel): 256-wide layers the caller declares flat (1x1, stride 1, no padding) whose item list fills
-  // the 74 pairs at least once; the weight image is then split into the two 128-row halves the two CTAs of a pair load
-  out->pair = (allow_pair && bn == 256 && kc == 4 && env_int("PREMVOS_PAIR", 1) != 0 &&
-               ((m_hint + 255) / 256) * out->ntiles >= env_int("PREMVOS_PAIR_MIN_ITEMS", 74)) ? 1 : 0;
+  out->pair = (pair && bn == 256 && kc == 4) ? 1 : 0;
   const int KP = out->kblocks * kc * 8;
   const int taps = R * S;
   const size_t plane_elems = (size_t)kc * bn * 8;   // one (tap, k-block) operand image of one plane
@@ -1203,11 +1291,27 @@ void free_conv_weights_umma(ConvWeightsUmma* w) {
 }
 
 
+constexpr int PAIR_SLOTS = 80;   // >= CTA pairs of a launch (74 on B200)
+int conv_workspace_reserve(ConvWorkspace* ws) {
+  if (ws->base) return 0;
+  const size_t partial_bytes = (size_t)PAIR_SLOTS * 2 * 128 * 256 * sizeof(float), flag_bytes = (size_t)PAIR_SLOTS * 2 * 8 * sizeof(unsigned);
+  PV_CUDA(cudaMalloc(&ws->base, partial_bytes + flag_bytes));
+  PV_CUDA(cudaMemset((char*)ws->base + partial_bytes, 0, flag_bytes));   // flags are lowered again by the kernel that consumes them
+  ws->partial = (float*)ws->base;
+  ws->flags = (unsigned*)((char*)ws->base + partial_bytes);
+  return 0;
+}
+void conv_workspace_free(ConvWorkspace* ws) {
+  if (ws->base) cudaFree(ws->base);
+  ws->base = nullptr; ws->partial = nullptr; ws->flags = nullptr;
+}
+
 // Plan of a CTA-pair launch (conv_pair_kernel): flattened 128-pixel tiles per image, pairs of tiles x 256-wide channel tiles.
 static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g, bool flat,
-                          int real_hw, int cp_cout, int f32_first) {
+                          int real_hw, int cp_cout, int f32_first, ConvWorkspace* ws) {
   PV_CHECK(flat && w.BN == 256 && w.KC == 4, PREMVOS_ERR_INVALID_ARG,
            "conv_umma: weights were packed for the CTA-pair kernel, which needs a 1x1 / stride-1 / unpadded layer (BN %d KC %d)", w.BN, w.KC);
+  PV_CHECK(out.cp.hi && !out.f32.p, PREMVOS_ERR_UNSUPPORTED, "conv_umma: the CTA-pair kernel writes CP8 outputs only");
   UmmaConvArgs& a = *reinterpret_cast<UmmaConvArgs*>(plan->args);
   const int geoH = (real_hw + 7) / 8;
   a.pair = 1;
@@ -1238,27 +1342,17 @@ static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& ou
   const int mtiles = in.N * a.tiles_y;
   a.total_work = ((mtiles + 1) / 2) * w.ntiles;
   plan->grid_x = a.total_work; plan->grid_y = 1; plan->grid_z = 1; plan->ctas_per_sm = 1;
-  // tail split as in plan_conv_umma: slots = CTA pairs
+  // stream-K workspace (partial sums + flags of up to PAIR_SLOTS pairs): the caller's (one per network: layers run one after the
+  // other on one stream and reuse it, so it stays in the L2) or a private one
   a.tail_items = 0; a.tail_split = 1; a.tail_kb_per = a.kblocks; a.main_work = a.total_work;
-  if (env_int("PREMVOS_TAIL", 1) != 0) {
-    int num_sms = 148;
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
-    const int slots = num_sms / 2, rem = a.total_work % slots;
-    if (a.total_work > slots && rem > 0 && rem * 3 <= slots && a.kblocks >= 4) {
-      int split = std::min(slots / rem, a.kblocks / 2);
-      split = std::min(split, env_int("PREMVOS_TAIL_SPLIT", 16));
-      if (split >= 2) {
-        a.tail_kb_per = (a.kblocks + split - 1) / split;
-        a.tail_split = (a.kblocks + a.tail_kb_per - 1) / a.tail_kb_per;
-        a.tail_items = rem;
-        a.main_work = a.total_work - rem;
-        const size_t elems = (size_t)a.tail_split * rem * 2 * 128 * w.BN;
-        PV_CUDA(cudaMalloc((void**)&a.partial, elems * sizeof(float)));
-        PV_CUDA(cudaMemset(a.partial, 0, elems * sizeof(float)));
-        plan->scratch = a.partial;
-        a.total_work = a.main_work + rem * a.tail_split;
-      }
-    }
+  if (ws) {
+    PV_TRY(conv_workspace_reserve(ws));
+    a.partial = ws->partial; a.sk_flags = ws->flags;
+  } else {
+    ConvWorkspace own;
+    PV_TRY(conv_workspace_reserve(&own));
+    a.partial = own.partial; a.sk_flags = own.flags;
+    plan->scratch = own.base;
   }
   // tensor maps: activations [N][chunks][ceil(HW/8)][64], weights [rows][64] (128-byte rows of the packed image)
   const int vchunks = (in.C + 7) / 8;
@@ -1288,7 +1382,7 @@ static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& ou
 }
 
 // Plans one convolution launch: tensor maps of the input view are encoded here (host only, no device work).
-int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g) {
+int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, const ConvWeightsUmma& w, const ConvGeom& g, ConvWorkspace* ws) {
   PV_CHECK(in.hi && in.lo, PREMVOS_ERR_INVALID_ARG, "conv_umma: null input view");
   PV_CHECK(round_up(in.C, 8) == round_up(w.CinPhys, 8), PREMVOS_ERR_INVALID_ARG,
            "conv_umma: input view has %d channels, weights were packed for %d", in.C, w.CinPhys);
@@ -1329,7 +1423,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
   a.merged_x = (g.stride == 1) ? 1 : 0;
   a.w_plane = w.KC * w.BN * 16;
-  if (w.pair) return plan_conv_pair(plan, in, out, w, g, flat, real_hw, cp_cout, f32_first);
+  if (w.pair) return plan_conv_pair(plan, in, out, w, g, flat, real_hw, cp_cout, f32_first, ws);
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
   // two sub-tiles per CTA either stacked (32 x 8 pixels) or side by side (16 x 16): take the one that pads less
   const long tiles_v = (long)((geoW + 7) / 8) * ((geoH + 31) / 32), tiles_h = (long)((geoW + 15) / 16) * ((geoH + 15) / 16);
@@ -1505,12 +1599,38 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
 }
 
 
+
+static int dbg_report(int dbg, int grid, cudaStream_t st) {
+  unsigned long long r[8];
+  PV_CUDA(cudaStreamSynchronize(st));
+  PV_CUDA(cudaMemcpyFromSymbol(r, g_dbg_cta, sizeof(r)));
+  fprintf(stderr, "conv_umma dbg: %llu CTAs, first start -> last end %.2f us, CTA duration min %.2f avg %.2f max %.2f us\n", r[5],
+          (r[1] - r[0]) * 1e-3, r[4] * 1e-3, r[5] ? r[2] * 1e-3 / r[5] : 0.0, r[3] * 1e-3);
+  if (dbg & 128) {
+    static unsigned long long rec[512][6];
+    PV_CUDA(cudaMemcpyFromSymbol(rec, g_dbg_rec, sizeof(rec)));
+    std::vector<int> order;
+    for (int i = 0; i < grid && i < 512; i++) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return rec[x][2] - rec[x][1] > rec[y][2] - rec[y][1]; });
+    for (size_t k = 0; k < order.size(); k += (k < 12 ? 1 : 16)) {
+      const unsigned long long* q = rec[order[k]];
+      fprintf(stderr, "  cta %3d sm %3llu: start +%6.2f  first MMA +%6.2f  last item MMAs issued +%6.2f  epilogue done +%6.2f  end +%6.2f us\n", order[k], q[0],
+              (q[1] - r[0]) * 1e-3, (q[3] - q[1]) * 1e-3, (q[4] - q[1]) * 1e-3, (q[5] - q[1]) * 1e-3, (q[2] - q[1]) * 1e-3);
+    }
+  }
+  return 0;
+}
+static int dbg_reset() {
+  const unsigned long long init[8] = {~0ull, 0, 0, 0, ~0ull, 0, 0, 0};
+  PV_CUDA(cudaMemcpyToSymbol(g_dbg_cta, init, sizeof(init)));
+  return 0;
+}
+
 static int launch_conv_pair(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   UmmaConvArgs a = *reinterpret_cast<const UmmaConvArgs*>(plan.args);
-  if (active_n >= 0 && active_n < plan.N) {   // a smaller active batch: plain item list, no tail split
+  if (active_n >= 0 && active_n < plan.N) {   // a smaller active batch: a shorter item list
     a.n_images = active_n;
     a.total_work = ((active_n * a.tiles_y + 1) / 2) * a.ntiles;
-    a.tail_items = 0; a.main_work = a.total_work;
   }
   if (a.total_work == 0) return 0;
   static int num_sms = 0;
@@ -1519,7 +1639,10 @@ static int launch_conv_pair(const ConvPlanUmma& plan, cudaStream_t st, int activ
     PV_CUDA(cudaGetDevice(&dev));
     PV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int pairs = std::min(a.total_work, num_sms / 2);
+  // at most two pairs per item: a stream-K range is then at least half an item, an item is finished from at most two partial sums
+  const int pairs = (int)std::max<long>(1, std::min<long>(std::min(num_sms / 2, PAIR_SLOTS), 2L * a.total_work));
+  a.stream_k_all = env_int("PREMVOS_STREAMK_ALL", 0);
+  if (a.dbg & 32) PV_TRY(dbg_reset());
   prof_before(st);
   conv_pair_kernel<<<2 * pairs, 384, plan.smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(plan.map_a_hi),
                                                            *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo),
@@ -1529,17 +1652,12 @@ static int launch_conv_pair(const ConvPlanUmma& plan, cudaStream_t st, int activ
   static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
   if (per_layer && profiling_enabled()) {
     char buf[256];
-    snprintf(buf, sizeof(buf), "conv_pair[n%d_%dx1_cin%d_cout%d|BN%d_KC%d_st%d_items%d_tail%dx%d]", a.n_images, a.flat_hw, a.kblocks * a.KC * 8,
-             a.Cout, a.BN, a.KC, a.w_stages, a.total_work, a.tail_items, a.tail_split);
+    snprintf(buf, sizeof(buf), "conv_pair[n%d_%dx1_cin%d_cout%d|BN%d_KC%d_st%d_items%d_pairs%d]", a.n_images, a.flat_hw, a.kblocks * a.KC * 8,
+             a.Cout, a.BN, a.KC, a.w_stages, a.total_work, pairs);
     label = prof_intern(buf);
   }
   PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));
-  if (a.tail_items > 0) {
-    const long total = (long)a.tail_items * 2 * 128 * (a.BN / 8);
-    prof_before(st);
-    conv_pair_finish_tail_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
-    PV_TRY(after_launch("conv_finish_kernel", st, 0.0, (double)total * 32.0 * (a.tail_split + 1)));
-  }
+  if (a.dbg & 32) PV_TRY(dbg_report(a.dbg, 2 * pairs, st));
   return 0;
 }
 
@@ -1594,25 +1712,7 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
     label = prof_intern(buf);
   }
   PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));
-  if (a.dbg & 32) {
-    unsigned long long r[8];
-    PV_CUDA(cudaStreamSynchronize(st));
-    PV_CUDA(cudaMemcpyFromSymbol(r, g_dbg_cta, sizeof(r)));
-    fprintf(stderr, "conv_umma dbg: %llu CTAs, first start -> last end %.2f us, CTA duration min %.2f avg %.2f max %.2f us\n", r[5],
-            (r[1] - r[0]) * 1e-3, r[4] * 1e-3, r[5] ? r[2] * 1e-3 / r[5] : 0.0, r[3] * 1e-3);
-    if (a.dbg & 128) {
-      static unsigned long long rec[512][6];
-      PV_CUDA(cudaMemcpyFromSymbol(rec, g_dbg_rec, sizeof(rec)));
-      std::vector<int> order;
-      for (int i = 0; i < grid && i < 512; i++) order.push_back(i);
-      std::sort(order.begin(), order.end(), [&](int x, int y) { return rec[x][2] - rec[x][1] > rec[y][2] - rec[y][1]; });
-      for (size_t k = 0; k < order.size(); k += (k < 12 ? 1 : 16)) {
-        const unsigned long long* q = rec[order[k]];
-        fprintf(stderr, "  cta %3d sm %3llu: start +%6.2f  first MMA +%6.2f  last item MMAs issued +%6.2f  epilogue done +%6.2f  end +%6.2f us\n", order[k], q[0],
-                (q[1] - r[0]) * 1e-3, (q[3] - q[1]) * 1e-3, (q[4] - q[1]) * 1e-3, (q[5] - q[1]) * 1e-3, (q[2] - q[1]) * 1e-3);
-      }
-    }
-  }
+  if (a.dbg & 32) PV_TRY(dbg_report(a.dbg, grid, st));
   if (a.tail_items > 0) {
     const long total = (long)a.tail_items * a.MT * 128 * (a.BN / 8);
     prof_before(st);

@@ -41,6 +41,7 @@ struct premvos_refnet {
   std::vector<void*> allocs;
   std::vector<std::unique_ptr<ConvWeightsUmma>> conv_weights;
   std::vector<std::unique_ptr<ConvPlanUmma>> conv_plans;
+  ConvWorkspace conv_ws;   // stream-K scratch shared by the pointwise layers (they run one after the other on one stream)
   std::vector<Step> steps;
   std::map<std::string, CView> named;   // test hook
   cudaStream_t stream = nullptr;
@@ -153,7 +154,7 @@ int add_conv(premvos_refnet* n, const std::string& scope, bool bn, float eps, co
   const long m_out = out.cp.hi ? (long)out.cp.N * out.cp.H * out.cp.W : (long)out.f32.N * out.f32.H * out.f32.W;
   const bool flat = kh == 1 && kw == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0;
   PV_TRY(pack_conv_weights_umma(cw, w.data(), shift.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out, flat));
-  PV_TRY(plan_conv_umma(pl, in, out, *cw, g));
+  PV_TRY(plan_conv_umma(pl, in, out, *cw, g, &n->conv_ws));
   n->steps.push_back([pl](cudaStream_t st, int na) { return launch_conv_umma(*pl, st, na); });
   return 0;
 }
@@ -496,6 +497,7 @@ extern "C" void premvos_refnet_destroy(premvos_refnet_t* n) {
   for (void* p : n->allocs) cudaFree(p);
   for (auto& w : n->conv_weights) free_conv_weights_umma(w.get());
   for (auto& pl : n->conv_plans) free_conv_plan_umma(pl.get());
+  conv_workspace_free(&n->conv_ws);
   if (n->frame_dev) cudaFree(n->frame_dev);
   if (n->mask_dev) cudaFree(n->mask_dev);
   if (n->post_dev) cudaFree(n->post_dev);

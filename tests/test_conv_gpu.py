@@ -52,10 +52,11 @@ CASES = [
     (1, 64, 480, 160, 128, 3, 1, 1, (1, 1, 1, 1), 0.1, True),   # 300 items on 296 CTA slots: the last 4 are K-split (tail split),
                                                                 #   halo mode, residual through conv_finish_tail_kernel
     (2, 96, 240, 168, 72, 3, 1, 2, (2, 2, 2, 2), 0.0, False),   # tail split with ragged tiles / N tail, dilation 2
-    # CTA-pair kernel (cta_group::2; the three wide cases above run on it too: tail split with 11 and 2 K slices, k-block tail)
-    (15, 256, 25, 25, 512, 1, 1, 1, (0, 0, 0, 0), 0.1, True),   # 75 pixel tiles: the last pair has a dead peer tile; 76 items, 2 K-split
+    # CTA-pair kernel (cta_group::2, stream-K; the wide cases above run on it too: items split over 2-3 pairs, k-block tail)
+    (15, 256, 25, 25, 512, 1, 1, 1, (0, 0, 0, 0), 0.1, True),   # 75 pixel tiles: the last pair has a dead peer tile
     (40, 728, 25, 25, 728, 1, 1, 1, (0, 0, 0, 0), 0.0, True),   # the benchmarked launch plan of the middle flow (40 crops)
     (5, 1536, 25, 25, 2048, 1, 1, 1, (0, 0, 0, 0), 0.0, False), # exit flow: 8 channel tiles, K = 48 k-blocks, 13 pairs x 8 = 104 items
+    (1, 1024, 46, 83, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, True),   # stream-K with 6.5 k-blocks per pair: every item is finished from 5-6 partial sums
 ]
 
 

@@ -30,9 +30,10 @@ if "propnet" in which:
     report("proposal net %dx%d" % (H, W), prof)
     del net
 if "refnet" in which:
-    rn = refnet.RefinementNet(max_batch=20).load_params(synth.refnet_synthetic_params(2))
+    NB = int(os.environ.get("REFNET_BOXES", "40"))
+    rn = refnet.RefinementNet(max_batch=NB).load_params(synth.refnet_synthetic_params(2))
     frame = synth.synthetic_bgr_frame(H0, W0, seed=3)
-    boxes = synth.synthetic_boxes(20, H0, W0, seed=3)
+    boxes = synth.synthetic_boxes(NB, H0, W0, seed=3)
     rn.refine(frame, boxes)
     _lib.profile_begin(); rn.refine(frame, boxes); prof = _lib.profile_end()
-    report("refinement net, 20 crops", prof)
+    report("refinement net, %d crops" % NB, prof)

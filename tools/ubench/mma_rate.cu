@@ -91,6 +91,11 @@ int main() {
       {"1x1 flat MT1 BN256 (B lbo 4096)        ", 256, 128, 2048, 4096, 256, 1, 8192, 16384, 148},
       {"1x1 flat MT2 BN256 (A lbo 4096)        ", 256, 128, 4096, 4096, 512, 2, 16384, 16384, 148},
       {"A lbo 128 sbo 256 (K-adjacent) BN128   ", 128, 256, 128, 2048, 128, 1, 8192, 8192, 148},
+      // narrow N (round 2: is a block-diagonal "depthwise as MMA" affordable? cycles per 128 x N x 16 MMA at N = 16 / 32 / 64)
+      {"halo A, BN16 (B lbo 256)               ", 16, 160, 2880, 256, 32, 1, 4 * 2880, 1024, 148},
+      {"halo A, BN32 (B lbo 512)               ", 32, 160, 2880, 512, 32, 1, 4 * 2880, 2048, 148},
+      {"halo A, BN64 (B lbo 1024)              ", 64, 160, 2880, 1024, 64, 1, 4 * 2880, 4096, 148},
+      {"halo A, BN16, 2 accumulators           ", 16, 160, 2880, 256, 32, 2, 4 * 2880, 1024, 148},
   };
   for (auto& c : cfgs) {
     // B descriptor SBO is fixed at 128 in the kernel; for the K-adjacent B variant use sbo 256 via a_sbo trick is not possible -> note
