@@ -173,6 +173,20 @@ struct CView {
   size_t pixels() const { return (size_t)N * H * W; }
 };
 
+// ---- F8: channel-chunk-planar fp32 activations ----------------------------------------------------------
+// Same geometry as CP8 with one fp32 plane instead of two bf16 planes: element (n, c, y, x) lives at
+// p[(((n*chunks + c0 + c/8) * H + y) * W + x) * 8 + c%8].  Used for tensors that never are tensor-core operands (inputs of
+// depthwise convolutions, residuals): no hi/lo split on the way out of a GEMM, no re-assembly on the way into the next kernel.
+struct FView {
+  float* p = nullptr;
+  int N = 0, H = 0, W = 0;
+  int chunks = 0, c0 = 0, C = 0;
+  bool null() const { return p == nullptr; }
+  int vchunks() const { return (C + 7) / 8; }
+};
+// TMA descriptor over fp32 data (rank <= 5, no swizzle, zero fill outside): map128 = 128 bytes, 64-byte aligned
+int encode_tensor_map_f32(void* map128, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
 // ---- convolution on tcgen05 tensor cores (split-bf16 x3, fp32 accumulate), conv_umma.cu ----------
 struct ConvWeightsUmma {
   __nv_bfloat16* w = nullptr;  // device, packed shared-memory images [ntile][kblock][tap][hi|lo][KC][BN][8]
@@ -190,6 +204,8 @@ struct ConvOut {
   CView cp;    // CP8 split output (optional)
   TView f32;   // fp32 channels-last output (optional; small heads)
   CView res;   // optional residual added before the activation (same shape as the output)
+  FView f8;    // F8 output (optional, instead of or next to cp): all output channels, after the activation
+  FView res_f8;  // residual in F8 (instead of res)
   // channel routing (fused heads): output channels [0, cp_channels) go to `cp` (cp_channels < 0: all of them);
   // channels [f32_first, Cout) go to `f32` at channel index c - f32_first
   int cp_channels = -1, f32_first = 0;
@@ -200,7 +216,7 @@ struct ConvPlanUmma {  // everything one launch needs; built once per layer at f
   alignas(64) unsigned char map_a_hi[128];
   alignas(64) unsigned char map_a_lo[128];
   alignas(64) unsigned char map_w[128];   // CTA-pair kernel: packed weights as 128-byte rows
-  alignas(16) unsigned char args[320];
+  alignas(16) unsigned char args[384];
   int grid_x = 0, grid_y = 0, grid_z = 1, smem_bytes = 0, halo = 0, MT = 0, N = 0, ctas_per_sm = 1;
   void* scratch = nullptr;   // split-K partial sums (owned by the plan, see free_conv_plan_umma)
   double flops = 0, bytes = 0;
@@ -278,6 +294,18 @@ struct DetTailArgs {
 };
 int det_u8_to_f32(const unsigned char* src, float* dst, long n, cudaStream_t st);
 int det_frcnn_tail(const DetTailArgs& a, cudaStream_t st);                                  // train.py:275-295
+
+// ---- depthwise 3x3 on F8 inputs (TMA-pipelined), dw_f8.cu ------------------------------------------------------
+struct DwF8Plan {
+  alignas(64) unsigned char map_in[128];
+  alignas(16) unsigned char args[192];
+  int smem_bytes = 0, fast = 0, N = 0, tiles = 0, nch = 0;
+  double bytes_per_image = 0, flops_per_image = 0;
+};
+// w: [9][round_up(C,8)] with BN scale folded, bias [round_up(C,8)]; input coordinate = o*stride + tap*rate - pad; out is CP8
+int plan_depthwise3x3_f8(DwF8Plan* plan, const FView& in, const CView& out, const float* w, const float* bias, int stride, int rate, int pad,
+                         bool pre_relu, bool post_relu);
+int launch_depthwise3x3_f8(const DwF8Plan& plan, int n_active, cudaStream_t st);
 
 // ---- refinement-network kernels, refine_ops.cu ------------------------------------------------------------
 // frame uint8 RGB [H,W,3] + boxes [N,4] (x,y,w,h) -> network input CP8 [N,1 chunk,S,S] (RGB in [-1,1], guidance -1/+1) + crop boxes

@@ -282,6 +282,8 @@ struct UmmaConvArgs {
   // channel routing: [0, cp_cout) -> CP8 planes (activated); [f32_first, Cout) -> fp32 channels-last at channel c - f32_first
   int cp_cout, f32_first, f32_linear /*1: no activation on the fp32 outputs*/, f32_accum /*1: add to what is there*/;
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo; int res_chunks, res_c0;  // optional residual
+  float* out_f8; int f8_chunks, f8_c0;                 // optional F8 (fp32 chunk-planar) output, activated like the CP8 one
+  const float* res_f8; int resf_chunks, resf_c0;       // optional residual in F8 (instead of res_hi / res_lo)
   uint32_t tmem_cols;
   // split-K (grids smaller than the machine): blockIdx.z owns k-blocks [z*kb_per, (z+1)*kb_per) and stores raw fp32
   // partial sums; conv_finish_kernel adds them in a fixed order (deterministic) and applies the epilogue
@@ -602,6 +604,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               rres[2 * h] = *reinterpret_cast<const uint4*>(a.res_hi + ri);
               rres[2 * h + 1] = *reinterpret_cast<const uint4*>(a.res_lo + ri);
             }
+          } else if (a.res_f8) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              if (co0 + 8 * h >= a.Cout) continue;
+              const long ri = (((long)n_img * a.resf_chunks + a.resf_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+              rres[2 * h] = *reinterpret_cast<const uint4*>(a.res_f8 + ri);
+              rres[2 * h + 1] = *reinterpret_cast<const uint4*>(a.res_f8 + ri + 4);
+            }
           }
         }
         tmem_ld_wait();
@@ -656,6 +666,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
           }
         }
+        else if (a.res_f8) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (co0 + 8 * h >= a.Cout) continue;
+            const uint4 r0 = rres[2 * h], r1 = rres[2 * h + 1];
+            f[8 * h] += __uint_as_float(r0.x); f[8 * h + 1] += __uint_as_float(r0.y); f[8 * h + 2] += __uint_as_float(r0.z); f[8 * h + 3] += __uint_as_float(r0.w);
+            f[8 * h + 4] += __uint_as_float(r1.x); f[8 * h + 5] += __uint_as_float(r1.y); f[8 * h + 6] += __uint_as_float(r1.z); f[8 * h + 7] += __uint_as_float(r1.w);
+          }
+        }
         if (a.out_f32 && a.f32_linear) {  // fp32 outputs without activation (fused flow heads)
           float* pf = a.out_f32 + ((long)n_img * hw + pix) * a.out_cs + a.out_coff - a.f32_first + co0;
 #pragma unroll
@@ -664,6 +683,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
 #pragma unroll
         for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+        if (a.out_f8) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (co0 + 8 * h >= a.Cout) continue;
+            float* pf8 = a.out_f8 + (((long)n_img * a.f8_chunks + a.f8_c0 + (co0 >> 3) + h) * hw + pix) * 8;
+            reinterpret_cast<float4*>(pf8)[0] = make_float4(f[8 * h], f[8 * h + 1], f[8 * h + 2], f[8 * h + 3]);
+            reinterpret_cast<float4*>(pf8)[1] = make_float4(f[8 * h + 4], f[8 * h + 5], f[8 * h + 6], f[8 * h + 7]);
+          }
+        }
         if (a.out_hi) {
 #pragma unroll
           for (int h = 0; h < 2; h++) {
@@ -738,6 +766,10 @@ __device__ __forceinline__ void finish_store(const UmmaConvArgs& a, int n_img, l
       f[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
       f[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
     }
+  } else if (a.res_f8) {
+    const float4* rp = reinterpret_cast<const float4*>(a.res_f8 + (((long)n_img * a.resf_chunks + a.resf_c0 + c8) * hw + pix) * 8);
+    const float4 r0 = rp[0], r1 = rp[1];
+    f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
   }
   float* pf = a.out_f32 ? a.out_f32 + pg * a.out_cs + a.out_coff - a.f32_first + c8 * 8 : nullptr;
   if (pf && a.f32_linear) {
@@ -747,6 +779,11 @@ __device__ __forceinline__ void finish_store(const UmmaConvArgs& a, int n_img, l
   }
 #pragma unroll
   for (int j = 0; j < 8; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+  if (a.out_f8) {
+    float4* pf8 = reinterpret_cast<float4*>(a.out_f8 + (((long)n_img * a.f8_chunks + a.f8_c0 + c8) * hw + pix) * 8);
+    pf8[0] = make_float4(f[0], f[1], f[2], f[3]);
+    pf8[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
   if (a.out_hi && c8 * 8 < a.cp_cout) {
     uint32_t hw4[4], lw4[4];
 #pragma unroll
@@ -1034,10 +1071,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const long row = ((long)n_img * hw + pix);                          // pixel index inside its plane stack
       const long chunk_stride = hw * 8;                                     // elements between two chunk planes
       const int cg0 = (wk.ntile * a.BN + col_begin) >> 3;                   // first 8-channel chunk of this warp
-      __nv_bfloat16* ohi = a.out_hi + ((((long)n_img * a.out_chunks + a.out_c0 + cg0) * hw + pix) << 3);
-      __nv_bfloat16* olo = a.out_lo + (ohi - a.out_hi);
+      const long o_off = (((long)n_img * a.out_chunks + a.out_c0 + cg0) * hw + pix) << 3;
+      __nv_bfloat16* ohi = a.out_hi + o_off;
+      __nv_bfloat16* olo = a.out_lo + o_off;
       const __nv_bfloat16* rhi = a.res_hi ? a.res_hi + ((((long)n_img * a.res_chunks + a.res_c0 + cg0) * hw + pix) << 3) : nullptr;
       const __nv_bfloat16* rlo = a.res_hi ? a.res_lo + (rhi - a.res_hi) : nullptr;
+      float* of8 = a.out_f8 ? a.out_f8 + ((((long)n_img * a.f8_chunks + a.f8_c0 + cg0) * hw + pix) << 3) : nullptr;
+      const float* rf8 = a.res_f8 ? a.res_f8 + ((((long)n_img * a.resf_chunks + a.resf_c0 + cg0) * hw + pix) << 3) : nullptr;
       const float* bias = a.bias + wk.ntile * a.BN + col_begin;
       // partial sums: [pair slot][rank][column / 4 (64)][row (128)] float4 -- a warp's 32 rows of one float4 column are contiguous
       float4* ppart = reinterpret_cast<float4*>(a.partial) + (((long)pair_id * 2 + rank) * 64 + (col_begin >> 2)) * 128 + m;
@@ -1088,10 +1128,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
           }
         }
+        if (rf8) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (h == 1 && !second) break;
+            const float4* rp = reinterpret_cast<const float4*>(rf8 + (2 * g + h) * chunk_stride);
+            const float4 r0 = rp[0], r1 = rp[1];
+            f[8 * h] += r0.x; f[8 * h + 1] += r0.y; f[8 * h + 2] += r0.z; f[8 * h + 3] += r0.w;
+            f[8 * h + 4] += r1.x; f[8 * h + 5] += r1.y; f[8 * h + 6] += r1.z; f[8 * h + 7] += r1.w;
+          }
+        }
         if (a.slope != 1.f) {   // LeakyReLU / ReLU: max(f, slope * f) for 0 <= slope < 1
 #pragma unroll
           for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], f[j] * a.slope);
         }
+        if (of8) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (h == 1 && !second) break;
+            float4* pf8 = reinterpret_cast<float4*>(of8 + (2 * g + h) * chunk_stride);
+            pf8[0] = make_float4(f[8 * h], f[8 * h + 1], f[8 * h + 2], f[8 * h + 3]);
+            pf8[1] = make_float4(f[8 * h + 4], f[8 * h + 5], f[8 * h + 6], f[8 * h + 7]);
+          }
+        }
+        if (!a.out_hi) return;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           if (h == 1 && (!second || co0 + 8 >= a.cp_cout)) break;
@@ -1195,6 +1255,24 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
            box[0], box[1], box[2], box[3]);
   return 0;
 }
+
+}  // namespace
+
+int encode_tensor_map_f32(void* map128, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = nullptr;
+  PV_TRY(get_encode_fn(&fn));
+  cuuint64_t d[5] = {1, 1, 1, 1, 1}, s[4] = {0, 0, 0, 0};
+  cuuint32_t b[5] = {1, 1, 1, 1, 1}, e[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
+  CUresult r = fn((CUtensorMap*)map128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PV_CHECK(r == CUDA_SUCCESS, PREMVOS_ERR_INVALID_ARG, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
+           (int)r, rank, (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], b[0], b[1], b[2]);
+  return 0;
+}
+
+namespace {
 
 inline void split_bf16(float x, __nv_bfloat16* hi, __nv_bfloat16* lo) {
   *hi = __float2bfloat16_rn(x);
@@ -1311,7 +1389,7 @@ static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& ou
                           int real_hw, int cp_cout, int f32_first, ConvWorkspace* ws) {
   PV_CHECK(flat && w.BN == 256 && w.KC == 4, PREMVOS_ERR_INVALID_ARG,
            "conv_umma: weights were packed for the CTA-pair kernel, which needs a 1x1 / stride-1 / unpadded layer (BN %d KC %d)", w.BN, w.KC);
-  PV_CHECK(out.cp.hi && !out.f32.p, PREMVOS_ERR_UNSUPPORTED, "conv_umma: the CTA-pair kernel writes CP8 outputs only");
+  PV_CHECK((out.cp.hi || out.f8.p) && !out.f32.p, PREMVOS_ERR_UNSUPPORTED, "conv_umma: the CTA-pair kernel writes CP8 / F8 outputs only");
   UmmaConvArgs& a = *reinterpret_cast<UmmaConvArgs*>(plan->args);
   const int geoH = (real_hw + 7) / 8;
   a.pair = 1;
@@ -1335,6 +1413,8 @@ static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& ou
   a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
   a.cp_cout = cp_cout; a.f32_first = f32_first; a.f32_linear = out.f32_linear ? 1 : 0; a.f32_accum = out.f32_accumulate ? 1 : 0;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
+  a.out_f8 = out.f8.p; a.f8_chunks = out.f8.chunks; a.f8_c0 = out.f8.c0;
+  a.res_f8 = out.res_f8.p; a.resf_chunks = out.res_f8.chunks; a.resf_c0 = out.res_f8.c0;
   a.dbg = env_int("PREMVOS_DBG", 0);
   a.tmem_cols = 512;
   a.ksplit = 1; a.kb_per = a.kblocks; a.cout_pad = w.ntiles * w.BN; a.partial = nullptr; a.partial_stride = 0;
@@ -1403,7 +1483,13 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     PV_CHECK(out.f32.N == in.N && out.f32.H == Ho && out.f32.W == Wo && out.f32.C == w.Cout - f32_first, PREMVOS_ERR_INVALID_ARG,
              "conv_umma: fp32 output view shape mismatch");
   }
-  PV_CHECK(out.cp.hi || out.f32.p, PREMVOS_ERR_INVALID_ARG, "conv_umma: no output");
+  PV_CHECK(out.cp.hi || out.f32.p || out.f8.p, PREMVOS_ERR_INVALID_ARG, "conv_umma: no output");
+  if (out.f8.p)
+    PV_CHECK(out.f8.N == in.N && out.f8.H == Ho && out.f8.W == Wo && out.f8.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
+             "conv_umma: F8 output view shape mismatch");
+  if (out.res_f8.p)
+    PV_CHECK(!out.res.hi && out.res_f8.N == in.N && out.res_f8.H == Ho && out.res_f8.W == Wo && out.res_f8.C == w.Cout,
+             PREMVOS_ERR_INVALID_ARG, "conv_umma: F8 residual view shape mismatch");
   if (out.res.hi)
     PV_CHECK(out.res.N == in.N && out.res.H == Ho && out.res.W == Wo && out.res.C == w.Cout, PREMVOS_ERR_INVALID_ARG,
              "conv_umma: residual view shape mismatch");
@@ -1501,6 +1587,8 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   a.out_f32 = out.f32.p; a.out_cs = out.f32.cs; a.out_coff = out.f32.coff;
   a.cp_cout = cp_cout; a.f32_first = f32_first; a.f32_linear = out.f32_linear ? 1 : 0; a.f32_accum = out.f32_accumulate ? 1 : 0;
   a.res_hi = out.res.hi; a.res_lo = out.res.lo; a.res_chunks = out.res.chunks; a.res_c0 = out.res.c0;
+  a.out_f8 = out.f8.p; a.f8_chunks = out.f8.chunks; a.f8_c0 = out.f8.c0;
+  a.res_f8 = out.res_f8.p; a.resf_chunks = out.res_f8.chunks; a.resf_c0 = out.res_f8.c0;
   a.dbg = env_int("PREMVOS_DBG", 0);
   a.NACC = 1;   // accumulator replicas were an experiment (no gain: the dependent-MMA chain is not the limiter)
   PV_CHECK(a.NACC >= 1 && a.NACC <= 3 && a.NACC * a.MT * w.BN <= 512, PREMVOS_ERR_INVALID_ARG, "conv_umma: NACC=%d does not fit TMEM", a.NACC);

@@ -9,6 +9,8 @@
 //     bilinear resize to the crop size, zero padding back to the frame (network/SegmentationOutputLayers.py:35-61,
 //     106-135) and the conf_score reduction of MergeTrack/refinement_net_functions.py:58-62 -- one kernel, the
 //     only thing that leaves the device is a uint8 mask per proposal and one float.
+#include <stdlib.h>
+
 #include <algorithm>
 #include "cp8.cuh"
 
@@ -436,7 +438,14 @@ int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const fl
   prof_before(st);
   kern<<<dim3(ntx * nty, in.vchunks(), n_active), threads, smem, st>>>(a);
   const double frac = (double)n_active / in.N;
-  return after_launch("depthwise3x3_kernel", st, 18.0 * total * 8, 4.0 * frac * ((double)in.pixels() + (double)out.pixels()) * in.C);
+  const char* label = "depthwise3x3_kernel";
+  static const int per_layer = getenv("PREMVOS_PROFILE_LAYERS") ? atoi(getenv("PREMVOS_PROFILE_LAYERS")) : 0;
+  if (per_layer && profiling_enabled()) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "dw_cp8[n%d_%dx%d_c%d_s%d_r%d]", n_active, out.H, out.W, in.C, stride, rate);
+    label = prof_intern(buf);
+  }
+  return after_launch(label, st, 18.0 * total * 8, 4.0 * frac * ((double)in.pixels() + (double)out.pixels()) * in.C);
 }
 
 int resize_bilinear_ac_cp8(const CView& in, const CView& out, int n_active, cudaStream_t st) {

@@ -41,6 +41,7 @@ struct premvos_refnet {
   std::vector<void*> allocs;
   std::vector<std::unique_ptr<ConvWeightsUmma>> conv_weights;
   std::vector<std::unique_ptr<ConvPlanUmma>> conv_plans;
+  std::vector<std::unique_ptr<DwF8Plan>> dw_plans;
   ConvWorkspace conv_ws;   // stream-K scratch shared by the pointwise layers (they run one after the other on one stream)
   std::vector<Step> steps;
   std::map<std::string, CView> named;   // test hook
@@ -122,6 +123,12 @@ int alloc_cview(premvos_refnet* n, CView* v, int C, int H, int W) {
   return 0;
 }
 
+int alloc_fview(premvos_refnet* n, FView* v, int C, int H, int W) {
+  v->N = n->NB; v->H = H; v->W = W; v->chunks = (C + 7) / 8; v->c0 = 0; v->C = C;
+  PV_TRY(dev_alloc(n, &v->p, (size_t)v->N * v->chunks * H * W * 8 + 64));
+  return 0;
+}
+
 // BatchNorm inference folded to (scale, shift): slim.batch_norm, (x - mean) * rsqrt(var + eps) * gamma + beta
 void bn_fold(premvos_refnet* n, const std::string& scope, float eps, std::vector<float>* scale, std::vector<float>* shift) {
   const std::vector<float>&g = n->params[scope + "/BatchNorm/gamma"], &b = n->params[scope + "/BatchNorm/beta"];
@@ -151,7 +158,8 @@ int add_conv(premvos_refnet* n, const std::string& scope, bool bn, float eps, co
   n->conv_plans.emplace_back(new ConvPlanUmma());
   ConvWeightsUmma* cw = n->conv_weights.back().get();
   ConvPlanUmma* pl = n->conv_plans.back().get();
-  const long m_out = out.cp.hi ? (long)out.cp.N * out.cp.H * out.cp.W : (long)out.f32.N * out.f32.H * out.f32.W;
+  const long m_out = out.cp.hi ? (long)out.cp.N * out.cp.H * out.cp.W
+                               : (out.f8.p ? (long)out.f8.N * out.f8.H * out.f8.W : (long)out.f32.N * out.f32.H * out.f32.W);
   const bool flat = kh == 1 && kw == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0;
   PV_TRY(pack_conv_weights_umma(cw, w.data(), shift.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out, flat));
   PV_TRY(plan_conv_umma(pl, in, out, *cw, g, &n->conv_ws));
@@ -178,6 +186,27 @@ int add_depthwise(premvos_refnet* n, const std::string& scope, float eps, const 
   return 0;
 }
 
+// the same on an F8 input (a pointwise output that is not a tensor-core operand): TMA-pipelined kernel, dw_f8.cu
+int add_depthwise_f8(premvos_refnet* n, const std::string& scope, float eps, const FView& in, const CView& out, int stride, int rate,
+                     bool pre_relu, bool post_relu) {
+  const int C = in.C, cpad = round_up(C, 8);
+  const std::vector<float>& W = n->params[scope + "/depthwise_weights"];  // [3][3][C][1]
+  std::vector<float> scale, shift, w((size_t)9 * cpad, 0.f), b(cpad, 0.f);
+  bn_fold(n, scope, eps, &scale, &shift);
+  for (int t = 0; t < 9; t++)
+    for (int c = 0; c < C; c++) w[(size_t)t * cpad + c] = W[(size_t)t * C + c] * scale[c];
+  for (int c = 0; c < C; c++) b[c] = shift[c];
+  float *dw = nullptr, *db = nullptr;
+  PV_TRY(dev_alloc(n, &dw, w.size())); PV_TRY(dev_alloc(n, &db, b.size()));
+  PV_CUDA(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  PV_CUDA(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  n->dw_plans.emplace_back(new DwF8Plan());
+  DwF8Plan* pl = n->dw_plans.back().get();
+  PV_TRY(plan_depthwise3x3_f8(pl, in, out, dw, db, stride, rate, rate, pre_relu, post_relu));
+  n->steps.push_back([pl](cudaStream_t st, int na) { return launch_depthwise3x3_f8(*pl, na, st); });
+  return 0;
+}
+
 int build_network(premvos_refnet* n) {
   const int S = n->S;
   PV_TRY(alloc_cview(n, &n->input, 8, S, S));
@@ -195,42 +224,75 @@ int build_network(premvos_refnet* n) {
     ConvOut o2; o2.cp = c12;
     PV_TRY(add_conv(n, x + "entry_flow/conv1_2", true, XC_EPS, c11, o2, ConvGeom::same3x3(1, 0.f)));
   }
+  // Formats (see dw_f8.cu): a tensor that is a tensor-core operand (input of a shortcut / ASPP / decoder convolution) is CP8; a
+  // pointwise output consumed only by the next depthwise convolution is F8 with the consumer's leading ReLU already applied; a
+  // unit output consumed by the next unit's first depthwise + sum skip (middle flow, exit block 2) is F8, raw.
+  const bool use_f8 = getenv("PREMVOS_REFNET_F8") ? atoi(getenv("PREMVOS_REFNET_F8")) != 0 : true;
   CView cur = c12, low_level;
+  FView cur_f;   // the unit input when it is F8 (cur is null then)
   const int target = 16 / 2;  // output_stride 16, halved by the stride-2 root conv (xception.py:424-429)
   int current_stride = 1, rate = 1;
-  for (const BlockSpec& b : block_specs(n->middle_units))
+  const std::vector<BlockSpec> specs = block_specs(n->middle_units);
+  for (size_t bi = 0; bi < specs.size(); bi++) {
+    const BlockSpec& b = specs[bi];
     for (int u = 0; u < b.units; u++) {
       const std::string s = x + b.scope + "/unit_" + std::to_string(u + 1) + "/xception_module";
       int stride = b.stride, unit_rate = 1;
       if (current_stride == target) { stride = 1; unit_rate = rate; rate *= b.stride; }   // xception.py:341-355
       else current_stride *= b.stride;
-      const int Ho = stride == 2 ? (cur.H - 1) / 2 + 1 : cur.H, Wo = stride == 2 ? (cur.W - 1) / 2 + 1 : cur.W;
+      const int inH = cur_f.p ? cur_f.H : cur.H, inW = cur_f.p ? cur_f.W : cur.W, inC = cur_f.p ? cur_f.C : cur.C;
+      const int Ho = stride == 2 ? (inH - 1) / 2 + 1 : inH, Wo = stride == 2 ? (inW - 1) / 2 + 1 : inW;
+      // what consumes this unit's output: the next unit (same block or first unit of the next block) or the ASPP
+      const BlockSpec* next = (u + 1 < b.units) ? &b : nullptr;
+      for (size_t bj = bi + 1; !next && bj < specs.size(); bj++)
+        if (specs[bj].units > 0) next = &specs[bj];
+      const bool out_f8 = use_f8 && next && next->skip != 1;   // no shortcut convolution reads it
       CView sc;
       if (b.skip == 1) {  // 1x1 stride-s shortcut + BN, no activation
+        PV_CHECK(!cur.null(), PREMVOS_ERR_INVALID_ARG, "refnet: shortcut convolution needs a CP8 input");
         PV_TRY(alloc_cview(n, &sc, b.depth[2], Ho, Wo));
         ConvGeom g; g.stride = stride;
         ConvOut o; o.cp = sc;
         PV_TRY(add_conv(n, s + "/shortcut", true, XC_EPS, cur, o, g));
       }
-      CView t = cur;
+      CView t = cur;    // input of the next separable convolution: CP8 ...
+      FView tf = cur_f;  // ... or F8
+      bool t_relu_applied = false;   // the F8 producer already applied the consumer's leading ReLU
+      int tC = inC, tH = inH, tW = inW;
       for (int i = 0; i < 3; i++) {
         const int st_i = i == 2 ? stride : 1;
-        const int h_i = st_i == 2 ? Ho : t.H, w_i = st_i == 2 ? Wo : t.W;
+        const int h_i = st_i == 2 ? Ho : tH, w_i = st_i == 2 ? Wo : tW;
         const std::string ss = s + "/separable_conv" + std::to_string(i + 1);
-        CView d, p;
-        PV_TRY(alloc_cview(n, &d, t.C, h_i, w_i));
-        PV_TRY(alloc_cview(n, &p, b.depth[i], h_i, w_i));
-        PV_TRY(add_depthwise(n, ss + "_depthwise", XC_EPS, t, d, st_i, unit_rate, !b.act_in_sep, b.act_in_sep));
+        CView d;
+        PV_TRY(alloc_cview(n, &d, tC, h_i, w_i));
+        if (tf.p)
+          PV_TRY(add_depthwise_f8(n, ss + "_depthwise", XC_EPS, tf, d, st_i, unit_rate, !b.act_in_sep && !t_relu_applied, b.act_in_sep));
+        else
+          PV_TRY(add_depthwise(n, ss + "_depthwise", XC_EPS, t, d, st_i, unit_rate, !b.act_in_sep, b.act_in_sep));
+        const bool is_low_level = std::string(b.scope) == "entry_flow/block2" && i == 1;   // feature_extractor.py:89-94
         ConvGeom g; g.slope = b.act_in_sep ? 0.f : 1.f;
-        ConvOut o; o.cp = p;
+        ConvOut o;
+        CView p; FView pf;
+        if (i < 2 && use_f8 && !is_low_level) {   // only the next depthwise reads it: F8, ReLU of the next separable conv applied here
+          PV_TRY(alloc_fview(n, &pf, b.depth[i], h_i, w_i));
+          o.f8 = pf; g.slope = 0.f; t_relu_applied = true;
+        } else if (i == 2 && out_f8) {
+          PV_TRY(alloc_fview(n, &pf, b.depth[i], h_i, w_i));
+          o.f8 = pf; t_relu_applied = false;
+        } else {
+          PV_TRY(alloc_cview(n, &p, b.depth[i], h_i, w_i));
+          o.cp = p; t_relu_applied = false;
+        }
         if (i == 2 && b.skip == 1) o.res = sc;
-        if (i == 2 && b.skip == 2) o.res = cur;
+        if (i == 2 && b.skip == 2) { if (cur_f.p) o.res_f8 = cur_f; else o.res = cur; }
         PV_TRY(add_conv(n, ss + "_pointwise", true, XC_EPS, d, o, g));
-        if (std::string(b.scope) == "entry_flow/block2" && i == 1) low_level = p;   // feature_extractor.py:89-94
-        t = p;
+        if (is_low_level) low_level = p;
+        t = p; tf = pf; tC = b.depth[i]; tH = h_i; tW = w_i;
       }
-      cur = t;
+      cur = t; cur_f = tf;
     }
+  }
+  PV_CHECK(!cur.null(), PREMVOS_ERR_INVALID_ARG, "refnet: the backbone output must be CP8");
   n->named["xception_out"] = cur;
   n->named["low_level"] = low_level;
   const int fh = cur.H, fw = cur.W;
@@ -292,9 +354,12 @@ int build_network(premvos_refnet* n) {
       return resize_bilinear_ac_cp8(l_src, l_dst, na, st);
     });
     PV_TRY(add_depthwise(n, "decoder/decoder_conv0_depthwise", ASPP_EPS, dec_in, d0, 1, 1, false, true));
-    ConvOut o0; o0.cp = p0;
+    ConvOut o0;
+    FView p0f;
+    if (use_f8) { PV_TRY(alloc_fview(n, &p0f, 256, dh, dh)); o0.f8 = p0f; } else o0.cp = p0;
     PV_TRY(add_conv(n, "decoder/decoder_conv0_pointwise", true, ASPP_EPS, d0, o0, g));
-    PV_TRY(add_depthwise(n, "decoder/decoder_conv1_depthwise", ASPP_EPS, p0, d1, 1, 1, false, true));
+    if (use_f8) PV_TRY(add_depthwise_f8(n, "decoder/decoder_conv1_depthwise", ASPP_EPS, p0f, d1, 1, 1, false, true));
+    else PV_TRY(add_depthwise(n, "decoder/decoder_conv1_depthwise", ASPP_EPS, p0, d1, 1, 1, false, true));
     ConvOut o1; o1.cp = p1;
     PV_TRY(add_conv(n, "decoder/decoder_conv1_pointwise", true, ASPP_EPS, d1, o1, g));
   }
