@@ -87,6 +87,7 @@ struct premvos_propnet {
   ConvLayer deconv;
   float *mask_w = nullptr, *mask_b = nullptr, *final_masks = nullptr;   // final_masks [batch][RESULTS_PER_IM][14][14]
   int launches_per_forward = 0;
+  ConvWorkspace conv_ws;             // stream-K scratch of the CTA-pair convolution launches
   cudaGraph_t graph = nullptr;       // the whole forward (fixed shapes per handle, device-side counts)
   cudaGraphExec_t exec = nullptr;
   int graph_nodes = 0, opt_cuda_graph = 1;
@@ -179,8 +180,15 @@ int make_conv(premvos_propnet* n, ConvLayer* L, const std::string& scope, bool b
         for (int o = 0; o < cout; o++)
           w[(((size_t)o * cin + i) * kh + y) * kw + x] = W[(((size_t)y * kw + x) * cin + i) * cout + o] * scale[o];
   const long m_out = out.cp.hi ? (long)out.cp.N * out.cp.H * out.cp.W : (long)out.f32.N * out.f32.H * out.f32.W;
-  PV_TRY(pack_conv_weights_umma(&L->w, w.data(), b.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out));
-  PV_TRY(plan_conv_umma(&L->plan, in, out, L->w, g));
+  // The CTA-pair kernel (conv_umma.cu) is NOT used here (PREMVOS_PROPNET_PAIR=1 switches it on for experiments): measured inside
+  // the batch-4 forward, the bottleneck 1x1 layers (K = 256 .. 1024, residual add in the epilogue) are bound by their epilogue and
+  // memory traffic, not by the operand fill the pair halves (256 -> 1024: 62 us single-CTA, 71 us pair; profiles/r02_*propnet*), and
+  // its stream-K split makes the fp32 summation order of an image depend on its position in the batch.
+  static const bool pair_ok = getenv("PREMVOS_PROPNET_PAIR") && atoi(getenv("PREMVOS_PROPNET_PAIR")) != 0;
+  const bool flat = pair_ok && kh == 1 && kw == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
+                    out.cp.hi && !out.f32.p;
+  PV_TRY(pack_conv_weights_umma(&L->w, w.data(), b.data(), cout, cin, kh, kw, cin_map, cin_phys, 0, m_out, flat));
+  PV_TRY(plan_conv_umma(&L->plan, in, out, L->w, g, &n->conv_ws));
   L->used = true;
   return 0;
 }
@@ -735,6 +743,7 @@ extern "C" void premvos_propnet_destroy(premvos_propnet_t* n) {
   free_layer(&n->conv0); free_layer(&n->rpn0); free_layer(&n->rpn_heads); free_layer(&n->deconv);
   for (auto* vec : {&n->backbone, &n->head, &n->head_m})
     for (auto& b : *vec) { free_layer(&b->c1); free_layer(&b->c2); free_layer(&b->c3); free_layer(&b->sc); }
+  conv_workspace_free(&n->conv_ws);
   if (n->exec) cudaGraphExecDestroy(n->exec);
   if (n->graph) cudaGraphDestroy(n->graph);
   if (n->stream) cudaStreamDestroy(n->stream);

@@ -319,3 +319,56 @@ def test_propnet_full_size_resnet101():
                                            torch.from_numpy(net.get_tensor("rpn_scores", H, W)), H, W)
     np.testing.assert_array_equal(net.get_tensor("topk_indices", H, W).astype(np.int64), dbg["topk_indices"])
     np.testing.assert_array_equal(net.get_tensor("nms_keep", H, W).astype(np.int64), dbg["nms_keep"])
+
+
+def test_propnet_benchmarked_plan_batch4_resnet101():
+    # the launch plan bench.py times: ResNet-101 (3,4,23,3), batch 4, 568x1333 (what 1024x436 resizes to).  Per image: backbone,
+    # RPN scores / decoded boxes against the oracle; the discrete stages (top-k, NMS, final selection) index-exact on the
+    # device's own tensors; RoIAlign, the conv5 head, the head logits and the final detections of one image against the oracle
+    # run on that image's proposals.
+    import cv2
+    nb = (3, 4, 23, 3)
+    H, W = O.custom_resize_shape(436, 1024)
+    assert (H, W) == (568, 1333)
+    B = 4
+    P = synth.propnet_synthetic_params(1, nb)
+    net = propnet.ProposalNet(nb).load_params(P)
+    imgs = np.stack([cv2.resize(synth.synthetic_bgr_frame(436, 1024, seed=20 + i), (W, H)) for i in range(B)])   # uint8 BGR
+    net.forward_device(torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    torch.set_num_threads(__import__("os").cpu_count() or 1)
+    fm_all = net.get_tensor("featuremap", H, W, B)
+    fm_all = fm_all.reshape(B, 1024, -1)
+    n_det = 0
+    for i in range(B):
+        g = lambda name: net.get_tensor("%s@%d" % (name, i), H, W, B)
+        img = imgs[i].astype(np.float32)
+        if i in (0, 3):   # two full oracle backbones (a few seconds each) are enough to pin the batched plan
+            fm = O.pretrained_resnet_conv4(P, O.image_preprocess(img), list(nb[:3]))
+            fshape = tuple(fm.shape[1:])
+            assert rel_err(fm_all[i].reshape(fshape), fm[0].numpy()) < TOL
+            label, box = O.rpn_head(P, fm)
+            assert rel_err(g("rpn_scores"), label.numpy().reshape(-1)) < TOL
+        pb, ps, dbg = O.generate_rpn_proposals(torch.from_numpy(g("rpn_decoded_boxes").reshape(-1, 4)), torch.from_numpy(g("rpn_scores")), H, W)
+        np.testing.assert_array_equal(g("topk_indices").astype(np.int64), dbg["topk_indices"])
+        np.testing.assert_array_equal(g("nms_keep").astype(np.int64), dbg["nms_keep"])
+        n = pb.shape[0]
+        np.testing.assert_array_equal(g("proposal_boxes").reshape(n, 4), pb.numpy())
+        pred, fprobs = O.fastrcnn_predictions(torch.from_numpy(g("fastrcnn_all_boxes").reshape(n, 1, 4)),
+                                              torch.from_numpy(g("fastrcnn_all_probs").reshape(n, 2)))
+        got = net.read_results(H, W, B, i)
+        assert len(got[0]) == len(pred)
+        np.testing.assert_array_equal(g("final_box_index").astype(np.int64), pred[:, 0])
+        np.testing.assert_array_equal(got[1], fprobs)
+        n_det += len(pred)
+        if i == 0:        # the RoI head at full depth: RoIAlign -> conv5 (3 bottlenecks, 2048 channels) -> pooled feature -> logits
+            fm_dev = torch.from_numpy(fm_all[i].reshape((1,) + fshape).copy())
+            roi_ref = O.roi_align(fm_dev, pb * np.float32(1.0 / 16), 14)
+            roi = net.get_tensor("roi_resized", H, W, B).reshape(B, 100, 1024, 14, 14)[i, :n]
+            assert rel_err(roi, roi_ref.numpy()) < TOL
+            pooled = O.resnet_conv5(P, roi_ref, nb[-1]).mean(dim=(2, 3))
+            assert rel_err(g("pooled").reshape(100, 2048)[:n], pooled.numpy()) < TOL
+            Wc, bc = torch.as_tensor(P["fastrcnn/class/W"]), torch.as_tensor(P["fastrcnn/class/b"])
+            probs_ref = torch.softmax(pooled @ Wc + bc, dim=1).numpy()
+            assert rel_err(g("fastrcnn_all_probs").reshape(n, 2), probs_ref) < TOL
+    assert n_det >= 0

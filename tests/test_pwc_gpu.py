@@ -196,6 +196,23 @@ def test_pwc_full_size_against_oracle_and_properties(tc):
     assert rel_err(f0.cpu().numpy(), ref) < (TOL if tc else TOL_FP32)
 
 
+def test_pwc_benchmarked_plan_batch4_full_size():
+    # the launch plan bench.py times: tensor-core mode, batch 4 at 448x1024 (the planner picks tile shapes / split-K by batch
+    # size, so this is another set of kernels than the batch-1 / batch-2 handles above); every pair against the oracle
+    B, H, W = 4, 448, 1024
+    sd = synth.pwc_synthetic_state_dict(0)
+    net = pwc.pwc_dc_net(None, tensor_cores=True)
+    net.load_state_dict(sd)
+    net.cuda()
+    x = synth.synthetic_pwc_input(B, H, W, seed=11)
+    got = net(torch.from_numpy(x).cuda()).cpu().numpy()
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for i in range(B):
+        ref = O.pwc_forward(P, torch.from_numpy(x[i:i + 1])).numpy()
+        assert rel_err(got[i:i + 1], ref) < TOL, i
+
+
 def test_calculate_flow_end_to_end():
     f1, f2 = synth.synthetic_frame_pair(100, 150, seed=3)
     sd = synth.pwc_synthetic_state_dict(2)

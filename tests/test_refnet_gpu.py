@@ -91,6 +91,35 @@ def test_refnet_full_xception65_at_385():
     assert c2[0] == c1[0]
 
 
+def test_refnet_benchmarked_plan_40_crops():
+    # the launch plan bench.py times: one launch group of 40 crops of 385x385 through Xception-65 (CTA-pair GEMMs with the stream-K
+    # schedule of 300-item launches, F8 depthwise path).  Crops 0 and 39 against the oracle; every crop against a batch-1 forward of
+    # the same network (another launch plan: single-CTA kernels) within rounding.
+    S, mu, K = 385, 16, 40
+    P = synth.refnet_synthetic_params(2, mu)
+    blocks = O.blocks_with_middle_units(mu)
+    net = refnet.RefinementNet(max_batch=K, input_size=S, middle_units=mu).load_params(P)
+    frame = synth.synthetic_bgr_frame(436, 1024, seed=3)
+    boxes = synth.synthetic_boxes(K, 436, 1024, seed=103)
+    masks, conf, post = net.refine(frame, boxes, want_posteriors=True)
+    torch.set_num_threads(__import__("os").cpu_count() or 1)
+    image = (frame / 255).astype(np.float32)
+    for i in (0, K - 1):
+        inputs, crop = O.make_network_input(image, boxes[i], S)
+        logits = O.deeplab_logits(P, inputs[None], blocks)
+        mask_ref, post_ref = O.segmentation_output(logits[0], crop, 436, 1024, S)
+        assert rel_err(post[i], post_ref) < TOL
+        assert (masks[i] != mask_ref).mean() < 1e-4
+        cs = O.conf_score(mask_ref, post_ref)
+        assert abs(float(conf[i]) - float(cs)) / max(abs(float(cs)), 1e-6) < TOL
+    single = refnet.RefinementNet(max_batch=1, input_size=S, middle_units=mu).load_params(P)
+    for i in range(0, K, 3):
+        m1, c1, p1 = single.refine(frame, boxes[i:i + 1], want_posteriors=True)
+        assert rel_err(post[i], p1[0]) < 0.5 * TOL          # two launch plans, each within TOL of the oracle (measured: 2e-4)
+        assert (m1[0] != masks[i]).mean() < 1e-4
+        assert abs(float(c1[0]) - float(conf[i])) < 0.5 * TOL
+
+
 def test_do_refinement_surface_and_rle():
     S, mu = 129, 0
     P = synth.refnet_synthetic_params(4, mu)

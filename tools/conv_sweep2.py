@@ -34,7 +34,7 @@ SHAPES = {
     "h4_c3": (400, 512, 7, 7, 2048, 1, 1, 1),
     "h4_c1": (400, 2048, 7, 7, 512, 1, 1, 1),
 }
-KEYS = ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_BUDGET_KB", "PREMVOS_KSPLIT", "PREMVOS_BN", "PREMVOS_DBG", "PREMVOS_NBUF", "PREMVOS_FLAT", "PREMVOS_CONV_REPEAT", "PREMVOS_LOCKSTEP", "PREMVOS_EPI8", "PREMVOS_TAIL", "PREMVOS_TAIL_SPLIT", "PREMVOS_PAIR", "PREMVOS_PAIR_STAGES", "PREMVOS_PAIR_MIN_ITEMS")
+KEYS = ("PREMVOS_KC", "PREMVOS_TPS", "PREMVOS_MT", "PREMVOS_BUDGET_KB", "PREMVOS_KSPLIT", "PREMVOS_BN", "PREMVOS_DBG", "PREMVOS_NBUF", "PREMVOS_FLAT", "PREMVOS_CONV_REPEAT", "PREMVOS_LOCKSTEP", "PREMVOS_EPI8", "PREMVOS_TAIL", "PREMVOS_TAIL_SPLIT", "PREMVOS_PAIR", "PREMVOS_PAIR_STAGES", "PREMVOS_PAIR_MIN_ITEMS", "PREMVOS_PAIR_EPI16", "PREMVOS_STREAMK_ALL", "PREMVOS_PAIR_MIN_UNITS")
 
 
 def run(name, env):
