@@ -206,19 +206,114 @@ class _Trainer:
 
 
 class Engine:
-    def __init__(self, net: RefinementNet):
-        self.net = net
+    """refinement_net/core/Engine.py as far as inference goes: `Engine(config)` builds the network and restores the weights the
+    config names, `.run()` is the stage-5 forwarder; `Engine(net)` wraps an already loaded RefinementNet."""
+
+    def __init__(self, net_or_config, params=None, **kw):
+        self.config = None
+        if isinstance(net_or_config, RefinementNet):
+            self.net = net_or_config
+        else:
+            self.config = net_or_config if isinstance(net_or_config, Config) else Config(net_or_config)
+            self.net = _net_from_config(self.config, params, **kw)
         self.valid_data = _ValidData()
-        self.trainer = _Trainer(net)
+        self.trainer = _Trainer(self.net)
+
+    def run(self, log=None):
+        if self.config is None:
+            raise RuntimeError("Engine.run() needs the config the engine was built from (bb_input_dir / output_dir)")
+        return run_forwarder(self.config, engine=self, log=log)
 
 
-def refinement_net_init(params=None, **kw) -> Engine:
-    """refinement_net_functions.py:19-24.  `params`: slim variables (the reference restores
-    weights/PReMVOS_weights/refinement_net/specific_weights; pass the loaded dict here)."""
+class Config:
+    """refinement_net/core/Config.py: the JSON config files of the reference (`configs/live`, `configs/run`), typed getters."""
+
+    def __init__(self, path_or_dict):
+        import json
+        if isinstance(path_or_dict, dict):
+            self._d, self.path = dict(path_or_dict), None
+        else:
+            self.path = path_or_dict
+            with open(path_or_dict) as f:
+                self._d = json.load(f)
+
+    def string(self, key, default=None):
+        v = self._d.get(key, default)
+        if v is None and default is None and key not in self._d:
+            raise KeyError("config has no '%s'" % key)
+        return v
+
+    def int(self, key, default=None):
+        return int(self.string(key, default))
+
+    def bool(self, key, default=None):
+        return bool(self.string(key, default))
+
+    def int_list(self, key, default=None):
+        return [int(v) for v in self.string(key, default)]
+
+
+LIVE_CONFIG = "refinement_net/configs/live"      # refinement_net_functions.py:20, relative to the reference's cwd `code/`
+
+
+def _net_from_config(config: "Config", params=None, **kw) -> RefinementNet:
+    """Network from the config's input size, weights from config["load"] (a TensorFlow checkpoint prefix, or an .npz / .npy dump of
+    the same variables) unless `params` are given."""
+    size = config.int_list("input_size_train", [385, 385])
+    if size[0] != size[1]:
+        raise ValueError("input_size_train must be square, got %s" % (size,))
+    kw.setdefault("input_size", size[0])
     net = RefinementNet(**kw)
-    if params is not None:
-        net.load_params(params)
-    return Engine(net)
+    if params is None:
+        from . import weights
+        load = config.string("load")
+        try:
+            params = weights.load_refinement_net_variables(load, middle_units=net.middle_units)
+        except (OSError, IOError) as e:
+            raise FileNotFoundError("refinement_net weights '%s' (config %s) cannot be read: %s" % (load, config.path, e)) from e
+    return net.load_params(params)
+
+
+def refinement_net_init(params=None, config_path=None, **kw) -> Engine:
+    """refinement_net_functions.py:19-24: no arguments -- reads `refinement_net/configs/live` relative to the current directory
+    (the reference runs from `code/`) and restores the checkpoint its "load" entry names.  Extensions: `params` (an already loaded
+    variable dict, no file access), `config_path`, and RefinementNet keyword arguments (max_batch, middle_units)."""
+    if params is not None and config_path is None:
+        net = RefinementNet(**kw).load_params(params)
+        return Engine(net)
+    return Engine(Config(config_path or LIVE_CONFIG), params, **kw)
+
+
+def run_forwarder(config, engine: Engine = None, params=None, log=None, **kw):
+    """The stage-5 batch job `Engine(Config(path)).run()` with "task": "few_shot_segmentation" and need_train false
+    (refinement_net/main.py:19-32 -> forwarding/FewShotSegmentationForwarder.py:85-155): for every
+    `<bb_input_dir>/<video>/<frame>.json` read the proposals, refine them on `<image_input_dir>/<video>/<frame>.jpg` and write the
+    list -- every proposal now with 'segmentation' and 'conf_score' -- to `<output_dir>/<video>/<frame>.json`.
+    `config`: path, dict or Config.  Returns the number of frames written."""
+    import glob
+    import json
+    import os
+    if not isinstance(config, Config):
+        config = Config(config)
+    if engine is None:
+        engine = Engine(config, params, **kw)
+    img_dir, bb_dir, out_dir = config.string("image_input_dir"), config.string("bb_input_dir"), config.string("output_dir")
+    frames = 0
+    for fn in sorted(glob.glob(os.path.join(bb_dir, "*", "*.json"))):
+        video, name = os.path.basename(os.path.dirname(fn)), os.path.basename(fn)
+        with open(fn) as f:
+            proposals = json.load(f)
+        image_fn = os.path.join(img_dir, video, name[:-5] + ".jpg")
+        if not os.path.exists(image_fn):
+            raise FileNotFoundError("frame %s of the proposals %s is missing" % (image_fn, fn))
+        proposals = do_refinement(proposals, image_fn, engine)
+        os.makedirs(os.path.join(out_dir, video), exist_ok=True)
+        with open(os.path.join(out_dir, video, name), "w") as f:
+            json.dump(proposals, f)
+        frames += 1
+        if log:
+            log("refined %s/%s: %d proposals" % (video, name, len(proposals)))
+    return frames
 
 
 def do_refinement(proposals, image_fn, refinement_net: Engine):
