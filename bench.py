@@ -27,6 +27,13 @@ premvos_b200.pipeline.FramePipeline; the metric is whole-job frame pairs per sec
              one at a time as the reference iterates) -- the bounded sample of the product arm's 4-unit step; --steps / --warmup
              are honoured as given.  (The reference's own CPU path cannot run: its CPU correlation is a stub, warp() hard-codes
              .cuda(), TensorFlow 1.8 / tensorpack are not installable.)
+  N > 1    : every rank packs the results of its step (flow, detections, conf_scores, bit-packed masks: pipeline.pack_step_results)
+             into one flat buffer and gathers it to rank 0 with ONE NCCL collective per step (shard.gather_tensor, asynchronous, two
+             buffers in flight) INSIDE the timed region: `value` is gather-inclusive.
+  e2e_detected : the product mode of the pipeline, run_frames_host(boxes=None): every unit refines the boxes its own two proposal
+             passes detect (a device->host read of the counts mid-step; data-dependent work, mean boxes per frame reported).
+  --c5     : BASELINE configs[4]: a 90-frame 854x480 synthetic video, units sharded round-robin over the ranks, detected boxes,
+             per-step results gathered to rank 0; value = frame pairs of the video / wall time of the slowest rank.
   library_baseline : the oracle graphs on the GPU through torch / cuDNN in fp32 and TF32 (baseline/library_baseline.py) -- what a
              plain library implementation of the same arithmetic does on this GPU; context, not the product path.
   c1_correlation : BASELINE configs[0] on the device: the cost-volume kernel alone, GB/s of algorithmic bytes vs the HBM peak.
@@ -231,6 +238,111 @@ def c1_correlation(peak_gbs):
     return out
 
 
+def run_c5(args, rank, local_rank, world):
+    """BASELINE configs[4] / SURVEY 8(d) C5: a 90-frame 854x480 synthetic video through stages 1, 2, 3, 5 (simple_run.sh:19-61), units
+    (frame pairs) sharded round-robin over the ranks (shard.shard_units), every unit refining its own detections, the per-step
+    results gathered to rank 0 (bit-packed masks, one NCCL gather per step).  Timed: whole video, wall clock of the slowest rank,
+    decode-time host preparation excluded (frames are resident in pinned host memory, as a decoder would hand them over)."""
+    import torch
+    import torch.distributed as dist
+    from premvos_b200 import pipeline, shard, synth
+    Hc, Wc = 480, 854
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+
+    def weights(make):
+        sd = {k: torch.from_numpy(np.asarray(v)) for k, v in make().items()} if rank == 0 else {}
+        return shard.broadcast_state_dict(sd, src=0)
+    sd_flow = weights(lambda: synth.pwc_synthetic_state_dict(0))
+    P_gen = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(8)).items()}
+    P_spec = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(3)).items()}
+    P_ref = {k: v.numpy() for k, v in weights(lambda: synth.refnet_synthetic_params(2)).items()}
+    B, K = args.pairs, args.boxes
+    pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (Hc, Wc), pairs_per_step=B, boxes_per_frame=K)
+    f1, f2 = synth.synthetic_frame_pair(Hc, Wc, seed=1)
+    frames = [np.ascontiguousarray(np.roll(f1 if t % 2 == 0 else f2, shift=(3 * t, 5 * t), axis=(0, 1))) for t in range(args.frames)]
+    units = shard.shard_units(len(frames) - 1, rank, world)
+    steps = [units[i:i + B] for i in range(0, len(units), B)]
+    steps = [c + [c[-1]] * (B - len(c)) for c in steps]          # the last step of a shard is padded by repeating its last unit
+    n_steps_all = -(-(-(-(len(frames) - 1) // world)) // B)      # every rank runs the same number of collectives
+    prev = [torch.from_numpy(np.stack([frames[t] for t in c])).pin_memory() for c in steps]
+    cur = [torch.from_numpy(np.stack([frames[t + 1] for t in c])).pin_memory() for c in steps]
+    flats = [pipe.pack_step_results() for _ in range(2)]
+
+    def run_video():
+        pending = [None, None]
+        nb = 0
+        for i in range(n_steps_all):
+            j = i & 1
+            if i < len(steps):
+                r = pipe.run_frames_host(prev[i], cur[i])
+                nb += int(np.sum(r["num_boxes"][:len(set(steps[i]))]))
+            if pending[j] is not None and pending[j][1] is not None:
+                pending[j][1].wait()
+            pipe.pack_step_results(out=flats[j])
+            pending[j] = shard.gather_tensor(flats[j], dst=0, async_op=True)
+        for p in pending:
+            if p is not None and p[1] is not None:
+                p[1].wait()
+        torch.cuda.synchronize()
+        return nb
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+
+    run_video()                                                   # warm-up: one whole pass
+    reps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    nb = 0
+    for _ in range(reps):
+        nb += run_video()
+    barrier()
+    sec = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([sec, float(nb)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sec, nb = float(tmax[0]), float(t[1])
+    pairs = (len(frames) - 1) * reps
+    if rank == 0:
+        print(json.dumps({"metric": "frame-pairs/sec, end-to-end 90-frame 854x480 video (flow + 2 x proposals + refinement of the detected "
+                                    "boxes), sharded over the ranks, results gathered to rank 0",
+                          "value": pairs / sec, "unit": UNIT, "n_gpus": world, "steps": reps, "warmup": 1, "ms_per_step": sec / reps * 1e3,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "bf16x3 split-fp32 (fp32 accumulate)", "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[4] (SURVEY 8d C5): %d frames 854x480, %d frame pairs, pairs_per_step %d, "
+                                                 "up to %d boxes per frame from the unit's own detections" % (len(frames), len(frames) - 1, B, K),
+                                     "mean_boxes_refined_per_frame": nb / pairs, "parallelism": "dp%d" % world,
+                                     "gather_bytes_per_rank_per_step": int(flats[0].numel()),
+                                     "timing": "wall clock of the slowest rank over the whole video incl. host<->device copies and the "
+                                               "NCCL gathers; a step of this line = one pass over the video"}}), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+class stdout_to_stderr:
+    """NCCL prints its version banner on the process's stdout when the communicator is created (first collective); the contract is ONE
+    JSON line on stdout, so file descriptor 1 points at stderr while the process group comes up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def time_stage(fn, iters, warm=2):
     import torch
     for _ in range(warm):
@@ -257,12 +369,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-network context timings")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch / cuDNN context timings")
+    ap.add_argument("--c5", action="store_true", help="BASELINE configs[4]: 90-frame 854x480 video sharded over the ranks")
+    ap.add_argument("--frames", type=int, default=90, help="frames of the --c5 video")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.c5:
+        return run_c5(args, rank, local_rank, world)
 
     import torch
     import torch.distributed as dist
@@ -273,8 +389,9 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()                                        # creates the communicator (and prints NCCL's banner) now
     args.warmup = max(args.warmup, 3)
     B, K = args.pairs, args.boxes
 
@@ -283,8 +400,8 @@ def main():
         sd = {k: torch.from_numpy(np.asarray(v)) for k, v in make().items()} if rank == 0 else {}
         return shard.broadcast_state_dict(sd, src=0)
     sd_flow = weights(lambda: synth.pwc_synthetic_state_dict(0))
-    P_gen = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(1)).items()}
-    P_spec = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(4)).items()}
+    P_gen = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(8)).items()}
+    P_spec = {k: v.numpy() for k, v in weights(lambda: synth.propnet_synthetic_params(3)).items()}
     P_ref = {k: v.numpy() for k, v in weights(lambda: synth.refnet_synthetic_params(2)).items()}
     pipe = pipeline.FramePipeline(sd_flow, P_gen, P_spec, P_ref, (H_IN, W_IN), pairs_per_step=B, boxes_per_frame=K, refine_batch=args.refine_batch or None)
 
@@ -311,9 +428,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # N > 1: the per-step results of every rank are gathered to rank 0 inside the timed region (one NCCL gather of the flat,
+    # bit-packed result buffer per step; asynchronous: the gather of step i overlaps the compute of step i + 1)
+    flats = [pipe.pack_step_results() for _ in range(2)] if distributed else None
+    pending = [None, None]
+
+    def step_device(i):
+        pipe.run_frames_device(*dev_sets[i % sets])
+        if distributed:
+            j = i & 1
+            if pending[j] is not None:
+                pending[j][1].wait()            # the buffer's previous gather is done before it is overwritten
+            pipe.pack_step_results(out=flats[j])
+            pending[j] = shard.gather_tensor(flats[j], dst=0, async_op=True)
+
+    def drain():
+        for j in range(2):
+            if pending[j] is not None:
+                pending[j][1].wait()
+                pending[j] = None
+
     # ---- device-resident arm ----
     for i in range(args.warmup):
-        pipe.run_frames_device(*dev_sets[i % sets])
+        step_device(i)
+    drain()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -322,7 +460,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        pipe.run_frames_device(*dev_sets[i % sets])
+        step_device(i)
+    drain()
     e1.record()
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -340,6 +479,22 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     e2e = world * B * args.steps / e2e_s
+
+    # ---- the product mode: boxes from the unit's own proposal passes (data-dependent work) ----
+    det_steps = max(1, min(args.steps, 10))
+    pipe.run_frames_host(host_sets[0][0], host_sets[0][1])
+    barrier()
+    t0 = time.perf_counter()
+    nboxes = 0
+    for i in range(det_steps):
+        r = pipe.run_frames_host(host_sets[i % sets][0], host_sets[i % sets][1])
+        nboxes += int(np.sum(r["num_boxes"]))
+    torch.cuda.synchronize()
+    det_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_detected = {"value": world * B * det_steps / det_s, "unit": UNIT, "steps": det_steps,
+                    "mean_boxes_refined_per_frame": nboxes / (det_steps * B),
+                    "call": "FramePipeline.run_frames_host(boxes=None): each unit refines the boxes its two proposal passes detect "
+                            "(random-init heads: the count is data dependent), one device->host read of the counts mid-step"}
 
     # ---- per-launch profile of one step (rank 0), stages serial on one stream -> roofline of the dominant kernel ----
     roofline, kernels = None, None
@@ -422,6 +577,9 @@ def main():
                         "call": "FramePipeline.run_frames_host: pinned uint8 frames t, t+1 + boxes in (as a decoder hands them over; the stage "
                                 "drivers' cv2.resize calls run on the device, bit-exact), flow + detections + per-box masks + conf_scores "
                                 "out to pinned host memory, synchronous per step"},
+                "e2e_detected": e2e_detected,
+                "gather": ({"bytes_per_rank_per_step": int(flats[0].numel()), "collective": "NCCL gather to rank 0, one per step, inside the "
+                            "timed region, asynchronous (two buffers in flight)"} if distributed else None),
                 "gpu_launches": int(launches), "launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "library_baseline": library_baseline,
                 "c1_correlation": c1, "kernels": kernels, "stages": stages}

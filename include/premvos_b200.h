@@ -135,6 +135,15 @@ int premvos_warp_masks_u8(const unsigned char* masks_dev, int n, int height, int
 int premvos_flow_postprocess(const float* flow2_dev, int batch, int net_h, int net_w, float* out_dev, int height, int width,
                              void* stream);
 
+/*
+ * premvos_pack_mask_bits: the per-proposal full-frame masks the refinement stage returns (refinement_net/forwarding/
+ * FewShotSegmentationForwarder.py:139-141 hands `mask` to pycocotools' RLE encoder one proposal at a time) packed 8 pixels per
+ * byte on the device before they leave it: masks_dev uint8 [n_masks, hw] (any non-zero = 1) -> out_dev [n_masks, 8 * ceil(hw / 64)]
+ * bytes, pixel i of a mask = bit (i % 8) of byte (i / 8) (numpy.unpackbits(..., bitorder="little")); every mask starts on an
+ * 8-byte boundary, out_dev must be 8-byte aligned.  Enqueues on `stream`, never synchronises.
+ */
+int premvos_pack_mask_bits(const unsigned char* masks_dev, long long n_masks, long long hw, unsigned char* out_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PWC-DC-Net forward (optical flow).
  *

@@ -12,7 +12,7 @@ EXPORTS = [
     "premvos_version", "premvos_last_error", "premvos_kernel_launch_count", "premvos_profile_begin",
     "premvos_profile_end",
     "premvos_corr_output_shape", "premvos_corr_forward", "premvos_conv2d_forward", "premvos_resize_linear_u8",
-    "premvos_warp_masks_u8", "premvos_flow_postprocess",
+    "premvos_warp_masks_u8", "premvos_flow_postprocess", "premvos_pack_mask_bits",
     "premvos_pwc_create", "premvos_pwc_set_param", "premvos_pwc_finalize", "premvos_pwc_forward",
     "premvos_pwc_forward_host", "premvos_pwc_forward_host_u8", "premvos_pwc_forward_u8",
     "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
@@ -57,6 +57,7 @@ def lib() -> ctypes.CDLL:
     L.premvos_resize_linear_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.premvos_warp_masks_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     L.premvos_flow_postprocess.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
+    L.premvos_pack_mask_bits.argtypes = [c_void_p, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]
     L.premvos_pwc_create.argtypes = [P(c_void_p), c_int, c_int, c_int]
     L.premvos_pwc_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
     L.premvos_pwc_finalize.argtypes = [c_void_p]

@@ -86,3 +86,33 @@ def resize_linear_u8(img: torch.Tensor, dst_h: int, dst_w: int, reverse_channels
         _lib.check(_lib.lib().premvos_resize_linear_u8(img.data_ptr(), B, H, W, out.data_ptr(), int(dst_h), int(dst_w), C,
                                                        1 if reverse_channels else 0, st))
     return out
+
+
+def packed_mask_bytes(hw: int) -> int:
+    """Bytes of one bit-packed mask of `hw` pixels (whole 64-pixel words)."""
+    return 8 * ((int(hw) + 63) // 64)
+
+
+def pack_mask_bits(masks: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """uint8 CUDA masks [..., H, W] (non-zero = 1) -> uint8 [..., packed_mask_bytes(H*W)], 8 pixels per byte, pixel i of a mask
+    at bit i % 8 of byte i / 8 (premvos_pack_mask_bits).  Enqueues on the current stream."""
+    if not isinstance(masks, torch.Tensor) or not masks.is_cuda or masks.dtype != torch.uint8 or not masks.is_contiguous() or masks.dim() < 2:
+        raise TypeError("masks must be a contiguous CUDA uint8 tensor [..., H, W] (premvos_b200 has no CPU path)")
+    hw = int(masks.shape[-2]) * int(masks.shape[-1])
+    n = masks.numel() // hw if hw else 0
+    shape = tuple(masks.shape[:-2]) + (packed_mask_bytes(hw),)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=masks.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CUDA uint8 tensor of shape %s" % (shape,))
+    with torch.cuda.device(masks.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_pack_mask_bits(masks.data_ptr(), n, hw, out.data_ptr(), st))
+    return out
+
+
+def unpack_mask_bits(packed, height: int, width: int) -> np.ndarray:
+    """Host inverse of pack_mask_bits: uint8 [..., packed_mask_bytes(H*W)] (numpy or CPU tensor) -> uint8 0/1 [..., H, W]."""
+    a = packed.numpy() if isinstance(packed, torch.Tensor) else np.asarray(packed)
+    bits = np.unpackbits(np.ascontiguousarray(a, dtype=np.uint8), axis=-1, bitorder="little")
+    return bits[..., :height * width].reshape(a.shape[:-1] + (height, width))

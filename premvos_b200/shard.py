@@ -62,3 +62,17 @@ def gather_results(local: dict, dst: int = 0):
     for d in bucket:
         merged.update(d)
     return merged
+
+
+def gather_tensor(t, dst: int = 0, async_op: bool = False):
+    """One equally-shaped tensor per rank -> list of `world` tensors on rank `dst` (None elsewhere), as ONE collective on the
+    tensors' own device: NCCL over NVLink for CUDA tensors (the packed per-unit results of a step, pipeline.pack_step_results;
+    SURVEY.md section 8e), gloo for CPU tensors.  No pickling, no host round trip.  async_op=True returns (bucket, work): the
+    collective runs on the backend's stream, call work.wait() before reading `bucket` or overwriting `t`."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return ([t], None) if async_op else [t]
+    bucket = [torch.empty_like(t) for _ in range(dist.get_world_size())] if dist.get_rank() == dst else None
+    work = dist.gather(t, bucket, dst=dst, async_op=async_op)
+    return (bucket, work) if async_op else bucket

@@ -187,3 +187,29 @@ def test_pipeline_from_original_frames_equals_host_prepared_inputs(parts):
     host = pipe.run_frames_host(prev.pin_memory(), cur.pin_memory(), boxes.pin_memory())
     for k in want:
         np.testing.assert_array_equal(host[k].numpy(), want[k])
+
+
+def test_pack_mask_bits_round_trip_and_flat_step_results(parts):
+    # the transport format of the masks: 8 pixels per byte, any non-zero byte = 1, masks of a size that is not a multiple of 64
+    from premvos_b200 import ops
+    rng = np.random.default_rng(5)
+    for shape in ((3, 2, 37, 53), (5, 100, 140), (1, 1, 8, 8)):
+        m = (rng.random(shape) < 0.4).astype(np.uint8) * rng.integers(1, 255, shape).astype(np.uint8)
+        packed = ops.pack_mask_bits(torch.from_numpy(m).cuda())
+        assert tuple(packed.shape) == shape[:-2] + (ops.packed_mask_bytes(shape[-2] * shape[-1]),)
+        np.testing.assert_array_equal(ops.unpack_mask_bits(packed.cpu(), shape[-2], shape[-1]), (m != 0).astype(np.uint8))
+    with pytest.raises(TypeError):
+        ops.pack_mask_bits(torch.zeros(4, 4, dtype=torch.uint8))
+    # one flat buffer per step == the separate outputs
+    pipe, sd, G, S, R, frames = parts
+    B, K = pipe.B, pipe.K
+    prev = torch.from_numpy(np.stack([frames[0]] * B)).cuda()
+    cur = torch.from_numpy(np.stack([frames[1]] * B)).cuda()
+    boxes = torch.from_numpy(np.stack([synth.synthetic_boxes(K, pipe.H, pipe.W, seed=3, min_size=20, max_size=80)] * B)).cuda()
+    out = pipe.run_frames_device(prev, cur, boxes)
+    flat = pipe.pack_step_results()
+    torch.cuda.synchronize()
+    assert flat.numel() < 0.5 * sum(v.numel() * v.element_size() for v in out.values())   # masks 8x smaller
+    back = pipe.unpack_step_results(flat)
+    for k in ("flow", "det_count", "det_boxes", "det_probs", "conf", "masks"):
+        np.testing.assert_array_equal(back[k], out[k].cpu().numpy())

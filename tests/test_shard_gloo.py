@@ -32,6 +32,19 @@ def _worker(rank, world, port, q):
         mine = shard.shard_units(5, rank, world)
         local = {i: np.full((2, 2), float(i), dtype=np.float32) * sd["b"][0].item() for i in mine}
         merged = shard.gather_results(local, dst=0)
+        # the data-plane collective of the sharded path: one flat uint8 buffer per rank and step, gathered as a tensor (no pickle),
+        # asynchronously (two buffers in flight, as bench.py does it)
+        works = []
+        for step in range(3):
+            flat = torch.full((1000,), 10 * step + rank, dtype=torch.uint8)
+            bucket, work = shard.gather_tensor(flat, dst=0, async_op=True)
+            works.append((step, bucket, work))
+        for step, bucket, work in works:
+            work.wait()
+            if rank == 0:
+                assert len(bucket) == world and all(int(bucket[r][0]) == 10 * step + r and int(bucket[r][-1]) == 10 * step + r for r in range(world))
+            else:
+                assert bucket is None
         t = torch.tensor([float(len(mine))])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)       # the bench's max-over-ranks step
         if rank == 0:
