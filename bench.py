@@ -506,6 +506,19 @@ def main():
         total_ms = sum(v["ms"] for v in prof.values()) or 1.0
         kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / total_ms}
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        # the tensor-core convolution runs as two kernels (conv_umma_kernel<4|8>: one CTA per tile; conv_pair_kernel: cta_group::2 CTA
+        # pairs for the wide 1x1 layers); the roofline entry is the one with the larger share of the step, the other one and their
+        # sum are listed beside it
+        def tensor_entry(names):
+            ms = sum(prof[n]["ms"] for n in names if n in prof)
+            fl = sum(prof[n]["flops"] for n in names if n in prof)
+            ln = sum(prof[n]["launches"] for n in names if n in prof)
+            if not ln:
+                return None
+            ach = fl / (ms * 1e-3) / 1e12
+            return {"kernel": "+".join(n for n in names if n in prof), "achieved": ach, "frac": ach / peaks["tensor_sustained"],
+                    "tensor_pipe_frac": 3 * ach / peaks["tensor_sustained"], "ms_per_step": ms, "launches_per_step": ln,
+                    "avg_launch_us": ms * 1e3 / ln, "algorithmic_gflop_per_step": fl / 1e9, "share_of_step": ms / total_ms}
         name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
         sec = top["ms"] * 1e-3
         traffic = load_traffic(name)
@@ -519,7 +532,10 @@ def main():
                         "note": "achieved = algorithmic fp32 FLOPs of all launches of this kernel in one step / their summed device "
                                 "time; every algorithmic FLOP is issued as 3 bf16 tensor-core FLOPs (split-bf16 x3 for 1e-3 fp32 "
                                 "parity), so tensor-pipe occupancy is 3x frac; traffic = mean DRAM bytes per launch (ncu)",
-                        "bf16_tflops_issued": 3 * ach, "tensor_pipe_frac": 3 * ach / peak}
+                        "bf16_tflops_issued": 3 * ach, "tensor_pipe_frac": 3 * ach / peak,
+                        "tensor_core_kernels": {"conv_umma_kernel": tensor_entry(["conv_umma_kernel"]),
+                                                "conv_pair_kernel": tensor_entry(["conv_pair_kernel"]),
+                                                "both": tensor_entry(["conv_umma_kernel", "conv_pair_kernel"])}}
         else:
             ach = top["bytes"] / sec / 1e9
             peak = peaks["hbm"]

@@ -303,6 +303,7 @@ struct UmmaConvArgs {
   int lockstep;              // 1x1 layers: A and weight rings advance together and share one barrier pair per k-block
   int epi_warps;             // 4 or 8 epilogue warps (8: kernel instantiation with 384 threads, one CTA per SM)
   int pair;                  // 1: conv_pair_kernel (cta_group::2, 256 pixels x 256 output channels per CTA pair); see there
+  int bias_smem;             // pair kernel: floats of bias staged in shared memory (ntiles * BN, or 0: read from global memory)
   int stream_k_all;          // pair kernel: 1 = no round-robin phase, all items are cut into equal k-block ranges (tuning switch)
   unsigned* sk_flags;        // pair kernel, stream-K: [pairs][2 ranks][8 epilogue warps] flags; `partial` = [pairs][2][128][256] fp32
 };
@@ -895,6 +896,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* tmem_full_bar = empty + MAX_W_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]  (used in the leader CTA, 2 * EPI_WARPS arrivals)
   uint32_t* tmem_addr_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  // The layer's whole bias vector lives in shared memory (<= 8 KB): with 192 KB of operand stages the L1 has no capacity left, so
+  // a bias load in the epilogue is an L2 round trip per 16 columns (38 % of the epilogue's stall samples were waiting for it)
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  for (int i = threadIdx.x; i < a.bias_smem; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1078,7 +1083,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const __nv_bfloat16* rlo = a.res_hi ? a.res_lo + (rhi - a.res_hi) : nullptr;
       float* of8 = a.out_f8 ? a.out_f8 + ((((long)n_img * a.f8_chunks + a.f8_c0 + cg0) * hw + pix) << 3) : nullptr;
       const float* rf8 = a.res_f8 ? a.res_f8 + ((((long)n_img * a.resf_chunks + a.resf_c0 + cg0) * hw + pix) << 3) : nullptr;
-      const float* bias = a.bias + wk.ntile * a.BN + col_begin;
+      const float* bias = (a.bias_smem ? bias_s : a.bias) + wk.ntile * a.BN + col_begin;
       // partial sums: [pair slot][rank][column / 4 (64)][row (128)] float4 -- a warp's 32 rows of one float4 column are contiguous
       float4* ppart = reinterpret_cast<float4*>(a.partial) + (((long)pair_id * 2 + rank) * 64 + (col_begin >> 2)) * 128 + m;
       (void)row;
@@ -1110,7 +1115,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const float4* bp = reinterpret_cast<const float4*>(bias + (g << 4));
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const float4 b4 = __ldg(bp + j);
+          const float4 b4 = bp[j];
           f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
         }
         const bool second = co0 + 8 < a.Cout;   // the second chunk of this step exists
@@ -1401,12 +1406,14 @@ static int plan_conv_pair(ConvPlanUmma* plan, const CView& in, const ConvOut& ou
   a.w_plane = w.KC * 128 * 16;       // ONE CTA's half of a (hi or lo) weight plane
   a.w_stage = 2 * a.w_plane;
   const int stage_bytes = 2 * a.a_plane + a.w_stage;
-  int st = (SMEM_LIMIT - 1024) / stage_bytes;
+  // short K loops only (epilogue-bound layers: -14 % at K = 256); long ones keep the seventh operand stage instead
+  a.bias_smem = (w.ntiles * w.BN * 4 <= 8192 && w.kblocks <= 16 && env_int("PREMVOS_PAIR_BIAS_SMEM", 1)) ? w.ntiles * w.BN : 0;
+  int st = (SMEM_LIMIT - 1024 - a.bias_smem * 4) / stage_bytes;
   st = std::max(2, std::min(st, MAX_W_STAGES));
   st = env_int("PREMVOS_PAIR_STAGES", st);
   PV_CHECK(st >= 2 && st <= MAX_W_STAGES, PREMVOS_ERR_INVALID_ARG, "conv_umma: PREMVOS_PAIR_STAGES=%d", st);
   a.a_stages = a.w_stages = st;
-  plan->smem_bytes = st * stage_bytes + 128 + 512;
+  plan->smem_bytes = st * stage_bytes + 128 + 512 + a.bias_smem * 4;
   PV_CHECK(plan->smem_bytes <= SMEM_LIMIT, PREMVOS_ERR_UNSUPPORTED, "conv_umma: %d bytes of shared memory needed", plan->smem_bytes);
   a.w = w.w; a.bias = w.bias; a.slope = g.slope;
   a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
@@ -1736,7 +1743,7 @@ static int launch_conv_pair(const ConvPlanUmma& plan, cudaStream_t st, int activ
                                                            *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo),
                                                            *reinterpret_cast<const CUtensorMap*>(plan.map_w), a);
   const double frac = (double)a.n_images / plan.N;
-  const char* label = "conv_umma_kernel";   // one roofline entry for the tensor-core convolution, whichever instantiation ran
+  const char* label = "conv_pair_kernel";
   static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
   if (per_layer && profiling_enabled()) {
     char buf[256];

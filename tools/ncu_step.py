@@ -1,7 +1,7 @@
 """Target of the ncu captures (GPU box only): builds the resident pipeline (or one network), warms up, then runs ONE unit of
 work between cudaProfilerStart/Stop so that `ncu --profile-from-start off` sees exactly that work.
     python tools/ncu_step.py pipeline      one bench step (4 frame pairs: flow + 2 proposal passes + 40 refine boxes each)
-    python tools/ncu_step.py refnet        one refinement launch group (20 crops)
+    python tools/ncu_step.py refnet        one refinement launch group (40 crops, the benchmarked group)
     python tools/ncu_step.py flow          one PWC forward (4 pairs)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,13 +13,13 @@ import bench
 what = sys.argv[1] if len(sys.argv) > 1 else "pipeline"
 H, W = bench.H_IN, bench.W_IN
 if what == "refnet":
-    rn = refnet.RefinementNet(max_batch=20).load_params(synth.refnet_synthetic_params(2))
+    rn = refnet.RefinementNet(max_batch=40).load_params(synth.refnet_synthetic_params(2))
     frame = torch.from_numpy(synth.synthetic_bgr_frame(H, W, seed=3)).cuda()
-    boxes = torch.from_numpy(synth.synthetic_boxes(20, H, W, seed=3)).cuda()
+    boxes = torch.from_numpy(synth.synthetic_boxes(40, H, W, seed=3)).cuda()
     run = lambda: rn.refine_device(frame, boxes)
 else:
     sd = {k: torch.from_numpy(v) for k, v in synth.pwc_synthetic_state_dict(0).items()}
-    pipe = pipeline.FramePipeline(sd, synth.propnet_synthetic_params(1), synth.propnet_synthetic_params(4),
+    pipe = pipeline.FramePipeline(sd, synth.propnet_synthetic_params(8), synth.propnet_synthetic_params(3),
                                   synth.refnet_synthetic_params(2), (H, W), pairs_per_step=4, boxes_per_frame=40)
     units = bench.make_units(4, 40)
     dev = [torch.from_numpy(np.stack([u[i] for u in units])).cuda() for i in range(3)]
