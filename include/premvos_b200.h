@@ -50,7 +50,9 @@ int64_t premvos_kernel_launch_count(void);
 /* Per-launch profiling for bench.py's roofline leg.  Between begin and end every kernel launched by
  * this library is bracketed by CUDA events on its launching stream (CUDA graphs are bypassed while
  * profiling).  premvos_profile_end synchronises and writes one text line per kernel name into buf:
- * "name launches total_ms algorithmic_flops algorithmic_bytes\n". */
+ * "name launches total_ms algorithmic_flops algorithmic_bytes\n".  Returns 0; when buflen is too small for the report, nothing is
+ * written and the number of bytes needed is returned (> 0): call again with a buffer of that size, the report is kept.  The record
+ * list is guarded by a mutex (launchers may run on several host threads). */
 int premvos_profile_begin(void);
 int premvos_profile_end(char* buf, int buflen);
 
@@ -143,6 +145,18 @@ int premvos_flow_postprocess(const float* flow2_dev, int batch, int net_h, int n
  * 8-byte boundary, out_dev must be 8-byte aligned.  Enqueues on `stream`, never synchronises.
  */
 int premvos_pack_mask_bits(const unsigned char* masks_dev, long long n_masks, long long hw, unsigned char* out_dev, void* stream);
+
+/*
+ * Coefficient tables of premvos_resize_linear_u8 / premvos_flow_postprocess (OpenCV's per-axis source indices and weights for one
+ * (source size, destination size) pair, a few KB).  Both enqueue-only entry points build the tables of a new geometry on first use:
+ * that FIRST call allocates device memory and copies synchronously, i.e. it is not capturable into a CUDA graph and may block.
+ * Call the matching *_prepare once per geometry beforehand (same device) to take that cost out of the stream; *_release frees every
+ * table of this process (they are rebuilt on demand).
+ */
+int premvos_resize_linear_u8_prepare(int src_h, int src_w, int dst_h, int dst_w);
+void premvos_resize_linear_u8_release(void);
+int premvos_flow_postprocess_prepare(int net_h, int net_w, int height, int width);
+void premvos_flow_postprocess_release(void);
 
 /* ---------------------------------------------------------------------------------------------
  * PWC-DC-Net forward (optical flow).

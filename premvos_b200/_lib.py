@@ -13,6 +13,7 @@ EXPORTS = [
     "premvos_profile_end",
     "premvos_corr_output_shape", "premvos_corr_forward", "premvos_conv2d_forward", "premvos_resize_linear_u8",
     "premvos_warp_masks_u8", "premvos_flow_postprocess", "premvos_pack_mask_bits",
+    "premvos_resize_linear_u8_prepare", "premvos_resize_linear_u8_release", "premvos_flow_postprocess_prepare", "premvos_flow_postprocess_release",
     "premvos_pwc_create", "premvos_pwc_set_param", "premvos_pwc_finalize", "premvos_pwc_forward",
     "premvos_pwc_forward_host", "premvos_pwc_forward_host_u8", "premvos_pwc_forward_u8",
     "premvos_pwc_launches_per_forward", "premvos_pwc_set_option",
@@ -118,7 +119,11 @@ def profile_begin() -> None:
 def profile_end() -> dict:
     """-> {kernel name: {"launches", "ms", "flops", "bytes"}} for everything launched since profile_begin()."""
     buf = ctypes.create_string_buffer(1 << 16)
-    check(lib().premvos_profile_end(buf, len(buf)))
+    need = lib().premvos_profile_end(buf, len(buf))
+    if need > 0:        # the report (per-layer labels) did not fit: the library kept it, ask again with the size it named
+        buf = ctypes.create_string_buffer(need + 16)
+        need = lib().premvos_profile_end(buf, len(buf))
+    check(need)
     out = {}
     for line in buf.value.decode().splitlines():
         name, cnt, ms, fl, by = line.rsplit(" ", 4)

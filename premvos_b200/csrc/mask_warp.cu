@@ -378,6 +378,23 @@ __global__ void __launch_bounds__(256) pack_mask_bits_kernel(const unsigned char
 }  // namespace pack_bits
 }  // namespace premvos
 
+// Builds (and uploads, synchronously) the coefficient tables premvos_flow_postprocess needs for this geometry on the current
+// device.  The enqueue-only entry point builds them on first use too, but that first call allocates and copies synchronously and
+// therefore must not happen inside a stream capture: call this once per geometry beforehand.
+extern "C" int premvos_flow_postprocess_prepare(int net_h, int net_w, int height, int width) {
+  PV_CHECK(net_h > 0 && net_w > 0 && height > 0 && width > 0 && net_h % 4 == 0 && net_w % 4 == 0, PREMVOS_ERR_INVALID_ARG,
+           "premvos_flow_postprocess_prepare: bad sizes");
+  premvos::FlowTables t;
+  return premvos::get_tables(net_h / 4, net_w / 4, height, width, &t);
+}
+
+// Frees the coefficient tables of premvos_flow_postprocess (all devices, all geometries); they are rebuilt on demand.
+extern "C" void premvos_flow_postprocess_release(void) {
+  std::lock_guard<std::mutex> lock(premvos::g_mu);
+  for (auto& kv : premvos::g_tables) { cudaFree(kv.second.cols); cudaFree(kv.second.rows); }
+  premvos::g_tables.clear();
+}
+
 extern "C" int premvos_pack_mask_bits(const unsigned char* masks_dev, long long n_masks, long long hw, unsigned char* out_dev, void* stream) {
   PV_CHECK(masks_dev && out_dev, PREMVOS_ERR_INVALID_ARG, "premvos_pack_mask_bits: null argument");
   PV_CHECK(n_masks >= 0 && hw > 0, PREMVOS_ERR_INVALID_ARG, "premvos_pack_mask_bits: bad sizes");

@@ -75,7 +75,11 @@ __global__ void __launch_bounds__(256) refine_input_kernel(PreArgs a) {
     // guidance: nearest-neighbour resize of the box mask (Util.py:27-28, BoundingBox.py:15-19)
     const int sy = min((int)floorf(__fmul_rn((float)y, __fdiv_rn((float)ch, (float)a.S))), ch - 1) + cy0;
     const int sx = min((int)floorf(__fmul_rn((float)x, __fdiv_rn((float)cw, (float)a.S))), cw - 1) + cx0;
-    const float g = (sy >= max(gy0, 0) && sy < gy1 && sx >= max(gx0, 0) && sx < gx1) ? 1.f : 0.f;
+    // encoded[y0:y1, x0:x1] = 1 with numpy's slice rules: a negative bound counts from the far edge (so a box that starts left of /
+    // above the frame usually selects nothing), bounds are clamped to the array, start >= stop is empty
+    auto sl = [](int v, int n) { return v < 0 ? max(v + n, 0) : min(v, n); };
+    const int ys = sl(gy0, a.H), ye = sl(gy1, a.H), xs = sl(gx0, a.W), xe = sl(gx1, a.W);
+    const float g = (sy >= ys && sy < ye && sx >= xs && sx < xe) ? 1.f : 0.f;
     f.v[3] = __fsub_rn(__fmul_rn(2.0f / 255.0f, __fmul_rn(g, 255.f)), 1.0f);
   }
   st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, 0, y, x), f);

@@ -118,3 +118,19 @@ extern "C" int premvos_resize_linear_u8(const unsigned char* src_dev, int batch,
     resize_linear_u8_kernel<1><<<grid, 256, 0, st>>>(src_dev, src_w, src_img, dst_dev, dst_h, dst_w, dst_img, t.cols, t.rows, 0);
   return after_launch("resize_linear_u8_kernel", st, 0.0, (double)batch * (dst_img + 4.0 * dst_img));
 }
+
+// Builds (and uploads, synchronously) the fixed-point coefficient tables of one geometry on the current device.  The enqueue-only
+// entry point builds them on first use too, but that first call allocates and copies synchronously and therefore must not happen
+// inside a stream capture: call this once per geometry beforehand.
+extern "C" int premvos_resize_linear_u8_prepare(int src_h, int src_w, int dst_h, int dst_w) {
+  PV_CHECK(src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, PREMVOS_ERR_INVALID_ARG, "premvos_resize_linear_u8_prepare: bad sizes");
+  premvos::ResizeTables t;
+  return premvos::get_tables(src_h, src_w, dst_h, dst_w, &t);
+}
+
+// Frees the coefficient tables of premvos_resize_linear_u8 (all devices, all geometries); they are rebuilt on demand.
+extern "C" void premvos_resize_linear_u8_release(void) {
+  std::lock_guard<std::mutex> lock(premvos::g_mu);
+  for (auto& kv : premvos::g_tables) { cudaFree(kv.second.cols); cudaFree(kv.second.rows); }
+  premvos::g_tables.clear();
+}

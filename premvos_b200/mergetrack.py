@@ -26,8 +26,13 @@ from .refnet import rle_encode
 
 
 def get_flow(filename):
-    """merge_functions.py:197-207."""
-    return readFlowFile(filename)
+    """merge_functions.py:197-207, error behaviour included: a file with a wrong magic number prints the reference's message and
+    yields None (readFlowFile raises instead)."""
+    try:
+        return readFlowFile(filename)
+    except ValueError:
+        print("Magic number incorrect. Invalid .flo file")
+        return None
 
 
 def _cuda_u8(t, name):

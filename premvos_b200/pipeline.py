@@ -312,7 +312,7 @@ def combine_proposals(general_x1y1x2y2, specific_x1y1x2y2, frame_hw, resized_hw)
         b = np.array(boxes, dtype=np.float32).reshape(-1, 4) / scale
         b = _propnet.clip_boxes(b, (H, W))
         for box in b:
-            box = np.array(box, dtype=np.float64)
+            box = np.array(box, dtype=np.float32)     # float32 subtraction and np.float32 rounding, as train.py:396-401 does
             box[2] -= box[0]
             box[3] -= box[1]
             out.append([float(round(x, 1)) for x in box])

@@ -67,7 +67,8 @@ class ProposalNet:
 
     def _handle(self, H, W, batch=1):
         """Device handle for resized images of H x W, `batch` frames per forward (premvos_propnet_set_option "batch")."""
-        key = (H, W) if batch == 1 else (H, W, int(batch))
+        import torch
+        key = (torch.cuda.current_device(), H, W, int(batch))   # per device: a handle owns device buffers and a captured graph
         if key in self._handles:
             return self._handles[key]
         if not self._params:
@@ -255,8 +256,12 @@ def convert_results_to_json(results, img_idx=None):
     """train.py:388-428: [{'bbox': [x, y, w, h] (1 decimal), 'score': (2 decimals)}]"""
     img_res = []
     for r in results:
-        box = np.array(r.box, dtype=np.float64)
+        box = np.array(r.box, dtype=np.float32)      # the reference subtracts in place on the float32 box and rounds np.float32 values
         box[2] -= box[0]
         box[3] -= box[1]
-        img_res.append({"bbox": list(map(lambda x: float(round(x, 1)), box)), "score": float(round(float(r.score), 2))})
+        res = {"bbox": list(map(lambda x: float(round(x, 1)), box)), "score": float(round(r.score, 2))}
+        if r.mask is not None:                        # train.py:421-426: COCO RLE of the pasted mask
+            from .refnet import rle_encode
+            res["segmentation"] = rle_encode(np.asarray(r.mask))
+        img_res.append(res)
     return img_res

@@ -162,7 +162,9 @@ class PWCDCNet:
             pass
 
     def _handle(self, B, H, W):
-        key = (B, H, W)
+        # one handle (buffers, captured graph) per (device, batch, size): a handle built on one GPU must never serve tensors of
+        # another; callers enter torch.cuda.device(tensor.device) first.  A handle supports ONE stream at a time.
+        key = (torch.cuda.current_device(), B, H, W)
         if key in self._handles:
             return self._handles[key]
         L = _lib.lib()

@@ -63,6 +63,10 @@ class RefinementNet:
 
     def _h(self):
         if self._handle is not None:
+            import torch
+            if torch.cuda.current_device() != self._handle_device:
+                raise RuntimeError("RefinementNet handle lives on cuda:%d, called with cuda:%d current (one net object per device)"
+                                   % (self._handle_device, torch.cuda.current_device()))
             return self._handle
         if self._params is None:
             raise RuntimeError("RefinementNet: load_params() first")
@@ -76,7 +80,9 @@ class RefinementNet:
         except Exception:
             L.premvos_refnet_destroy(h)
             raise
+        import torch
         self._handle = h
+        self._handle_device = torch.cuda.current_device()
         return h
 
     def refine(self, image_rgb_uint8, boxes_xywh, want_posteriors=False):

@@ -51,3 +51,12 @@ def test_read_props(tmp_path):
     props = mergetrack.read_props(str(fn))
     assert len(props) == 2 and np.isinf(props[0]["ReID"]).all() and len(props[0]["ReID"]) == 128 and props[1]["ReID"] == [0.0] * 128
     assert mergetrack.read_props(str(tmp_path / "missing.json")) == []
+
+
+def test_get_flow_bad_magic_prints_and_returns_none(tmp_path, capsys):
+    # merge_functions.py:197-207: no exception, the reference prints and falls through (returns None)
+    from premvos_b200 import mergetrack
+    p = tmp_path / "bad.flo"
+    p.write_bytes(np.array([1.0], np.float32).tobytes() + np.array([2, 2], np.int32).tobytes() + np.zeros(8, np.float32).tobytes())
+    assert mergetrack.get_flow(str(p)) is None
+    assert "Magic number incorrect" in capsys.readouterr().out

@@ -68,6 +68,18 @@ def test_refnet_small_net_matches_oracle():
     _check(P, blocks, net, frame, boxes, S)
 
 
+def test_guidance_of_boxes_with_negative_origin_follows_numpy_slicing():
+    # util/BoundingBox.py:15-19 writes encoded[y0:y1, x0:x1] = 1: a negative start counts from the far edge (numpy), so a box that
+    # begins left of / above the frame selects a different (usually empty) region -- reproduced, not "fixed"
+    S, mu = 129, 0
+    P = synth.refnet_synthetic_params(3, mu)
+    blocks = O.blocks_with_middle_units(mu)
+    net = refnet.RefinementNet(max_batch=4, input_size=S, middle_units=mu).load_params(P)
+    frame = synth.synthetic_bgr_frame(120, 160, seed=6)
+    boxes = np.array([[-12.0, 10.0, 70.0, 60.0], [20.0, -8.0, 50.0, 70.0], [-30.0, -20.0, 100.0, 90.0], [10.0, 10.0, 60.0, 60.0]], np.float32)
+    _check(P, blocks, net, frame, boxes, S, check_inter=True)
+
+
 def test_refnet_full_xception65_at_385():
     # BASELINE config C4 geometry: 385x385 crops, Xception-65 (16 middle units), DAVIS-shaped 480x854 frame
     S, mu = 385, 16
