@@ -346,6 +346,40 @@ int premvos_refnet_launches_per_forward(const premvos_refnet_t* net);
 int premvos_refnet_get_tensor(premvos_refnet_t* net, const char* name, float* host_out, int64_t* numel);
 void premvos_refnet_destroy(premvos_refnet_t* net);
 
+/* ---------------------------------------------------------------------------------------------
+ * ReID network forward: the 128-d appearance embedding MergeTrack attaches to every proposal
+ * (MergeTrack/ReID_net_functions.py:26-45 `add_ReID`: `engine.forward(net, [{"boxes", "image_paths"}])["ys"]`), i.e. the graph
+ * ReID_net/configs/run:33-65 builds -- conv0, 17 pre-activation ResidualUnit2 (network/NetworkLayers.py:157-210), conv1 +
+ * 3x3/3 max pool, fc1, fc2, outputTriplet (FullyConnected, NetworkLayers.py:536-567) -- together with the in-graph crop
+ * pipeline of ReID_net/datasets/Similarity/DAVIS_Forward_Feed.py:34-120 (context region x1.2, tf.round, clipping, 128 x 128
+ * legacy bilinear resize, zeros for crops with a side <= 10 px, ImageNet normalisation).
+ *
+ * Life cycle: create(max_batch crops per launch group, <= 256 = configs/run "batch_size") -> set_param(name, host fp32,
+ *   numel) for every variable, names and layouts as in the TF checkpoint: "conv0/W" (HWIO), "res<k>/W0" (1x1 projection,
+ *   only where the unit changes shape), "res<k>/W<i>", "res<k>/bn<j>/{beta,gamma,mean_ema,var_ema}" (bn0 in front of the
+ *   unit, bn<i> in front of W<i> for i >= 2), "conv1/{W,bn/...}", "{fc1,fc2,outputTriplet}/{W,b,bn/...}"
+ *   -> finalize() -> forward_host()* -> destroy().
+ *
+ * forward_host: frame = uint8 RGB [height, width, 3]; boxes = [num_boxes, 4] fp32 x, y, w, h (proposal['bbox']); any
+ *   number of boxes.  Output (HOST): embeddings fp32 [num_boxes, 128] = "ys".
+ * forward: the same with DEVICE pointers, enqueued on `stream`, never synchronises.
+ * get_tensor (test hook, state of the LAST batch): "net_input" (NCHW [max_batch,8,128,128], channels 0..2 used), "conv0",
+ *   "res0".."res16" (NCHW raw unit outputs), "conv1" ([max_batch,4,4,512] channels-last, 500 used, before the max pool),
+ *   "crops" ([max_batch,4] x y w h after context region + clipping).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct premvos_reidnet premvos_reidnet_t;
+
+int premvos_reidnet_create(premvos_reidnet_t** out, int max_batch);
+int premvos_reidnet_set_param(premvos_reidnet_t* net, const char* name, const float* host_data, int64_t numel);
+int premvos_reidnet_finalize(premvos_reidnet_t* net);
+int premvos_reidnet_forward(premvos_reidnet_t* net, const unsigned char* frame_rgb_dev, int height, int width,
+                            const float* boxes_xywh_dev, int num_boxes, float* embeddings_dev, void* stream);
+int premvos_reidnet_forward_host(premvos_reidnet_t* net, const unsigned char* frame_rgb, int height, int width,
+                                 const float* boxes_xywh, int num_boxes, float* embeddings_out);
+int premvos_reidnet_launches_per_forward(const premvos_reidnet_t* net);
+int premvos_reidnet_get_tensor(premvos_reidnet_t* net, const char* name, float* host_out, int64_t* numel);
+void premvos_reidnet_destroy(premvos_reidnet_t* net);
+
 #ifdef __cplusplus
 }
 #endif

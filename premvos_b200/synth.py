@@ -327,3 +327,70 @@ def synthetic_masks(n, h, w, seed=4):
             ry, rx = rng.uniform(0.05, 0.3) * h, rng.uniform(0.05, 0.3) * w
             masks[i] |= ((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) < 1).astype(np.uint8)
     return masks
+
+
+# ---- ReID network (MergeTrack/ReID_net_functions.py, ReID_net/configs/run:33-65) -------------------------------------------------
+REID_UNITS = (
+    [("res0", [128, 128], [3, 3], [2, 1])] + [("res%d" % i, [128, 128], [3, 3], [1, 1]) for i in (1, 2)] +
+    [("res3", [256, 256], [3, 3], [2, 1])] + [("res%d" % i, [256, 256], [3, 3], [1, 1]) for i in (4, 5)] +
+    [("res6", [512, 512], [3, 3], [2, 1])] + [("res%d" % i, [512, 512], [3, 3], [1, 1]) for i in range(7, 12)] +
+    [("res12", [512, 1024], [3, 3], [1, 2]), ("res13", [512, 1024], [3, 3], [1, 1]), ("res14", [512, 1024], [3, 3], [1, 1]),
+     ("res15", [512, 1024, 2048], [1, 3, 1], [1, 2, 1]), ("res16", [1024, 2048, 4096], [1, 3, 1], [1, 1, 1])])
+
+
+def reid_param_shapes():
+    """Variable names and shapes of the ReID network (TensorFlow scopes of ReID_net/network/NetworkLayers.py: conv kernels HWIO
+    `<layer>/W[i]`, BatchNorm `<layer>/bn[i]/{beta,gamma,mean_ema,var_ema}`, fully connected `<layer>/{W,b}`)."""
+    t = OrderedDict()
+
+    def bn(scope, c):
+        for v in ("beta", "gamma", "mean_ema", "var_ema"):
+            t["%s/%s" % (scope, v)] = (c,)
+    t["conv0/W"] = (3, 3, 3, 64)
+    cin = 64
+    for name, feats, ks, strides in REID_UNITS:
+        bn(name + "/bn0", cin)
+        if feats[-1] != cin or int(np.prod(strides)) != 1:
+            t[name + "/W0"] = (1, 1, cin, feats[-1])
+        c = cin
+        for i, (f, k) in enumerate(zip(feats, ks)):
+            if i > 0:
+                bn("%s/bn%d" % (name, i + 1), c)
+            t["%s/W%d" % (name, i + 1)] = (k, k, c, f)
+            c = f
+        cin = feats[-1]
+    bn("conv1/bn", cin)
+    t["conv1/W"] = (3, 3, cin, 500)
+    for name, fin, fout in (("fc1", 2000, 500), ("fc2", 500, 500), ("outputTriplet", 500, 128)):
+        bn(name + "/bn", fin)
+        t[name + "/W"] = (fin, fout)
+        t[name + "/b"] = (fout,)
+    return t
+
+
+def reid_synthetic_params(seed=0):
+    """Seeded ReID-network variables (He-normal kernels; the convolution closing a residual unit is damped so that 17 stacked
+    pre-activation units with near-identity BatchNorm statistics keep their activations within a few orders of magnitude)."""
+    rng = np.random.default_rng(seed)
+    P = OrderedDict()
+    last_conv = {"%s/W%d" % (name, len(feats)) for name, feats, _, _ in REID_UNITS}
+    for name, shape in reid_param_shapes().items():
+        leaf = name.rsplit("/", 1)[1]
+        if leaf.startswith("W") and len(shape) == 4:
+            std = np.sqrt(2.0 / (shape[0] * shape[1] * shape[2]))
+            if name in last_conv:
+                std *= 0.5
+            P[name] = (rng.standard_normal(shape, dtype=np.float32) * np.float32(std))
+        elif leaf == "W":
+            P[name] = (rng.standard_normal(shape, dtype=np.float32) * np.float32(np.sqrt(2.0 / shape[0])))
+        elif leaf == "b":
+            P[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+        elif leaf == "gamma":
+            P[name] = (1.0 + 0.1 * rng.uniform(-1, 1, shape)).astype(np.float32)
+        elif leaf in ("beta", "mean_ema"):
+            P[name] = (0.05 * rng.standard_normal(shape)).astype(np.float32)
+        elif leaf == "var_ema":
+            P[name] = (1.0 + 0.1 * rng.uniform(-1, 1, shape)).astype(np.float32)
+        else:
+            raise AssertionError(name)
+    return P

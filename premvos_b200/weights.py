@@ -23,7 +23,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from .synth import propnet_param_shapes, refnet_param_shapes
+from .synth import propnet_param_shapes, refnet_param_shapes, reid_param_shapes
 
 _DROP_SUFFIXES = ("/Momentum", "/Adam", "/Adam_1", "/ExponentialMovingAverage", "/AccumGrad", "/RMSProp", "/RMSProp_1")
 _DROP_NAMES = {"global_step", "learning_rate", "beta1_power", "beta2_power"}
@@ -109,6 +109,12 @@ def load_refinement_net_variables(path, middle_units=16, n_classes=2):
     """`.npz` / `.npy` dictionary of the slim variables (xception_65/..., aspp*, decoder/..., logits/...) -> the dict
     RefinementNet.load_params takes."""
     return _select(_read_dict(path), refnet_param_shapes(middle_units, n_classes), "refinement_net")
+
+
+def load_reid_net_variables(path):
+    """`.npz` / `.npy` dictionary or TensorFlow checkpoint prefix of the ReID network's variables (conv0/W, res<k>/..., conv1/...,
+    fc1/..., fc2/..., outputTriplet/...) -> the dict ReIDNet.load_params takes."""
+    return _select(_read_dict(path), reid_param_shapes(), "ReID_net")
 
 
 def save_variables(path, params):

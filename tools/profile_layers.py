@@ -37,3 +37,18 @@ if "refnet" in which:
     rn.refine(frame, boxes)
     _lib.profile_begin(); rn.refine(frame, boxes); prof = _lib.profile_end()
     report("refinement net, %d crops" % NB, prof)
+if "reid" in which:
+    from premvos_b200 import reid
+    NB = int(os.environ.get("REID_BOXES", "40"))
+    net = reid.ReIDNet(max_batch=NB).load_params(synth.reid_synthetic_params(0))
+    frame = torch.from_numpy(synth.synthetic_bgr_frame(H0, W0, seed=3)).cuda()
+    boxes = torch.from_numpy(synth.synthetic_boxes(NB, H0, W0, seed=3)).cuda()
+    net.embed_device(frame, boxes); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        net.embed_device(frame, boxes)
+    e1.record(); torch.cuda.synchronize()
+    print("ReID net, %d crops: %.3f ms per frame (device, 5 runs back to back), %d launches" % (NB, e0.elapsed_time(e1) / 5, net.launches_per_forward()))
+    _lib.profile_begin(); net.embed_device(frame, boxes); torch.cuda.synchronize(); prof = _lib.profile_end()
+    report("ReID net, %d crops" % NB, prof, top=60)
