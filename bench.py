@@ -506,9 +506,10 @@ def main():
         total_ms = sum(v["ms"] for v in prof.values()) or 1.0
         kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / total_ms}
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        # the tensor-core convolution runs as two kernels (conv_umma_kernel<4|8>: one CTA per tile; conv_pair_kernel: cta_group::2 CTA
-        # pairs for the wide 1x1 layers); the roofline entry is the one with the larger share of the step, the other one and their
-        # sum are listed beside it
+        # The tensor-core convolution (launch_conv_umma in csrc/conv_umma.cu -- the launch set round 1 reported as "conv_umma_kernel")
+        # runs as two kernels since round 2: conv_umma_kernel<4|8> (one CTA per tile) and conv_pair_kernel (cta_group::2 CTA pairs,
+        # stream-K, for the wide 1x1 layers).  The roofline entry covers ALL of its launches; each kernel alone is listed beside it.
+        CONV = ["conv_umma_kernel", "conv_pair_kernel"]
         def tensor_entry(names):
             ms = sum(prof[n]["ms"] for n in names if n in prof)
             fl = sum(prof[n]["flops"] for n in names if n in prof)
@@ -522,20 +523,23 @@ def main():
         name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
         sec = top["ms"] * 1e-3
         traffic = load_traffic(name)
-        if "conv" in name and "small" not in name:
-            ach = top["flops"] / sec / 1e12
+        if name in CONV:
+            both = tensor_entry(CONV)
             peak = peaks["tensor_sustained"]
-            roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + " bf16 sustained",
-                        "avg_launch_us": top["ms"] * 1e3 / top["launches"], "launches_per_step": top["launches"],
-                        "algorithmic_gflop_per_step": top["flops"] / 1e9, "serial_step_ms": total_ms,
-                        "note": "achieved = algorithmic fp32 FLOPs of all launches of this kernel in one step / their summed device "
-                                "time; every algorithmic FLOP is issued as 3 bf16 tensor-core FLOPs (split-bf16 x3 for 1e-3 fp32 "
-                                "parity), so tensor-pipe occupancy is 3x frac; traffic = mean DRAM bytes per launch (ncu)",
-                        "bf16_tflops_issued": 3 * ach, "tensor_pipe_frac": 3 * ach / peak,
-                        "tensor_core_kernels": {"conv_umma_kernel": tensor_entry(["conv_umma_kernel"]),
-                                                "conv_pair_kernel": tensor_entry(["conv_pair_kernel"]),
-                                                "both": tensor_entry(["conv_umma_kernel", "conv_pair_kernel"])}}
+            roofline = {"kernel": both["kernel"], "bound": "tensor", "achieved": both["achieved"], "peak": peak, "unit": "TFLOP/s",
+                        "frac": both["frac"], "traffic": traffic, "peak_source": peaks["source"] + " bf16 sustained",
+                        "avg_launch_us": both["avg_launch_us"], "launches_per_step": both["launches_per_step"],
+                        "algorithmic_gflop_per_step": both["algorithmic_gflop_per_step"], "share_of_step": both["share_of_step"],
+                        "serial_step_ms": total_ms,
+                        "note": "the tcgen05 convolution (csrc/conv_umma.cu, one launcher, two kernels: per_kernel); achieved = algorithmic "
+                                "fp32 FLOPs of all its launches in one step / their summed device time; every algorithmic FLOP is issued "
+                                "as 3 bf16 tensor-core FLOPs (split-bf16 x3 for 1e-3 fp32 parity), so tensor-pipe occupancy is 3x frac; "
+                                "traffic = mean DRAM bytes per launch (ncu)",
+                        "bf16_tflops_issued": 3 * both["achieved"], "tensor_pipe_frac": both["tensor_pipe_frac"],
+                        "per_kernel": {n: tensor_entry([n]) for n in CONV},
+                        "traffic_per_kernel": {n: load_traffic(n) for n in CONV},
+                        "traffic_note": "ncu --set full capture of the refinement network's launch group (profiles/r02_ncu_full_refnet."
+                                        "summary.txt): mean DRAM bytes per launch; `traffic` is the value of " + name}
         else:
             ach = top["bytes"] / sec / 1e9
             peak = peaks["hbm"]

@@ -306,6 +306,11 @@ struct UmmaConvArgs {
   int bias_smem;             // pair kernel: floats of bias staged in shared memory (ntiles * BN, or 0: read from global memory)
   int stream_k_all;          // pair kernel: 1 = no round-robin phase, all items are cut into equal k-block ranges (tuning switch)
   unsigned* sk_flags;        // pair kernel, stream-K: [pairs][2 ranks][8 epilogue warps] flags; `partial` = [pairs][2][128][256] fp32
+  // folded small maps (Ho*Wo <= 64): one 128-row tile holds `fold` whole images, row m = g * slot + oy * Wo + ox.  The A box of a
+  // (tap, k-block) is {8 channels, Wo, Ho, fold images, KC chunks} of a 5-D map whose 4th dimension is the image, so every image
+  // gets its own zero padding from the TMA's out-of-bounds fill; `n_images` counts image GROUPS, `n_real` images.
+  int fold, slot, n_real;
+  int a_lbo;                 // bytes between the two 8-channel chunks of a K step in the A stage (0: box_h * box_w * 16)
 };
 
 // EPI_WARPS = 4: 256 threads, up to two CTAs per SM.  EPI_WARPS = 8: 384 threads, one CTA per SM owning the whole TMEM (256-wide N
@@ -349,7 +354,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     const int tile = t % tiles_per_img;
     int r = t / tiles_per_img;
-    w.n_img = r % a.n_images; r /= a.n_images;
+    w.n_img = (r % a.n_images) * (a.fold > 0 ? a.fold : 1); r /= a.n_images;
     w.ntile = r % a.ntiles;
     w.z = r / a.ntiles;
     w.ty0 = (tile / a.tiles_x) * (a.mt_horizontal ? 16 : 16 * a.MT);
@@ -394,7 +399,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         } else if (elect_one()) {
           uint8_t* dst = a_smem + (size_t)w_st * 2 * a.a_plane;
           mbar_arrive_expect_tx(&w_full[w_st], 2u * (uint32_t)a.a_box_bytes + w_bytes);
-          if (a.merged_x) {
+          if (a.fold) {
+            tma_load_5d(&tmA_hi, &w_full[w_st], dst, 0, bx, by, n_img, kb * a.KC);
+            tma_load_5d(&tmA_lo, &w_full[w_st], dst + a.a_plane, 0, bx, by, n_img, kb * a.KC);
+          } else if (a.merged_x) {
             tma_load_4d(&tmA_hi, &w_full[w_st], dst, bx * 8, by, kb * a.KC, n_img);
             tma_load_4d(&tmA_lo, &w_full[w_st], dst + a.a_plane, bx * 8, by, kb * a.KC, n_img);
           } else {
@@ -422,7 +430,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             } else if (elect_one()) {
               uint8_t* dst = a_smem + (size_t)a_st * 2 * a.a_plane;
               mbar_arrive_expect_tx(&a_full[a_st], 2u * (uint32_t)a.a_box_bytes);
-              if (a.merged_x) {
+              if (a.fold) {
+                tma_load_5d(&tmA_hi, &a_full[a_st], dst, 0, px, py, n_img, kb * a.KC);
+                tma_load_5d(&tmA_lo, &a_full[a_st], dst + a.a_plane, 0, px, py, n_img, kb * a.KC);
+              } else if (a.merged_x) {
                 tma_load_4d(&tmA_hi, &a_full[a_st], dst, px * 8, py, kb * a.KC, n_img);
                 tma_load_4d(&tmA_lo, &a_full[a_st], dst + a.a_plane, px * 8, py, kb * a.KC, n_img);
               } else {
@@ -452,7 +463,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====  the whole warp walks the (warp-uniform) loop, one elected lane issues
     const uint32_t idesc = make_idesc_bf16(128, a.BN);
-    const uint32_t a_sbo = (uint32_t)a.box_w * 16u, a_lbo = (uint32_t)a.box_h * a.box_w * 16u;
+    const uint32_t a_sbo = (uint32_t)a.box_w * 16u, a_lbo = a.a_lbo ? (uint32_t)a.a_lbo : (uint32_t)a.box_h * a.box_w * 16u;
     const uint32_t w_sbo = 128u, w_lbo = (uint32_t)a.BN * 16u;
     // descriptor = constant high word (SBO, version) + low word (LBO | start address >> 4)
     const uint32_t a_hi32 = (a_sbo >> 4) | (1u << 14), w_hi32 = (w_sbo >> 4) | (1u << 14);
@@ -572,17 +583,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // accumulator columns of this warp: all of them, or one half when two warps share a lane quarter
     const int col_part = (warp - 4) >> 2, col_span = EPI_WARPS == 8 ? a.BN / 2 : a.BN;
     const int col_begin = col_part * col_span, col_end = col_begin + col_span;
+    // folded small maps: this thread's accumulator row is pixel (f_oy, f_ox) of image f_g of the group, for every item
+    const int f_g = a.fold ? m / a.slot : 0, f_p = a.fold ? m - f_g * a.slot : 0, f_oy = a.fold ? f_p / a.Wo : 0, f_ox = a.fold ? f_p - f_oy * a.Wo : 0;
     for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
     const Work wk = decode(t);
-    const int n_img = wk.n_img, ty0 = wk.ty0, tx0 = wk.tx0, ntile = wk.ntile;
+    const int n_img = wk.n_img + f_g, ty0 = wk.ty0, tx0 = wk.tx0, ntile = wk.ntile;
     mbar_wait(&tmem_full_bar[buf], (full_ph >> buf) & 1u);
     full_ph ^= 1u << buf;
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base + buf * buf_cols;
     for (int mt = 0; mt < a.MT; mt++) {
-      const int oy = ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
+      const int oy = a.fold ? f_oy : ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = a.fold ? f_ox : tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
       const long pix = (long)oy * a.Wo + ox;
-      const bool in_img = a.flat_hw > 0 ? pix < hw : (oy < a.Ho && ox < a.Wo);
+      const bool in_img = a.fold ? (f_g < a.fold && n_img < a.n_real) : a.flat_hw > 0 ? pix < hw : (oy < a.Ho && ox < a.Wo);
       for (int c0 = col_begin; c0 < col_end; c0 += 16) {
         uint32_t v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
@@ -1507,7 +1520,16 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const int taps = w.R * w.S;
   // 1x1 / stride 1 / no padding: the spatial structure is irrelevant -> tile the flattened pixel list (needs the
   // 128 bytes of slack every activation buffer is allocated with: the last 8-pixel row may straddle the plane end)
-  const bool flat = taps == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
+  // small output maps (RoI heads at 7x7, the ReID network's 8x8 / 4x4 stages): several whole images share one 128-row tile
+  int fold = 0;
+  if (!w.pair && env_int("PREMVOS_FOLD", 1) != 0 && Ho * Wo <= 64 && in.N >= 2 && Wo * g.stride <= 256 && Ho * g.stride <= 256)
+    fold = std::min(128 / (Ho * Wo), in.N);
+  if (fold < 2) fold = 0;
+  // measured (profiles/r02_fold_layers.txt): 3x3 stride-1 layers keep halo mode (one box per k-block serves all taps) down to two
+  // images per tile -- at 7x7 / 8x8 the per-tap boxes of a folded tile cost more than the half-empty halo tile; from 4 images per
+  // tile on, and for every layer that runs in tap mode anyway (1x1, strided), folding wins (4x4 maps: 2-4x)
+  if (fold && fold < 4 && taps > 1 && g.stride == 1 && env_int("PREMVOS_FOLD", 1) != 2) fold = 0;
+  const bool flat = !fold && taps == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
                     env_int("PREMVOS_FLAT", 1) != 0 && (long)in.H * in.W >= 8;
   const int real_hw = Ho * Wo;
   const int geoH = flat ? (real_hw + 7) / 8 : Ho, geoW = flat ? 8 : Wo;
@@ -1524,7 +1546,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
   int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && taps > 1) ? 2 : 1;   // 1x1 layers measured best with one sub-tile at BN = 128
   const bool wide = w.BN > 128;                                           // 256-wide N tile: one CTA per SM owns the whole TMEM
-  if (wide) mt_pref = 1;   // measured (tools/conv_sweep2.py): 256 x 256 single-buffered tiles lose to 128 x 256 double-buffered ones
+  if (wide || fold) mt_pref = 1;   // measured (tools/conv_sweep2.py): 256 x 256 single-buffered tiles lose to 128 x 256 double-buffered ones
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
   const int tps_env = env_int("PREMVOS_TPS", 0);
@@ -1543,7 +1565,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     // halo mode only when it moves fewer bytes into shared memory than per-tap boxes
     // (measured: from dilation 4 on the halo box is so large that one CTA per SM remains; per-tap boxes win)
     const bool halo_ok = g.stride == 1 && taps > 1 && g.dil < 4 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
-    if (want_halo && !halo_ok) continue;
+    if (want_halo && (!halo_ok || fold)) continue;
     a.MT = mt;
     a.mt_horizontal = hz ? 1 : 0;
     a.halo = want_halo ? 1 : 0;
@@ -1551,6 +1573,12 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     a.box_h = a.halo ? halo_h : (hz ? 16 : 16 * mt);
     a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
     a.a_plane = round_up(a.a_box_bytes, 128);
+    if (fold) {   // rows are consecutive pixels of consecutive images; the MMA always reads 128 rows per chunk
+      a.fold = fold; a.slot = Ho * Wo; a.n_real = in.N; a.merged_x = 0;
+      a.a_lbo = fold * a.slot * 16;
+      a.a_box_bytes = w.KC * a.a_lbo;
+      a.a_plane = round_up(std::max(a.a_box_bytes, (w.KC - 1) * a.a_lbo + 2048), 128);
+    }
     a.a_stages = a.halo ? 2 : 3;
     // taps per weight stage: fewer, larger bulk copies (a TMA request has a fixed cost) -- the largest group of <= 32 KB
     // that still leaves room for two CTAs per SM; only if nothing fits 110 KB is the whole SM used
@@ -1568,8 +1596,9 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   }
   PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);
   const int tile_w = a.mt_horizontal ? 16 : 8, tile_h = a.mt_horizontal ? 16 : 16 * a.MT;
-  a.tiles_x = (geoW + tile_w - 1) / tile_w;
-  a.tiles_y = (geoH + tile_h - 1) / tile_h;
+  a.tiles_x = fold ? 1 : (geoW + tile_w - 1) / tile_w;
+  a.tiles_y = fold ? 1 : (geoH + tile_h - 1) / tile_h;
+  const int n_groups = fold ? (in.N + fold - 1) / fold : in.N;   // images, or groups of `fold` images, per output-channel tile
   // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
   int budget = (!wide && a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
   if (env_int("PREMVOS_BUDGET_KB", 0) > 0) budget = env_int("PREMVOS_BUDGET_KB", 0) * 1024;
@@ -1602,7 +1631,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   uint32_t cols = 32;
   while ((int)cols < a.NACC * a.MT * w.BN) cols <<= 1;
   a.tmem_cols = cols;
-  plan->grid_x = a.tiles_x * a.tiles_y * in.N;
+  plan->grid_x = a.tiles_x * a.tiles_y * n_groups;
   plan->grid_y = w.ntiles;
   // split-K when the grid cannot fill the machine: the K loop of a CTA is a serial chain of barrier handshakes
   a.ksplit = 1; a.kb_per = a.kblocks; a.cout_pad = w.ntiles * w.BN; a.partial = nullptr; a.partial_stride = 0;
@@ -1624,7 +1653,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     }
   }
   plan->grid_z = a.ksplit;
-  a.ntiles = w.ntiles; a.n_images = in.N;
+  a.ntiles = w.ntiles; a.n_images = n_groups;
   a.total_work = plan->grid_x * plan->grid_y * a.ksplit;
   // two CTAs per SM when shared memory and TMEM allow it; a second accumulator buffer when TMEM allows that too
   const int cps = (!wide && plan->smem_bytes <= 112 * 1024 && a.NACC * a.MT * w.BN <= 256) ? 2 : 1;
@@ -1636,7 +1665,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   plan->ctas_per_sm = cps;
   // tail split (see UmmaConvArgs): only for un-split layers with at least one full wave and a small remainder
   a.tail_items = 0; a.tail_split = 1; a.tail_kb_per = a.kblocks; a.main_work = a.total_work;
-  if (a.ksplit == 1 && env_int("PREMVOS_TAIL", 1) != 0) {
+  if (a.ksplit == 1 && !fold && env_int("PREMVOS_TAIL", 1) != 0) {
     int num_sms = 148;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
     const int slots = num_sms * cps, rem = a.total_work % slots;
@@ -1666,7 +1695,13 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   __nv_bfloat16* bases[2] = {in.hi + (size_t)in.c0 * in.H * in.W * 8, in.lo + (size_t)in.c0 * in.H * in.W * 8};
   CUtensorMap* maps[2] = {(CUtensorMap*)plan->map_a_hi, (CUtensorMap*)plan->map_a_lo};
   for (int k = 0; k < 2; k++) {
-    if (flat) {
+    if (fold) {
+      cuuint64_t dims[5] = {8, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N, (cuuint64_t)vchunks};
+      cuuint64_t strides[4] = {16, (cuuint64_t)in.W * 16, plane_bytes * in.chunks, plane_bytes};
+      cuuint32_t box[5] = {8, (cuuint32_t)(Wo * g.stride), (cuuint32_t)(Ho * g.stride), (cuuint32_t)fold, (cuuint32_t)w.KC};
+      cuuint32_t estr[5] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1, 1};
+      PV_TRY(encode_map(maps[k], bases[k], 5, dims, strides, box, estr));
+    } else if (flat) {
       cuuint64_t dims[4] = {64, (cuuint64_t)geoH, (cuuint64_t)vchunks, (cuuint64_t)in.N};
       cuuint64_t strides[3] = {128, plane_bytes, plane_bytes * in.chunks};
       cuuint32_t box[4] = {(cuuint32_t)a.box_w * 8, (cuuint32_t)a.box_h, (cuuint32_t)w.KC, 1};
@@ -1773,10 +1808,13 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   if (a.pair) return launch_conv_pair(plan, st, active_n);
   if (active_n >= 0 && active_n < plan.N) {   // a smaller active batch: plain item list, no tail split
     const int items = a.tail_items > 0 ? a.main_work + a.tail_items : a.total_work;
-    a.total_work = items / plan.N * active_n;
-    a.n_images = active_n;
+    const int groups = a.fold ? (active_n + a.fold - 1) / a.fold : active_n;
+    a.total_work = items / a.n_images * groups;
+    a.n_images = groups;
+    a.n_real = active_n;
     a.tail_items = 0; a.main_work = a.total_work;
   }
+  const int n_act = (active_n >= 0 && active_n < plan.N) ? active_n : plan.N;
   if (a.total_work == 0) return 0;
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -1796,14 +1834,14 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   else
     conv_umma_kernel<4><<<grid, UMMA_THREADS, plan.smem_bytes, st>>>(
         *reinterpret_cast<const CUtensorMap*>(plan.map_a_hi), *reinterpret_cast<const CUtensorMap*>(plan.map_a_lo), a);
-  const double frac = (double)a.n_images / plan.N;
+  const double frac = (double)n_act / plan.N;
   const char* label = "conv_umma_kernel";
   static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
   if (per_layer && profiling_enabled()) {   // per-layer breakdown for tools/profile_nets.py
     char buf[256];
-    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d_tail%dx%d]", a.n_images,
+    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d_tail%dx%d_fold%d]", n_act,
              a.flat_hw > 0 ? a.flat_hw : a.Ho, a.flat_hw > 0 ? 1 : a.Wo, a.kblocks * a.KC * 8, a.Cout, a.R, a.stride, a.dil, a.MT, a.BN,
-             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep, a.tail_items, a.tail_split);
+             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep, a.tail_items, a.tail_split, a.fold);
     label = prof_intern(buf);
   }
   PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));

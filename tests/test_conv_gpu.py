@@ -57,6 +57,14 @@ CASES = [
     (40, 728, 25, 25, 728, 1, 1, 1, (0, 0, 0, 0), 0.0, True),   # the benchmarked launch plan of the middle flow (40 crops)
     (5, 1536, 25, 25, 2048, 1, 1, 1, (0, 0, 0, 0), 0.0, False), # exit flow: 8 channel tiles, K = 48 k-blocks, 13 pairs x 8 = 104 items
     (1, 1024, 46, 83, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, True),   # stream-K with 6.5 k-blocks per pair: every item is finished from 5-6 partial sums
+    # folded small maps: several whole images per 128-row tile, per-image zero padding from the TMA's out-of-bounds fill
+    (9, 512, 7, 7, 512, 3, 1, 1, (1, 1, 1, 1), 0.0, True),      # RoI head 3x3 at 7x7: 2 images per tile (98 rows), odd image count
+    (40, 1024, 4, 4, 2048, 3, 1, 1, (1, 1, 1, 1), 0.0, False),  # ReID res16: 8 images per tile, 5 groups x 16 channel tiles
+    (13, 1024, 14, 14, 512, 1, 2, 1, (0, 0, 0, 0), 0.0, False), # RoI head entry: 1x1 stride 2 onto 7x7 (element strides in the folded box)
+    (21, 2048, 4, 4, 4096, 1, 1, 1, (0, 0, 0, 0), 1.0, True),   # 1x1 on 4x4 maps + residual: last group holds 5 of 8 images
+    (6, 512, 8, 8, 1024, 3, 2, 1, (0, 0, 1, 1), 1.0, False),    # TF SAME stride 2 (pad after only) onto 4x4: 6 images in one tile, split-K
+    (5, 64, 8, 8, 64, 3, 1, 1, (1, 1, 1, 1), 0.1, False),       # 8x8 maps: 2 images per exact 128-row tile
+    (3, 96, 5, 11, 40, 3, 1, 1, (1, 1, 1, 1), 0.1, True),       # 55-pixel maps wider than a tile row: 2 per tile, ragged channels
 ]
 
 
@@ -74,6 +82,17 @@ def test_conv2d_matches_torch(case):
     got = ops.conv2d(x.cuda(), w, b, stride, dil, pad, slope, None if res is None else res.cuda()).cpu()
     assert got.shape == ref.shape
     assert rel_err(got.numpy(), ref.numpy()) < TOL
+
+
+def test_conv2d_folded_tiles_for_halo_capable_layers(monkeypatch):
+    """3x3 stride-1 layers on 7x7 / 8x8 maps keep halo mode by default (measured faster); PREMVOS_FOLD=2 forces the folded
+    tiling for them too, so that path stays covered for every geometry it accepts."""
+    monkeypatch.setenv("PREMVOS_FOLD", "2")
+    for case in CASES:
+        N, Cin, H, W, Cout, k, stride, dil, pad, slope, use_res = case
+        if not (k == 3 and stride == 1 and H * W <= 64 and N >= 2):
+            continue
+        test_conv2d_matches_torch(case)
 
 
 def test_conv2d_linearity_and_zero_padding_at_full_size():
