@@ -369,6 +369,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-network context timings")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch / cuDNN context timings")
+    ap.add_argument("--no-reid", action="store_true", help="skip the ReID network's context timing (stages.reid)")
     ap.add_argument("--c5", action="store_true", help="BASELINE configs[4]: 90-frame 854x480 video sharded over the ranks")
     ap.add_argument("--frames", type=int, default=90, help="frames of the --c5 video")
     args = ap.parse_args()
@@ -565,6 +566,15 @@ def main():
                              "algorithmic_tflop_per_s": GFLOP_CROP * K / t_ref},
                   "sum_serial_ms_per_pair": t_flow / B + 2 * t_prop + t_ref,
                   "note": "each network alone on one stream, CUDA events; a unit = flow + 2 proposal passes + refine"}
+        if not args.no_reid:
+            # SURVEY 8(f) N2, not part of the headline unit: the ReID embeddings MergeTrack adds to the proposals of a frame
+            from premvos_b200 import reid
+            rnet = reid.ReIDNet(max_batch=K).load_params(synth.reid_synthetic_params(0))
+            t_reid = time_stage(lambda: rnet.embed_device(fr[0], bx[0]), 5)
+            stages["reid"] = {"ms_per_frame_of_%d_boxes" % K: t_reid, "crops_per_s": 1e3 * K / t_reid,
+                              "note": "ReID network (128 x 128 crops, 17 residual units, 124.9M parameters), not in the headline unit"}
+            rnet.close()
+            del rnet
 
     h2d_bytes, d2h_bytes = pipe.h2d_bytes_per_step(original_frames=True), pipe.d2h_bytes_per_step()
     launches_per_step = pipe.launches_per_step_from_frames()

@@ -310,6 +310,9 @@ struct UmmaConvArgs {
   // (tap, k-block) is {8 channels, Wo, Ho, fold images, KC chunks} of a 5-D map whose 4th dimension is the image, so every image
   // gets its own zero padding from the TMA's out-of-bounds fill; `n_images` counts image GROUPS, `n_real` images.
   int fold, slot, n_real;
+  // stacked halo tiles (3x3 stride-1 layers on maps at most 8 wide): the halo box of a k-block is {W*8, hf_pitch rows, fold images,
+  // KC chunks}; image g of the group occupies tile rows [g * hf_pitch, g * hf_pitch + Ho) and brings its own zero padding rows
+  int hf_pitch;
   int a_lbo;                 // bytes between the two 8-channel chunks of a K step in the A stage (0: box_h * box_w * 16)
 };
 
@@ -399,7 +402,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         } else if (elect_one()) {
           uint8_t* dst = a_smem + (size_t)w_st * 2 * a.a_plane;
           mbar_arrive_expect_tx(&w_full[w_st], 2u * (uint32_t)a.a_box_bytes + w_bytes);
-          if (a.fold) {
+          if (a.fold && !a.hf_pitch) {
             tma_load_5d(&tmA_hi, &w_full[w_st], dst, 0, bx, by, n_img, kb * a.KC);
             tma_load_5d(&tmA_lo, &w_full[w_st], dst + a.a_plane, 0, bx, by, n_img, kb * a.KC);
           } else if (a.merged_x) {
@@ -430,7 +433,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             } else if (elect_one()) {
               uint8_t* dst = a_smem + (size_t)a_st * 2 * a.a_plane;
               mbar_arrive_expect_tx(&a_full[a_st], 2u * (uint32_t)a.a_box_bytes);
-              if (a.fold) {
+              if (a.hf_pitch) {
+                tma_load_4d(&tmA_hi, &a_full[a_st], dst, px * 8, py, n_img, kb * a.KC);
+                tma_load_4d(&tmA_lo, &a_full[a_st], dst + a.a_plane, px * 8, py, n_img, kb * a.KC);
+              } else if (a.fold) {
                 tma_load_5d(&tmA_hi, &a_full[a_st], dst, 0, px, py, n_img, kb * a.KC);
                 tma_load_5d(&tmA_lo, &a_full[a_st], dst + a.a_plane, 0, px, py, n_img, kb * a.KC);
               } else if (a.merged_x) {
@@ -584,18 +590,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int col_part = (warp - 4) >> 2, col_span = EPI_WARPS == 8 ? a.BN / 2 : a.BN;
     const int col_begin = col_part * col_span, col_end = col_begin + col_span;
     // folded small maps: this thread's accumulator row is pixel (f_oy, f_ox) of image f_g of the group, for every item
-    const int f_g = a.fold ? m / a.slot : 0, f_p = a.fold ? m - f_g * a.slot : 0, f_oy = a.fold ? f_p / a.Wo : 0, f_ox = a.fold ? f_p - f_oy * a.Wo : 0;
+    const bool tfold = a.fold && !a.hf_pitch;
+    const int f_g = tfold ? m / a.slot : 0, f_p = tfold ? m - f_g * a.slot : 0, f_oy = tfold ? f_p / a.Wo : 0, f_ox = tfold ? f_p - f_oy * a.Wo : 0;
     for (int t = blockIdx.x; t < a.total_work; t += gridDim.x) {
     const Work wk = decode(t);
-    const int n_img = wk.n_img + f_g, ty0 = wk.ty0, tx0 = wk.tx0, ntile = wk.ntile;
+    const int n_img0 = wk.n_img + f_g, ty0 = wk.ty0, tx0 = wk.tx0, ntile = wk.ntile;
     mbar_wait(&tmem_full_bar[buf], (full_ph >> buf) & 1u);
     full_ph ^= 1u << buf;
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base + buf * buf_cols;
     for (int mt = 0; mt < a.MT; mt++) {
-      const int oy = a.fold ? f_oy : ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = a.fold ? f_ox : tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
+      int oy = tfold ? f_oy : ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), n_img = n_img0;
+      const int ox = tfold ? f_ox : tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
+      bool in_group = true;
+      if (a.hf_pitch) {   // stacked halo tile: tile row -> (image of the group, row of that image)
+        const int g = oy / a.hf_pitch;
+        oy -= g * a.hf_pitch;
+        n_img += g;
+        in_group = g < a.fold && n_img < a.n_real;
+      }
       const long pix = (long)oy * a.Wo + ox;
-      const bool in_img = a.fold ? (f_g < a.fold && n_img < a.n_real) : a.flat_hw > 0 ? pix < hw : (oy < a.Ho && ox < a.Wo);
+      const bool in_img = tfold ? (f_g < a.fold && n_img < a.n_real) : a.flat_hw > 0 ? pix < hw : (in_group && oy < a.Ho && ox < a.Wo);
       for (int c0 = col_begin; c0 < col_end; c0 += 16) {
         uint32_t v[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
@@ -1529,6 +1544,20 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   // images per tile -- at 7x7 / 8x8 the per-tap boxes of a folded tile cost more than the half-empty halo tile; from 4 images per
   // tile on, and for every layer that runs in tap mode anyway (1x1, strided), folding wins (4x4 maps: 2-4x)
   if (fold && fold < 4 && taps > 1 && g.stride == 1 && env_int("PREMVOS_FOLD", 1) != 2) fold = 0;
+  // stacked halo tiles for the 3x3 stride-1 layers that stay in halo mode: images of at most 8 x 16 share a tile at a row pitch of
+  // Ho + halo rows (RoI head 7x7: 2 images per 16 x 8 tile, 38 % -> 77 % of the rows; 8x8 maps: 3 per 32 x 8 tile, 50 % -> 75 %)
+  int hfold = 0, hf_pitch = 0, hf_mt = 1;
+  if (!fold && !w.pair && env_int("PREMVOS_FOLD", 1) != 0 && env_int("PREMVOS_HFOLD", 1) != 0 && taps > 1 && g.stride == 1 && g.dil == 1 &&
+      Wo <= 8 && in.N >= 2 && Wo == in.W + g.pad_l + g.pad_r - (w.S - 1)) {
+    const int pitch = Ho + (w.R - 1) * g.dil;
+    double best = 1.3 * Ho * Wo / (128.0 * ((Ho + 15) / 16));   // must beat one image per tile column by a margin
+    for (int mt = 1; mt <= 2; mt++) {
+      if (Ho > 16 * mt) continue;
+      const int G = std::min((16 * mt - Ho) / pitch + 1, in.N);
+      const double util = (double)G * Ho * Wo / (128.0 * mt);
+      if (G >= 2 && util > best) { best = util; hfold = G; hf_pitch = pitch; hf_mt = mt; }
+    }
+  }
   const bool flat = !fold && taps == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
                     env_int("PREMVOS_FLAT", 1) != 0 && (long)in.H * in.W >= 8;
   const int real_hw = Ho * Wo;
@@ -1546,6 +1575,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   const long ctas_mt2 = std::min(tiles_v, tiles_h) * in.N * w.ntiles;
   int mt_pref = (ctas_mt2 >= 2 * 148 && geoH > 16 && taps > 1) ? 2 : 1;   // 1x1 layers measured best with one sub-tile at BN = 128
   const bool wide = w.BN > 128;                                           // 256-wide N tile: one CTA per SM owns the whole TMEM
+  if (hfold) mt_pref = hf_mt;
   if (wide || fold) mt_pref = 1;   // measured (tools/conv_sweep2.py): 256 x 256 single-buffered tiles lose to 128 x 256 double-buffered ones
   mt_pref = env_int("PREMVOS_MT", mt_pref);
   PV_CHECK(mt_pref == 1 || mt_pref == 2, PREMVOS_ERR_INVALID_ARG, "conv_umma: MT=%d", mt_pref);
@@ -1559,7 +1589,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     const bool want_halo = cand < 2;
     if ((halo_env == 0 && want_halo) || (halo_env == 1 && !want_halo)) continue;   // tuning override
     if ((cand & 1) && mt_pref == 1) continue;
-    const bool hz = horiz && mt == 2;
+    const bool hz = horiz && mt == 2 && !hfold;
     const int halo_w = (hz ? 16 : 8) + (w.S - 1) * g.dil, halo_h = (hz ? 16 : 16 * mt) + (w.R - 1) * g.dil;
     const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * mt;
     // halo mode only when it moves fewer bytes into shared memory than per-tap boxes
@@ -1573,6 +1603,13 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     a.box_h = a.halo ? halo_h : (hz ? 16 : 16 * mt);
     a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
     a.a_plane = round_up(a.a_box_bytes, 128);
+    a.fold = 0; a.hf_pitch = 0;
+    if (hfold && a.halo && mt == hf_mt) {   // the box holds hfold images of hf_pitch rows; the MMAs still walk halo_h rows per chunk
+      a.fold = hfold; a.hf_pitch = hf_pitch; a.n_real = in.N;
+      a.box_h = hfold * hf_pitch;
+      a.a_box_bytes = w.KC * a.box_h * a.box_w * 16;
+      a.a_plane = round_up(std::max(a.a_box_bytes, ((w.KC - 1) * a.box_h + halo_h) * a.box_w * 16), 128);
+    }
     if (fold) {   // rows are consecutive pixels of consecutive images; the MMA always reads 128 rows per chunk
       a.fold = fold; a.slot = Ho * Wo; a.n_real = in.N; a.merged_x = 0;
       a.a_lbo = fold * a.slot * 16;
@@ -1596,9 +1633,10 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   }
   PV_CHECK(found, PREMVOS_ERR_UNSUPPORTED, "conv_umma: no pipeline configuration fits shared memory (KC=%d BN=%d dil=%d)", w.KC, w.BN, g.dil);
   const int tile_w = a.mt_horizontal ? 16 : 8, tile_h = a.mt_horizontal ? 16 : 16 * a.MT;
-  a.tiles_x = fold ? 1 : (geoW + tile_w - 1) / tile_w;
-  a.tiles_y = fold ? 1 : (geoH + tile_h - 1) / tile_h;
-  const int n_groups = fold ? (in.N + fold - 1) / fold : in.N;   // images, or groups of `fold` images, per output-channel tile
+  if (!a.hf_pitch) hfold = 0;   // the stacked-halo candidate did not fit: plain tiles
+  a.tiles_x = (fold || hfold) ? 1 : (geoW + tile_w - 1) / tile_w;
+  a.tiles_y = (fold || hfold) ? 1 : (geoH + tile_h - 1) / tile_h;
+  const int n_groups = a.fold ? (in.N + a.fold - 1) / a.fold : in.N;   // images, or groups of `fold` images, per output-channel tile
   // deepen the rings; stay under 110 KB when the minimal pipeline does (two CTAs per SM), else use the whole SM
   int budget = (!wide && a.a_stages * 2 * a.a_plane + 2 * a.w_stage + 1024 <= 110 * 1024) ? 110 * 1024 : SMEM_LIMIT - 1024;
   if (env_int("PREMVOS_BUDGET_KB", 0) > 0) budget = env_int("PREMVOS_BUDGET_KB", 0) * 1024;
@@ -1665,7 +1703,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   plan->ctas_per_sm = cps;
   // tail split (see UmmaConvArgs): only for un-split layers with at least one full wave and a small remainder
   a.tail_items = 0; a.tail_split = 1; a.tail_kb_per = a.kblocks; a.main_work = a.total_work;
-  if (a.ksplit == 1 && !fold && env_int("PREMVOS_TAIL", 1) != 0) {
+  if (a.ksplit == 1 && !a.fold && env_int("PREMVOS_TAIL", 1) != 0) {
     int num_sms = 148;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
     const int slots = num_sms * cps, rem = a.total_work % slots;
@@ -1695,7 +1733,13 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   __nv_bfloat16* bases[2] = {in.hi + (size_t)in.c0 * in.H * in.W * 8, in.lo + (size_t)in.c0 * in.H * in.W * 8};
   CUtensorMap* maps[2] = {(CUtensorMap*)plan->map_a_hi, (CUtensorMap*)plan->map_a_lo};
   for (int k = 0; k < 2; k++) {
-    if (fold) {
+    if (hfold) {
+      cuuint64_t dims[4] = {(cuuint64_t)in.W * 8, (cuuint64_t)in.H, (cuuint64_t)in.N, (cuuint64_t)vchunks};
+      cuuint64_t strides[3] = {(cuuint64_t)in.W * 16, plane_bytes * in.chunks, plane_bytes};
+      cuuint32_t box[4] = {(cuuint32_t)a.box_w * 8, (cuuint32_t)hf_pitch, (cuuint32_t)hfold, (cuuint32_t)w.KC};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      PV_TRY(encode_map(maps[k], bases[k], 4, dims, strides, box, estr));
+    } else if (fold) {
       cuuint64_t dims[5] = {8, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N, (cuuint64_t)vchunks};
       cuuint64_t strides[4] = {16, (cuuint64_t)in.W * 16, plane_bytes * in.chunks, plane_bytes};
       cuuint32_t box[5] = {8, (cuuint32_t)(Wo * g.stride), (cuuint32_t)(Ho * g.stride), (cuuint32_t)fold, (cuuint32_t)w.KC};
@@ -1839,9 +1883,9 @@ int launch_conv_umma(const ConvPlanUmma& plan, cudaStream_t st, int active_n) {
   static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
   if (per_layer && profiling_enabled()) {   // per-layer breakdown for tools/profile_nets.py
     char buf[256];
-    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d_tail%dx%d_fold%d]", n_act,
+    snprintf(buf, sizeof(buf), "conv_umma[n%d_%dx%d_cin%d_cout%d_k%d_s%d_d%d|MT%d_BN%d_KC%d_halo%d_ks%d_cps%d_nbuf%d_ws%d_as%d_ls%d_tail%dx%d_fold%d_hp%d]", n_act,
              a.flat_hw > 0 ? a.flat_hw : a.Ho, a.flat_hw > 0 ? 1 : a.Wo, a.kblocks * a.KC * 8, a.Cout, a.R, a.stride, a.dil, a.MT, a.BN,
-             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep, a.tail_items, a.tail_split, a.fold);
+             a.KC, a.halo, a.ksplit, plan.ctas_per_sm, a.nbuf, a.w_stages, a.a_stages, a.lockstep, a.tail_items, a.tail_split, a.fold, a.hf_pitch);
     label = prof_intern(buf);
   }
   PV_TRY(after_launch(label, st, plan.flops * frac, plan.bytes * frac));

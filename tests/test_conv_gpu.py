@@ -58,13 +58,14 @@ CASES = [
     (5, 1536, 25, 25, 2048, 1, 1, 1, (0, 0, 0, 0), 0.0, False), # exit flow: 8 channel tiles, K = 48 k-blocks, 13 pairs x 8 = 104 items
     (1, 1024, 46, 83, 256, 1, 1, 1, (0, 0, 0, 0), 0.0, True),   # stream-K with 6.5 k-blocks per pair: every item is finished from 5-6 partial sums
     # folded small maps: several whole images per 128-row tile, per-image zero padding from the TMA's out-of-bounds fill
-    (9, 512, 7, 7, 512, 3, 1, 1, (1, 1, 1, 1), 0.0, True),      # RoI head 3x3 at 7x7: 2 images per tile (98 rows), odd image count
+    (9, 512, 7, 7, 512, 3, 1, 1, (1, 1, 1, 1), 0.0, True),      # RoI head 3x3 at 7x7: stacked halo tile, 2 images at a row pitch of 9, odd image count
     (40, 1024, 4, 4, 2048, 3, 1, 1, (1, 1, 1, 1), 0.0, False),  # ReID res16: 8 images per tile, 5 groups x 16 channel tiles
     (13, 1024, 14, 14, 512, 1, 2, 1, (0, 0, 0, 0), 0.0, False), # RoI head entry: 1x1 stride 2 onto 7x7 (element strides in the folded box)
     (21, 2048, 4, 4, 4096, 1, 1, 1, (0, 0, 0, 0), 1.0, True),   # 1x1 on 4x4 maps + residual: last group holds 5 of 8 images
     (6, 512, 8, 8, 1024, 3, 2, 1, (0, 0, 1, 1), 1.0, False),    # TF SAME stride 2 (pad after only) onto 4x4: 6 images in one tile, split-K
-    (5, 64, 8, 8, 64, 3, 1, 1, (1, 1, 1, 1), 0.1, False),       # 8x8 maps: 2 images per exact 128-row tile
+    (5, 64, 8, 8, 64, 3, 1, 1, (1, 1, 1, 1), 0.1, False),       # 8x8 maps: stacked halo tile with two sub-tiles, 3 images at a row pitch of 10
     (3, 96, 5, 11, 40, 3, 1, 1, (1, 1, 1, 1), 0.1, True),       # 55-pixel maps wider than a tile row: 2 per tile, ragged channels
+    (7, 40, 6, 5, 24, 3, 1, 1, (1, 1, 1, 1), 0.1, True),        # stacked halo tile: 2 images of 6x5 at a row pitch of 8, odd image count
 ]
 
 
