@@ -17,9 +17,12 @@ Follows the reference (paths relative to /root/reference/code):
                                      (tf.image.resize_images, TF1 legacy: in = out * in_size / out_size) unless min(h, w) <= 10
                                      (zeros); normalize with the ImageNet mean / std (datasets/Util/Normalization.py:9-22)
 
-PARITY UNPINNED: the reference ships no vectors for this network and TensorFlow cannot be imported here; the restated
+PARITY UNPINNED for the network: the reference ships no vectors for it and TensorFlow cannot be imported here; the restated
 third-party arithmetic (SAME padding of strided convolutions / max pooling, legacy resize) is the published TensorFlow 1.x
-behaviour, the legacy resize shared with oracle/refnet_oracle.py (pinned there by hand-derived cases).
+behaviour, the legacy resize shared with oracle/refnet_oracle.py (pinned there by hand-derived cases).  PINNED
+(tests/golden/reid_reference_golden.npz, made by tests/golden/make_reid_reference_goldens.py): `apply_context_region` against the
+reference method's own source executed with a numpy stand-in for its six TensorFlow ops (80 boxes, bit-exact), `normalize`
+against the reference's numpy function, the layer table against the reference's configs/live.
 """
 from __future__ import annotations
 
@@ -82,8 +85,9 @@ def apply_context_region(boxes_xywh, H, W, factor=CONTEXT_REGION_FACTOR):
     b = np.asarray(boxes_xywh, dtype=np.float32).reshape(-1, 4).copy()
     f = np.float32(factor)
     xs, ys, ws, hs = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
-    xs = xs - np.float32(0.5) * ws * (f - np.float32(1.0))
-    ys = ys - np.float32(0.5) * hs * (f - np.float32(1.0))
+    fm1 = np.float32(factor - 1.0)            # the python double 0.19999999999999996 meets a float32 tensor: 0.2f, not 1.2f - 1.0f
+    xs = xs - np.float32(0.5) * ws * fm1
+    ys = ys - np.float32(0.5) * hs * fm1
     ws = ws * f
     hs = hs * f
     xs, ys, ws, hs = (np.rint(v).astype(np.int32) for v in (xs, ys, ws, hs))      # tf.round: half to even

@@ -64,7 +64,7 @@ __device__ __forceinline__ void legacy_axis(int o, float scale, int in_size, int
 
 // DAVIS_Forward_Feed.py:36-58 in float32 / int32 as TensorFlow evaluates it
 __device__ __forceinline__ void reid_crop_box(const float* b, int H, int W, int* x, int* y, int* w, int* h) {
-  const float f = 1.2f, fm1 = __fsub_rn(f, 1.0f);
+  const float f = 1.2f, fm1 = (float)(1.2 - 1.0);   // python evaluates `factor - 1.0` in double before it meets the float32 tensor
   float xs = __fsub_rn(b[0], __fmul_rn(__fmul_rn(0.5f, b[2]), fm1));
   float ys = __fsub_rn(b[1], __fmul_rn(__fmul_rn(0.5f, b[3]), fm1));
   float ws = __fmul_rn(b[2], f), hs = __fmul_rn(b[3], f);

@@ -124,3 +124,37 @@ def test_host_surface_checks(params, tmp_path):
     out = reid.add_ReID([{"bbox": [1, 2, 30, 40]}, {"bbox": [5, 6, 70, 80]}], np.zeros((50, 60, 3), np.uint8), eng)
     assert out[1]["ReID"][:2] == [128.0, 129.0] and len(out[0]["ReID"]) == 128
     assert reid.add_ReID([], np.zeros((50, 60, 3), np.uint8), eng) == []
+
+
+def test_pinned_against_reference_source_vectors(golden_dir):
+    """tests/golden/reid_reference_golden.npz (make_reid_reference_goldens.py): the reference's apply_contex_region source run on a
+    numpy stand-in for TensorFlow's ops, its numpy normalize, and its configs/live."""
+    import os
+    g = np.load(os.path.join(golden_dir, "reid_reference_golden.npz"))
+    H, W = int(g["ctx_dims"][0]), int(g["ctx_dims"][1])
+    assert np.array_equal(RO.apply_context_region(g["ctx_boxes"], H, W), g["ctx_out"].astype(np.int32))
+    mean, std = RO.IMAGENET_RGB_MEAN, RO.IMAGENET_RGB_STD
+    assert np.array_equal((g["norm_in"] - mean) / std, g["norm_out"])
+    cfg = json.loads(bytes(g["config_live_json"]).decode())
+    assert cfg["input_size"] == [RO.INPUT_SIZE, RO.INPUT_SIZE] and cfg["context_region_factor_val"] == RO.CONTEXT_REGION_FACTOR
+    assert cfg["num_classes"] == RO.EMBEDDING_DIM and cfg["output_embedding_layer"] == "outputTriplet"
+    net = cfg["network"]
+    prev = "conv0"
+    assert net["conv0"] == {"class": "Conv", "n_features": 64, "activation": "linear"}
+    feats_now = None
+    for name, feats, ks, strides in RO.RESIDUAL_UNITS:
+        spec = net[name]
+        assert spec["class"] == "ResidualUnit2" and spec["from"] == [prev]
+        nf = spec.get("n_features", feats_now[-1] if feats_now else 64)   # ResidualUnit2: n_features=None -> the input's width
+        feats_now = tuple(nf) if isinstance(nf, list) else (nf,) * spec.get("n_convs", 2)
+        assert tuple(feats) == feats_now, name
+        assert len(feats) == spec.get("n_convs", 2)
+        want_strides = [s[0] for s in spec["strides"]] if "strides" in spec else [1] * len(feats)
+        assert list(strides) == want_strides, name
+        want_ks = [f[0] for f in spec["filter_size"]] if "filter_size" in spec else [3] * len(feats)
+        assert list(ks) == want_ks, name
+        prev = name
+    assert net["conv1"]["from"] == [prev] and net["conv1"]["n_features"] == 500 and net["conv1"]["pool_size"] == [3, 3]
+    assert net["conv1"]["batch_norm"] is True and net["conv1"]["filter_size"] == [3, 3]
+    assert net["fc1"]["n_features"] == 500 and net["fc2"]["n_features"] == 500 and net["fc1"]["batch_norm"] and net["fc2"]["batch_norm"]
+    assert net["outputTriplet"]["class"] == "FullyConnectedWithTripletLoss" and net["outputTriplet"]["from"] == ["fc2"]
