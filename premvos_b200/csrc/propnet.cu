@@ -56,6 +56,11 @@ struct premvos_propnet {
   std::map<std::string, std::vector<int64_t>> shapes;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;
+  // the per-image detection tails (top-k, NMS, RoIAlign, final selection: short latency-bound kernels) of a batched forward run as
+  // parallel branches: image b > 0 on side[b - 1], forked from / joined to the launching stream by events (also under capture)
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> ev_join;
+  cudaEvent_t ev_fork = nullptr;
 
   float* img_dev = nullptr;  // [batch][H][W][3] fp32 BGR 0..255
   // every per-image buffer below holds `batch` consecutive copies (strides: the S_* constants)
@@ -390,8 +395,27 @@ int build_network(premvos_propnet* n) {
   return 0;
 }
 
-int run_network(premvos_propnet* n, cudaStream_t st) {
+// branch of image b: the launching stream for image 0, a side stream that waits for everything enqueued so far otherwise
+static int fork_branch(premvos_propnet* n, cudaStream_t st, int b, cudaStream_t* out) {
+  *out = st;
+  if (n->side.empty()) return 0;
+  if (b == 0) { PV_CUDA(cudaEventRecord(n->ev_fork, st)); return 0; }   // the fork point: before image 0's own kernels
+  PV_CUDA(cudaStreamWaitEvent(n->side[b - 1], n->ev_fork, 0));
+  *out = n->side[b - 1];
+  return 0;
+}
+static int join_branches(premvos_propnet* n, cudaStream_t st) {
+  if (n->side.empty()) return 0;
+  for (int b = 1; b < n->batch; b++) {
+    PV_CUDA(cudaEventRecord(n->ev_join[b - 1], n->side[b - 1]));
+    PV_CUDA(cudaStreamWaitEvent(st, n->ev_join[b - 1], 0));
+  }
+  return 0;
+}
+
+int run_network(premvos_propnet* n, cudaStream_t st0) {
   const int NB = n->batch, nsec = n->second_num_class > 0 ? n->second_num_class : 1;
+  cudaStream_t st = st0;
   for (int b = 0; b < NB; b++) PV_TRY(det_preprocess(n->img_dev + (size_t)b * n->H * n->W * 3, n->img.batch_range(b, 1), st));
   // backbone + RPN head: every frame of the batch in the same launches
   PV_TRY(launch_conv_umma(n->conv0.plan, st));
@@ -400,6 +424,7 @@ int run_network(premvos_propnet* n, cudaStream_t st) {
   PV_TRY(launch_conv_umma(n->rpn0.plan, st));
   PV_TRY(launch_conv_umma(n->rpn_heads.plan, st));
   for (int b = 0; b < NB; b++) {
+    PV_TRY(fork_branch(n, st0, b, &st));
     const size_t na = (size_t)n->n_anchor_total;
     float *scores = n->d_scores + b * na, *boxes = n->d_boxes + b * na * 4;
     PV_TRY(det_rpn_decode(n->rpn_out.p + (size_t)b * n->fh * n->fw * n->rpn_out.cs, n->rpn_out.cs, n->fh, n->fw, NUM_ANCHOR, n->cell_anchors,
@@ -416,10 +441,13 @@ int run_network(premvos_propnet* n, cudaStream_t st) {
     PV_TRY(det_roi_align(n->featuremap.batch_range(b, 1), n->prop_boxes + b * S_KEEP * 4, 1.0f / ANCHOR_STRIDE, 14,
                          n->roi.batch_range(b * POST_NMS_TOPK, POST_NMS_TOPK), st));
   }
+  st = st0;
+  PV_TRY(join_branches(n, st));
   // conv5 head on the RoIs of all frames, pooled features -> heads
   for (auto& b : n->head) PV_TRY(run_bottleneck(b.get(), st));
   PV_TRY(det_gap_fc(n->head.back()->out, n->fc_w, n->fc_b, n->nfc, n->pooled, n->fc_out, st));
   for (int b = 0; b < NB; b++) {
+    PV_TRY(fork_branch(n, st0, b, &st));
     DetTailArgs t;
     t.logits = n->fc_out + (size_t)b * POST_NMS_TOPK * n->nfc; t.nfc = n->nfc; t.nsecond = n->second_num_class;
     t.prop_boxes = n->prop_boxes + b * S_KEEP * 4; t.prop_count = n->keep_count + b;
@@ -432,6 +460,8 @@ int run_network(premvos_propnet* n, cudaStream_t st) {
     t.second_final_posterior = n->second_final_posterior + (size_t)b * RESULTS_PER_IM * nsec; t.final_box_index = n->final_box_index + b * RESULTS_PER_IM;
     PV_TRY(det_frcnn_tail(t, st));
   }
+  st = st0;
+  PV_TRY(join_branches(n, st));
   if (n->mode_mask) {
     // rows >= n_out of final_boxes hold older / zero boxes: their masks are computed and never read
     for (int b = 0; b < NB; b++)
@@ -524,6 +554,15 @@ extern "C" int premvos_propnet_finalize(premvos_propnet_t* n) {
   for (auto& kv : n->shapes)
     if (!n->params.count(kv.first)) return fail(PREMVOS_ERR_NOT_READY, "premvos_propnet_finalize: missing variable '%s'", kv.first.c_str());
   PV_CUDA(cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking));
+  const char* fork_env = getenv("PREMVOS_PROPNET_FORK");
+  if (n->batch > 1 && (fork_env == nullptr || atoi(fork_env) != 0)) {
+    PV_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+    n->side.resize(n->batch - 1); n->ev_join.resize(n->batch - 1);
+    for (int b = 0; b + 1 < n->batch; b++) {
+      PV_CUDA(cudaStreamCreateWithFlags(&n->side[b], cudaStreamNonBlocking));
+      PV_CUDA(cudaEventCreateWithFlags(&n->ev_join[b], cudaEventDisableTiming));
+    }
+  }
   PV_TRY(build_network(n));
   n->params.clear();
   const int64_t before = g_launch_count.load();
@@ -747,6 +786,9 @@ extern "C" void premvos_propnet_destroy(premvos_propnet_t* n) {
   if (n->exec) cudaGraphExecDestroy(n->exec);
   if (n->graph) cudaGraphDestroy(n->graph);
   if (n->stream) cudaStreamDestroy(n->stream);
+  for (cudaStream_t s : n->side) cudaStreamDestroy(s);
+  for (cudaEvent_t e : n->ev_join) cudaEventDestroy(e);
+  if (n->ev_fork) cudaEventDestroy(n->ev_fork);
   delete n;
 }
 
