@@ -196,6 +196,7 @@ struct ConvWeightsUmma {
 };
 struct ConvGeom {
   int stride = 1, dil = 1;
+  int stride_x = 0;   // horizontal stride when it differs from the vertical one (0: same as `stride`); tap mode only
   int pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0;
   float slope = 1.f;  // LeakyReLU slope applied after bias (+ residual): 1 = identity, 0 = ReLU
   static ConvGeom same3x3(int dil, float slope) { ConvGeom g; g.dil = dil; g.pad_t = g.pad_l = g.pad_b = g.pad_r = dil; g.slope = slope; return g; }
@@ -265,6 +266,9 @@ int cp8_to_nchw(const CView& src, int ch_off, float* dst, cudaStream_t st);
 
 // ---- detection-side kernels of the proposal network, det_ops.cu ---------------------------------------
 int det_preprocess(const float* img_hwc_dev, const CView& out, cudaStream_t st);           // basemodel.py:12-26
+// the same normalisation written as the ROW IM2COL of the 7x7 / stride-2 stem: out [1][3 chunks][H][Wo], channel s*3 + c of pixel
+// (y, xo) = normalised img(y, 2*xo + s - pad_l, c) (0 outside the image: the stem pads the NORMALISED image with zeros)
+int det_preprocess_rows7(const float* img_hwc_dev, int W, int pad_l, const CView& out, cudaStream_t st);
 int det_maxpool3x3s2(const CView& in, const CView& out, cudaStream_t st);                  // basemodel.py:81-82
 int det_rpn_decode(const float* rpn, int cs, int fh, int fw, int na, const float* cell_anchors, float stride, float clip,
                    float* scores, float* boxes, cudaStream_t st);                          // model.py:114-139

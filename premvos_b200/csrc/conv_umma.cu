@@ -258,6 +258,7 @@ struct UmmaConvArgs {
   int mt_horizontal;         // ... side by side in x (1) or stacked in y (0), whichever pads the image less
   int Ho, Wo;                // output size
   int stride, R, S, dil, pad_t, pad_l;
+  int stride_x;              // horizontal stride (== stride unless the layer was planned with ConvGeom::stride_x)
   int halo;                  // 1: one A box per k-block serves all taps; 0: one A box per (tap, k-block)
   int merged_x;              // 1: tensor map dim 0 = W*8 elements (stride-1 layers); 0: dims {8, W, ...}
   int box_w, box_h;          // A box (pixels) as it lies in shared memory
@@ -390,7 +391,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const Work wk = decode(t);
     const int n_img = wk.n_img;
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)wk.ntile * a.kblocks + wk.kb_begin) * taps * 2 * a.w_plane;
-    const int bx = wk.tx0 * a.stride - a.pad_l, by = wk.ty0 * a.stride - a.pad_t;
+    const int bx = wk.tx0 * a.stride_x - a.pad_l, by = wk.ty0 * a.stride - a.pad_t;
     if (a.lockstep) {
       // 1x1 layers: one ring, one barrier pair per k-block -- the A box and the weight block of a k-block share the stage
       // index and the w_full / w_empty barriers (a tcgen05.commit per ring per k-block costs more than the k-block's MMAs)
@@ -1503,7 +1504,10 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
            "conv_umma: input view has %d channels, weights were packed for %d", in.C, w.CinPhys);
   PV_CHECK(g.stride == 1 || g.stride == 2, PREMVOS_ERR_UNSUPPORTED, "conv_umma: stride %d", g.stride);
   const int Ho = (in.H + g.pad_t + g.pad_b - g.dil * (w.R - 1) - 1) / g.stride + 1;
-  const int Wo = (in.W + g.pad_l + g.pad_r - g.dil * (w.S - 1) - 1) / g.stride + 1;
+  const int sx = g.stride_x > 0 ? g.stride_x : g.stride;   // horizontal stride; a layer with sx != stride runs in plain tap mode
+  PV_CHECK(sx == 1 || sx == 2, PREMVOS_ERR_UNSUPPORTED, "conv_umma: horizontal stride %d", sx);
+  const bool mixed = sx != g.stride;
+  const int Wo = (in.W + g.pad_l + g.pad_r - g.dil * (w.S - 1) - 1) / sx + 1;
   PV_CHECK(Ho > 0 && Wo > 0, PREMVOS_ERR_INVALID_ARG, "conv_umma: empty output");
   const int cp_cout = out.cp.hi ? (out.cp_channels >= 0 ? out.cp_channels : w.Cout) : 0;
   const int f32_first = out.f32.p ? out.f32_first : 0;
@@ -1537,7 +1541,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   // 128 bytes of slack every activation buffer is allocated with: the last 8-pixel row may straddle the plane end)
   // small output maps (RoI heads at 7x7, the ReID network's 8x8 / 4x4 stages): several whole images share one 128-row tile
   int fold = 0;
-  if (!w.pair && env_int("PREMVOS_FOLD", 1) != 0 && Ho * Wo <= 64 && in.N >= 2 && Wo * g.stride <= 256 && Ho * g.stride <= 256)
+  if (!w.pair && !mixed && env_int("PREMVOS_FOLD", 1) != 0 && Ho * Wo <= 64 && in.N >= 2 && Wo * g.stride <= 256 && Ho * g.stride <= 256)
     fold = std::min(128 / (Ho * Wo), in.N);
   if (fold < 2) fold = 0;
   // measured (profiles/r02_fold_layers.txt): 3x3 stride-1 layers keep halo mode (one box per k-block serves all taps) down to two
@@ -1547,7 +1551,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   // stacked halo tiles for the 3x3 stride-1 layers that stay in halo mode: images of at most 8 x 16 share a tile at a row pitch of
   // Ho + halo rows (RoI head 7x7: 2 images per 16 x 8 tile, 38 % -> 77 % of the rows; 8x8 maps: 3 per 32 x 8 tile, 50 % -> 75 %)
   int hfold = 0, hf_pitch = 0, hf_mt = 1;
-  if (!fold && !w.pair && env_int("PREMVOS_FOLD", 1) != 0 && env_int("PREMVOS_HFOLD", 1) != 0 && taps > 1 && g.stride == 1 && g.dil == 1 &&
+  if (!fold && !w.pair && env_int("PREMVOS_FOLD", 1) != 0 && env_int("PREMVOS_HFOLD", 1) != 0 && taps > 1 && g.stride == 1 && !mixed && g.dil == 1 &&
       Wo <= 8 && in.N >= 2 && Wo == in.W + g.pad_l + g.pad_r - (w.S - 1)) {
     const int pitch = Ho + (w.R - 1) * g.dil;
     double best = 1.3 * Ho * Wo / (128.0 * ((Ho + 15) / 16));   // must beat one image per tile column by a margin
@@ -1558,14 +1562,14 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
       if (G >= 2 && util > best) { best = util; hfold = G; hf_pitch = pitch; hf_mt = mt; }
     }
   }
-  const bool flat = !fold && taps == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
+  const bool flat = !fold && !mixed && taps == 1 && g.stride == 1 && g.pad_t == 0 && g.pad_l == 0 && g.pad_b == 0 && g.pad_r == 0 &&
                     env_int("PREMVOS_FLAT", 1) != 0 && (long)in.H * in.W >= 8;
   const int real_hw = Ho * Wo;
   const int geoH = flat ? (real_hw + 7) / 8 : Ho, geoW = flat ? 8 : Wo;
   a.Ho = geoH; a.Wo = geoW; a.flat_hw = flat ? real_hw : 0;
-  a.stride = g.stride; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
+  a.stride = g.stride; a.stride_x = sx; a.R = w.R; a.S = w.S; a.dil = g.dil; a.pad_t = g.pad_t; a.pad_l = g.pad_l;
   a.KC = w.KC; a.kblocks = w.kblocks; a.BN = w.BN; a.Cout = w.Cout;
-  a.merged_x = (g.stride == 1) ? 1 : 0;
+  a.merged_x = (g.stride == 1 && !mixed) ? 1 : 0;
   a.w_plane = w.KC * w.BN * 16;
   if (w.pair) return plan_conv_pair(plan, in, out, w, g, flat, real_hw, cp_cout, f32_first, ws);
   // MT = 2 halves the weight traffic per pixel; only worth it when the grid still fills the machine twice over
@@ -1594,7 +1598,7 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     const long halo_px = (long)halo_w * halo_h, tap_px = (long)taps * 128 * mt;
     // halo mode only when it moves fewer bytes into shared memory than per-tap boxes
     // (measured: from dilation 4 on the halo box is so large that one CTA per SM remains; per-tap boxes win)
-    const bool halo_ok = g.stride == 1 && taps > 1 && g.dil < 4 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
+    const bool halo_ok = g.stride == 1 && !mixed && taps > 1 && g.dil < 4 && halo_px * 5 < tap_px * 4 && halo_w * 8 <= 256 && halo_h <= 256;
     if (want_halo && (!halo_ok || fold)) continue;
     a.MT = mt;
     a.mt_horizontal = hz ? 1 : 0;
@@ -1760,8 +1764,8 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
     } else {
       cuuint64_t dims[5] = {8, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)vchunks, (cuuint64_t)in.N};
       cuuint64_t strides[4] = {16, (cuuint64_t)in.W * 16, plane_bytes, plane_bytes * in.chunks};
-      cuuint32_t box[5] = {8, (cuuint32_t)(a.box_w * g.stride), (cuuint32_t)(a.box_h * g.stride), (cuuint32_t)w.KC, 1};
-      cuuint32_t estr[5] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1, 1};
+      cuuint32_t box[5] = {8, (cuuint32_t)(a.box_w * sx), (cuuint32_t)(a.box_h * g.stride), (cuuint32_t)w.KC, 1};
+      cuuint32_t estr[5] = {1, (cuuint32_t)sx, (cuuint32_t)g.stride, 1, 1};
       PV_TRY(encode_map(maps[k], bases[k], 5, dims, strides, box, estr));
     }
   }

@@ -59,6 +59,25 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict
   st_chunk(out.hi, out.lo, ((long)out.c0 * hw + p) * 8, f);
 }
 
+// Row im2col of the stem (see common.cuh): one thread per (pixel of the half-width grid, chunk of 8 of the 21 + 3 channels)
+__global__ void __launch_bounds__(256) preprocess_rows7_kernel(const float* __restrict__ img, int W, int pad_l, CV out) {
+  const long hw = (long)out.H * out.W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= hw * 3) return;
+  const int ch = (int)(idx / hw);
+  const long p = idx - (long)ch * hw;
+  const int y = (int)(p / out.W), xo = (int)(p - (long)y * out.W);
+  const float mean[3] = {0.406f, 0.456f, 0.485f}, stdv[3] = {0.225f, 0.224f, 0.229f};
+  F8 f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = ch * 8 + j, s = k / 3, c = k - s * 3, x = 2 * xo + s - pad_l;
+    f.v[j] = 0.f;
+    if (k < 21 && x >= 0 && x < W) f.v[j] = __fdiv_rn(__fsub_rn(__fmul_rn(img[((long)y * W + x) * 3 + c], 1.0f / 255), mean[c]), stdv[c]);
+  }
+  st_chunk(out.hi, out.lo, (((long)(out.c0 + ch)) * hw + p) * 8, f);
+}
+
 // uint8 frame -> the fp32 image tensor the graph is fed with (eval.py:75-78 hands pred_func the resized uint8 image)
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, long n,
                                                         int aligned) {
@@ -610,6 +629,14 @@ int det_preprocess(const float* img_hwc, const CView& out, cudaStream_t st) {
   prof_before(st);
   preprocess_kernel<<<blocks_for(hw), 256, 0, st>>>(img_hwc, dev(out));
   return after_launch("preprocess_kernel", st, 0.0, (double)hw * (12.0 + 32.0));
+}
+
+int det_preprocess_rows7(const float* img_hwc, int W, int pad_l, const CView& out, cudaStream_t st) {
+  PV_CHECK(out.C == 24 && out.N == 1, PREMVOS_ERR_INVALID_ARG, "det_preprocess_rows7: the output view is one image of 3 chunks");
+  const long total = (long)out.H * out.W * 3;
+  prof_before(st);
+  preprocess_rows7_kernel<<<blocks_for(total), 256, 0, st>>>(img_hwc, W, pad_l, dev(out));
+  return after_launch("preprocess_kernel", st, 0.0, (double)out.H * W * 12.0 + (double)total * 32.0);
 }
 
 int det_u8_to_f32(const unsigned char* src, float* dst, long n, cudaStream_t st) {

@@ -51,6 +51,7 @@ struct premvos_propnet {
   int blocks[4] = {3, 4, 23, 3};
   int mode_mask = 0;         // option "mode_mask": also run the Mask R-CNN mask head on the final boxes (config.MODE_MASK)
   int batch = 1;             // frames per forward (option "batch"): one launch group for all of them
+  int stem_rows = 1;         // conv0 as a 7x1 convolution over the row im2col of the input (see build_network)
   bool finalized = false;
   std::map<std::string, std::vector<float>> params;
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -264,12 +265,35 @@ void make_cell_anchors(float* out /*[15][4]*/) {
 int build_network(premvos_propnet* n) {
   const int H = n->H, W = n->W, NB = n->batch;
   PV_TRY(dev_alloc(n, &n->img_dev, (size_t)NB * H * W * 3));
-  PV_TRY(alloc_cview(n, &n->img, NB, 8, H, W));
-  n->img.C = 8;
-  // conv0: pad (2,3) + 7x7 stride 2 VALID + BN + ReLU (basemodel.py:79-80)
+  // conv0: pad (2,3) + 7x7 stride 2 VALID + BN + ReLU (basemodel.py:79-80).  With 3 input channels a per-tap K step would be
+  // 13/16 zeros and the layer 49 operand boxes per tile; the preprocessing kernel therefore writes the ROW IM2COL of the
+  // normalised image -- [H][W0] pixels of 7 horizontal taps x 3 channels = 21 (+3 zero) channels, the horizontal stride and
+  // padding already applied -- and conv0 runs as a 7x1 convolution over it (vertical stride 2, horizontal stride 1, K = 32 per
+  // tap: 14 boxes per tile).  Same products, same zero padding; the fp32 sum of a pixel is taken in a different order.
   const int H0 = (H + 5 - 7) / 2 + 1, W0 = (W + 5 - 7) / 2 + 1;
+  static const bool rows7 = !(getenv("PREMVOS_STEM_ROWS") && atoi(getenv("PREMVOS_STEM_ROWS")) == 0);
+  n->stem_rows = rows7 ? 1 : 0;
+  if (rows7) PV_TRY(alloc_cview(n, &n->img, NB, 24, H, W0));
+  else { PV_TRY(alloc_cview(n, &n->img, NB, 8, H, W)); n->img.C = 8; }
   PV_TRY(alloc_cview(n, &n->c0, NB, 64, H0, W0));
-  {
+  if (rows7) {
+    const std::vector<float>& W7 = n->params["conv0/W"];   // HWIO [7][7][3][64]
+    const std::vector<float>&gm = n->params["conv0/bn/gamma"], &bt = n->params["conv0/bn/beta"];
+    const std::vector<float>&mu = n->params["conv0/bn/mean/EMA"], &var = n->params["conv0/bn/variance/EMA"];
+    std::vector<float> w((size_t)64 * 21 * 7), b(64);
+    for (int o = 0; o < 64; o++) {
+      const float scale = gm[o] / sqrtf(var[o] + BN_EPS);
+      b[o] = bt[o] - mu[o] * scale;
+      for (int r = 0; r < 7; r++)
+        for (int s = 0; s < 7; s++)
+          for (int c = 0; c < 3; c++) w[((size_t)o * 21 + s * 3 + c) * 7 + r] = W7[(((size_t)r * 7 + s) * 3 + c) * 64 + o] * scale;   // [Cout][21][7][1]
+    }
+    ConvGeom g; g.stride = 2; g.stride_x = 1; g.pad_t = 2; g.pad_b = 3; g.slope = 0.f;
+    ConvOut o; o.cp = n->c0;
+    PV_TRY(pack_conv_weights_umma(&n->conv0.w, w.data(), b.data(), 64, 21, 7, 1, nullptr, 0, 0, (long)NB * H0 * W0, false));
+    PV_TRY(plan_conv_umma(&n->conv0.plan, n->img, o, n->conv0.w, g, &n->conv_ws));
+    n->conv0.used = true;
+  } else {
     ConvGeom g; g.stride = 2; g.pad_t = g.pad_l = 2; g.pad_b = g.pad_r = 3; g.slope = 0.f;
     ConvOut o; o.cp = n->c0;
     const int map3[3] = {0, 1, 2};
@@ -416,7 +440,10 @@ static int join_branches(premvos_propnet* n, cudaStream_t st) {
 int run_network(premvos_propnet* n, cudaStream_t st0) {
   const int NB = n->batch, nsec = n->second_num_class > 0 ? n->second_num_class : 1;
   cudaStream_t st = st0;
-  for (int b = 0; b < NB; b++) PV_TRY(det_preprocess(n->img_dev + (size_t)b * n->H * n->W * 3, n->img.batch_range(b, 1), st));
+  for (int b = 0; b < NB; b++) {
+    if (n->stem_rows) PV_TRY(det_preprocess_rows7(n->img_dev + (size_t)b * n->H * n->W * 3, n->W, 2, n->img.batch_range(b, 1), st));
+    else PV_TRY(det_preprocess(n->img_dev + (size_t)b * n->H * n->W * 3, n->img.batch_range(b, 1), st));
+  }
   // backbone + RPN head: every frame of the batch in the same launches
   PV_TRY(launch_conv_umma(n->conv0.plan, st));
   PV_TRY(det_maxpool3x3s2(n->c0, n->pool, st));
