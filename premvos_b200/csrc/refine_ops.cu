@@ -35,6 +35,8 @@ struct PreArgs {
   const float* boxes;                      // [N][4] x, y, w, h (proposal 'bbox')
   int N, S;                                // S = network input size (385)
   CV out;                                  // [N][1 chunk][S][S]: ch 0..2 RGB in [-1,1], ch 3 guidance -1/+1
+  int rows3;                               // 1: `out` is the ROW IM2COL of the 3x3 / stride-2 root convolution instead:
+                                           // [N][2 chunks][S][(S+1)/2], channel s*4 + c of (y, xo) = input(y, 2*xo + s - 1, c)
   int* crops;                              // [N][4] y0 x0 y1 x1 (CROP_BOXES_y0x0y1x1)
 };
 
@@ -82,7 +84,30 @@ __global__ void __launch_bounds__(256) refine_input_kernel(PreArgs a) {
     const float g = (sy >= ys && sy < ye && sx >= xs && sx < xe) ? 1.f : 0.f;
     f.v[3] = __fsub_rn(__fmul_rn(2.0f / 255.0f, __fmul_rn(g, 255.f)), 1.0f);
   }
-  st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, 0, y, x), f);
+  if (!a.rows3) {
+    st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, 0, y, x), f);
+    return;
+  }
+  // row im2col: pixel x is tap 1 of output column x/2 (x even), or tap 0 of column (x+1)/2 and tap 2 of column (x-1)/2 (x odd);
+  // the slots no pixel maps to (tap 0 of column 0, taps beyond the right border) keep the zeros the buffer was allocated with
+  uint32_t h0, l0, h1, l1;
+  {
+    const __nv_bfloat16 a0 = __float2bfloat16_rn(f.v[0]), a1 = __float2bfloat16_rn(f.v[1]), a2 = __float2bfloat16_rn(f.v[2]), a3 = __float2bfloat16_rn(f.v[3]);
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(f.v[0] - __bfloat162float(a0)), b1 = __float2bfloat16_rn(f.v[1] - __bfloat162float(a1));
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(f.v[2] - __bfloat162float(a2)), b3 = __float2bfloat16_rn(f.v[3] - __bfloat162float(a3));
+    h0 = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
+    h1 = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(a3) << 16);
+    l0 = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+    l1 = (uint32_t)__bfloat16_as_ushort(b2) | ((uint32_t)__bfloat16_as_ushort(b3) << 16);
+  }
+  auto put = [&](int chunk, int xo, int half) {
+    if (xo < 0 || xo >= a.out.W) return;
+    const long e = cv_elem(a.out, n, chunk, y, xo) + half * 4;
+    *reinterpret_cast<uint2*>(a.out.hi + e) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(a.out.lo + e) = make_uint2(l0, l1);
+  };
+  if ((x & 1) == 0) put(0, x >> 1, 1);
+  else { put(0, (x + 1) >> 1, 0); put(1, (x - 1) >> 1, 0); }
 }
 
 // ---- depthwise 3x3 -----------------------------------------------------------------------------------------------
@@ -397,8 +422,9 @@ __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ poole
 
 int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float* boxes_xywh, int N, int S, const CView& out, int* crops,
                       cudaStream_t st) {
-  PV_CHECK(out.H == S && out.W == S && N <= out.N, PREMVOS_ERR_INVALID_ARG, "refine_make_input: shape mismatch");
-  PreArgs a{frame_rgb, H, W, boxes_xywh, N, S, dev(out), crops};
+  const int rows3 = (out.C == 16 && out.W == (S - 1) / 2 + 1) ? 1 : 0;
+  PV_CHECK(out.H == S && (rows3 || out.W == S) && N <= out.N, PREMVOS_ERR_INVALID_ARG, "refine_make_input: shape mismatch");
+  PreArgs a{frame_rgb, H, W, boxes_xywh, N, S, dev(out), rows3, crops};
   const long total = (long)N * S * S;
   if (total == 0) return 0;
   prof_before(st);

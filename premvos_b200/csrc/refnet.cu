@@ -35,6 +35,7 @@ typedef std::function<int(cudaStream_t, int)> Step;
 
 struct premvos_refnet {
   int NB = 0, S = 0, middle_units = 16, n_classes = 2;
+  int stem_rows = 1;   // conv1_1 as a 3x1 convolution over the row im2col of the network input (see build_network)
   bool finalized = false;
   std::map<std::string, std::vector<float>> params;
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -209,18 +210,42 @@ int add_depthwise_f8(premvos_refnet* n, const std::string& scope, float eps, con
 
 int build_network(premvos_refnet* n) {
   const int S = n->S;
-  PV_TRY(alloc_cview(n, &n->input, 8, S, S));
   const std::string x = "xception_65/";
   const int map4[4] = {0, 1, 2, 3};
   // root: conv2d_same 3x3 s2 (explicit pad 1,1 + VALID) and 3x3 s1 SAME (xception.py:430-433)
   const int S1 = (S + 2 - 3) / 2 + 1;
+  // With 4 input channels a per-tap K step would be 3/4 zeros; the input kernel therefore writes the ROW IM2COL of the network
+  // input ([S][S1] pixels of 3 horizontal taps x 4 channels, horizontal stride and padding applied) and conv1_1 runs as a 3x1
+  // convolution over it (vertical stride 2, horizontal stride 1): 3 operand boxes per tile instead of 9, K = 16 with 12 used.
+  n->stem_rows = !(getenv("PREMVOS_STEM_ROWS") && atoi(getenv("PREMVOS_STEM_ROWS")) == 0);
+  if (n->stem_rows) PV_TRY(alloc_cview(n, &n->input, 16, S, S1));
+  else PV_TRY(alloc_cview(n, &n->input, 8, S, S));
   CView c11, c12;
   PV_TRY(alloc_cview(n, &c11, 32, S1, S1));
   PV_TRY(alloc_cview(n, &c12, 64, S1, S1));
   {
     ConvGeom g; g.stride = 2; g.pad_t = g.pad_l = g.pad_b = g.pad_r = 1; g.slope = 0.f;
     ConvOut o; o.cp = c11;
-    PV_TRY(add_conv(n, x + "entry_flow/conv1_1", true, XC_EPS, n->input, o, g, map4, 8));
+    if (n->stem_rows) {
+      const std::string scope = x + "entry_flow/conv1_1";
+      const std::vector<float>& W = n->params[scope + "/weights"];   // HWIO [3][3][4][32]
+      std::vector<float> w((size_t)32 * 12 * 3), scale(32, 1.f), shift(32, 0.f);
+      bn_fold(n, scope, XC_EPS, &scale, &shift);
+      for (int oc = 0; oc < 32; oc++)
+        for (int r = 0; r < 3; r++)
+          for (int sx = 0; sx < 3; sx++)
+            for (int c = 0; c < 4; c++) w[((size_t)oc * 12 + sx * 4 + c) * 3 + r] = W[(((size_t)r * 3 + sx) * 4 + c) * 32 + oc] * scale[oc];   // [Cout][12][3][1]
+      g.stride_x = 1; g.pad_l = g.pad_r = 0;
+      n->conv_weights.emplace_back(new ConvWeightsUmma());
+      n->conv_plans.emplace_back(new ConvPlanUmma());
+      ConvWeightsUmma* cw = n->conv_weights.back().get();
+      ConvPlanUmma* pl = n->conv_plans.back().get();
+      PV_TRY(pack_conv_weights_umma(cw, w.data(), shift.data(), 32, 12, 3, 1, nullptr, 0, 0, (long)n->NB * S1 * S1, false));
+      PV_TRY(plan_conv_umma(pl, n->input, o, *cw, g, &n->conv_ws));
+      n->steps.push_back([pl](cudaStream_t st, int na) { return launch_conv_umma(*pl, st, na); });
+    } else {
+      PV_TRY(add_conv(n, x + "entry_flow/conv1_1", true, XC_EPS, n->input, o, g, map4, 8));
+    }
     ConvOut o2; o2.cp = c12;
     PV_TRY(add_conv(n, x + "entry_flow/conv1_2", true, XC_EPS, c11, o2, ConvGeom::same3x3(1, 0.f)));
   }
@@ -540,6 +565,34 @@ extern "C" int premvos_refnet_get_tensor(premvos_refnet_t* n, const char* name, 
     return 0;
   }
   CView cv;
+  if (k == "net_input" && n->stem_rows) {   // undo the row im2col: even x = tap 1 of column x/2, odd x = tap 0 of column (x+1)/2
+    const CView& im = n->input;
+    const int S = n->S, Wo = im.W;
+    *numel = (int64_t)n->NB * 8 * S * S;
+    if (!host_out) return 0;
+    const size_t cols = (size_t)im.N * 16 * S * Wo;
+    float* dtmp = nullptr;
+    PV_CUDA(cudaMalloc((void**)&dtmp, cols * sizeof(float)));
+    std::vector<float> t(cols);
+    int r = cp8_to_nchw(im, 0, dtmp, nullptr);
+    if (r == 0 && cudaMemcpy(t.data(), dtmp, cols * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+      r = fail(PREMVOS_ERR_INVALID_ARG, "premvos_refnet_get_tensor: copy failed");
+    cudaFree(dtmp);
+    if (r != 0) return r;
+    for (int b = 0; b < n->NB; b++)
+      for (int c = 0; c < 8; c++)
+        for (int y = 0; y < S; y++)
+          for (int xx = 0; xx < S; xx++) {
+            float v = 0.f;
+            if (c < 4) {
+              if (!(xx & 1)) v = t[(((size_t)b * 16 + 4 + c) * S + y) * Wo + xx / 2];
+              else if ((xx + 1) / 2 < Wo) v = t[(((size_t)b * 16 + c) * S + y) * Wo + (xx + 1) / 2];
+              else v = t[(((size_t)b * 16 + 8 + c) * S + y) * Wo + (xx - 1) / 2];   // last column of an even-sized input: tap 2
+            }
+            host_out[(((size_t)b * 8 + c) * S + y) * S + xx] = v;
+          }
+    return 0;
+  }
   if (k == "net_input") cv = n->input;
   else if (n->named.count(k)) cv = n->named[k];
   else return fail(PREMVOS_ERR_INVALID_ARG, "premvos_refnet_get_tensor: unknown tensor '%s'", name);
