@@ -505,8 +505,19 @@ def main():
         pipe.run_frames_device(*dev_sets[0], concurrent=False)
         prof = _lib.profile_end()
         total_ms = sum(v["ms"] for v in prof.values()) or 1.0
-        kernels = {k: {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / total_ms}
-                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        # every kernel of the step with its share and its fraction of the roofline that bounds it: algorithmic bytes (or FLOPs, x3
+        # issued bf16 FLOPs for the split-bf16 convolutions) of its launches / their summed device time / the measured peak
+        kernels = {}
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            e = {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / total_ms}
+            sec = max(v["ms"], 1e-9) * 1e-3
+            if k in ("conv_umma_kernel", "conv_pair_kernel"):
+                e.update({"bound": "tensor", "algorithmic_tflops": v["flops"] / sec / 1e12,
+                          "frac_of_bf16_peak": v["flops"] / sec / 1e12 / peaks["tensor_sustained"],
+                          "tensor_pipe_frac": 3 * v["flops"] / sec / 1e12 / peaks["tensor_sustained"]})
+            elif v["bytes"] > 0:
+                e.update({"bound": "hbm", "algorithmic_gbs": v["bytes"] / sec / 1e9, "frac_of_hbm_peak": v["bytes"] / sec / 1e9 / peaks["hbm"]})
+            kernels[k] = e
         # The tensor-core convolution (launch_conv_umma in csrc/conv_umma.cu -- the launch set round 1 reported as "conv_umma_kernel")
         # runs as two kernels since round 2: conv_umma_kernel<4|8> (one CTA per tile) and conv_pair_kernel (cta_group::2 CTA pairs,
         # stream-K, for the wide 1x1 layers).  The roofline entry covers ALL of its launches; each kernel alone is listed beside it.

@@ -314,6 +314,10 @@ struct UmmaConvArgs {
   // stacked halo tiles (3x3 stride-1 layers on maps at most 8 wide): the halo box of a k-block is {W*8, hf_pitch rows, fold images,
   // KC chunks}; image g of the group occupies tile rows [g * hf_pitch, g * hf_pitch + Ho) and brings its own zero padding rows
   int hf_pitch;
+  // work order: 0 = output-channel tile outermost (weights of a tile stay hot, A streamed once per tile: right while A fits the L2),
+  // 1 = output-channel tile innermost (the ntiles CTAs that share an A tile run side by side, A comes from DRAM once: layers whose
+  // input is larger than the L2, e.g. the RoI head's entry on 400 x 14 x 14 x 1024)
+  int n_fastest;
   int a_lbo;                 // bytes between the two 8-channel chunks of a K step in the A stage (0: box_h * box_w * 16)
 };
 
@@ -356,11 +360,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       tz = u - w.tail_slot * a.tail_split;
       t = a.main_work + w.tail_slot;
     }
-    const int tile = t % tiles_per_img;
-    int r = t / tiles_per_img;
-    w.n_img = (r % a.n_images) * (a.fold > 0 ? a.fold : 1); r /= a.n_images;
-    w.ntile = r % a.ntiles;
-    w.z = r / a.ntiles;
+    int tile, r;
+    if (a.n_fastest) {
+      w.ntile = t % a.ntiles; r = t / a.ntiles;
+      tile = r % tiles_per_img; r /= tiles_per_img;
+      w.n_img = (r % a.n_images) * (a.fold > 0 ? a.fold : 1);
+      w.z = r / a.n_images;
+    } else {
+      tile = t % tiles_per_img;
+      r = t / tiles_per_img;
+      w.n_img = (r % a.n_images) * (a.fold > 0 ? a.fold : 1); r /= a.n_images;
+      w.ntile = r % a.ntiles;
+      w.z = r / a.ntiles;
+    }
     w.ty0 = (tile / a.tiles_x) * (a.mt_horizontal ? 16 : 16 * a.MT);
     w.tx0 = (tile % a.tiles_x) * (a.mt_horizontal ? 8 * a.MT : 8);
     w.kb_begin = a.ksplit > 1 ? w.z * a.kb_per : 0;
@@ -872,10 +884,17 @@ __global__ void __launch_bounds__(256) conv_finish_tail_kernel(const UmmaConvArg
   // decode the item exactly as the convolution kernel does
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int t = a.main_work + slot;
-  const int tile = t % tiles_per_img;
-  int r = t / tiles_per_img;
-  const int n_img = r % a.n_images; r /= a.n_images;
-  const int ntile = r % a.ntiles;
+  int tile, r, n_img, ntile;
+  if (a.n_fastest) {
+    ntile = t % a.ntiles; r = t / a.ntiles;
+    tile = r % tiles_per_img; r /= tiles_per_img;
+    n_img = r % a.n_images;
+  } else {
+    tile = t % tiles_per_img;
+    r = t / tiles_per_img;
+    n_img = r % a.n_images; r /= a.n_images;
+    ntile = r % a.ntiles;
+  }
   const int ty0 = (tile / a.tiles_x) * (a.mt_horizontal ? 16 : 16 * a.MT), tx0 = (tile % a.tiles_x) * (a.mt_horizontal ? 8 * a.MT : 8);
   const int mt = row >> 7, m = row & 127;
   const int oy = ty0 + (a.mt_horizontal ? 0 : mt * 16) + (m >> 3), ox = tx0 + (a.mt_horizontal ? mt * 8 : 0) + (m & 7);
@@ -1697,6 +1716,11 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
   plan->grid_z = a.ksplit;
   a.ntiles = w.ntiles; a.n_images = n_groups;
   a.total_work = plan->grid_x * plan->grid_y * a.ksplit;
+  {
+    const double a_bytes = 4.0 * (double)in.N * in.H * in.W * w.CinPhys;
+    const int dflt = (w.ntiles > 1 && a_bytes > 96e6) ? 1 : 0;
+    a.n_fastest = env_int("PREMVOS_NFAST", dflt) != 0 ? 1 : 0;
+  }
   // two CTAs per SM when shared memory and TMEM allow it; a second accumulator buffer when TMEM allows that too
   const int cps = (!wide && plan->smem_bytes <= 112 * 1024 && a.NACC * a.MT * w.BN <= 256) ? 2 : 1;
   a.nbuf = (2 * a.NACC * a.MT * w.BN <= (cps == 2 ? 256 : 512)) ? 2 : 1;

@@ -118,16 +118,18 @@ def warp_proposals(proposals, optflow_fn):
 
 
 class LivePropagator:
-    """The resident form of merge.py:95-100 for one video: masks of frame t + the pair (t, t+1) -> flow -> frame-resolution
-    flow -> warped masks + their boxes -> refinement on frame t+1.  Everything stays on the device and on one stream.
+    """The resident form of merge.py:95-101 for one video: masks of frame t + the pair (t, t+1) -> flow -> frame-resolution
+    flow -> warped masks + their boxes -> refinement on frame t+1 (+ the ReID embeddings of the same boxes, merge.py:101, when a
+    ReID network is given).  Everything stays on the device and on one stream.
 
-    flow_net: premvos_b200.pwc.PWCDCNet (cuda, eval), refine_net: premvos_b200.refnet.RefinementNet (params loaded)."""
+    flow_net: premvos_b200.pwc.PWCDCNet (cuda, eval), refine_net: premvos_b200.refnet.RefinementNet (params loaded),
+    reid_net: premvos_b200.reid.ReIDNet (params loaded) or None."""
 
-    def __init__(self, flow_net, refine_net, frame_hw, max_objects=None):
+    def __init__(self, flow_net, refine_net, frame_hw, max_objects=None, reid_net=None):
         from .pipeline import flow_input_shape
         from . import ops
         self._ops = ops
-        self.flow_net, self.refine_net = flow_net, refine_net
+        self.flow_net, self.refine_net, self.reid_net = flow_net, refine_net, reid_net
         self.H, self.W = int(frame_hw[0]), int(frame_hw[1])
         self.Hn, self.Wn = flow_input_shape(self.H, self.W)
         self.max_objects = int(max_objects or refine_net.max_batch)
@@ -148,12 +150,16 @@ class LivePropagator:
 
     def step(self, masks_t, frame_t, frame_t1):
         """masks_t CUDA uint8 [n,H,W] (0/1, the selected proposals of frame t) -> dict of CUDA tensors:
-        warped [n,H,W], bbox [n,4] (xywh of the warped masks), masks [n,H,W] (refined on frame t+1), conf [n], flow [H,W,2].
-        An object whose warped mask is empty has bbox 0,0,0,0 (the reference refines that box too)."""
+        warped [n,H,W], bbox [n,4] (xywh of the warped masks), masks [n,H,W] (refined on frame t+1), conf [n], flow [H,W,2],
+        and with a ReID network 'reid' [n,128] (add_ReID embeds prop['bbox'], which do_refinement leaves untouched).
+        An object whose warped mask is empty has bbox 0,0,0,0 (the reference refines / embeds that box too)."""
         flow = self.flow(frame_t, frame_t1)
         warped, bbox = warp_masks_device(masks_t, flow)
         masks, conf = self.refine_net.refine_device(frame_t1, bbox)
-        return {"flow": flow, "warped": warped, "bbox": bbox, "masks": masks, "conf": conf}
+        out = {"flow": flow, "warped": warped, "bbox": bbox, "masks": masks, "conf": conf}
+        if self.reid_net is not None:
+            out["reid"] = self.reid_net.embed_device(frame_t1, bbox)
+        return out
 
 
 # ---- on-disk formats of stage 7 (host side; SURVEY.md 8(f) N3) -------------------------------------------------------------

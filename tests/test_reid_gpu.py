@@ -76,3 +76,24 @@ def test_device_entry_point_and_surface(setup):
         assert isinstance(p["ReID"], list) and len(p["ReID"]) == 128 and isinstance(p["ReID"][0], float)
         assert rel_err(p["ReID"], r["ReID"]) < 1e-3
     assert net.launches_per_forward() > 50
+
+
+def test_live_propagator_attaches_embeddings(setup):
+    """merge.py:95-101 resident: flow -> warp -> boxes -> refinement AND the ReID embeddings of the same boxes on frame t+1."""
+    from premvos_b200 import mergetrack, pwc, refnet
+    P, net, _ = setup
+    h, w = 100, 140
+    f1, f2 = synth.synthetic_frame_pair(h, w, seed=5)
+    flow_net = pwc.pwc_dc_net(None)
+    flow_net.load_state_dict(synth.pwc_synthetic_state_dict(3))
+    flow_net.cuda().eval()
+    rn = refnet.RefinementNet(max_batch=3, input_size=129, middle_units=0).load_params(synth.refnet_synthetic_params(0, 0))
+    live = mergetrack.LivePropagator(flow_net, rn, (h, w), reid_net=net)
+    masks = synth.synthetic_masks(3, h, w, seed=6)
+    res = live.step(torch.from_numpy(masks).cuda(), torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda())
+    torch.cuda.synchronize()
+    bbox = res["bbox"].cpu().numpy()
+    assert res["reid"].shape == (3, 128)
+    want = RO.reid_forward(P, RO.make_crops(f2, bbox)).numpy()
+    assert rel_err(res["reid"].cpu().numpy(), want) < 1e-3
+    assert np.array_equal(res["reid"].cpu().numpy(), net.embed(f2, bbox))
