@@ -422,14 +422,14 @@ int build_network(premvos_propnet* n) {
 // branch of image b: the launching stream for image 0, a side stream that waits for everything enqueued so far otherwise
 static int fork_branch(premvos_propnet* n, cudaStream_t st, int b, cudaStream_t* out) {
   *out = st;
-  if (n->side.empty()) return 0;
+  if (n->side.empty() || profiling_enabled()) return 0;   // the per-launch profile is serial by definition: one stream, clean brackets
   if (b == 0) { PV_CUDA(cudaEventRecord(n->ev_fork, st)); return 0; }   // the fork point: before image 0's own kernels
   PV_CUDA(cudaStreamWaitEvent(n->side[b - 1], n->ev_fork, 0));
   *out = n->side[b - 1];
   return 0;
 }
 static int join_branches(premvos_propnet* n, cudaStream_t st) {
-  if (n->side.empty()) return 0;
+  if (n->side.empty() || profiling_enabled()) return 0;
   for (int b = 1; b < n->batch; b++) {
     PV_CUDA(cudaEventRecord(n->ev_join[b - 1], n->side[b - 1]));
     PV_CUDA(cudaStreamWaitEvent(st, n->ev_join[b - 1], 0));

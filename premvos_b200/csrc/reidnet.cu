@@ -502,7 +502,10 @@ extern "C" int premvos_reidnet_forward_host(premvos_reidnet_t* n, const unsigned
   }
   float *bdev = nullptr, *edev = nullptr;
   PV_CUDA(cudaMalloc((void**)&bdev, (size_t)num_boxes * 4 * sizeof(float)));
-  PV_CUDA(cudaMalloc((void**)&edev, (size_t)num_boxes * 128 * sizeof(float)));
+  if (cudaMalloc((void**)&edev, (size_t)num_boxes * 128 * sizeof(float)) != cudaSuccess) {
+    cudaFree(bdev);
+    return fail(PREMVOS_ERR_INVALID_ARG, "premvos_reidnet_forward_host: out of device memory for %d embeddings", num_boxes);
+  }
   int r = 0;
   cudaError_t e = cudaMemcpyAsync(n->frame_dev, frame_rgb, hw * 3, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(bdev, boxes_xywh, (size_t)num_boxes * 4 * sizeof(float), cudaMemcpyHostToDevice, st);
