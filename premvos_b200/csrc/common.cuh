@@ -185,6 +185,8 @@ struct FView {
   int vchunks() const { return (C + 7) / 8; }
 };
 // TMA descriptor over fp32 data (rank <= 5, no swizzle, zero fill outside): map128 = 128 bytes, 64-byte aligned
+// corr_tma.cu: 81-displacement correlation, NCHW fp32, TMA-staged; returns 1 when not applicable (W % 4 != 0 or unaligned pointers)
+int corr81_nchw_tma(const float* f1, const float* f2, float* out, int B, int C, int H, int W, cudaStream_t st);
 int encode_tensor_map_f32(void* map128, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 // ---- convolution on tcgen05 tensor cores (split-bf16 x3, fp32 accumulate), conv_umma.cu ----------

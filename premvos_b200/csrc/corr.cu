@@ -14,6 +14,8 @@
 //                               into the decoder slab with LeakyReLU fused, optional c1 copy)
 //   corr81_kernel<NHWC=false> : NCHW in / out (the C ABI drop-in for corr_cuda_forward)
 //   corr_generic_kernel       : any pad/kernel_size/stride1/stride2/max_displacement (NCHW), slow path
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace premvos {
@@ -258,6 +260,12 @@ extern "C" int premvos_corr_forward(const float* input1, const float* input2, fl
   PV_TRY(premvos_corr_output_shape(height, width, pad_size, kernel_size, max_displacement, stride1, stride2, &oc, &oh, &ow));
   cudaStream_t st = (cudaStream_t)stream;
   if (pad_size == MDISP && max_displacement == MDISP && kernel_size == 1 && stride1 == 1 && stride2 == 1) {
+    // PWC-Net's configuration: TMA-staged kernel (corr_tma.cu) when the rows are 16-byte multiples, else the per-pixel kernel
+    static const bool use_tma = !(getenv("PREMVOS_CORR_TMA") && atoi(getenv("PREMVOS_CORR_TMA")) == 0);
+    if (use_tma) {
+      const int r = corr81_nchw_tma(input1, input2, output, batch, channels, height, width, st);
+      if (r != 1) return r;
+    }
     static bool attr_set = false;
     if (!attr_set) {
       PV_CUDA(cudaFuncSetAttribute(corr81_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));
