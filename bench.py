@@ -577,6 +577,16 @@ def main():
                              "algorithmic_tflop_per_s": GFLOP_CROP * K / t_ref},
                   "sum_serial_ms_per_pair": t_flow / B + 2 * t_prop + t_ref,
                   "note": "each network alone on one stream, CUDA events; a unit = flow + 2 proposal passes + refine"}
+        # BASELINE configs[2] / [3] at their own sizes (context): one 854x480 DAVIS-shaped frame -> 749x1333 after CustomResize, one
+        # frame per forward; 100 crops through the refinement network (launch groups of K)
+        from premvos_b200 import ops as _ops, propnet as _propnet
+        Hd, Wd = _propnet.custom_resize_shape(480, 854)
+        davis = _ops.resize_linear_u8(torch.from_numpy(synth.synthetic_bgr_frame(480, 854, seed=21)).cuda(), Hd, Wd)
+        t_c3 = time_stage(lambda: pipe.general.forward_device(davis), 10)
+        bx100 = torch.from_numpy(synth.synthetic_boxes(100, H_IN, W_IN, seed=22)).cuda()
+        t_c4 = time_stage(lambda: pipe.refine.refine_device(fr[0], bx100), 3)
+        stages["c3_proposal_854x480"] = {"ms_per_frame": t_c3, "input": [Hd, Wd], "batch": 1}
+        stages["c4_refine_100_crops"] = {"ms": t_c4, "crops_per_s": 1e5 / t_c4, "launch_groups_of": K}
         if not args.no_reid:
             # SURVEY 8(f) N2, not part of the headline unit: the ReID embeddings MergeTrack adds to the proposals of a frame
             from premvos_b200 import reid

@@ -21,6 +21,8 @@
  *                             Model (train.py:107-309, 653-657), called by eval.py:61-110 / train.py:508
  *   premvos_refnet_*       <- refinement_net Engine: `engine.trainer.validation_step(feed_dict, extraction_keys)` per
  *                             proposal (core/Trainer.py:128-133), as driven by MergeTrack/refinement_net_functions.py:38-65
+ *   premvos_reidnet_*      <- MergeTrack/ReID_net_functions.py:26-45 `add_ReID`: ReID_net.session.run([outputs, crop_list],
+ *                             feed_dict={image, boxes}) on the graph of ReID_net/configs/live
  *   premvos_conv2d_forward <- one nn.Conv2d / tensorpack Conv2D layer (bring-up hook)
  */
 #ifndef PREMVOS_B200_H
@@ -70,6 +72,8 @@ int premvos_profile_end(char* buf, int buflen);
  * corr_type_multiply must be 1 (PWCNet.py:69); 0 (the L1 "subtract" variant) returns
  * PREMVOS_ERR_UNSUPPORTED.  stream is a cudaStream_t (NULL = default stream).
  * The reference returns 1 always and exit(-1)s on a launch error; this returns an error code.
+ * PWC-Net's configuration (pad 4, kernel 1, displacement 4, strides 1) runs the TMA-staged kernel (csrc/corr_tma.cu) when
+ * width % 4 == 0 and the pointers are 16-byte aligned, the per-pixel tile kernel otherwise; any other configuration the generic one.
  * --------------------------------------------------------------------------------------------- */
 int premvos_corr_output_shape(int height, int width, int pad_size, int kernel_size,
                               int max_displacement, int stride1, int stride2, int* out_channels,
