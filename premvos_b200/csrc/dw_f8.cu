@@ -239,6 +239,7 @@ int plan_depthwise3x3_f8(DwF8Plan* plan, const FView& in, const CView& out, cons
            "depthwise3x3_f8: tile too large (stride %d rate %d)", stride, rate);
   a.stage_bytes = round_up(a.RH * a.RW * 32, 128);
   a.stages = std::max(2, std::min(DW_STAGES_MAX, (72 * 1024) / a.stage_bytes));
+  if (getenv("PREMVOS_DWF8_STAGES")) a.stages = std::max(2, std::min(DW_STAGES_MAX, atoi(getenv("PREMVOS_DWF8_STAGES"))));
   plan->smem_bytes = a.stages * a.stage_bytes + 64;
   PV_CHECK(plan->smem_bytes <= 200 * 1024, PREMVOS_ERR_UNSUPPORTED, "depthwise3x3_f8: tile does not fit shared memory");
   plan->fast = fast ? 1 : 0; plan->N = in.N; plan->tiles = a.ntx * a.nty; plan->nch = a.nch;
@@ -273,10 +274,14 @@ int launch_depthwise3x3_f8(const DwF8Plan& plan, int n_active, cudaStream_t st) 
     attr_set = true;
   }
   Kern kern = kerns[(plan.fast ? 2 : 0) + (a.pre_relu ? 1 : 0)];
-  const int per_sm = std::max(1, std::min(3, (220 * 1024) / plan.smem_bytes));
+  // resident CTAs per SM: shared memory and the register budget of the launch bounds (256 threads: 2 for the strip kernels, 3 for
+  // the generic ones); one CTA per resident slot -- more would run as a second, half-empty wave
+  static const int threads = getenv("PREMVOS_DWF8_THREADS") ? atoi(getenv("PREMVOS_DWF8_THREADS")) : 256;
+  int per_sm = std::max(1, std::min((plan.fast ? 2 : 3) * (256 / threads), (220 * 1024) / plan.smem_bytes));
+  if (getenv("PREMVOS_DWF8_PER_SM")) per_sm = atoi(getenv("PREMVOS_DWF8_PER_SM"));
   const int grid = (int)std::min<long>(a.items, (long)num_sms * per_sm);
   prof_before(st);
-  kern<<<grid, 256, plan.smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(plan.map_in), a);
+  kern<<<grid, threads, plan.smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(plan.map_in), a);
   const char* label = "depthwise3x3_kernel";
   static const int per_layer = getenv("PREMVOS_PROFILE_LAYERS") ? atoi(getenv("PREMVOS_PROFILE_LAYERS")) : 0;
   if (per_layer && profiling_enabled()) {
