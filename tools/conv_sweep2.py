@@ -27,6 +27,9 @@ SHAPES = {
     "xc40_dec": (40, 304, 97, 97, 256, 1, 1, 1),
     "xc40_e3": (40, 728, 49, 49, 728, 1, 1, 1),
     # proposal network, batch 4 (568 x 1333 -> C4 35 x 83)
+    "p4_c2": (4, 256, 35, 83, 256, 3, 1, 1),
+    "p4_rpn": (4, 1024, 35, 83, 1024, 3, 1, 1),
+    "p4_g1c2": (4, 128, 71, 166, 128, 3, 1, 1),
     "p4_c3": (4, 256, 35, 83, 1024, 1, 1, 1),
     "p4_c1": (4, 1024, 35, 83, 256, 1, 1, 1),
     "p4_g1c3": (4, 128, 71, 166, 512, 1, 1, 1),
