@@ -185,6 +185,11 @@ struct FView {
   int vchunks() const { return (C + 7) / 8; }
 };
 // TMA descriptor over fp32 data (rank <= 5, no swizzle, zero fill outside): map128 = 128 bytes, 64-byte aligned
+// TMA descriptor over bf16 data (one plane of a CP8 buffer), same conventions as encode_tensor_map_f32
+int encode_tensor_map_bf16(void* map128, const __nv_bfloat16* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+// corr_tma.cu: the same correlation on CP8 features inside PWC-Net (output = 11 chunk planes of the decoder slab, LeakyReLU fused,
+// optional copy of f1 next to it), TMA-staged
+int corr81_cp8_tma(const CView& f1, const CView& f2, const CView& out, const CView& c1_copy, float slope, cudaStream_t st);
 // corr_tma.cu: 81-displacement correlation, NCHW fp32, TMA-staged; returns 1 when not applicable (W % 4 != 0 or unaligned pointers)
 int corr81_nchw_tma(const float* f1, const float* f2, float* out, int B, int C, int H, int W, cudaStream_t st);
 int encode_tensor_map_f32(void* map128, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);

@@ -1311,6 +1311,14 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
 
 }  // namespace
 
+int encode_tensor_map_bf16(void* map128, const __nv_bfloat16* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t d[5] = {1, 1, 1, 1, 1}, s[4] = {0, 0, 0, 0};
+  cuuint32_t b[5] = {1, 1, 1, 1, 1}, e[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
+  return encode_map((CUtensorMap*)map128, (void*)base, rank, d, s, b, e);
+}
+
 int encode_tensor_map_f32(void* map128, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = nullptr;
   PV_TRY(get_encode_fn(&fn));

@@ -13,7 +13,9 @@
 // 119-121) and stored as float4 (4 consecutive x of one displacement plane).
 #include <cuda.h>
 
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "cp8.cuh"
 
 namespace premvos {
 
@@ -137,6 +139,153 @@ __global__ void __launch_bounds__(THREADS, 2) corr81_tma_kernel(const __grid_con
   }
 }
 
+// ---- the same on CP8 features (inside PWC-Net) -------------------------------------------------------------------------------
+// Operands are split-bf16 chunk planes [N][C/8][H][W][8]: per 8-channel chunk the hi and lo planes of the f2 halo tile and of the
+// f1 tile arrive by TMA (5-D boxes {8, 40, 16} / {8, 32, 8}; zero fill = padding) through a 2-stage ring; all threads then turn
+// the chunk into fp32 channel planes [c][y][x] in a third buffer (hi + lo, 8 conflict-free STS per pixel: 5 % of the chunk's
+// instructions) and the inner loop is the one of corr81_tma_kernel.  The 81 results per pixel go through shared memory once more
+// to leave as 11 chunk planes of the decoder slab (LeakyReLU fused, split to hi / lo); f1's planes are copied next to them.
+constexpr int CP_STAGES = 2;
+constexpr int CP_F2_PLANE = HH * HW * 8 * 2, CP_F1_PLANE = TH * TW * 8 * 2;          // bytes of one bf16 plane tile
+constexpr int CP_STAGE_BYTES = 2 * CP_F2_PLANE + 2 * CP_F1_PLANE;                      // 28 672
+constexpr int CP_CONV_BYTES = (8 * HH * HW + 8 * TH * TW) * 4;                         // 28 672
+constexpr int OUT_PITCH = 84;                                                          // floats per pixel in the output staging
+constexpr size_t CP_SMEM = (size_t)CP_STAGES * CP_STAGE_BYTES + CP_CONV_BYTES + 64;
+static_assert((size_t)TH * TW * OUT_PITCH * 4 <= (size_t)CP_STAGES * CP_STAGE_BYTES + CP_CONV_BYTES, "output staging must fit the operand buffers");
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+struct CorrCp8TmaArgs {
+  cp8::CV f1, f2, out, c1;
+  int has_c1, tiles_x, tiles_y;
+  float slope;
+};
+
+__global__ void __launch_bounds__(THREADS, 2)
+corr81_cp8_tma_kernel(const __grid_constant__ CUtensorMap tm1h, const __grid_constant__ CUtensorMap tm1l, const __grid_constant__ CUtensorMap tm2h,
+                      const __grid_constant__ CUtensorMap tm2l, const CorrCp8TmaArgs a) {
+  using namespace cp8;
+  extern __shared__ __align__(128) unsigned char cp_sm[];
+  unsigned char* conv_b = cp_sm + (size_t)CP_STAGES * CP_STAGE_BYTES;
+  float* c2 = reinterpret_cast<float*>(conv_b);                      // [8][HH][HW]
+  float* c1 = c2 + 8 * HH * HW;                                      // [8][TH][TW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(conv_b + CP_CONV_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int t = blockIdx.x;
+  const int tx = t % a.tiles_x; t /= a.tiles_x;
+  const int ty = t % a.tiles_y;
+  const int n = t / a.tiles_y;
+  const int x0 = tx * TW, y0 = ty * TH;
+  const int H = a.f1.H, W = a.f1.W, C = a.f1.C;
+  const int nchunks = (C + 7) / 8;
+  if (tid == 0) {
+    for (int s = 0; s < CP_STAGES; s++) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int chunk, int s) {   // one thread
+    unsigned char* dst = cp_sm + (size_t)s * CP_STAGE_BYTES;
+    mbar_arrive_expect_tx(&full[s], CP_STAGE_BYTES);
+    tma_load_5d(&tm2h, &full[s], dst, 0, x0 - MD, y0 - MD, a.f2.c0 + chunk, n);
+    tma_load_5d(&tm2l, &full[s], dst + CP_F2_PLANE, 0, x0 - MD, y0 - MD, a.f2.c0 + chunk, n);
+    tma_load_5d(&tm1h, &full[s], dst + 2 * CP_F2_PLANE, 0, x0, y0, a.f1.c0 + chunk, n);
+    tma_load_5d(&tm1l, &full[s], dst + 2 * CP_F2_PLANE + CP_F1_PLANE, 0, x0, y0, a.f1.c0 + chunk, n);
+  };
+  if (tid == 0)
+    for (int s = 0; s < CP_STAGES && s < nchunks; s++) issue(s, s);
+
+  const int grp = warp >> 1;
+  const int py = (warp & 1) * 4 + (lane >> 3), gx = lane & 7;
+  float acc[3][9][4];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int d = 0; d < 9; d++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[r][d][j] = 0.f;
+
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    const int s = chunk % CP_STAGES;
+    mbar_wait(&full[s], (uint32_t)(chunk / CP_STAGES) & 1u);
+    const unsigned char* st = cp_sm + (size_t)s * CP_STAGE_BYTES;
+    // ---- hi + lo -> fp32 channel planes ----
+    for (int u = tid; u < HH * HW + TH * TW; u += THREADS) {
+      const bool is2 = u < HH * HW;
+      const int p = is2 ? u : u - HH * HW;
+      const uint4 h = *reinterpret_cast<const uint4*>(st + (is2 ? 0 : 2 * CP_F2_PLANE) + (size_t)p * 16);
+      const uint4 l = *reinterpret_cast<const uint4*>(st + (is2 ? CP_F2_PLANE : 2 * CP_F2_PLANE + CP_F1_PLANE) + (size_t)p * 16);
+      const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+      float* dst = is2 ? c2 + p : c1 + p;
+      const int plane = is2 ? HH * HW : TH * TW;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        dst[(2 * j) * plane] = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+        dst[(2 * j + 1) * plane] = __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+      }
+      if (!is2 && a.has_c1) {   // fused copy of f1 (raw hi / lo bits) into the decoder slab
+        const int gy = y0 + p / TW, gxx = x0 + p % TW;
+        if (gy < H && gxx < W) {
+          const long o = cv_elem(a.c1, n, chunk, gy, gxx);
+          *reinterpret_cast<uint4*>(a.c1.hi + o) = h;
+          *reinterpret_cast<uint4*>(a.c1.lo + o) = l;
+        }
+      }
+    }
+    __syncthreads();   // planes complete; stage s may be refilled
+    if (tid == 0 && chunk + CP_STAGES < nchunks) issue(chunk + CP_STAGES, s);
+    const float* s2 = c2 + ((py + 3 * grp) * HW + gx * 4);
+    const float* s1 = c1 + (py * TW + gx * 4);
+#pragma unroll 2
+    for (int c = 0; c < 8; c++) {
+      const float4 f1 = *reinterpret_cast<const float4*>(s1 + c * TH * TW);
+      const float f1v[4] = {f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const float4* row = reinterpret_cast<const float4*>(s2 + c * HH * HW + r * HW);
+        const float4 q0 = row[0], q1 = row[1], q2 = row[2];
+        const float f2v[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+        for (int d = 0; d < 9; d++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[r][d][j] = fmaf(f1v[j], f2v[j + d], acc[r][d][j]);
+      }
+    }
+    __syncthreads();   // the planes may be overwritten by the next chunk
+  }
+
+  // ---- 81 results per pixel -> shared memory [pixel][84] -> 11 chunk planes ----
+  float* so = reinterpret_cast<float*>(cp_sm);
+  const float cdiv = (float)C;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float* o = so + (py * TW + gx * 4 + j) * OUT_PITCH + grp * 27;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int d = 0; d < 9; d++) {
+        float v = acc[r][d][j] / cdiv;   // corr_cuda_kernel.cu:119-121
+        o[r * 9 + d] = v > 0.f ? v : v * a.slope;
+      }
+    if (grp == 2) { o[27] = 0.f; o[28] = 0.f; o[29] = 0.f; }   // channels 81 .. 83 of the last chunk
+  }
+  __syncthreads();
+  for (int u = tid; u < 11 * TH * TW; u += THREADS) {
+    const int q = u / (TH * TW), tp = u - q * (TH * TW);
+    const int yy = y0 + tp / TW, xx = x0 + tp % TW;
+    if (yy >= H || xx >= W) continue;
+    const float4 v0 = *reinterpret_cast<const float4*>(so + tp * OUT_PITCH + q * 8);
+    const float4 v1 = q < 10 ? *reinterpret_cast<const float4*>(so + tp * OUT_PITCH + q * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    F8 f;
+    f.v[0] = v0.x; f.v[1] = v0.y; f.v[2] = v0.z; f.v[3] = v0.w; f.v[4] = v1.x; f.v[5] = v1.y; f.v[6] = v1.z; f.v[7] = v1.w;
+    st_chunk(a.out.hi, a.out.lo, cv_elem(a.out, n, q, yy, xx), f);
+  }
+}
+
 }  // namespace
 
 // -> 0 launched, 1 not applicable (caller falls back to corr81_kernel), < 0 / > 1 error
@@ -160,6 +309,38 @@ int corr81_nchw_tma(const float* f1, const float* f2, float* out, int B, int C, 
   prof_before(st);
   corr81_tma_kernel<<<(unsigned)ctas, THREADS, SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(m1), *reinterpret_cast<const CUtensorMap*>(m2), a);
   return after_launch("corr81_tma_kernel", st, 2.0 * 81 * C * px, 4.0 * (2.0 * C + 81) * px);
+}
+
+// CP8 features inside PWC-Net; -> 0 launched, 1 not selected (the caller runs corr81_cp8_kernel), else error
+int corr81_cp8_tma(const CView& f1, const CView& f2, const CView& out, const CView& c1_copy, float slope, cudaStream_t st) {
+  // Opt-in (PREMVOS_CORR_CP8_TMA=1).  Measured inside the batch-4 forward (tools/pwc_time.py): 0.254 ms per forward with this kernel
+  // on level 2 and 0.311 ms on all five levels against 0.242 ms for the plain-load kernel -- in CP8 the cost volume is bound by
+  // its OUTPUT (324 B per pixel leave against 256 B that arrive at C = 32) and by the hi / lo conversions around it, not by the
+  // operand staging, and the small levels are a handful of tiles with up to 25 serial chunks.  Kept as a tested alternative.
+  const char* env = getenv("PREMVOS_CORR_CP8_TMA");
+  if (!(env && atoi(env) != 0)) return 1;
+  alignas(64) unsigned char maps[4][128];
+  const CView* views[2] = {&f1, &f2};
+  for (int k = 0; k < 2; k++) {
+    const CView& v = *views[k];
+    const uint64_t dims[5] = {8, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.chunks, (uint64_t)v.N};
+    const uint64_t strides[4] = {16, (uint64_t)v.W * 16, (uint64_t)v.W * v.H * 16, (uint64_t)v.W * v.H * 16 * v.chunks};
+    const uint32_t box[5] = {8, (uint32_t)(k == 0 ? TW : HW), (uint32_t)(k == 0 ? TH : HH), 1, 1};
+    PV_TRY(encode_tensor_map_bf16(maps[2 * k], v.hi, 5, dims, strides, box));
+    PV_TRY(encode_tensor_map_bf16(maps[2 * k + 1], v.lo, 5, dims, strides, box));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PV_CUDA(cudaFuncSetAttribute(corr81_cp8_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM));
+    attr_set = true;
+  }
+  CorrCp8TmaArgs a{cp8::dev(f1), cp8::dev(f2), cp8::dev(out), cp8::dev(c1_copy), c1_copy.null() ? 0 : 1, (f1.W + TW - 1) / TW, (f1.H + TH - 1) / TH, slope};
+  const long ctas = (long)a.tiles_x * a.tiles_y * f1.N;
+  const double px = (double)f1.pixels();
+  prof_before(st);
+  corr81_cp8_tma_kernel<<<(unsigned)ctas, THREADS, CP_SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(maps[0]), *reinterpret_cast<const CUtensorMap*>(maps[1]),
+                                                               *reinterpret_cast<const CUtensorMap*>(maps[2]), *reinterpret_cast<const CUtensorMap*>(maps[3]), a);
+  return after_launch("corr81_cp8_kernel", st, 2.0 * 81 * f1.C * px, 4.0 * (2.0 * f1.C + 81) * px);
 }
 
 }  // namespace premvos

@@ -387,6 +387,10 @@ int corr81_cp8(const CView& f1, const CView& f2, const CView& out, const CView& 
                out.N == f1.N, PREMVOS_ERR_INVALID_ARG, "corr81_cp8: shape mismatch");
   PV_CHECK(c1_copy.null() || (c1_copy.C == f1.C && c1_copy.H == f1.H && c1_copy.W == f1.W && c1_copy.N == f1.N),
            PREMVOS_ERR_INVALID_ARG, "corr81_cp8: c1 copy shape mismatch");
+  {   // TMA-staged alternative (corr_tma.cu, opt-in: measured slower in CP8, see there)
+    const int r = corr81_cp8_tma(f1, f2, out, c1_copy, slope, st);
+    if (r != 1) return r;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     PV_CUDA(cudaFuncSetAttribute(corr81_cp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORR_SMEM));

@@ -213,6 +213,23 @@ def test_pwc_benchmarked_plan_batch4_full_size():
         assert rel_err(got[i:i + 1], ref) < TOL, i
 
 
+def test_tma_staged_cp8_correlation_gives_the_same_flow(monkeypatch):
+    # the opt-in TMA-staged correlation of the CP8 path (csrc/corr_tma.cu, PREMVOS_CORR_CP8_TMA=1): same products, same channel
+    # order per accumulator -> the same bits as the default kernel, on a size with ragged tiles and five pyramid levels
+    B, H, W = 2, 192, 320
+    sd = synth.pwc_synthetic_state_dict(4)
+    x = torch.from_numpy(synth.synthetic_pwc_input(B, H, W, seed=12)).cuda()
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PREMVOS_CORR_CP8_TMA", flag)
+        net = pwc.pwc_dc_net(None, tensor_cores=True)
+        net.load_state_dict(sd)
+        net.cuda()
+        outs.append(net(x).cpu().numpy())
+        del net
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_calculate_flow_end_to_end():
     f1, f2 = synth.synthetic_frame_pair(100, 150, seed=3)
     sd = synth.pwc_synthetic_state_dict(2)
