@@ -325,6 +325,8 @@ int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float*
 // w: [9][round_up(C,8)] with BN scale folded, bias [round_up(C,8)]; input coordinate = o*stride + tap*rate - pad
 int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const float* bias, int stride, int rate, int pad, bool pre_relu,
                      bool post_relu, int n_active, cudaStream_t st);
+int depthwise3x3_cp8_ex(const CView& in, const CView* up_src, const CView& out, const float* w, const float* bias, int w_c0, int cpad, int stride,
+                        int rate, int pad, bool pre_relu, bool post_relu, int n_active, cudaStream_t st);
 int resize_bilinear_ac_cp8(const CView& in, const CView& out, int n_active, cudaStream_t st);   // align_corners=True
 int broadcast_vec_cp8(const float* vec, int C, bool relu, const CView& out, int n_active, cudaStream_t st);
 int gap_fc_relu(const CView& feat, const float* Wt /*[C][nout]*/, const float* bias, int nout, bool relu, float* pooled_scratch /*[N][C]*/,

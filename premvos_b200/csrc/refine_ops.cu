@@ -127,6 +127,11 @@ struct DwArgs {
   int TH, TW, ntx;         // output tile, tiles per row of tiles
   int RH, RW;              // unclipped input region of a tile
   int clip;                // 1: keep only the part of the region inside the image, taps test the bounds
+  int w_c0, cpad;          // first 8-channel chunk of this launch inside w / bias, their padded channel count
+  // fused align-corners upsampling: the depthwise input is `src` bilinearly resized to in.H x in.W (in.hi / in.lo unused); the
+  // staging loop samples it instead of loading -- the resized tensor never exists in HBM (decoder: 25x25 -> 97x97, 256 channels)
+  CV src;
+  int upsample;
 };
 
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t* hi, uint32_t* lo) {
@@ -160,6 +165,36 @@ __global__ void __launch_bounds__(256) depthwise3x3_tile_kernel(DwArgs a) {
   const long plane = cv_elem(a.in, n, ch, 0, 0);
   const int total = RH * RW * 2;
   const unsigned magic = (1u << 20) / (unsigned)max(RW, 1) + 1u;   // e / RW for e < 2^20 / RW (host-checked)
+  if (a.upsample) {
+    // resize_bilinear(align_corners=True) of `src`, the operations of resize_ac_kernel in the same order, kept in fp32
+    const float sy = a.in.H > 1 ? __fdiv_rn((float)(a.src.H - 1), (float)(a.in.H - 1)) : __fdiv_rn((float)a.src.H, (float)a.in.H);
+    const float sx = a.in.W > 1 ? __fdiv_rn((float)(a.src.W - 1), (float)(a.in.W - 1)) : __fdiv_rn((float)a.src.W, (float)a.in.W);
+    const long splane = cv_elem(a.src, n, ch, 0, 0);
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int half = idx & 1, e = idx >> 1, ry = (int)(((unsigned)e * magic) >> 20), rx = e - ry * RW;
+      const int gy = ry0 + ry, gx = rx0 + rx;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < a.in.H && gx >= 0 && gx < a.in.W) {
+        int ylo, yhi, xlo, xhi; float yl, xl;
+        legacy_axis(gy, sy, a.src.H, &ylo, &yhi, &yl);
+        legacy_axis(gx, sx, a.src.W, &xlo, &xhi, &xl);
+        auto ld = [&](int yy, int xx) {
+          const long el = splane + (long)(yy * a.src.W + xx) * 8 + half * 4;
+          const uint2 h = *reinterpret_cast<const uint2*>(a.src.hi + el), l = *reinterpret_cast<const uint2*>(a.src.lo + el);
+          return make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16), __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                             __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16), __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+        };
+        const float4 tl = ld(ylo, xlo), tr = ld(ylo, xhi), bl = ld(yhi, xlo), br = ld(yhi, xhi);
+        auto mix = [&](float p, float q, float r, float t) {
+          const float top = __fadd_rn(p, __fmul_rn(__fsub_rn(q, p), xl)), bot = __fadd_rn(r, __fmul_rn(__fsub_rn(t, r), xl));
+          return __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+        };
+        f = make_float4(mix(tl.x, tr.x, bl.x, br.x), mix(tl.y, tr.y, bl.y, br.y), mix(tl.z, tr.z, bl.z, br.z), mix(tl.w, tr.w, bl.w, br.w));
+        if (a.pre_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+      }
+      dw_sm[idx] = f;
+    }
+  } else
   for (int base = threadIdx.x; base < total; base += 8 * blockDim.x) {
     uint2 h[8], l[8];
 #pragma unroll
@@ -189,7 +224,7 @@ __global__ void __launch_bounds__(256) depthwise3x3_tile_kernel(DwArgs a) {
   }
   __syncthreads();
   // ---- compute ----
-  const int cpad = ((a.in.C + 7) / 8) * 8;
+  const int cpad = a.cpad, wch = a.w_c0 + ch;
   const int units = FAST ? (a.TH / RS) * a.TW * 2 : a.TH * a.TW * 2;
   const unsigned tw_magic = (1u << 20) / (unsigned)a.TW + 1u;
   for (int u = threadIdx.x; u < units; u += blockDim.x) {
@@ -198,8 +233,8 @@ __global__ void __launch_bounds__(256) depthwise3x3_tile_kernel(DwArgs a) {
     if (ox >= a.out.W) continue;
     float4 wv[9];
 #pragma unroll
-    for (int t = 0; t < 9; t++) wv[t] = *reinterpret_cast<const float4*>(a.w + t * cpad + ch * 8 + half * 4);
-    const float4 bv = *reinterpret_cast<const float4*>(a.bias + ch * 8 + half * 4);
+    for (int t = 0; t < 9; t++) wv[t] = *reinterpret_cast<const float4*>(a.w + t * cpad + wch * 8 + half * 4);
+    const float4 bv = *reinterpret_cast<const float4*>(a.bias + wch * 8 + half * 4);
     if (FAST) {
       float4 acc[RS];
 #pragma unroll
@@ -434,7 +469,16 @@ int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float*
 
 int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const float* bias, int stride, int rate, int pad, bool pre_relu,
                      bool post_relu, int n_active, cudaStream_t st) {
+  return depthwise3x3_cp8_ex(in, nullptr, out, w, bias, 0, round_up(in.C, 8), stride, rate, pad, pre_relu, post_relu, n_active, st);
+}
+
+// General form: weights / bias of this launch start at chunk w_c0 of arrays padded to cpad channels (one depthwise layer run as
+// several launches over channel ranges); up_src != nullptr: the input is *up_src resized (align_corners=True) to in.H x in.W,
+// sampled while staging (in's planes are not read).
+int depthwise3x3_cp8_ex(const CView& in, const CView* up_src, const CView& out, const float* w, const float* bias, int w_c0, int cpad, int stride,
+                        int rate, int pad, bool pre_relu, bool post_relu, int n_active, cudaStream_t st) {
   PV_CHECK(in.C == out.C && in.N == out.N, PREMVOS_ERR_INVALID_ARG, "depthwise3x3_cp8: shape mismatch");
+  PV_CHECK(!up_src || (up_src->C == in.C && up_src->N == in.N && up_src->hi), PREMVOS_ERR_INVALID_ARG, "depthwise3x3_cp8: upsampling source mismatch");
   const long total = (long)n_active * in.vchunks() * out.H * out.W;
   if (total == 0) return 0;
   const bool fast = stride == 1 && rate == 1;
@@ -462,7 +506,8 @@ int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const fl
   const int units = fast ? (TH / RS) * TW * 2 : TH * TW * 2;
   const int iters = (units + 255) / 256;
   const int threads = std::min(256, ((units + iters - 1) / iters + 31) / 32 * 32);
-  DwArgs a{dev(in), dev(out), w, bias, stride, rate, pad, pre_relu ? 1 : 0, post_relu ? 1 : 0, TH, TW, ntx, RH, RW, clip};
+  DwArgs a{dev(in), dev(out), w, bias, stride, rate, pad, pre_relu ? 1 : 0, post_relu ? 1 : 0, TH, TW, ntx, RH, RW, clip, w_c0, cpad,
+           up_src ? dev(*up_src) : dev(in), up_src ? 1 : 0};
   auto kern = fast ? (RS == 5 ? depthwise3x3_tile_kernel<5, true> : depthwise3x3_tile_kernel<4, true>) : depthwise3x3_tile_kernel<4, false>;
   if (smem > 48 * 1024) PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_before(st);
@@ -472,10 +517,10 @@ int depthwise3x3_cp8(const CView& in, const CView& out, const float* w, const fl
   static const int per_layer = getenv("PREMVOS_PROFILE_LAYERS") ? atoi(getenv("PREMVOS_PROFILE_LAYERS")) : 0;
   if (per_layer && profiling_enabled()) {
     char buf[160];
-    snprintf(buf, sizeof(buf), "dw_cp8[n%d_%dx%d_c%d_s%d_r%d]", n_active, out.H, out.W, in.C, stride, rate);
+    snprintf(buf, sizeof(buf), "dw_cp8[n%d_%dx%d_c%d_s%d_r%d%s]", n_active, out.H, out.W, in.C, stride, rate, up_src ? "_upsampled" : "");
     label = prof_intern(buf);
   }
-  return after_launch(label, st, 18.0 * total * 8, 4.0 * frac * ((double)in.pixels() + (double)out.pixels()) * in.C);
+  return after_launch(label, st, 18.0 * total * 8, 4.0 * frac * ((double)(up_src ? up_src->pixels() : in.pixels()) + (double)out.pixels()) * in.C);
 }
 
 int resize_bilinear_ac_cp8(const CView& in, const CView& out, int n_active, cudaStream_t st) {

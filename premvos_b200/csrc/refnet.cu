@@ -36,6 +36,7 @@ typedef std::function<int(cudaStream_t, int)> Step;
 struct premvos_refnet {
   int NB = 0, S = 0, middle_units = 16, n_classes = 2;
   int stem_rows = 1;   // conv1_1 as a 3x1 convolution over the row im2col of the network input (see build_network)
+  std::map<std::string, std::function<int(cudaStream_t, int)>> lazy;   // test-hook tensors that only exist on request
   bool finalized = false;
   std::map<std::string, std::vector<float>> params;
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -374,11 +375,39 @@ int build_network(premvos_refnet* n) {
     ConvOut o; o.cp = low48;
     PV_TRY(add_conv(n, "decoder/feature_projection0", true, ASPP_EPS, low_level, o, g));
     CView a_src = aspp_out, a_dst = dec_in.slice(0, 256), l_src = low48, l_dst = dec_in.slice(32, 48);
-    n->steps.push_back([=](cudaStream_t st, int na) {
+    auto make_concat = [=](cudaStream_t st, int na) {   // model.py:566-577: resize both to the decoder size, concat (views)
       PV_TRY(resize_bilinear_ac_cp8(a_src, a_dst, na, st));
       return resize_bilinear_ac_cp8(l_src, l_dst, na, st);
-    });
-    PV_TRY(add_depthwise(n, "decoder/decoder_conv0_depthwise", ASPP_EPS, dec_in, d0, 1, 1, false, true));
+    };
+    const bool fuse_up = low48.H == dh && low48.W == dh && !(getenv("PREMVOS_REFNET_FUSE_UP") && atoi(getenv("PREMVOS_REFNET_FUSE_UP")) == 0);
+    if (fuse_up) {
+      // The concat is consumed by decoder_conv0's depthwise convolution only: that layer runs as two launches over its channel
+      // ranges -- 256 channels sampled straight from the 25 x 25 ASPP output while staging (the 97 x 97 x 256 resized tensor, 385 MB
+      // per 40 crops written and read back, never exists), 48 channels from the projected low-level features, which already
+      // have the decoder size.  The concat buffer is only filled when the test hook asks for it.
+      n->lazy["decoder_in"] = make_concat;
+      const std::string scope = "decoder/decoder_conv0_depthwise";
+      const int C = 304, cpad = 304;
+      const std::vector<float>& W = n->params[scope + "/depthwise_weights"];  // [3][3][C][1]
+      std::vector<float> scale, shift, w((size_t)9 * cpad, 0.f), b(cpad, 0.f);
+      bn_fold(n, scope, ASPP_EPS, &scale, &shift);
+      for (int t = 0; t < 9; t++)
+        for (int c = 0; c < C; c++) w[(size_t)t * cpad + c] = W[(size_t)t * C + c] * scale[c];
+      for (int c = 0; c < C; c++) b[c] = shift[c];
+      float *dw = nullptr, *db = nullptr;
+      PV_TRY(dev_alloc(n, &dw, w.size())); PV_TRY(dev_alloc(n, &db, b.size()));
+      PV_CUDA(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+      PV_CUDA(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+      CView up_geom = a_dst;            // geometry of the resized tensor (its planes are not touched)
+      CView d0a = d0.slice(0, 256), d0l = d0.slice(32, 48);
+      n->steps.push_back([=](cudaStream_t st, int na) {
+        PV_TRY(depthwise3x3_cp8_ex(up_geom, &a_src, d0a, dw, db, 0, cpad, 1, 1, 1, false, true, na, st));
+        return depthwise3x3_cp8_ex(l_src, nullptr, d0l, dw, db, 32, cpad, 1, 1, 1, false, true, na, st);
+      });
+    } else {
+      n->steps.push_back(make_concat);
+      PV_TRY(add_depthwise(n, "decoder/decoder_conv0_depthwise", ASPP_EPS, dec_in, d0, 1, 1, false, true));
+    }
     ConvOut o0;
     FView p0f;
     if (use_f8) { PV_TRY(alloc_fview(n, &p0f, 256, dh, dh)); o0.f8 = p0f; } else o0.cp = p0;
@@ -563,6 +592,10 @@ extern "C" int premvos_refnet_get_tensor(premvos_refnet_t* n, const char* name, 
       for (size_t i = 0; i < t.size(); i++) host_out[i] = (float)t[i];
     }
     return 0;
+  }
+  if (n->lazy.count(k)) {   // a tensor the production path never materialises: produce it now from the last batch's buffers
+    PV_TRY(n->lazy[k](n->stream, n->NB));
+    PV_CUDA(cudaStreamSynchronize(n->stream));
   }
   CView cv;
   if (k == "net_input" && n->stem_rows) {   // undo the row im2col: even x = tap 1 of column x/2, odd x = tap 0 of column (x+1)/2
