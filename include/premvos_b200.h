@@ -101,6 +101,15 @@ int premvos_conv2d_forward(const float* x, const float* w, const float* bias, co
                            int dilation, int pad_top, int pad_left, int pad_bottom, int pad_right, float slope,
                            void* stream);
 
+/* One separable convolution on the FUSED path (bring-up / parity hook): depthwise 3x3 (SAME, stride 1) computed into the A
+ * operand of the pointwise tcgen05 GEMM -- slim `separable_conv2d` + folded BatchNorms as refinement_net/network/deeplab/core/
+ * xception.py:152-190 builds it.  x device fp32 NCHW [batch, channels, height, width]; dw_w HOST [channels][3][3], dw_bias HOST
+ * [channels] or NULL; pw_w HOST [cout][channels], pw_bias HOST [cout] or NULL; out device fp32 NCHW [batch, cout, height, width];
+ * out = act(pw(relu_mid?(dw(relu_in?(x)) + dw_bias)) + pw_bias), act = LeakyReLU(slope).  cout <= 128.  Synchronises `stream`. */
+int premvos_sepconv2d_forward(const float* x, const float* dw_w, const float* dw_bias, const float* pw_w, const float* pw_bias,
+                              float* out, int batch, int channels, int height, int width, int cout, int relu_in, int relu_mid,
+                              float slope, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for uint8 images, on the device, BIT-EXACT with OpenCV
  * (8-bit linear resize is integer arithmetic on 11-bit fixed-point coefficients, modules/imgproc/src/resize.cpp).

@@ -25,6 +25,7 @@ EXPORTS = [
     "premvos_refnet_create", "premvos_refnet_set_param", "premvos_refnet_finalize", "premvos_refnet_forward",
     "premvos_refnet_forward_host",
     "premvos_refnet_launches_per_forward", "premvos_refnet_get_tensor", "premvos_refnet_destroy",
+    "premvos_sepconv2d_forward",
     "premvos_reidnet_create", "premvos_reidnet_set_param", "premvos_reidnet_finalize", "premvos_reidnet_forward",
     "premvos_reidnet_forward_host", "premvos_reidnet_launches_per_forward", "premvos_reidnet_get_tensor",
     "premvos_reidnet_destroy",
@@ -84,6 +85,8 @@ def lib() -> ctypes.CDLL:
     L.premvos_refnet_get_tensor.argtypes = [c_void_p, c_char_p, c_void_p, P(c_i64)]
     L.premvos_refnet_destroy.argtypes = [c_void_p]
     L.premvos_refnet_destroy.restype = None
+    L.premvos_sepconv2d_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            ctypes.c_float, c_void_p]
     L.premvos_reidnet_create.argtypes = [P(c_void_p), c_int]
     L.premvos_reidnet_set_param.argtypes = [c_void_p, c_char_p, c_void_p, c_i64]
     L.premvos_reidnet_finalize.argtypes = [c_void_p]

@@ -318,6 +318,19 @@ int plan_depthwise3x3_f8(DwF8Plan* plan, const FView& in, const CView& out, cons
                          bool pre_relu, bool post_relu);
 int launch_depthwise3x3_f8(const DwF8Plan& plan, int n_active, cudaStream_t st);
 
+// ---- fused separable convolution (depthwise 3x3 computed into the pointwise GEMM's A operand), conv_umma.cu -----------------------
+// Eligible: F8 input, stride 1, rate 1, SAME padding, a pointwise layer with ONE channel tile (Cout <= 128, packed with kc_hint 4),
+// F8 and / or CP8 output, no residual.  dw_w [9][cpad] (BN scale folded), dw_b [cpad]; cpad >= 32 * k-blocks.
+struct SepConvPlan {
+  alignas(64) unsigned char map_in[128];
+  alignas(16) unsigned char args[192];
+  int smem_bytes = 0, N = 0;
+  double flops_per_image = 0, bytes_per_image = 0;
+};
+int plan_sepconv_fused(SepConvPlan* plan, const FView& in, const float* dw_w, const float* dw_b, int cpad, bool pre_relu, bool post_relu,
+                       const ConvWeightsUmma& pw, const ConvOut& out, float slope);
+int launch_sepconv_fused(const SepConvPlan& plan, int n_active, cudaStream_t st);
+
 // ---- refinement-network kernels, refine_ops.cu ------------------------------------------------------------
 // frame uint8 RGB [H,W,3] + boxes [N,4] (x,y,w,h) -> network input CP8 [N,1 chunk,S,S] (RGB in [-1,1], guidance -1/+1) + crop boxes
 int refine_make_input(const unsigned char* frame_rgb, int H, int W, const float* boxes_xywh, int N, int S, const CView& out, int* crops,

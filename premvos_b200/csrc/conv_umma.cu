@@ -915,6 +915,261 @@ __global__ void __launch_bounds__(256) conv_finish_tail_kernel(const UmmaConvArg
 }
 
 
+// ---- fused separable convolution: depthwise 3x3 (+BN) computed INTO the pointwise GEMM's A operand -------------------------------
+// For the HBM-bound separable convolutions of the Xception entry flow (193 x 193 x 128: 763 MB per tensor and 40 crops) the
+// depthwise output is the largest tensor of the layer pair and lives only to be read back by the pointwise GEMM.  Here it never
+// leaves the SM: per 16 x 8 pixel tile and 32-channel k-block
+//   warp 0        TMA: the fp32 (F8) input tile + halo, box {10 px * 8 ch, 18 rows, 4 chunks}, zero fill = SAME padding; the packed
+//                 pointwise weights of the k-block (bulk copy);
+//   warps 4-11    depthwise: 9 LDS.128 + 36 FMA per 4 channels of a pixel (BatchNorm folded, optional ReLU in / out), split into
+//                 bf16 hi / lo and written straight into the A stage in the un-swizzled K-major layout [4 chunks][128 pixels][8]
+//                 (generic-proxy writes, made visible to the tensor core with fence.proxy.async);
+//   warp 1        three tcgen05.mma per 16 channels into one of two TMEM accumulators;
+//   warps 12-19   epilogue of the previous tile (bias, ReLU, F8 and / or CP8 stores) while the next one is produced.
+// A layer pair with ONE output-channel tile (Cout <= 128) is eligible: the depthwise tile is computed once.  The 728-channel
+// middle flow is not (three channel tiles = three recomputations, and it is tensor-bound, not HBM-bound).
+constexpr int SF_THREADS = 640, SF_DW_WARPS = 8, SF_EPI_WARPS = 8;
+constexpr int SF_XS = 4, SF_AS = 4, SF_WS = 3;
+constexpr int SF_HW = 10, SF_HH = 18;                              // halo tile of a 16 x 8 output tile
+constexpr int SF_X_BYTES = 4 * SF_HH * SF_HW * 32;                 // 4 chunks x 18 x 10 pixels x 8 fp32 = 23 040
+constexpr int SF_A_PLANE = 4 * 128 * 16;                           // one bf16 plane of an A stage: [4 chunks][128 rows][8] = 8 192
+constexpr int SF_A_BYTES = 2 * SF_A_PLANE;
+
+struct SepFusedArgs {
+  const float* dw_w;     // [9][cpad], BatchNorm scale folded
+  const float* dw_b;     // [cpad]
+  const __nv_bfloat16* pw_w;   // packed [kblock][hi|lo][4][BN][8] (pack_conv_weights_umma, 1x1, KC = 4, one channel tile)
+  const float* pw_b;     // [BN]
+  float* out_f8; int f8_chunks, f8_c0;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_chunks, out_c0;
+  int H, W, in_c0, chunks, cpad, kblocks, BN, Cout;
+  int pre_relu, post_relu;   // around the depthwise convolution
+  float slope;               // after the pointwise convolution (1 = identity, 0 = ReLU)
+  int tiles_x, tiles_y, n_active, total;
+  int w_stage;               // bytes of one pointwise weight stage = 2 * 4 * BN * 16
+  int dbg;                   // PREMVOS_DBG ablations: 1 = depthwise producers skip the arithmetic, 2 = epilogue drains TMEM only
+};
+
+__global__ void __launch_bounds__(SF_THREADS, 1) sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const SepFusedArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* x_smem = smem;                                   // [XS][4][18][10][8] fp32
+  uint8_t* a_smem = x_smem + SF_XS * SF_X_BYTES;             // [AS][hi | lo][4][128][8] bf16
+  uint8_t* w_smem = a_smem + SF_AS * SF_A_BYTES;             // [WS][hi | lo][4][BN][8] bf16
+  float* dww = reinterpret_cast<float*>(w_smem + SF_WS * a.w_stage);   // [9][cpad]
+  float* dwb = dww + 9 * a.cpad;                                        // [cpad]
+  float* pwb = dwb + a.cpad;                                            // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pwb + a.BN);
+  uint64_t *x_full = bars, *x_empty = bars + SF_XS, *a_full = bars + 2 * SF_XS, *a_empty = a_full + SF_AS, *w_full = a_empty + SF_AS,
+           *w_empty = w_full + SF_WS, *t_full = w_empty + SF_WS, *t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+  for (int i = threadIdx.x; i < 10 * a.cpad; i += SF_THREADS) dww[i] = i < 9 * a.cpad ? a.dw_w[i] : a.dw_b[i - 9 * a.cpad];
+  for (int i = threadIdx.x; i < a.BN; i += SF_THREADS) pwb[i] = a.pw_b[i];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_in);
+    for (int s = 0; s < SF_XS; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], SF_DW_WARPS); }
+    for (int s = 0; s < SF_AS; s++) { mbar_init(&a_full[s], SF_DW_WARPS); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SF_WS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], SF_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 2u * (uint32_t)a.BN < 32u ? 32u : (2u * (uint32_t)a.BN <= 64u ? 64u : (2u * (uint32_t)a.BN <= 128u ? 128u : 256u)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    uint32_t xs = 0, xph = 0, ws = 0, wph = 0;
+    for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+      const int tile = t % tiles_per_img, n = t / tiles_per_img;
+      const int ty0 = (tile / a.tiles_x) * 16, tx0 = (tile % a.tiles_x) * 8;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.pw_w);
+      for (int kb = 0; kb < a.kblocks; kb++) {
+        mbar_wait(&x_empty[xs], xph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&x_full[xs], SF_X_BYTES);
+          tma_load_4d(&tm_in, &x_full[xs], x_smem + (size_t)xs * SF_X_BYTES, (tx0 - 1) * 8, ty0 - 1, a.in_c0 + kb * 4, n);
+        }
+        __syncwarp();
+        if (++xs == SF_XS) { xs = 0; xph ^= 1u; }
+        mbar_wait(&w_empty[ws], wph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&w_full[ws], (uint32_t)a.w_stage);
+          bulk_load_1d(w_smem + (size_t)ws * a.w_stage, wsrc, (uint32_t)a.w_stage, &w_full[ws]);
+        }
+        __syncwarp();
+        wsrc += a.w_stage;
+        if (++ws == SF_WS) { ws = 0; wph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_bf16(128, a.BN);
+    const uint32_t a_hi32 = (128u >> 4) | (1u << 14), w_hi32 = (128u >> 4) | (1u << 14);           // SBO = 128 B
+    const uint32_t a_lo32 = (2048u >> 4) << 16, w_lo32 = (((uint32_t)a.BN * 16u) >> 4) << 16;         // LBO: next 8 channels
+    const uint32_t a_base = smem_u32(a_smem), w_base = smem_u32(w_smem);
+    const uint32_t w_plane16 = ((uint32_t)a.w_stage / 2u) >> 4, a_plane16 = (uint32_t)SF_A_PLANE >> 4;
+    const uint32_t a_k16 = (2u * 2048u) >> 4, w_k16 = (2u * (uint32_t)a.BN * 16u) >> 4;
+    uint32_t as = 0, aph = 0, ws = 0, wph = 0, buf = 0, eph = 0;
+    for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+      mbar_wait(&t_empty[buf], ((eph >> buf) & 1u) ^ 1u);
+      eph ^= 1u << buf;
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * (uint32_t)a.BN;
+      uint32_t accum = 0;
+      for (int kb = 0; kb < a.kblocks; kb++) {
+        mbar_wait(&a_full[as], aph);
+        mbar_wait(&w_full[ws], wph);
+        tc_fence_after();
+        if (elect_one()) {
+          uint32_t aH = a_lo32 + ((a_base + as * (uint32_t)SF_A_BYTES) >> 4), wH = w_lo32 + ((w_base + ws * (uint32_t)a.w_stage) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++, aH += a_k16, wH += w_k16) {
+            umma_bf16_lo(d, aH + a_plane16, a_hi32, wH, w_hi32, idesc, accum);           // lo * hi
+            umma_bf16_lo(d, aH, a_hi32, wH + w_plane16, w_hi32, idesc, 1u);              // hi * lo
+            umma_bf16_lo(d, aH, a_hi32, wH, w_hi32, idesc, 1u);                          // hi * hi
+            accum = 1u;
+          }
+          umma_commit(&a_empty[as]);
+          umma_commit(&w_empty[ws]);
+        }
+        accum = 1u;
+        __syncwarp();
+        if (++as == SF_AS) { as = 0; aph ^= 1u; }
+        if (++ws == SF_WS) { ws = 0; wph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(&t_full[buf]);
+      __syncwarp();
+      buf ^= 1u;
+    }
+  } else if (warp >= 4 && warp < 4 + SF_DW_WARPS) {
+    // ===== depthwise producers: 256 threads; thread = (chunk q of the k-block, strip of 4 rows, column, half of the chunk): its 9 tap
+    // weights stay in registers for the whole k-block, a 6 x 3 window of LDS.128 feeds 4 vertically adjacent outputs, and the 16
+    // lanes of a half warp read one 256-byte tile row (conflict-free) =====
+    const int dt = (warp - 4) * 32 + lane;
+    const int half = dt & 1, tx = (dt >> 1) & 7, sr = (dt >> 4) & 3, q = dt >> 6;
+    uint32_t xs = 0, xph = 0, as = 0, aph = 0;
+    for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+      for (int kb = 0; kb < a.kblocks; kb++) {
+        const int c4 = (kb * 4 + q) * 8 + half * 4;
+        float4 wv[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) wv[k] = *reinterpret_cast<const float4*>(dww + k * a.cpad + c4);
+        const float4 bv = *reinterpret_cast<const float4*>(dwb + c4);
+        mbar_wait(&x_full[xs], xph);
+        mbar_wait(&a_empty[as], aph ^ 1u);
+        const float4* xp = reinterpret_cast<const float4*>(x_smem + (size_t)xs * SF_X_BYTES) + ((q * SF_HH + sr * 4) * SF_HW + tx) * 2 + half;
+        uint8_t* dst = a_smem + (size_t)as * SF_A_BYTES + q * 2048 + ((sr * 4) * 8 + tx) * 16 + half * 8;
+        if (!(a.dbg & 1)) {
+          float4 acc[4] = {bv, bv, bv, bv};
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            float4 v[3];
+#pragma unroll
+            for (int s2 = 0; s2 < 3; s2++) {
+              v[s2] = xp[(r * SF_HW + s2) * 2];
+              if (a.pre_relu) { v[s2].x = fmaxf(v[s2].x, 0.f); v[s2].y = fmaxf(v[s2].y, 0.f); v[s2].z = fmaxf(v[s2].z, 0.f); v[s2].w = fmaxf(v[s2].w, 0.f); }
+            }
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+              const int tr = r - o;   // tap row of output o fed by window row r
+              if (tr < 0 || tr > 2) continue;
+#pragma unroll
+              for (int s2 = 0; s2 < 3; s2++) {
+                const float4 w4 = wv[tr * 3 + s2];
+                acc[o].x = fmaf(v[s2].x, w4.x, acc[o].x); acc[o].y = fmaf(v[s2].y, w4.y, acc[o].y);
+                acc[o].z = fmaf(v[s2].z, w4.z, acc[o].z); acc[o].w = fmaf(v[s2].w, w4.w, acc[o].w);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 0; o < 4; o++) {
+            float4 f = acc[o];
+            if (a.post_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(f.x, f.y), h1 = __floats2bfloat162_rn(f.z, f.w);
+            const uint32_t hw0 = *reinterpret_cast<const uint32_t*>(&h0), hw1 = *reinterpret_cast<const uint32_t*>(&h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(f.x - __uint_as_float(hw0 << 16), f.y - __uint_as_float(hw0 & 0xffff0000u));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(f.z - __uint_as_float(hw1 << 16), f.w - __uint_as_float(hw1 & 0xffff0000u));
+            *reinterpret_cast<uint2*>(dst + o * 128) = make_uint2(hw0, hw1);
+            *reinterpret_cast<uint2*>(dst + o * 128 + SF_A_PLANE) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&a_full[as]); mbar_arrive(&x_empty[xs]); }
+        if (++xs == SF_XS) { xs = 0; xph ^= 1u; }
+        if (++as == SF_AS) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 + SF_DW_WARPS) {
+    // ===== epilogue: two warps per TMEM lane quarter, each one half of the accumulator columns =====
+    const int ew = warp - (4 + SF_DW_WARPS), q = warp & 3, part = ew >> 2;
+    const int m = q * 32 + lane;
+    const int col_span = a.BN / 2, col_begin = part * col_span, col_end = col_begin + col_span;
+    const long hw = (long)a.H * a.W;
+    uint32_t buf = 0, fph = 0;
+    for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+      const int tile = t % tiles_per_img, n = t / tiles_per_img;
+      const int oy = (tile / a.tiles_x) * 16 + (m >> 3), ox = (tile % a.tiles_x) * 8 + (m & 7);
+      const bool in_img = oy < a.H && ox < a.W;
+      const long pix = (long)oy * a.W + ox;
+      mbar_wait(&t_full[buf], (fph >> buf) & 1u);
+      fph ^= 1u << buf;
+      tc_fence_after();
+      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)a.BN + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 16 >= col_end) {   // all columns of this warp are in registers: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+        if (!in_img || c0 >= a.Cout || (a.dbg & 2)) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const float x = __uint_as_float(v[j]) + pwb[c0 + j];
+          f[j] = x > 0.f ? x : x * a.slope;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (c0 + 8 * h >= a.Cout) continue;
+          if (a.out_f8) {
+            float* pf = a.out_f8 + (((long)n * a.f8_chunks + a.f8_c0 + (c0 >> 3) + h) * hw + pix) * 8;
+            reinterpret_cast<float4*>(pf)[0] = make_float4(f[8 * h], f[8 * h + 1], f[8 * h + 2], f[8 * h + 3]);
+            reinterpret_cast<float4*>(pf)[1] = make_float4(f[8 * h + 4], f[8 * h + 5], f[8 * h + 6], f[8 * h + 7]);
+          }
+          if (a.out_hi) {
+            uint32_t hw4[4], lw4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float x0 = f[8 * h + 2 * j], x1 = f[8 * h + 2 * j + 1];
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+              hw4[j] = *reinterpret_cast<const uint32_t*>(&hh);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __uint_as_float(hw4[j] << 16), x1 - __uint_as_float(hw4[j] & 0xffff0000u));
+              lw4[j] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            const long oi = (((long)n * a.out_chunks + a.out_c0 + (c0 >> 3) + h) * hw + pix) * 8;
+            *reinterpret_cast<uint4*>(a.out_hi + oi) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+            *reinterpret_cast<uint4*>(a.out_lo + oi) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+          }
+        }
+      }
+      buf ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2u * (uint32_t)a.BN < 32u ? 32u : (2u * (uint32_t)a.BN <= 64u ? 64u : (2u * (uint32_t)a.BN <= 128u ? 128u : 256u)));
+}
+
 // ---- CTA-pair kernel for 1x1 / stride-1 layers -------------------------------------------------------------------------
 // A 1x1 layer moves 9x more A bytes per MMA than a 3x3 layer in halo mode; at 128 x 256 tiles one SM has to ingest 62.5 B/clk of
 // operands to keep its tensor pipe busy, the L2 delivers ~43-46.  A CTA PAIR (cluster of 2 = the two SMs of a TPC) computes a
@@ -1809,6 +2064,70 @@ int plan_conv_umma(ConvPlanUmma* plan, const CView& in, const ConvOut& out, cons
 }
 
 
+
+// ---- fused separable convolution: host side ----
+int plan_sepconv_fused(SepConvPlan* plan, const FView& in, const float* dw_w, const float* dw_b, int cpad, bool pre_relu, bool post_relu,
+                       const ConvWeightsUmma& pw, const ConvOut& out, float slope) {
+  PV_CHECK(in.p && pw.R == 1 && pw.S == 1 && pw.ntiles == 1 && pw.KC == 4 && !pw.pair && pw.BN % 32 == 0 && pw.BN <= 128, PREMVOS_ERR_UNSUPPORTED,
+           "sepconv_fused: needs a 1x1 pointwise layer with one channel tile of 32..128 (BN %d, KC %d, tiles %d)", pw.BN, pw.KC, pw.ntiles);
+  PV_CHECK(round_up(in.C, 8) == round_up(pw.CinPhys, 8) && cpad >= round_up(in.C, 8) && cpad % 8 == 0, PREMVOS_ERR_INVALID_ARG,
+           "sepconv_fused: channel mismatch (input %d, pointwise %d, depthwise arrays %d)", in.C, pw.CinPhys, cpad);
+  PV_CHECK((out.f8.p || out.cp.hi) && !out.f32.p && !out.res.hi && !out.res_f8.p, PREMVOS_ERR_UNSUPPORTED,
+           "sepconv_fused: F8 / CP8 outputs without residual only");
+  if (out.f8.p) PV_CHECK(out.f8.N == in.N && out.f8.H == in.H && out.f8.W == in.W && out.f8.C == pw.Cout, PREMVOS_ERR_INVALID_ARG, "sepconv_fused: F8 output shape");
+  if (out.cp.hi) PV_CHECK(out.cp.N == in.N && out.cp.H == in.H && out.cp.W == in.W && out.cp.C == pw.Cout, PREMVOS_ERR_INVALID_ARG, "sepconv_fused: CP8 output shape");
+  static_assert(sizeof(SepFusedArgs) <= sizeof(plan->args), "SepConvPlan::args too small");
+  SepFusedArgs& a = *reinterpret_cast<SepFusedArgs*>(plan->args);
+  memset(&a, 0, sizeof(a));
+  a.dw_w = dw_w; a.dw_b = dw_b; a.pw_w = pw.w; a.pw_b = pw.bias;
+  a.out_f8 = out.f8.p; a.f8_chunks = out.f8.chunks; a.f8_c0 = out.f8.c0;
+  a.out_hi = out.cp.hi; a.out_lo = out.cp.lo; a.out_chunks = out.cp.chunks; a.out_c0 = out.cp.c0;
+  a.H = in.H; a.W = in.W; a.in_c0 = in.c0; a.chunks = (in.C + 7) / 8; a.cpad = cpad; a.kblocks = pw.kblocks; a.BN = pw.BN; a.Cout = pw.Cout;
+  PV_CHECK(a.kblocks * 32 <= cpad, PREMVOS_ERR_INVALID_ARG, "sepconv_fused: depthwise arrays must cover %d k-blocks of 32 channels (cpad %d)", a.kblocks, cpad);
+  a.pre_relu = pre_relu ? 1 : 0; a.post_relu = post_relu ? 1 : 0; a.slope = slope;
+  a.tiles_x = (in.W + 7) / 8; a.tiles_y = (in.H + 15) / 16;
+  a.w_stage = 2 * 4 * pw.BN * 16;
+  a.dbg = env_int("PREMVOS_DBG", 0);
+  plan->N = in.N;
+  plan->smem_bytes = SF_XS * SF_X_BYTES + SF_AS * SF_A_BYTES + SF_WS * a.w_stage + (10 * cpad + pw.BN) * 4 + 256 + 128;
+  PV_CHECK(plan->smem_bytes <= SMEM_LIMIT, PREMVOS_ERR_UNSUPPORTED, "sepconv_fused: %d bytes of shared memory needed", plan->smem_bytes);
+  plan->flops_per_image = 2.0 * in.H * in.W * ((double)pw.Cout * pw.Cin + 9.0 * in.C);
+  plan->bytes_per_image = 4.0 * in.H * in.W * ((double)in.C + pw.Cout);
+  const uint64_t dims[4] = {(uint64_t)in.W * 8, (uint64_t)in.H, (uint64_t)in.chunks, (uint64_t)in.N};
+  const uint64_t strides[3] = {(uint64_t)in.W * 32, (uint64_t)in.H * in.W * 32, (uint64_t)in.chunks * in.H * in.W * 32};
+  const uint32_t box[4] = {SF_HW * 8, SF_HH, 4, 1};
+  return encode_tensor_map_f32(plan->map_in, in.p, 4, dims, strides, box);
+}
+
+int launch_sepconv_fused(const SepConvPlan& plan, int n_active, cudaStream_t st) {
+  SepFusedArgs a = *reinterpret_cast<const SepFusedArgs*>(plan.args);
+  if (n_active < 0 || n_active > plan.N) n_active = plan.N;
+  a.n_active = n_active;
+  a.total = a.tiles_x * a.tiles_y * n_active;
+  if (a.total == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PV_CUDA(cudaFuncSetAttribute(sepconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PV_CUDA(cudaGetDevice(&dev));
+    PV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = std::min(a.total, num_sms);
+  prof_before(st);
+  sepconv_fused_kernel<<<grid, SF_THREADS, plan.smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(plan.map_in), a);
+  const char* label = "sepconv_fused_kernel";
+  static const int per_layer = env_int("PREMVOS_PROFILE_LAYERS", 0);
+  if (per_layer && profiling_enabled()) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "sepconv_fused[n%d_%dx%d_cin%d_cout%d]", n_active, a.H, a.W, a.chunks * 8, a.Cout);
+    label = prof_intern(buf);
+  }
+  return after_launch(label, st, plan.flops_per_image * n_active, plan.bytes_per_image * n_active);
+}
 
 static int dbg_report(int dbg, int grid, cudaStream_t st) {
   unsigned long long r[8];

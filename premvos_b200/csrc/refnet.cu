@@ -37,6 +37,7 @@ struct premvos_refnet {
   int NB = 0, S = 0, middle_units = 16, n_classes = 2;
   int stem_rows = 1;   // conv1_1 as a 3x1 convolution over the row im2col of the network input (see build_network)
   std::map<std::string, std::function<int(cudaStream_t, int)>> lazy;   // test-hook tensors that only exist on request
+  std::vector<std::unique_ptr<SepConvPlan>> sep_plans;
   bool finalized = false;
   std::map<std::string, std::vector<float>> params;
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -209,6 +210,37 @@ int add_depthwise_f8(premvos_refnet* n, const std::string& scope, float eps, con
   return 0;
 }
 
+// depthwise 3x3 + BN fused into the pointwise 1x1 + BN GEMM (conv_umma.cu: sepconv_fused_kernel): F8 in, no depthwise output in HBM
+int add_sepconv_fused(premvos_refnet* n, const std::string& dw_scope, const std::string& pw_scope, float eps, const FView& in, const ConvOut& out,
+                      bool pre_relu, bool post_relu, float slope) {
+  const int C = in.C, cpad = round_up((C + 7) / 8, 4) * 8;
+  const std::vector<float>& Wd = n->params[dw_scope + "/depthwise_weights"];  // [3][3][C][1]
+  std::vector<float> scale, shift, w((size_t)9 * cpad, 0.f), b(cpad, 0.f);
+  bn_fold(n, dw_scope, eps, &scale, &shift);
+  for (int t = 0; t < 9; t++)
+    for (int c = 0; c < C; c++) w[(size_t)t * cpad + c] = Wd[(size_t)t * C + c] * scale[c];
+  for (int c = 0; c < C; c++) b[c] = shift[c];
+  float *dw = nullptr, *db = nullptr;
+  PV_TRY(dev_alloc(n, &dw, w.size())); PV_TRY(dev_alloc(n, &db, b.size()));
+  PV_CUDA(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  PV_CUDA(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  const std::vector<int64_t>& ws = n->shapes[pw_scope + "/weights"];   // [1][1][C][Cout]
+  const int cout = (int)ws[3];
+  const std::vector<float>& Wp = n->params[pw_scope + "/weights"];
+  std::vector<float> pscale, pshift, wp((size_t)cout * C);
+  bn_fold(n, pw_scope, eps, &pscale, &pshift);
+  for (int i = 0; i < C; i++)
+    for (int o = 0; o < cout; o++) wp[(size_t)o * C + i] = Wp[(size_t)i * cout + o] * pscale[o];
+  n->conv_weights.emplace_back(new ConvWeightsUmma());
+  ConvWeightsUmma* cw = n->conv_weights.back().get();
+  PV_TRY(pack_conv_weights_umma(cw, wp.data(), pshift.data(), cout, C, 1, 1, nullptr, 0, 4, 0, false));
+  n->sep_plans.emplace_back(new SepConvPlan());
+  SepConvPlan* pl = n->sep_plans.back().get();
+  PV_TRY(plan_sepconv_fused(pl, in, dw, db, cpad, pre_relu, post_relu, *cw, out, slope));
+  n->steps.push_back([pl](cudaStream_t st, int na) { return launch_sepconv_fused(*pl, na, st); });
+  return 0;
+}
+
 int build_network(premvos_refnet* n) {
   const int S = n->S;
   const std::string x = "xception_65/";
@@ -254,6 +286,7 @@ int build_network(premvos_refnet* n) {
   // pointwise output consumed only by the next depthwise convolution is F8 with the consumer's leading ReLU already applied; a
   // unit output consumed by the next unit's first depthwise + sum skip (middle flow, exit block 2) is F8, raw.
   const bool use_f8 = getenv("PREMVOS_REFNET_F8") ? atoi(getenv("PREMVOS_REFNET_F8")) != 0 : true;
+  const bool fuse_sep = getenv("PREMVOS_REFNET_FUSE_SEP") ? atoi(getenv("PREMVOS_REFNET_FUSE_SEP")) != 0 : true;
   CView cur = c12, low_level;
   FView cur_f;   // the unit input when it is F8 (cur is null then)
   const int target = 16 / 2;  // output_stride 16, halved by the stride-2 root conv (xception.py:424-429)
@@ -289,12 +322,19 @@ int build_network(premvos_refnet* n) {
         const int st_i = i == 2 ? stride : 1;
         const int h_i = st_i == 2 ? Ho : tH, w_i = st_i == 2 ? Wo : tW;
         const std::string ss = s + "/separable_conv" + std::to_string(i + 1);
+        // HBM-bound separable convolutions with ONE output-channel tile: the depthwise tile is computed inside the pointwise GEMM
+        const bool has_res = i == 2 && b.skip != 0;
+        const bool fuse = fuse_sep && tf.p && st_i == 1 && unit_rate == 1 && b.depth[i] <= 128 && b.depth[i] % 32 == 0 && !has_res &&
+                          (long)h_i * w_i >= 4096;
+        const bool dw_pre_relu = !b.act_in_sep && !(tf.p && t_relu_applied);
         CView d;
-        PV_TRY(alloc_cview(n, &d, tC, h_i, w_i));
-        if (tf.p)
-          PV_TRY(add_depthwise_f8(n, ss + "_depthwise", XC_EPS, tf, d, st_i, unit_rate, !b.act_in_sep && !t_relu_applied, b.act_in_sep));
-        else
-          PV_TRY(add_depthwise(n, ss + "_depthwise", XC_EPS, t, d, st_i, unit_rate, !b.act_in_sep, b.act_in_sep));
+        if (!fuse) {
+          PV_TRY(alloc_cview(n, &d, tC, h_i, w_i));
+          if (tf.p)
+            PV_TRY(add_depthwise_f8(n, ss + "_depthwise", XC_EPS, tf, d, st_i, unit_rate, dw_pre_relu, b.act_in_sep));
+          else
+            PV_TRY(add_depthwise(n, ss + "_depthwise", XC_EPS, t, d, st_i, unit_rate, !b.act_in_sep, b.act_in_sep));
+        }
         const bool is_low_level = std::string(b.scope) == "entry_flow/block2" && i == 1;   // feature_extractor.py:89-94
         ConvGeom g; g.slope = b.act_in_sep ? 0.f : 1.f;
         ConvOut o;
@@ -311,7 +351,8 @@ int build_network(premvos_refnet* n) {
         }
         if (i == 2 && b.skip == 1) o.res = sc;
         if (i == 2 && b.skip == 2) { if (cur_f.p) o.res_f8 = cur_f; else o.res = cur; }
-        PV_TRY(add_conv(n, ss + "_pointwise", true, XC_EPS, d, o, g));
+        if (fuse) PV_TRY(add_sepconv_fused(n, ss + "_depthwise", ss + "_pointwise", XC_EPS, tf, o, dw_pre_relu, b.act_in_sep, g.slope));
+        else PV_TRY(add_conv(n, ss + "_pointwise", true, XC_EPS, d, o, g));
         if (is_low_level) low_level = p;
         t = p; tf = pf; tC = b.depth[i]; tH = h_i; tW = w_i;
       }

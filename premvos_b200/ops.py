@@ -43,6 +43,28 @@ def conv2d(x: torch.Tensor, weight, bias=None, stride=1, dilation=1, padding=(0,
     return out
 
 
+def sepconv2d(x: torch.Tensor, dw_weight, dw_bias, pw_weight, pw_bias, relu_in=False, relu_mid=False, slope=1.0) -> torch.Tensor:
+    """act(pointwise(relu_mid?(depthwise3x3(relu_in?(x)) + dw_bias)) + pw_bias) on the FUSED tcgen05 path
+    (premvos_sepconv2d_forward): the depthwise tile is computed into the pointwise GEMM's A operand.  x CUDA float32 [N,C,H,W];
+    dw_weight [C,3,3] (or [C,1,3,3]), pw_weight [Cout,C] (or [Cout,C,1,1]), Cout <= 128; depthwise SAME padding, stride 1."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise TypeError("x must be a CUDA float32 tensor (premvos_b200 has no CPU path)")
+    x = x.contiguous()
+    as_np = lambda t: None if t is None else np.ascontiguousarray(t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t, dtype=np.float32)
+    dw, db, pw, pb = as_np(dw_weight), as_np(dw_bias), as_np(pw_weight), as_np(pw_bias)
+    N, C, H, W = x.shape
+    dw = dw.reshape(C, 3, 3)
+    pw = pw.reshape(-1, C)
+    Cout = pw.shape[0]
+    out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
+    vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().premvos_sepconv2d_forward(x.data_ptr(), vp(dw), vp(db), vp(pw), vp(pb), out.data_ptr(), N, C, H, W, Cout,
+                                                        1 if relu_in else 0, 1 if relu_mid else 0, float(slope), st))
+    return out
+
+
 def top_k(scores: np.ndarray, k: int) -> np.ndarray:
     """tf.nn.top_k indices (proposal_net/model.py:189-190), ordered by (score desc, index asc); k <= 1024."""
     s = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1)

@@ -116,3 +116,33 @@ def test_conv2d_errors_are_loud():
         ops.conv2d(x, np.zeros((8, 8, 3, 3), np.float32), None, stride=3)
     with pytest.raises(ValueError):
         ops.conv2d(x, np.zeros((8, 4, 3, 3), np.float32))
+
+
+SEP_CASES = [
+    # (N, C, H, W, Cout, relu_in, relu_mid, slope)
+    (1, 32, 16, 8, 32, False, False, 1.0),       # one exact tile, one k-block
+    (2, 64, 37, 29, 128, True, False, 0.0),      # ragged tiles, two k-blocks, ReLU in front and behind (Xception entry flow)
+    (3, 128, 45, 52, 128, False, False, 0.0),    # entry-flow block1 separable_conv2 geometry (4 k-blocks), several tiles per CTA
+    (1, 40, 20, 21, 96, False, True, 1.0),       # channel tail inside the last k-block (40 = 5 chunks), ReLU between dw and pw, 96 outputs
+    (4, 128, 193, 193, 128, False, False, 0.0),  # full size: 4 crops of the benchmarked layer (persistent CTAs over 1 300 tiles)
+]
+
+
+@pytest.mark.parametrize("case", SEP_CASES, ids=lambda c: "n%d_c%d_%dx%d_o%d" % c[:5])
+def test_fused_separable_conv_matches_torch(case):
+    N, C, H, W, Cout, relu_in, relu_mid, slope = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(N, C, H, W, generator=g)
+    dw = torch.randn(C, 1, 3, 3, generator=g) / 3.0
+    db = torch.randn(C, generator=g) * 0.1
+    pw = torch.randn(Cout, C, 1, 1, generator=g) / np.sqrt(C)
+    pb = torch.randn(Cout, generator=g) * 0.1
+    xin = F.relu(x) if relu_in else x
+    mid = F.conv2d(xin.double(), dw.double(), db.double(), padding=1, groups=C)
+    if relu_mid:
+        mid = F.relu(mid)
+    y = F.conv2d(mid, pw.double(), pb.double())
+    ref = torch.where(y > 0, y, y * slope).float()
+    got = ops.sepconv2d(x.cuda(), dw, db, pw, pb, relu_in, relu_mid, slope).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(got.numpy(), ref.numpy()) < TOL
