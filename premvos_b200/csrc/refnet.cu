@@ -253,7 +253,10 @@ int build_network(premvos_refnet* n) {
   n->stem_rows = !(getenv("PREMVOS_STEM_ROWS") && atoi(getenv("PREMVOS_STEM_ROWS")) == 0);
   if (n->stem_rows) PV_TRY(alloc_cview(n, &n->input, 16, S, S1));
   else PV_TRY(alloc_cview(n, &n->input, 8, S, S));
+  const bool use_f8 = getenv("PREMVOS_REFNET_F8") ? atoi(getenv("PREMVOS_REFNET_F8")) != 0 : true;
+  const bool fuse_sep = use_f8 && (getenv("PREMVOS_REFNET_FUSE_SEP") ? atoi(getenv("PREMVOS_REFNET_FUSE_SEP")) != 0 : true);
   CView c11, c12;
+  FView c12f;   // conv1_2's output a second time in F8: the input of the fused first separable convolution (the CP8 copy feeds the shortcut)
   PV_TRY(alloc_cview(n, &c11, 32, S1, S1));
   PV_TRY(alloc_cview(n, &c12, 64, S1, S1));
   {
@@ -280,15 +283,14 @@ int build_network(premvos_refnet* n) {
       PV_TRY(add_conv(n, x + "entry_flow/conv1_1", true, XC_EPS, n->input, o, g, map4, 8));
     }
     ConvOut o2; o2.cp = c12;
+    if (fuse_sep && (long)S1 * S1 >= 4096) { PV_TRY(alloc_fview(n, &c12f, 64, S1, S1)); o2.f8 = c12f; }
     PV_TRY(add_conv(n, x + "entry_flow/conv1_2", true, XC_EPS, c11, o2, ConvGeom::same3x3(1, 0.f)));
   }
   // Formats (see dw_f8.cu): a tensor that is a tensor-core operand (input of a shortcut / ASPP / decoder convolution) is CP8; a
   // pointwise output consumed only by the next depthwise convolution is F8 with the consumer's leading ReLU already applied; a
   // unit output consumed by the next unit's first depthwise + sum skip (middle flow, exit block 2) is F8, raw.
-  const bool use_f8 = getenv("PREMVOS_REFNET_F8") ? atoi(getenv("PREMVOS_REFNET_F8")) != 0 : true;
-  const bool fuse_sep = getenv("PREMVOS_REFNET_FUSE_SEP") ? atoi(getenv("PREMVOS_REFNET_FUSE_SEP")) != 0 : true;
   CView cur = c12, low_level;
-  FView cur_f;   // the unit input when it is F8 (cur is null then)
+  FView cur_f = c12f;   // the unit input when it is F8 (cur is null then; the root's output exists in both formats when it is fused)
   const int target = 16 / 2;  // output_stride 16, halved by the stride-2 root conv (xception.py:424-429)
   int current_stride = 1, rate = 1;
   const std::vector<BlockSpec> specs = block_specs(n->middle_units);
