@@ -50,6 +50,13 @@ def test_argument_errors(L):
     assert L.premvos_corr_output_shape(2, 2, 0, 1, 4, 1, 1, None, None, None) == -1   # empty output
     assert L.premvos_corr_output_shape(8, 8, 4, 2, 4, 1, 1, None, None, None) == -1   # even kernel
     assert L.premvos_corr_forward(None, None, None, 1, 1, 2, 2, 0, 1, 0, 1, 1, 1, None) == -1
+    # the fused separable-convolution hook: null pointers, then (with dummy non-null pointers) more than one output-channel tile
+    assert L.premvos_sepconv2d_forward(None, None, None, None, None, None, 1, 32, 8, 8, 32, 0, 0, 1.0, None) == -1
+    buf = (ctypes.c_float * 4)()
+    assert L.premvos_sepconv2d_forward(buf, buf, None, buf, None, buf, 1, 32, 8, 8, 256, 0, 0, 1.0, None) == -2
+    assert b"cout <= 128" in L.premvos_last_error()
+    h2 = ctypes.c_void_p()
+    assert L.premvos_reidnet_create(ctypes.byref(h2), 0) == -1 and L.premvos_reidnet_create(None, 4) == -1
     with pytest.raises(_lib.PremvosError):
         _lib.check(L.premvos_pwc_forward(None, None, None, None))
 
